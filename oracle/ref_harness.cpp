@@ -99,6 +99,7 @@ public:
     }
     bool process (size_t partId, const Type& kmer, const CountVector& count, CountNumber sum)
     {
+        if (sum == 0)  { for (size_t i=0; i<count.size(); i++) sum += count[i]; }   /* like CountProcessorChain::process :130 */
         RefRec r; split (kmer, r.lo, r.hi); r.count = sum; _local.push_back (r);
         return true;
     }
@@ -202,7 +203,7 @@ API void ref_dsk_free (RefDsk* r) { delete r; }
  * ===================================================================================================== */
 /* Feeds 'n' abundances through the reference Histogram; returns clamped table [0..histo_max] + auto cutoff. */
 API void ref_histogram (const int32_t* abundances, uint64_t n, int histo_max, int min_auto_threshold,
-                    uint64_t* table_out, uint16_t* cutoff_out, uint64_t* nbsolids_out, uint16_t* first_peak_out)
+                    uint64_t* table_out, uint32_t* cutoff_out, uint64_t* nbsolids_out, uint32_t* first_peak_out)
 {
     Histogram h (histo_max);
     for (uint64_t i=0; i<n; i++)  h.inc (abundances[i]);
