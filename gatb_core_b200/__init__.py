@@ -1,0 +1,271 @@
+"""gatb_core_b200 -- B200-native k-mer counting behind GATB-core's DSK interface.
+
+This Python module is only a thin ctypes caller of the C ABI in include/gatb_gpu.h (libgatb_b200.so, built in-tree
+from gatb_core_b200/csrc/*.cu for sm_100a by build.py).  There is NO CPU fallback: importing works without a GPU
+(so the symbol table can be checked), but every compute call needs a CUDA device and raises GatbGpuError otherwise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgatb_b200.so")
+
+NSTATS = 16
+STAT_NAMES = ["kmers_nb_valid", "kmers_nb_invalid", "kmers_nb_distinct", "kmers_nb_solid", "records", "sequences",
+              "nucleotides", "bins", "overflow_bins", "retries", "record_bytes"]
+BLOOM_KINDS = {"basic": 0, "cache": 1, "neighbor": 2}
+
+# every symbol include/gatb_gpu.h declares (tests check the library exports exactly these)
+EXPORTS = ["gatb_gpu_create", "gatb_gpu_destroy", "gatb_gpu_last_error", "gatb_gpu_stream", "gatb_gpu_kernel_launches",
+           "gatb_gpu_sm_count", "gatb_gpu_count", "gatb_gpu_count_dev", "gatb_gpu_result_free", "gatb_gpu_superkmers",
+           "gatb_gpu_free_host", "gatb_gpu_bloom_params", "gatb_gpu_bloom_layout", "gatb_gpu_bloom", "gatb_gpu_bloom_dev",
+           "gatb_gpu_histogram_cutoff", "gatb_gpu_malloc", "gatb_gpu_free", "gatb_gpu_memcpy_h2d", "gatb_gpu_memcpy_d2h",
+           "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii"]
+
+
+class GatbGpuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("minimizer_size", C.c_int32), ("nb_partitions", C.c_int32),
+                ("nb_passes", C.c_int32), ("abundance_min", C.c_int32), ("abundance_max", C.c_int32),
+                ("histo_max", C.c_int32), ("minimizer_type", C.c_int32), ("emit_all", C.c_int32),
+                ("read_len", C.c_int32), ("table_log2", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class Result(C.Structure):
+    _fields_ = [("n_keys", C.c_uint64), ("n_items", C.c_uint64), ("part_offsets", C.c_void_p), ("kmers_lo", C.c_void_p),
+                ("kmers_hi", C.c_void_p), ("counts", C.c_void_p), ("histogram", C.c_void_p),
+                ("stats", C.c_uint64 * NSTATS), ("seconds", C.c_double * 8), ("on_device", C.c_int32), ("pad", C.c_int32),
+                ("owner", C.c_void_p)]
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise GatbGpuError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                           "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    VP, U64, I32 = C.c_void_p, C.c_uint64, C.c_int
+    L.gatb_gpu_create.restype = VP
+    L.gatb_gpu_create.argtypes = [I32]
+    L.gatb_gpu_destroy.argtypes = [VP]
+    L.gatb_gpu_last_error.restype = C.c_char_p
+    L.gatb_gpu_last_error.argtypes = [VP]
+    L.gatb_gpu_stream.restype = VP
+    L.gatb_gpu_stream.argtypes = [VP]
+    L.gatb_gpu_kernel_launches.restype = U64
+    L.gatb_gpu_kernel_launches.argtypes = [VP]
+    L.gatb_gpu_sm_count.argtypes = [VP]
+    for f in ("gatb_gpu_count", "gatb_gpu_count_dev"):
+        getattr(L, f).argtypes = [VP, C.POINTER(Params), VP, VP, VP, VP, U64, VP, C.POINTER(Result)]
+    L.gatb_gpu_result_free.argtypes = [VP, C.POINTER(Result)]
+    L.gatb_gpu_superkmers.argtypes = [VP, C.POINTER(Params), VP, VP, VP, U64, VP, C.POINTER(VP), VP, VP]
+    L.gatb_gpu_free_host.argtypes = [VP]
+    L.gatb_gpu_bloom_params.argtypes = [I32, U64, C.POINTER(U64), C.POINTER(C.c_int32)]
+    L.gatb_gpu_bloom_layout.argtypes = [I32, U64, C.POINTER(U64), C.POINTER(U64)]
+    L.gatb_gpu_bloom.argtypes = [VP, I32, U64, I32, I32, VP, VP, U64, VP]
+    L.gatb_gpu_bloom_dev.argtypes = [VP, I32, U64, I32, I32, VP, VP, U64, VP]
+    L.gatb_gpu_histogram_cutoff.argtypes = [VP, I32, I32, C.POINTER(C.c_uint32), C.POINTER(U64), C.POINTER(C.c_uint32)]
+    L.gatb_gpu_malloc.restype = VP
+    L.gatb_gpu_malloc.argtypes = [VP, U64]
+    L.gatb_gpu_free.argtypes = [VP, VP]
+    L.gatb_gpu_memcpy_h2d.argtypes = [VP, VP, VP, U64]
+    L.gatb_gpu_memcpy_d2h.argtypes = [VP, VP, VP, U64]
+    L.gatb_gpu_synchronize.argtypes = [VP]
+    L.gatb_gpu_synth_reads_dev.argtypes = [VP, U64, U64, U64, U64, I32, VP]
+    L.gatb_gpu_pack_ascii.argtypes = [VP, C.c_char_p, U64, VP, VP, C.POINTER(U64)]
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class GatbGpu:
+    """One context per GPU (one process per GPU for multi-GPU runs)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.ctx = self.L.gatb_gpu_create(device)
+        if not self.ctx:
+            raise GatbGpuError(self.L.gatb_gpu_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.gatb_gpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GatbGpuError(self.L.gatb_gpu_last_error(self.ctx).decode())
+
+    @property
+    def kernel_launches(self):
+        return self.L.gatb_gpu_kernel_launches(self.ctx)
+
+    @property
+    def stream(self):
+        return self.L.gatb_gpu_stream(self.ctx)
+
+    @property
+    def sm_count(self):
+        return self.L.gatb_gpu_sm_count(self.ctx)
+
+    # ---- DSK ---------------------------------------------------------------------------------------------------
+    @staticmethod
+    def make_params(k, m, nb_partitions=1, nb_passes=1, abundance_min=2, abundance_max=2**31 - 1, histo_max=10000,
+                    emit_all=False, read_len=0, table_log2=0):
+        p = Params()
+        p.kmer_size, p.minimizer_size, p.nb_partitions, p.nb_passes = k, m, nb_partitions, nb_passes
+        p.abundance_min, p.abundance_max, p.histo_max, p.minimizer_type = abundance_min, abundance_max, histo_max, 0
+        p.emit_all, p.read_len, p.table_log2 = int(emit_all), read_len, table_log2
+        return p
+
+    def count(self, packed, offsets, n_reads, params, repart=None, n_mask=None):
+        """Host buffers in, host arrays out.  Returns dict(parts={key:(lo,hi,counts)}, histogram, stats, seconds)."""
+        res = Result()
+        rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
+        self._check(self.L.gatb_gpu_count(self.ctx, C.byref(params), _ptr(rp), None, _ptr(packed), _ptr(offsets), n_reads,
+                                          _ptr(n_mask), C.byref(res)))
+        try:
+            return self._unpack_host(res, params)
+        finally:
+            self.L.gatb_gpu_result_free(self.ctx, C.byref(res))
+
+    def count_dev(self, d_packed, d_offsets, n_reads, params, repart=None, d_n_mask=None):
+        """Device pointers (ints) in; returns the raw Result (device arrays) -- free with result_free()."""
+        res = Result()
+        rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
+        self._check(self.L.gatb_gpu_count_dev(self.ctx, C.byref(params), _ptr(rp), None, _ptr(d_packed), _ptr(d_offsets),
+                                              n_reads, _ptr(d_n_mask), C.byref(res)))
+        return res
+
+    def result_free(self, res):
+        self.L.gatb_gpu_result_free(self.ctx, C.byref(res))
+
+    def result_to_host(self, res, params):
+        """Copies a device Result to numpy arrays (same layout as count())."""
+        W = 1 if params.kmer_size < 32 else 2
+        n, nk = int(res.n_items), int(res.n_keys)
+        offs = np.zeros(nk + 1, np.uint64)
+        lo, hi, cn = np.zeros(n, np.uint64), np.zeros(n if W == 2 else 0, np.uint64), np.zeros(n, np.int32)
+        hist = np.zeros(params.histo_max + 1, np.uint64)
+        self.d2h(offs, res.part_offsets)
+        self.d2h(hist, res.histogram)
+        if n:
+            self.d2h(lo, res.kmers_lo)
+            self.d2h(cn, res.counts)
+            if W == 2:
+                self.d2h(hi, res.kmers_hi)
+        return self._assemble(res, offs, lo, hi if W == 2 else np.zeros(n, np.uint64), cn, hist)
+
+    def _unpack_host(self, res, params):
+        W = 1 if params.kmer_size < 32 else 2
+        n, nk = int(res.n_items), int(res.n_keys)
+
+        def arr(ptr, count, dtype):
+            if count == 0 or not ptr:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (count,)).copy()
+        offs = arr(res.part_offsets, nk + 1, np.uint64)
+        lo, cn = arr(res.kmers_lo, n, np.uint64), arr(res.counts, n, np.int32)
+        hi = arr(res.kmers_hi, n, np.uint64) if W == 2 else np.zeros(n, np.uint64)
+        hist = arr(res.histogram, params.histo_max + 1, np.uint64)
+        return self._assemble(res, offs, lo, hi, cn, hist)
+
+    @staticmethod
+    def _assemble(res, offs, lo, hi, cn, hist):
+        parts = {}
+        for key in range(int(res.n_keys)):
+            a, b = int(offs[key]), int(offs[key + 1])
+            parts[key] = (lo[a:b], hi[a:b], cn[a:b])
+        stats = {name: int(res.stats[i]) for i, name in enumerate(STAT_NAMES)}
+        return {"parts": parts, "part_offsets": offs, "histogram": hist, "stats": stats,
+                "seconds": [float(x) for x in res.seconds], "n_items": int(res.n_items)}
+
+    # ---- GATB-exact super-k-mers ---------------------------------------------------------------------------------
+    def superkmers(self, packed, offsets, n_reads, params, repart=None, n_mask=None):
+        nk = params.nb_partitions * params.nb_passes
+        ptrs = (C.c_void_p * nk)()
+        sizes = np.zeros(nk, np.uint64)
+        stats = np.zeros(4, np.uint64)
+        rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
+        self._check(self.L.gatb_gpu_superkmers(self.ctx, C.byref(params), _ptr(rp), _ptr(packed), _ptr(offsets), n_reads,
+                                               _ptr(n_mask), ptrs, _ptr(sizes), _ptr(stats)))
+        out = []
+        for key in range(nk):
+            out.append(C.string_at(ptrs[key], int(sizes[key])))
+            self.L.gatb_gpu_free_host(ptrs[key])
+        return out, stats
+
+    # ---- Bloom ---------------------------------------------------------------------------------------------------
+    def bloom_params(self, k, nb_solid):
+        s, h = C.c_uint64(), C.c_int32()
+        if self.L.gatb_gpu_bloom_params(k, nb_solid, C.byref(s), C.byref(h)):
+            raise GatbGpuError("bad kmer size")
+        return s.value, h.value
+
+    def bloom_layout(self, kind, bloom_size):
+        nb, bits = C.c_uint64(), C.c_uint64()
+        if self.L.gatb_gpu_bloom_layout(BLOOM_KINDS[kind], bloom_size, C.byref(nb), C.byref(bits)):
+            raise GatbGpuError("bad Bloom kind")
+        return nb.value, bits.value
+
+    def bloom(self, kind, bloom_size, nb_hash, k, lo, hi=None):
+        nbytes, bits = self.bloom_layout(kind, bloom_size)
+        out = np.zeros(nbytes, np.uint8)
+        lo = np.ascontiguousarray(lo, np.uint64)
+        hi = None if hi is None else np.ascontiguousarray(hi, np.uint64)
+        self._check(self.L.gatb_gpu_bloom(self.ctx, BLOOM_KINDS[kind], bloom_size, nb_hash, k, _ptr(lo), _ptr(hi), len(lo), _ptr(out)))
+        return out, bits
+
+    def histogram_cutoff(self, histogram, min_auto_threshold=3):
+        h = np.ascontiguousarray(histogram, np.uint64)
+        c, n, p = C.c_uint32(), C.c_uint64(), C.c_uint32()
+        if self.L.gatb_gpu_histogram_cutoff(_ptr(h), len(h) - 1, min_auto_threshold, C.byref(c), C.byref(n), C.byref(p)):
+            raise GatbGpuError("bad histogram")
+        return c.value, n.value, p.value
+
+    # ---- device utilities ----------------------------------------------------------------------------------------
+    def malloc(self, nbytes):
+        p = self.L.gatb_gpu_malloc(self.ctx, nbytes)
+        if not p:
+            raise GatbGpuError(self.L.gatb_gpu_last_error(self.ctx).decode())
+        return p
+
+    def free(self, p):
+        self.L.gatb_gpu_free(self.ctx, p)
+
+    def h2d(self, dptr, arr):
+        self._check(self.L.gatb_gpu_memcpy_h2d(self.ctx, _ptr(dptr), _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        self._check(self.L.gatb_gpu_memcpy_d2h(self.ctx, _ptr(arr), _ptr(dptr), arr.nbytes))
+
+    def synchronize(self):
+        self._check(self.L.gatb_gpu_synchronize(self.ctx))
+
+    def synth_reads_dev(self, seed, genome_len, first_read, n_reads, L, d_packed):
+        self._check(self.L.gatb_gpu_synth_reads_dev(self.ctx, seed, genome_len, first_read, n_reads, L, _ptr(d_packed)))
+
+    def pack_ascii(self, ascii_bytes):
+        n = len(ascii_bytes)
+        packed = np.zeros((n + 3) // 4 + 16, np.uint8)
+        mask = np.zeros((n + 31) // 32 + 4, np.uint32)
+        bad = C.c_uint64()
+        self._check(self.L.gatb_gpu_pack_ascii(self.ctx, ascii_bytes, n, _ptr(packed), _ptr(mask), C.byref(bad)))
+        return packed, mask, bad.value

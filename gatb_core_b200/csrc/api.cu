@@ -1,0 +1,688 @@
+// api.cu -- the extern "C" boundary (include/gatb_gpu.h): context, buffers, stage orchestration.
+// No CPU fallback anywhere: every compute entry point needs the CUDA device of its context.
+#include "../../include/gatb_gpu.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "gatb_tables.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+static std::string g_create_error;
+
+// device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
+enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_FINECNT, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_NSLOTS };
+
+struct gatb_gpu_ctx
+{
+    int device; int sm_count; cudaStream_t stream; uint64_t launches;
+    std::string error;
+    void* slot[S_NSLOTS]; size_t slot_cap[S_NSLOTS];
+    cudaEvent_t ev[8];
+    void* pinned; size_t pinned_cap;
+    const uint16_t* repart_host_cached; uint64_t repart_bytes_cached;
+};
+
+static int fail (gatb_gpu_ctx* c, const char* fmt, ...)
+{
+    char buf[1024]; va_list ap; va_start (ap, fmt); vsnprintf (buf, sizeof(buf), fmt, ap); va_end (ap);
+    if (c) c->error = buf; else g_create_error = buf;
+    return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail (ctx, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString (e_)); } while (0)
+
+static int ensure (gatb_gpu_ctx* ctx, int s, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (ctx->slot_cap[s] >= bytes) return 0;
+    if (ctx->slot[s]) { cudaStreamSynchronize (ctx->stream); cudaFree (ctx->slot[s]); ctx->slot[s] = 0; ctx->slot_cap[s] = 0; }
+    size_t want = bytes + bytes / 16 + 256;                         // a little head-room against re-allocation
+    cudaError_t e = cudaMalloc (&ctx->slot[s], want);
+    if (e != cudaSuccess) { e = cudaMalloc (&ctx->slot[s], bytes); want = bytes; }
+    if (e != cudaSuccess) return fail (ctx, "cudaMalloc of %zu bytes (slot %d) failed: %s", bytes, s, cudaGetErrorString (e));
+    ctx->slot_cap[s] = want;
+    return 0;
+}
+static void release (gatb_gpu_ctx* ctx, int s)
+{ if (ctx->slot[s]) { cudaStreamSynchronize (ctx->stream); cudaFree (ctx->slot[s]); ctx->slot[s] = 0; ctx->slot_cap[s] = 0; } }
+
+static LaunchCtx lctx (gatb_gpu_ctx* ctx) { LaunchCtx L; L.stream = ctx->stream; L.sm_count = ctx->sm_count; L.launches = &ctx->launches; return L; }
+
+extern "C" {
+
+gatb_gpu_ctx* gatb_gpu_create (int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount (&n);
+    if (e != cudaSuccess || n == 0) { fail (0, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString (e)); return 0; }
+    if (device < 0 || device >= n) { fail (0, "device %d out of range (%d devices)", device, n); return 0; }
+    if ((e = cudaSetDevice (device)) != cudaSuccess) { fail (0, "cudaSetDevice(%d): %s", device, cudaGetErrorString (e)); return 0; }
+    gatb_gpu_ctx* ctx = new gatb_gpu_ctx ();
+    ctx->device = device; ctx->launches = 0; ctx->pinned = 0; ctx->pinned_cap = 0; ctx->repart_host_cached = 0; ctx->repart_bytes_cached = 0;
+    memset (ctx->slot, 0, sizeof(ctx->slot)); memset (ctx->slot_cap, 0, sizeof(ctx->slot_cap));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties (&prop, device)) != cudaSuccess) { fail (0, "cudaGetDeviceProperties: %s", cudaGetErrorString (e)); delete ctx; return 0; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail (0, "cudaStreamCreate: %s", cudaGetErrorString (e)); delete ctx; return 0; }
+    for (int i = 0; i < 8; i++) cudaEventCreate (&ctx->ev[i]);
+    return ctx;
+}
+void gatb_gpu_destroy (gatb_gpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice (ctx->device);
+    cudaStreamSynchronize (ctx->stream);
+    for (int s = 0; s < S_NSLOTS; s++) if (ctx->slot[s]) cudaFree (ctx->slot[s]);
+    if (ctx->pinned) cudaFreeHost (ctx->pinned);
+    for (int i = 0; i < 8; i++) cudaEventDestroy (ctx->ev[i]);
+    cudaStreamDestroy (ctx->stream);
+    delete ctx;
+}
+const char* gatb_gpu_last_error (gatb_gpu_ctx* ctx) { return ctx ? ctx->error.c_str () : g_create_error.c_str (); }
+void*    gatb_gpu_stream (gatb_gpu_ctx* ctx) { return (void*)ctx->stream; }
+uint64_t gatb_gpu_kernel_launches (gatb_gpu_ctx* ctx) { return ctx->launches; }
+int      gatb_gpu_sm_count (gatb_gpu_ctx* ctx) { return ctx->sm_count; }
+
+void* gatb_gpu_malloc (gatb_gpu_ctx* ctx, uint64_t bytes)
+{ cudaSetDevice (ctx->device); void* p = 0; if (cudaMalloc (&p, bytes ? bytes : 16) != cudaSuccess) { fail (ctx, "cudaMalloc(%llu) failed", (unsigned long long)bytes); return 0; } return p; }
+void gatb_gpu_free (gatb_gpu_ctx* ctx, void* p) { cudaSetDevice (ctx->device); if (p) cudaFree (p); }
+int gatb_gpu_memcpy_h2d (gatb_gpu_ctx* ctx, void* dst, const void* src, uint64_t bytes)
+{ cudaSetDevice (ctx->device); CK (cudaMemcpyAsync (dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); CK (cudaStreamSynchronize (ctx->stream)); return 0; }
+int gatb_gpu_memcpy_d2h (gatb_gpu_ctx* ctx, void* dst, const void* src, uint64_t bytes)
+{ cudaSetDevice (ctx->device); CK (cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); CK (cudaStreamSynchronize (ctx->stream)); return 0; }
+int gatb_gpu_synchronize (gatb_gpu_ctx* ctx) { cudaSetDevice (ctx->device); CK (cudaStreamSynchronize (ctx->stream)); return 0; }
+
+int gatb_gpu_synth_reads_dev (gatb_gpu_ctx* ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, uint64_t n_reads, int L, uint8_t* d_packed)
+{
+    cudaSetDevice (ctx->device);
+    if (genome_len < (uint64_t)L) return fail (ctx, "genome_len < read length");
+    CK (launch_synth_reads (lctx (ctx), seed, genome_len, first_read, n_reads, L, d_packed));
+    return 0;
+}
+
+int gatb_gpu_pack_ascii (gatb_gpu_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out, uint32_t* n_mask_out, uint64_t* n_invalid)
+{
+    cudaSetDevice (ctx->device);
+    uint64_t groups = (n + 31) / 32;
+    if (ensure (ctx, S_MISC, n + 64)) return 1;
+    if (ensure (ctx, S_MISC2, groups * 12 + 64)) return 1;
+    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
+    char* d_ascii = (char*)ctx->slot[S_MISC];
+    uint32_t* d_words = (uint32_t*)ctx->slot[S_MISC2]; uint32_t* d_mask = d_words + 2 * groups;
+    unsigned long long* d_bad = (unsigned long long*)ctx->slot[S_STATS];
+    CK (cudaMemcpyAsync (d_ascii, ascii, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK (cudaMemsetAsync (d_bad, 0, 8, ctx->stream));
+    CK (launch_pack_ascii (lctx (ctx), d_ascii, n, d_words, d_mask, d_bad));
+    CK (cudaMemcpyAsync (packed_out, d_words, (n + 3) / 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_mask_out) CK (cudaMemcpyAsync (n_mask_out, d_mask, groups * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long bad = 0;
+    CK (cudaMemcpyAsync (&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    if (n_invalid) *n_invalid = bad;
+    return 0;
+}
+
+} // extern "C"
+
+// =====================================================================================================================
+//  DSK
+// =====================================================================================================================
+struct DevResult      // device-side arrays of one gatb_gpu_count_dev call (freed by gatb_gpu_result_free)
+{
+    void* lo; void* hi; void* cnt; void* histo; void* offs;
+};
+
+static int check_params (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart)
+{
+    if (!p) return fail (ctx, "params is NULL");
+    if (p->kmer_size < 2 || p->kmer_size > 63) return fail (ctx, "kmer_size %d not supported (2..63: Kmer<32> and Kmer<64>)", p->kmer_size);
+    if (p->minimizer_size < 1 || p->minimizer_size > 12 || p->minimizer_size >= p->kmer_size)
+        return fail (ctx, "Bad values for kmer %d and minimizer %d", p->kmer_size, p->minimizer_size);     // Model.hpp:1014
+    if (p->nb_partitions < 1 || p->nb_passes < 1) return fail (ctx, "nb_partitions and nb_passes must be >= 1");
+    if ((uint64_t)p->nb_partitions * p->nb_passes > 65535) return fail (ctx, "too many partition keys");
+    if ((uint64_t)p->nb_partitions * p->nb_passes > 1 && !repart) return fail (ctx, "a Repartitor table is required when nb_partitions*nb_passes > 1");
+    if (p->minimizer_type != 0) return fail (ctx, "minimizer_type %d (frequency order) is not supported on the device path yet", p->minimizer_type);
+    if (p->histo_max < 1) return fail (ctx, "histo_max must be >= 1");
+    return 0;
+}
+
+static int pick_device_m (int k, uint64_t nbins_fine)
+{
+    // smallest m whose canonical m-mer space is >= 16x the number of device bins, within [8, 15] and < k
+    int m = 8;
+    while (m < 15 && (1ULL << (2*m - 1)) < 16 * nbins_fine) m++;
+    if (m > k - 1) m = k - 1;
+    if (m < 1) m = 1;
+    return m;
+}
+
+// total number of k-mer positions (device reduction is overkill for a bound: offsets are small or read_len fixed)
+__global__ void k_count_kmers (const uint64_t* offsets, uint64_t n_reads, int k, unsigned long long* out /* [0] kmers [1] nt [2] maxlen */)
+{
+    unsigned long long km = 0, nt = 0, mx = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t)gridDim.x * blockDim.x)
+    {
+        unsigned long long len = offsets[i+1] - offsets[i];
+        nt += len; if (len >= (unsigned long long)k) km += len - k + 1; if (len > mx) mx = len;
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { km += __shfl_xor_sync (FULL_MASK, km, o); nt += __shfl_xor_sync (FULL_MASK, nt, o); unsigned long long y = __shfl_xor_sync (FULL_MASK, mx, o); mx = y > mx ? y : mx; }
+    if ((threadIdx.x & 31) == 0) { atomicAdd (&out[0], km); atomicAdd (&out[1], nt); atomicMax (&out[2], mx); }
+}
+
+static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_host,
+                           const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
+                           gatb_gpu_result* out)
+{
+    LaunchCtx L = lctx (ctx);
+    const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
+    const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
+    const int histo_max = p->histo_max;
+    cudaEventRecord (ctx->ev[1], ctx->stream);
+
+    // ---- workload size ----
+    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
+    unsigned long long* d_stats = (unsigned long long*)ctx->slot[S_STATS];
+    uint64_t total_kmers = 0, total_nt = 0, max_len = 0;
+    if (!d_offsets)
+    {
+        if (p->read_len <= 0) return fail (ctx, "read_offsets_nt is NULL and read_len <= 0");
+        total_nt = n_reads * (uint64_t)p->read_len; max_len = p->read_len;
+        total_kmers = p->read_len >= k ? n_reads * (uint64_t)(p->read_len - k + 1) : 0;
+    }
+    else
+    {
+        CK (cudaMemsetAsync (d_stats + 32, 0, 3 * 8, ctx->stream));
+        if (n_reads) { k_count_kmers<<<ctx->sm_count * 4, 256, 0, ctx->stream>>> (d_offsets, n_reads, k, d_stats + 32); ctx->launches++; }
+        unsigned long long h[3];
+        CK (cudaMemcpyAsync (h, d_stats + 32, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+        total_kmers = h[0]; total_nt = h[1]; max_len = h[2];
+    }
+    if (max_len >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported by the partition kernel yet (longest: %llu)", (unsigned long long)max_len);
+
+    // ---- device binning geometry ----
+    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : 13;
+    if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
+    const uint64_t T = 1ULL << table_log2;
+    const uint64_t occ_per_bin = (T * 55) / 100;
+    const int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
+    uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
+    uint64_t nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits; if (nb1 < 1) nb1 = 1;
+    if (nb1 > (1ULL << 24)) return fail (ctx, "input too large for one device (%llu coarse bins)", (unsigned long long)nb1);
+    const uint64_t nbins = nb1 << fine_bits;
+    const int mg = pick_device_m (k, nbins);
+    const int w = k - mg + 1;
+    const int maxlen = (W == 1) ? 28 : 60;                                      // Sequence2SuperKmer.hpp:147
+    double est_records = (double)total_kmers * 2.0 / (w + 1) * 1.10 + (double)n_reads * 0.5 + 64;
+    uint64_t cap = (uint64_t)(est_records / nb1 * 1.30) + 64; cap = (cap + 7) & ~7ULL;
+    const size_t rec_bytes = 16 * W;
+
+    K1Params k1; memset (&k1, 0, sizeof(k1));
+    k1.words = (const uint64_t*)d_reads; k1.offsets = d_offsets; k1.nmask = d_nmask; k1.n_reads = n_reads; k1.read_len = p->read_len;
+    k1.k = k; k1.m = mg; k1.w = w; k1.maxlen = maxlen;
+    k1.mmask = (mg >= 16) ? 0xFFFFFFFFu : ((1u << (2*mg)) - 1); k1.mask_ma1 = 0;
+    k1.mode = K1_MODE_DEVICE; k1.nb1 = (uint32_t)nb1; k1.fine_bits = fine_bits; k1.count_only = 0;
+
+    if (ensure (ctx, S_CURSORS, nb1 * 4)) return 1;
+    if (ensure (ctx, S_FINECNT, nbins * 4)) return 1;
+    if (ensure (ctx, S_BINDESC, nbins * 8)) return 1;
+    uint64_t retries = 0;
+    unsigned long long h_stats[4];
+    for (;;)
+    {
+        if (cap * nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %llu x %llu bins)", (unsigned long long)cap, (unsigned long long)nb1);
+        if (ensure (ctx, S_COARSE, nb1 * cap * rec_bytes)) return 1;
+        k1.bins = ctx->slot[S_COARSE]; k1.cap = (uint32_t)cap;
+        k1.cursors = (uint32_t*)ctx->slot[S_CURSORS]; k1.fine_counts = (uint32_t*)ctx->slot[S_FINECNT]; k1.stats = d_stats;
+        CK (cudaMemsetAsync (k1.cursors, 0, nb1 * 4, ctx->stream));
+        CK (cudaMemsetAsync (k1.fine_counts, 0, nbins * 4, ctx->stream));
+        CK (cudaMemsetAsync (d_stats, 0, 4 * 8, ctx->stream));
+        if (n_reads) CK (launch_k1 (L, k1));
+        CK (cudaMemcpyAsync (h_stats, d_stats, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+        if (h_stats[3] == 0) break;
+        // a bin overflowed: the cursors hold the true demand -> size for the largest and run again
+        std::vector<uint32_t> cur (nb1);
+        CK (cudaMemcpy (cur.data (), k1.cursors, nb1 * 4, cudaMemcpyDeviceToHost));
+        uint32_t mx = 0; for (uint64_t i = 0; i < nb1; i++) if (cur[i] > mx) mx = cur[i];
+        cap = ((uint64_t)mx + 7) & ~7ULL;
+        if (++retries > 3) return fail (ctx, "partition kernel still overflows after %llu retries", (unsigned long long)retries);
+    }
+    cudaEventRecord (ctx->ev[2], ctx->stream);
+
+    // ---- k2a: fine split ----
+    if (ensure (ctx, S_FINE, nb1 * cap * rec_bytes)) return 1;
+    CK (launch_k2a_split (L, W, ctx->slot[S_COARSE], ctx->slot[S_FINE], k1.cursors, k1.fine_counts, (uint32_t)nb1, (uint32_t)cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
+    cudaEventRecord (ctx->ev[3], ctx->stream);
+
+    // ---- k2b: count.  The coarse buffer is dead now: it becomes the unsorted output. ----
+    const uint32_t amin = p->abundance_min < 1 ? 1 : (uint32_t)p->abundance_min;
+    const uint32_t amax = p->abundance_max < 0 ? 0x7fffffffu : (uint32_t)p->abundance_max;
+    const uint32_t emin = p->emit_all ? 1u : amin, emax = p->emit_all ? 0xffffffffu : amax;
+    uint64_t out_bound = total_kmers / emin + 1;                               // a k-mer emitted needs >= emin occurrences
+    const size_t item_bytes = 8 * W + 4;
+    uint64_t out_cap = ctx->slot_cap[S_COARSE] / item_bytes;
+    if (out_cap > out_bound) out_cap = out_bound;
+    if (out_cap < 1) out_cap = 1;
+    uint64_t* u_lo = (uint64_t*)ctx->slot[S_COARSE];
+    uint64_t* u_hi = (W == 2) ? u_lo + out_cap : 0;
+    uint32_t* u_cnt = (uint32_t*)(u_lo + out_cap * W);
+
+    if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
+    if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
+    if (ensure (ctx, S_OVFLIST, nbins * 4)) return 1;
+    unsigned long long* d_cnt = (unsigned long long*)ctx->slot[S_COUNTERS];
+    CK (cudaMemsetAsync (ctx->slot[S_HISTO], 0, (size_t)(histo_max + 1) * 8, ctx->stream));
+    CK (cudaMemsetAsync (d_cnt, 0, 16 * 8, ctx->stream));
+
+    K2Params k2; memset (&k2, 0, sizeof(k2));
+    k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins;
+    k2.cap = (uint32_t)cap; k2.fine_bits = fine_bits; k2.table_log2 = table_log2;
+    k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
+    k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
+    k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
+    k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST];
+    CK (launch_k2b_count (L, k2));
+    unsigned long long h_cnt[8];
+    CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    const uint64_t n_ovf = h_cnt[4];
+    if (n_ovf)
+    {   // ---- k2c: bins that did not fit the shared-memory table share one global table ----
+        CK (launch_k2c_measure (L, k2, (uint32_t)n_ovf));
+        CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+        uint64_t occ = h_cnt[5]; int g_log2 = 10; while ((1ULL << g_log2) < 2 * occ) g_log2++;
+        if (g_log2 > 31) return fail (ctx, "fallback table too large (%llu k-mers in overflowing bins)", (unsigned long long)occ);
+        size_t gT = (size_t)1 << g_log2;
+        if (ensure (ctx, S_GTABLE, gT * (8 * W + 4))) return 1;
+        k2.g_lo = (uint64_t*)ctx->slot[S_GTABLE]; k2.g_hi = (W == 2) ? k2.g_lo + gT : 0; k2.g_cnt = (uint32_t*)(k2.g_lo + gT * W); k2.g_log2 = g_log2;
+        if (W == 1) CK (cudaMemsetAsync (k2.g_lo, 0xFF, gT * 8, ctx->stream));
+        else      { CK (cudaMemsetAsync (k2.g_lo, 0, gT * 8, ctx->stream)); CK (cudaMemsetAsync (k2.g_hi, 0xFF, gT * 8, ctx->stream)); }
+        CK (cudaMemsetAsync (k2.g_cnt, 0, gT * 4, ctx->stream));
+        CK (launch_k2c_insert (L, k2, (uint32_t)n_ovf));
+        CK (launch_k2c_scan (L, k2));
+        CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+    }
+    const uint64_t n_items = h_cnt[0];
+    if (n_items > out_cap) return fail (ctx, "output capacity exceeded: %llu k-mers to emit, room for %llu", (unsigned long long)n_items, (unsigned long long)out_cap);
+    cudaEventRecord (ctx->ev[4], ctx->stream);
+
+    // ---- k3: partition id + ascending order ----
+    int t_bits = 0;
+    { uint64_t per_key = n_items / n_keys + 1; while (t_bits < 2*k && t_bits < 24 && (per_key >> t_bits) > 1024) t_bits++; }
+    while (t_bits > 0 && (n_keys << t_bits) > (1ULL << 30)) t_bits--;
+    const uint64_t n_buckets = n_keys << t_bits;
+    DevResult* dr = new DevResult (); memset (dr, 0, sizeof(*dr));
+    uint64_t n_alloc = n_items ? n_items : 1;
+    void* d_sorted = 0;
+    { cudaError_t e = cudaMalloc (&d_sorted, n_alloc * item_bytes + 64); if (e != cudaSuccess) { delete dr; return fail (ctx, "cudaMalloc of the result arrays (%llu items) failed: %s", (unsigned long long)n_items, cudaGetErrorString (e)); } }
+    dr->lo = d_sorted; dr->hi = (W == 2) ? (void*)((uint64_t*)d_sorted + n_alloc) : 0; dr->cnt = (void*)((uint64_t*)d_sorted + n_alloc * W);
+    void* d_offs = 0; void* d_hist = 0;
+    if (cudaMalloc (&d_offs, (n_keys + 1) * 8) != cudaSuccess || cudaMalloc (&d_hist, (size_t)(histo_max + 1) * 8) != cudaSuccess)
+    { cudaFree (d_sorted); delete dr; return fail (ctx, "cudaMalloc of the result tables failed"); }
+    dr->offs = d_offs; dr->histo = d_hist;
+
+    if (ensure (ctx, S_BUCKETOF, n_alloc * 4)) return 1;
+    if (ensure (ctx, S_BUCKETCNT, n_buckets * 4)) return 1;
+    if (ensure (ctx, S_BUCKETOFF, (n_buckets + 1) * 8)) return 1;
+    if (ensure (ctx, S_SCAN, scan_scratch_elems (n_buckets) * 8)) return 1;
+    if (ensure (ctx, S_BIGLIST, n_buckets * 8)) return 1;
+    if (n_keys > 1)
+    {
+        uint64_t rbytes = (1ULL << (2 * p->minimizer_size)) * 2;
+        if (ensure (ctx, S_REPART, rbytes)) return 1;
+        CK (cudaMemcpyAsync (ctx->slot[S_REPART], repart_host, rbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // the fine buffer is dead after k2b/k2c: it holds the bucket-ordered copy
+    if (ctx->slot_cap[S_FINE] < n_alloc * item_bytes) { if (ensure (ctx, S_FINE, n_alloc * item_bytes)) return 1; }
+    K3Params k3; memset (&k3, 0, sizeof(k3));
+    k3.k = k; k3.m = p->minimizer_size; k3.W = W;
+    k3.mmask = (1u << (2 * p->minimizer_size)) - 1; k3.mask_ma1 = gatb_mask_ma1 (p->minimizer_size);
+    k3.repart = (const uint16_t*)ctx->slot[S_REPART]; k3.nb_partitions = p->nb_partitions; k3.nb_passes = p->nb_passes; k3.n_keys = (uint32_t)n_keys;
+    k3.t_bits = t_bits; k3.n = n_items;
+    k3.in_lo = u_lo; k3.in_hi = u_hi; k3.in_cnt = u_cnt;
+    k3.bucket_of = (uint32_t*)ctx->slot[S_BUCKETOF]; k3.bucket_count = (uint32_t*)ctx->slot[S_BUCKETCNT];
+    k3.bucket_off = (const uint64_t*)ctx->slot[S_BUCKETOFF];
+    k3.tmp_lo = (uint64_t*)ctx->slot[S_FINE]; k3.tmp_hi = (W == 2) ? k3.tmp_lo + n_alloc : 0; k3.tmp_cnt = (uint32_t*)(k3.tmp_lo + n_alloc * W);
+    k3.out_lo = (uint64_t*)dr->lo; k3.out_hi = (uint64_t*)dr->hi; k3.out_cnt = (int32_t*)dr->cnt;
+    k3.n_buckets = (uint32_t)n_buckets; k3.big_list = (unsigned long long*)ctx->slot[S_BIGLIST]; k3.counters = d_cnt + 8;
+    CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
+    CK (launch_k3a_classify (L, k3));
+    CK (launch_scan_u32_to_u64 (L, k3.bucket_count, (uint64_t*)ctx->slot[S_BUCKETOFF], n_buckets, (uint64_t*)ctx->slot[S_SCAN]));
+    CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
+    CK (launch_k3b_scatter (L, k3));
+    CK (launch_k3c_sort (L, k3));
+    unsigned long long n_big = 0;
+    CK (cudaMemcpyAsync (&n_big, d_cnt + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    if (n_big) CK (launch_k3d_sort_big (L, k3, (uint32_t)n_big));
+    // part_offsets[key] = bucket_off[key << t_bits]
+    {
+        std::vector<uint64_t> offs (n_keys + 1);
+        for (uint64_t key = 0; key <= n_keys; key++)
+            CK (cudaMemcpyAsync (&offs[key], (const uint64_t*)ctx->slot[S_BUCKETOFF] + (key << t_bits), 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+        CK (cudaMemcpyAsync (d_offs, offs.data (), (n_keys + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK (cudaMemcpyAsync (d_hist, ctx->slot[S_HISTO], (size_t)(histo_max + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+    }
+    cudaEventRecord (ctx->ev[5], ctx->stream);
+    CK (cudaStreamSynchronize (ctx->stream));
+
+    // ---- result ----
+    memset (out, 0, sizeof(*out));
+    out->n_keys = n_keys; out->n_items = n_items; out->on_device = 1; out->owner = dr;
+    out->part_offsets = (uint64_t*)dr->offs; out->kmers_lo = (uint64_t*)dr->lo; out->kmers_hi = (uint64_t*)dr->hi;
+    out->counts = (int32_t*)dr->cnt; out->histogram = (uint64_t*)dr->histo;
+    out->stats[GATB_STAT_KMERS_VALID] = h_stats[0]; out->stats[GATB_STAT_KMERS_INVALID] = h_stats[1];
+    out->stats[GATB_STAT_DISTINCT] = h_cnt[1]; out->stats[GATB_STAT_SOLID] = h_cnt[2];
+    out->stats[GATB_STAT_RECORDS] = h_stats[2]; out->stats[GATB_STAT_SEQUENCES] = n_reads; out->stats[GATB_STAT_NUCLEOTIDES] = total_nt;
+    out->stats[GATB_STAT_BINS] = nbins; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf; out->stats[GATB_STAT_RETRIES] = retries;
+    out->stats[GATB_STAT_RECORD_BYTES] = h_stats[2] * rec_bytes;
+    float ms;
+    cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[2]); out->seconds[1] = ms * 1e-3;
+    cudaEventElapsedTime (&ms, ctx->ev[2], ctx->ev[3]); out->seconds[2] = ms * 1e-3;
+    cudaEventElapsedTime (&ms, ctx->ev[3], ctx->ev[4]); out->seconds[3] = ms * 1e-3;
+    cudaEventElapsedTime (&ms, ctx->ev[4], ctx->ev[5]); out->seconds[4] = ms * 1e-3;
+    cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[5]); out->seconds[6] = ms * 1e-3;
+    return 0;
+}
+
+extern "C" {
+
+int gatb_gpu_count_dev (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_table, const uint32_t* freq_order,
+                        const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads,
+                        const uint32_t* d_n_mask, gatb_gpu_result* out)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (!out) return fail (ctx, "out is NULL");
+    if (check_params (ctx, p, repart_table)) return 1;
+    (void)freq_order;
+    return count_dev_impl (ctx, p, repart_table, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, out);
+}
+
+void gatb_gpu_result_free (gatb_gpu_ctx* ctx, gatb_gpu_result* r)
+{
+    if (!r) return;
+    if (ctx) cudaSetDevice (ctx->device);
+    if (r->on_device)
+    {
+        DevResult* dr = (DevResult*)r->owner;
+        if (dr) { cudaFree (dr->lo); cudaFree (dr->offs); cudaFree (dr->histo); delete dr; }
+    }
+    else
+    {
+        free (r->part_offsets); free (r->kmers_lo); free (r->kmers_hi); free (r->counts); free (r->histogram);
+    }
+    memset (r, 0, sizeof(*r));
+}
+
+int gatb_gpu_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_table, const uint32_t* freq_order,
+                    const uint8_t* packed_reads, const uint64_t* read_offsets_nt, uint64_t n_reads, const uint32_t* n_mask,
+                    gatb_gpu_result* out)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (!out) return fail (ctx, "out is NULL");
+    if (check_params (ctx, p, repart_table)) return 1;
+    if (!read_offsets_nt && p->read_len <= 0) return fail (ctx, "read_offsets_nt is NULL and read_len <= 0");
+    cudaEventRecord (ctx->ev[0], ctx->stream);
+    const uint64_t total_nt = read_offsets_nt ? read_offsets_nt[n_reads] : n_reads * (uint64_t)p->read_len;
+    const uint64_t bytes = (total_nt + 3) / 4;
+    if (ensure (ctx, S_READS, bytes + 64)) return 1;
+    CK (cudaMemsetAsync ((uint8_t*)ctx->slot[S_READS] + (bytes & ~15ULL), 0, (bytes & 15) + 48, ctx->stream));     // zero the padding
+    CK (cudaMemcpyAsync (ctx->slot[S_READS], packed_reads, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t* d_off = 0; const uint32_t* d_mask = 0;
+    if (read_offsets_nt)
+    {
+        if (ensure (ctx, S_OFFSETS, (n_reads + 1) * 8)) return 1;
+        CK (cudaMemcpyAsync (ctx->slot[S_OFFSETS], read_offsets_nt, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_off = (const uint64_t*)ctx->slot[S_OFFSETS];
+    }
+    if (n_mask)
+    {
+        uint64_t mw = (total_nt + 31) / 32;
+        if (ensure (ctx, S_NMASK, mw * 4 + 16)) return 1;
+        CK (cudaMemsetAsync ((uint8_t*)ctx->slot[S_NMASK] + mw * 4, 0, 16, ctx->stream));
+        CK (cudaMemcpyAsync (ctx->slot[S_NMASK], n_mask, mw * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = (const uint32_t*)ctx->slot[S_NMASK];
+    }
+    gatb_gpu_result dres;
+    if (count_dev_impl (ctx, p, repart_table, (const uint8_t*)ctx->slot[S_READS], d_off, n_reads, d_mask, &dres)) return 1;
+    // ---- device -> host ----
+    cudaEventRecord (ctx->ev[6], ctx->stream);
+    const int W = p->kmer_size < 32 ? 1 : 2;
+    gatb_gpu_result h = dres; h.on_device = 0; h.owner = 0;
+    uint64_t n = dres.n_items, na = n ? n : 1;
+    h.part_offsets = (uint64_t*) malloc ((dres.n_keys + 1) * 8);
+    h.kmers_lo = (uint64_t*) malloc (na * 8); h.kmers_hi = (W == 2) ? (uint64_t*) malloc (na * 8) : 0;
+    h.counts = (int32_t*) malloc (na * 4); h.histogram = (uint64_t*) malloc ((size_t)(p->histo_max + 1) * 8);
+    if (!h.part_offsets || !h.kmers_lo || !h.counts || !h.histogram || (W == 2 && !h.kmers_hi)) { gatb_gpu_result_free (ctx, &dres); return fail (ctx, "host allocation of the result failed"); }
+    CK (cudaMemcpyAsync (h.part_offsets, dres.part_offsets, (dres.n_keys + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n)
+    {
+        CK (cudaMemcpyAsync (h.kmers_lo, dres.kmers_lo, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (W == 2) CK (cudaMemcpyAsync (h.kmers_hi, dres.kmers_hi, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaMemcpyAsync (h.counts, dres.counts, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK (cudaMemcpyAsync (h.histogram, dres.histogram, (size_t)(p->histo_max + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord (ctx->ev[7], ctx->stream);
+    CK (cudaStreamSynchronize (ctx->stream));
+    float ms;
+    cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[1]); h.seconds[0] = ms * 1e-3;
+    cudaEventElapsedTime (&ms, ctx->ev[6], ctx->ev[7]); h.seconds[5] = ms * 1e-3;
+    cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[7]); h.seconds[7] = ms * 1e-3;
+    gatb_gpu_result_free (ctx, &dres);
+    *out = h;
+    return 0;
+}
+
+// =====================================================================================================================
+//  GATB-exact super-k-mers (rows A3-A6)
+// =====================================================================================================================
+int gatb_gpu_superkmers (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_table,
+                         const uint8_t* packed_reads, const uint64_t* read_offsets_nt, uint64_t n_reads,
+                         const uint32_t* n_mask, uint8_t** streams, uint64_t* stream_sizes, uint64_t* stats_out)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (check_params (ctx, p, repart_table)) return 1;
+    if (!read_offsets_nt && p->read_len <= 0) return fail (ctx, "read_offsets_nt is NULL and read_len <= 0");
+    LaunchCtx L = lctx (ctx);
+    const int k = p->kmer_size, m = p->minimizer_size, W = (k < 32) ? 1 : 2;
+    const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
+    const uint64_t total_nt = read_offsets_nt ? read_offsets_nt[n_reads] : n_reads * (uint64_t)p->read_len;
+    const uint64_t bytes = (total_nt + 3) / 4;
+    if (ensure (ctx, S_READS, bytes + 64)) return 1;
+    CK (cudaMemsetAsync ((uint8_t*)ctx->slot[S_READS] + (bytes & ~15ULL), 0, (bytes & 15) + 48, ctx->stream));
+    CK (cudaMemcpyAsync (ctx->slot[S_READS], packed_reads, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t* d_off = 0; const uint32_t* d_mask = 0;
+    if (read_offsets_nt)
+    {
+        for (uint64_t i = 0; i < n_reads; i++) if (read_offsets_nt[i+1] - read_offsets_nt[i] >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported yet");
+        if (ensure (ctx, S_OFFSETS, (n_reads + 1) * 8)) return 1;
+        CK (cudaMemcpyAsync (ctx->slot[S_OFFSETS], read_offsets_nt, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_off = (const uint64_t*)ctx->slot[S_OFFSETS];
+    }
+    if (n_mask)
+    {
+        uint64_t mw = (total_nt + 31) / 32;
+        if (ensure (ctx, S_NMASK, mw * 4 + 16)) return 1;
+        CK (cudaMemsetAsync ((uint8_t*)ctx->slot[S_NMASK] + mw * 4, 0, 16, ctx->stream));
+        CK (cudaMemcpyAsync (ctx->slot[S_NMASK], n_mask, mw * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = (const uint32_t*)ctx->slot[S_NMASK];
+    }
+    if (ensure (ctx, S_REPART, (1ULL << (2*m)) * 2)) return 1;
+    if (repart_table) CK (cudaMemcpyAsync (ctx->slot[S_REPART], repart_table, (1ULL << (2*m)) * 2, cudaMemcpyHostToDevice, ctx->stream));
+    else              CK (cudaMemsetAsync (ctx->slot[S_REPART], 0, (1ULL << (2*m)) * 2, ctx->stream));
+    if (ensure (ctx, S_CURSORS, n_keys * 4)) return 1;
+    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
+    unsigned long long* d_stats = (unsigned long long*)ctx->slot[S_STATS];
+
+    K1Params k1; memset (&k1, 0, sizeof(k1));
+    k1.words = (const uint64_t*)ctx->slot[S_READS]; k1.offsets = d_off; k1.nmask = d_mask; k1.n_reads = n_reads; k1.read_len = p->read_len;
+    k1.k = k; k1.m = m; k1.w = k - m + 1; k1.maxlen = (W == 1) ? 28 : 60;
+    k1.mmask = (1u << (2*m)) - 1; k1.mask_ma1 = gatb_mask_ma1 (m);
+    k1.mode = K1_MODE_GATB; k1.repart = (const uint16_t*)ctx->slot[S_REPART]; k1.nb_partitions = p->nb_partitions; k1.nb_passes = p->nb_passes;
+    k1.nb1 = (uint32_t)n_keys; k1.fine_bits = 0; k1.fine_counts = 0; k1.cursors = (uint32_t*)ctx->slot[S_CURSORS]; k1.stats = d_stats;
+    // pass 1: demand per key; pass 2: fill exactly
+    k1.count_only = 1; k1.cap = 0; k1.bins = 0;
+    CK (cudaMemsetAsync (k1.cursors, 0, n_keys * 4, ctx->stream));
+    CK (cudaMemsetAsync (d_stats, 0, 4 * 8, ctx->stream));
+    if (n_reads) CK (launch_k1 (L, k1));
+    std::vector<uint32_t> cur (n_keys);
+    CK (cudaMemcpyAsync (cur.data (), k1.cursors, n_keys * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    uint64_t cap = 8; for (uint64_t i = 0; i < n_keys; i++) if (cur[i] > cap) cap = cur[i];
+    if (ensure (ctx, S_COARSE, n_keys * cap * 16 * W)) return 1;
+    k1.count_only = 0; k1.cap = (uint32_t)cap; k1.bins = ctx->slot[S_COARSE];
+    CK (cudaMemsetAsync (k1.cursors, 0, n_keys * 4, ctx->stream));
+    CK (cudaMemsetAsync (d_stats, 0, 4 * 8, ctx->stream));
+    if (n_reads) CK (launch_k1 (L, k1));
+    unsigned long long h_stats[4];
+    CK (cudaMemcpyAsync (h_stats, d_stats, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // serialise into the reference's byte format
+    if (ensure (ctx, S_COUNTERS, (2 * n_keys + 2) * 8 + 16 * 8)) return 1;
+    unsigned long long* d_bytes = (unsigned long long*)ctx->slot[S_COUNTERS]; unsigned long long* d_cur = d_bytes + n_keys;
+    CK (cudaMemsetAsync (d_bytes, 0, 2 * n_keys * 8, ctx->stream));
+    CK (launch_serialize_sizes (L, W, k, k1.bins, k1.cursors, (uint32_t)n_keys, (uint32_t)cap, d_bytes));
+    std::vector<unsigned long long> kb (n_keys);
+    CK (cudaMemcpyAsync (kb.data (), d_bytes, n_keys * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    std::vector<uint64_t> off (n_keys + 1, 0);
+    for (uint64_t i = 0; i < n_keys; i++) off[i+1] = off[i] + kb[i];
+    if (ensure (ctx, S_BUCKETOFF, (n_keys + 1) * 8)) return 1;
+    if (ensure (ctx, S_FINE, off[n_keys] + 16)) return 1;
+    CK (cudaMemcpyAsync (ctx->slot[S_BUCKETOFF], off.data (), (n_keys + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK (launch_serialize_write (L, W, k, k1.bins, k1.cursors, (uint32_t)n_keys, (uint32_t)cap, (const uint64_t*)ctx->slot[S_BUCKETOFF], d_cur, (uint8_t*)ctx->slot[S_FINE]));
+    for (uint64_t i = 0; i < n_keys; i++)
+    {
+        streams[i] = (uint8_t*) malloc (kb[i] ? kb[i] : 1); stream_sizes[i] = kb[i];
+        if (kb[i]) CK (cudaMemcpyAsync (streams[i], (uint8_t*)ctx->slot[S_FINE] + off[i], kb[i], cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK (cudaStreamSynchronize (ctx->stream));
+    if (stats_out) { stats_out[0] = h_stats[2]; stats_out[1] = h_stats[0]; stats_out[2] = h_stats[0]; stats_out[3] = h_stats[1]; }
+    return 0;
+}
+void gatb_gpu_free_host (void* p) { free (p); }
+
+// =====================================================================================================================
+//  Bloom
+// =====================================================================================================================
+static const double g_rvalues_col1[129] = GATB_RVALUES_COL1_INIT;
+
+int gatb_gpu_bloom_params (int kmer_size, uint64_t nb_solid, uint64_t* bloom_size, int32_t* nb_hash)
+{
+    if (kmer_size < 0 || kmer_size > 128) return 1;
+    float bits = (float) g_rvalues_col1[kmer_size];                    // DebloomAlgorithm.cpp:638
+    if (bits == 0) bits = 1;                                            // :648
+    uint64_t est = (uint64_t)(nb_solid * bits);                        // float32 product, BloomAlgorithm.cpp:162
+    if (est == 0) est = 1000;                                           // :165
+    *bloom_size = est; *nb_hash = (int32_t) floorf (0.7 * bits);        // :163
+    return 0;
+}
+// BloomContainer ctor (Bloom.hpp:184-199) and BloomCacheCoherent ctor (:437-442)
+static void bloom_layout (int kind, uint64_t bloom_size, uint64_t* nchar, uint64_t* tai_out, int* pow2_out, uint64_t* reduced_out)
+{
+    uint64_t tai = (kind == GATB_BLOOM_BASIC) ? bloom_size : bloom_size + 2 * 4096;
+    *nchar = 1 + tai / 8;
+    int pow2 = (tai && !(tai & (tai - 1)));
+    if (pow2) tai--;
+    *tai_out = tai; *pow2_out = pow2; *reduced_out = tai - 2 * 4096;
+}
+int gatb_gpu_bloom_layout (int kind, uint64_t bloom_size, uint64_t* nbytes, uint64_t* bit_size)
+{
+    if (kind < 0 || kind > 2) return 1;
+    uint64_t nchar, tai, reduced; int pow2;
+    bloom_layout (kind, bloom_size, &nchar, &tai, &pow2, &reduced);
+    *nbytes = nchar; *bit_size = (kind == GATB_BLOOM_BASIC) ? tai : reduced;
+    return 0;
+}
+int gatb_gpu_bloom_dev (gatb_gpu_ctx* ctx, int kind, uint64_t bloom_size, int nb_hash, int kmer_size,
+                        const uint64_t* d_lo, const uint64_t* d_hi, uint64_t n, uint8_t* d_out_bytes)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (kind < 0 || kind > 2) return fail (ctx, "bad Bloom kind %d in createBloom", kind);          // Bloom.hpp:1263
+    if (kmer_size < 3 || kmer_size > 63) return fail (ctx, "kmer_size %d not supported", kmer_size);
+    if (nb_hash < 1 || nb_hash > 10) return fail (ctx, "nb_hash must be in [1,10]");
+    const int W = kmer_size < 32 ? 1 : 2;
+    if (W == 2 && !d_hi) return fail (ctx, "kmers_hi is required for kmer_size >= 32");
+    uint64_t nchar, tai, reduced; int pow2;
+    bloom_layout (kind, bloom_size, &nchar, &tai, &pow2, &reduced);
+    if (kind != GATB_BLOOM_BASIC && bloom_size == 0) return fail (ctx, "bloom_size must be > 0");
+    CK (cudaMemsetAsync (d_out_bytes, 0, (nchar + 3) & ~3ULL, ctx->stream));
+    CK (launch_bloom_insert (lctx (ctx), kind, W, kmer_size, nb_hash, tai, pow2, reduced, d_lo, d_hi, n, (uint32_t*)d_out_bytes));
+    return 0;
+}
+int gatb_gpu_bloom (gatb_gpu_ctx* ctx, int kind, uint64_t bloom_size, int nb_hash, int kmer_size,
+                    const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out_bytes)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (kind < 0 || kind > 2) return fail (ctx, "bad Bloom kind %d in createBloom", kind);
+    const int W = kmer_size < 32 ? 1 : 2;
+    if (W == 2 && !hi) return fail (ctx, "kmers_hi is required for kmer_size >= 32");
+    uint64_t nchar, bits;
+    gatb_gpu_bloom_layout (kind, bloom_size, &nchar, &bits);
+    uint64_t na = n ? n : 1;
+    if (ensure (ctx, S_MISC, na * 8 * W)) return 1;
+    if (ensure (ctx, S_MISC2, nchar + 64)) return 1;
+    uint64_t* d_lo = (uint64_t*)ctx->slot[S_MISC]; uint64_t* d_hi = (W == 2) ? d_lo + na : 0;
+    if (n) { CK (cudaMemcpyAsync (d_lo, lo, n * 8, cudaMemcpyHostToDevice, ctx->stream)); if (W == 2) CK (cudaMemcpyAsync (d_hi, hi, n * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (gatb_gpu_bloom_dev (ctx, kind, bloom_size, nb_hash, kmer_size, d_lo, d_hi, n, (uint8_t*)ctx->slot[S_MISC2])) return 1;
+    CK (cudaMemcpyAsync (out_bytes, ctx->slot[S_MISC2], nchar, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    return 0;
+}
+
+// =====================================================================================================================
+//  Histogram cutoff: Histogram::compute_threshold, tools/misc/impl/Histogram.cpp:61-190.  A 10 001-entry table:
+//  host arithmetic in doubles exactly as the reference (the device produced the table).
+// =====================================================================================================================
+int gatb_gpu_histogram_cutoff (const uint64_t* h, int histo_max, int min_auto_threshold, uint32_t* cutoff_out, uint64_t* nb_solids, uint32_t* first_peak)
+{
+    if (!h || histo_max < 1) return 1;
+    const size_t length = histo_max;
+    std::vector<uint64_t> sm (length + 2, 0);
+    uint64_t sum_allk = 0; uint32_t cutoff = 0, peak = 0;
+    if (length >= 2) { sm[1] = (uint64_t)(0.6 * (double)h[1] + 0.4 * (double)h[2]); sum_allk += h[1]; }
+    int first_inc = -1, idx_max = -1; uint64_t max_val = 0;
+    for (size_t i = 2; i < length; i++)
+    {
+        sum_allk += h[i] * i;
+        sm[i] = (uint64_t)(0.2 * (double)h[i-1] + 0.6 * (double)h[i] + 0.2 * (double)h[i+1]);
+        if (first_inc == -1 && sm[i-1] < sm[i]) first_inc = (int)i - 1;
+        if (first_inc > 0 && sm[i] > max_val) { max_val = sm[i]; idx_max = (int)i; }
+    }
+    sum_allk += h[length] * length;
+    if (first_inc == -1) { *cutoff_out = (uint32_t)min_auto_threshold; *nb_solids = 0; *first_peak = 0; return 0; }
+    peak = (uint32_t)idx_max;
+    uint64_t min_val = 10000000000ULL; int idx_min = -1;
+    for (int i = first_inc; i <= idx_max; i++) if (sm[i] < min_val) { min_val = sm[i]; idx_min = i; }
+    if (idx_min != -1) cutoff = (uint32_t)idx_min;
+    uint64_t sum_elim = 0; size_t max_cutoff = 0;
+    for (size_t i = 0; i < length + 1; i++)
+    {
+        sum_elim += h[i] * i;
+        double ratio = (double)sum_elim / sum_allk;
+        if (ratio >= 0.25) { max_cutoff = i + 1; break; }
+    }
+    if (cutoff > max_cutoff) cutoff = (uint32_t)max_cutoff;
+    if (cutoff < (size_t)min_auto_threshold) cutoff = (uint32_t)min_auto_threshold;
+    uint64_t nbs = 0; for (size_t i = cutoff; i < length + 1; i++) nbs += h[i];
+    *cutoff_out = cutoff; *nb_solids = nbs; *first_peak = peak;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,272 @@
+// k1_partition.cu -- k1_superkmer_partition: reads -> super-k-mer records scattered into HBM bins.
+//
+// Replaces (paths relative to /root/reference/gatb-core/src/gatb/):
+//   ModelAbstract::iterate + ModelMinimizer::next         kmer/impl/Model.hpp:725-765, 1106-1139
+//   Sequence2SuperKmer::operator() / KmerFunctor          kmer/impl/Sequence2SuperKmer.hpp:81-159
+//   FillPartitions<span,true>::processSuperkmer           kmer/impl/SortingCountAlgorithm.cpp:1081-1151
+//   SuperKmer::save (+ CacheSuperKmerBinFiles)            kmer/impl/Model.hpp:1386-1471, tools/storage/impl/Storage.cpp:567-580
+//
+// Work shape (integer only, no tensor cores):
+//   * one thread <-> one read; the thread streams its 2-bit nucleotides through a 64-bit shift register refilled by
+//     8-byte loads (a warp's 32 reads are contiguous in the packed stream, so the loads of a warp hit the same few
+//     128-byte lines -- L1 serves them; DRAM sees each line once);
+//   * per nucleotide: rolling forward and reverse-complement m-mer (2 x 32 bit), canonical m-mer, rank key, and a
+//     sliding-window minimum over w = k-m+1 keys done WITHOUT data-dependent rescans: the stream of keys is cut in
+//     blocks of w, window min = min(suffix-min of the previous block, prefix-min of the current block); the per-thread
+//     ring of w keys lives in shared memory laid out [slot][thread] (bank-conflict free);
+//   * a super-k-mer closes when the window minimum changes, at an invalid k-mer, at maxlen k-mers, or at the end of
+//     the read -- the closing lane only pushes an 8-byte event into its warp's shared-memory queue;
+//   * every 8 nucleotides the warp drains the queue COOPERATIVELY (lane <-> event): builds the fixed-size record from
+//     the packed stream with funnel shifts, picks the bin, reserves a slot with one 32-bit global atomic and writes the
+//     record with one 16-byte store.  This keeps the divergent part (record construction) at full lane occupancy.
+//
+// Two rank functions share the kernel:
+//   K1_MODE_GATB   : key = GATB's mmer_lut value (min(mmer, revcomp) or 4^m-1 when an "AA" sits anywhere but at the
+//                    prefix; Model.hpp:1040-1064, 1220-1251) under integer '<' -- bit-exact super-k-mers and partitions
+//                    p = repart[minimizer] (PartiInfo.hpp:323), pass = minimizer % nb_passes.
+//   K1_MODE_DEVICE : key = multiplicative hash of the canonical m-mer (m up to 16) -- a *random* minimizer order, whose
+//                    buckets are balanced enough for one bin's distinct k-mers to fit a shared-memory hash table in k2b.
+//                    Any order works for counting because every occurrence of a canonical k-mer has the same
+//                    window minimum; GATB's own partition id is recomputed exactly for each emitted k-mer in k3a.
+#include "common.cuh"
+#include "kernels.h"
+
+#define K1_THREADS 128
+#define K1_QCAP    384        // events per warp queue: flush threshold 96 + 8 steps x 32 lanes + slack
+#define K1_QFLUSH  96
+
+__device__ __forceinline__ uint32_t k1_key_device (uint32_t cm) { uint32_t h = cm * 0x9E3779B1u; return h ^ (h >> 15); }
+
+template<int W>
+__device__ __forceinline__ void k1_store_record (const K1Params& P, uint32_t key, uint32_t meta, const uint64_t* roffs,
+                                                 unsigned long long& stored, unsigned long long& dropped)
+{
+    const int      olane = meta & 31;
+    const int      len   = (meta >> 5) & 63;
+    const uint32_t start = meta >> 11;
+    // ---- bin ----
+    uint32_t bin, fine = 0;
+    if (P.mode == K1_MODE_GATB)
+    {
+        uint32_t p = P.repart ? P.repart[key] : 0;
+        bin = (key % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + p;
+    }
+    else
+    {
+        uint32_t h = mix32 (key);
+        bin  = __umulhi (h, P.nb1);
+        fine = (h * 0x9E3779B1u) >> (32 - P.fine_bits);
+    }
+    uint32_t slot = atomicAdd (&P.cursors[bin], 1u);
+    if (P.count_only) return;
+    if (slot >= P.cap) { dropped++; return; }
+    if (P.fine_counts) atomicAdd (&P.fine_counts[((uint64_t)bin << P.fine_bits) + fine], 1u);
+    stored++;
+    // ---- record: nn = k+len-1 nucleotides starting at stream position roff+start ----
+    const uint64_t bp = 2 * (roffs[olane] + start);
+    const uint64_t* wp = P.words + (bp >> 6);
+    const int sh = (int)(bp & 63);
+    const int nn = P.k + len - 1;
+    if (W == 1)
+    {
+        uint64_t w0 = ldg64 (wp), w1 = ldg64 (wp + 1), w2 = ldg64 (wp + 2);
+        uint64_t lo = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
+        uint64_t hi = sh ? ((w1 >> sh) | (w2 << (64 - sh))) : w1;
+        if (nn <= 32) { lo &= mask2k64 (nn); hi = 0; } else { hi &= mask2k64 (nn - 32); }
+        hi |= ((uint64_t)len << REC_LEN_SHIFT_W1) | ((uint64_t)fine << REC_FINE_SHIFT_W1);
+        uint4 rec = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+        ((uint4*)P.bins)[(uint64_t)bin * P.cap + slot] = rec;
+    }
+    else
+    {
+        uint64_t w[5];
+        #pragma unroll
+        for (int i=0; i<5; i++) w[i] = ldg64 (wp + i);
+        uint64_t r[4];
+        #pragma unroll
+        for (int i=0; i<4; i++) r[i] = sh ? ((w[i] >> sh) | (w[i+1] << (64 - sh))) : w[i];
+        #pragma unroll
+        for (int i=0; i<4; i++)
+        {
+            int lo_nt = 32*i;                                   // first nucleotide held by word i
+            if (nn <= lo_nt) r[i] = 0; else if (nn < lo_nt + 32) r[i] &= mask2k64 (nn - lo_nt);
+        }
+        r[3] |= ((uint64_t)len << REC_LEN_SHIFT_W2) | ((uint64_t)fine << REC_FINE_SHIFT_W2);
+        uint4* dst = (uint4*)P.bins + 2 * ((uint64_t)bin * P.cap + slot);
+        dst[0] = make_uint4 ((uint32_t)r[0], (uint32_t)(r[0] >> 32), (uint32_t)r[1], (uint32_t)(r[1] >> 32));
+        dst[1] = make_uint4 ((uint32_t)r[2], (uint32_t)(r[2] >> 32), (uint32_t)r[3], (uint32_t)(r[3] >> 32));
+    }
+}
+
+template<int W, bool HAS_N, int MODE>
+__global__ void __launch_bounds__(K1_THREADS) k1_superkmer_partition (const K1Params P)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int w = P.w, k = P.k, m = P.m;
+    uint32_t* arr   = smem;                                                   // [w][K1_THREADS]
+    uint32_t* q     = smem + w * K1_THREADS + wid * (K1_QCAP * 2);            // [K1_QCAP][2] per warp
+    uint64_t* roffs = (uint64_t*)(smem + w * K1_THREADS + 4 * (K1_QCAP * 2)) + wid * 32;
+    uint32_t* qcnt  = (uint32_t*)((uint64_t*)(smem + w * K1_THREADS + 4 * (K1_QCAP * 2)) + 4 * 32) + wid;
+
+    const uint32_t mmask = P.mmask;
+    const int shift_m = 2 * (m - 1);
+    unsigned long long nvalid = 0, ninvalid = 0, stored = 0, dropped = 0;
+
+    const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        const uint64_t r = tile * K1_THREADS + tid;
+        uint64_t roff = 0; int len = 0;
+        if (r < P.n_reads)
+        {
+            if (P.offsets) { roff = P.offsets[r]; len = (int)(P.offsets[r+1] - roff); }
+            else           { roff = r * (uint64_t)P.read_len; len = P.read_len; }
+        }
+        roffs[lane] = roff;
+        if (lane == 0) *qcnt = 0;
+        int nm = (len >= k) ? (len - m + 1) : 0;            // reads shorter than k are skipped (Sequence2SuperKmer.hpp:144)
+        const int nm_max = __reduce_max_sync (FULL_MASK, nm);
+        __syncwarp ();
+
+        // ---- nucleotide (and invalid-flag) shift registers ----
+        const uint64_t* wp = P.words + (roff >> 5);
+        uint64_t cur = 0; int avail = 0;
+        const uint32_t* np = 0; uint32_t ncur = 0; int navail = 0;
+        if (nm > 0)
+        {
+            int sh = (int)((2 * roff) & 63);
+            cur = ldg64 (wp) >> sh; avail = (64 - sh) >> 1; wp++;
+            if (HAS_N) { np = P.nmask + (roff >> 5); int s2 = (int)(roff & 31); ncur = __ldg (np) >> s2; navail = 32 - s2; np++; }
+        }
+        uint32_t f = 0, rr = 0;
+        int since_bad = k;                                   // nucleotides since the last invalid one (saturating at "enough")
+        #define NEXT_NT(c)                                                                      \
+            { c = (uint32_t)cur & 3u; cur >>= 2; if (--avail == 0) { cur = ldg64 (wp); wp++; avail = 32; }          \
+              if (HAS_N) { bool bad = ncur & 1u; ncur >>= 1; if (--navail == 0) { ncur = __ldg (np); np++; navail = 32; } \
+                           since_bad = bad ? 0 : since_bad + 1; } }
+        if (nm > 0)
+            for (int i = 0; i < m - 1; i++)
+            {
+                uint32_t c; NEXT_NT (c);
+                f  = ((f << 2) | c) & mmask;
+                rr = (rr >> 2) | ((c ^ 2u) << shift_m);
+            }
+
+        // ---- main scan over m-mer index j; k-mer index i = j-(w-1) ----
+        uint32_t prefix = 0xFFFFFFFFu; int t = 0;
+        bool open = false; uint32_t sk_key = 0; int sk_start = 0, sk_len = 0;
+        #define PUSH_EVENT()                                                                    \
+            { uint32_t e = atomicAdd (qcnt, 1u); q[2*e] = sk_key; q[2*e+1] = ((uint32_t)sk_start << 11) | ((uint32_t)sk_len << 5) | (uint32_t)lane; }
+
+        for (int j = 0; j < nm_max; j++)
+        {
+            const bool act = j < nm;
+            uint32_t key = 0xFFFFFFFFu;
+            if (act)
+            {
+                uint32_t c; NEXT_NT (c);
+                f  = ((f << 2) | c) & mmask;
+                rr = (rr >> 2) | ((c ^ 2u) << shift_m);
+                uint32_t cm = min (f, rr);
+                key = (MODE == K1_MODE_GATB) ? gatb_mmer_key (cm, mmask, P.mask_ma1) : k1_key_device (cm);
+            }
+            const uint32_t s = (t + 1 < w) ? arr[(t + 1) * K1_THREADS + tid] : 0xFFFFFFFFu;
+            arr[t * K1_THREADS + tid] = key;
+            prefix = min (prefix, key);
+            const uint32_t wmin = min (prefix, s);
+            if (act && j >= w - 1)
+            {
+                const bool valid = !HAS_N || since_bad >= k;
+                if (valid)
+                {
+                    nvalid++;
+                    if (!open || wmin != sk_key || sk_len == P.maxlen)
+                    {
+                        if (open) PUSH_EVENT ();
+                        sk_start = j - (w - 1); sk_len = 0; sk_key = wmin; open = true;
+                    }
+                    sk_len++;
+                }
+                else
+                {
+                    ninvalid++;
+                    if (open) { PUSH_EVENT (); open = false; }
+                }
+                if (j == nm - 1 && open) { PUSH_EVENT (); open = false; }
+            }
+            if (++t == w)
+            {   // turn the finished block into suffix minima, in place
+                uint32_t run = arr[(w - 1) * K1_THREADS + tid];
+                for (int u = w - 2; u >= 0; u--) { run = min (run, arr[u * K1_THREADS + tid]); arr[u * K1_THREADS + tid] = run; }
+                prefix = 0xFFFFFFFFu; t = 0;
+            }
+            if ((j & 7) == 7 || j == nm_max - 1)
+            {
+                __syncwarp ();
+                const uint32_t nq = *qcnt;
+                if (nq >= K1_QFLUSH || (j == nm_max - 1 && nq > 0))
+                {
+                    for (uint32_t e = lane; e < nq; e += 32)
+                        k1_store_record<W> (P, q[2*e], q[2*e+1], roffs, stored, dropped);
+                    __syncwarp ();
+                    if (lane == 0) *qcnt = 0;
+                }
+                __syncwarp ();
+            }
+        }
+        #undef NEXT_NT
+        #undef PUSH_EVENT
+        __syncwarp ();
+    }
+    // ---- statistics: one atomic per warp ----
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        nvalid   += __shfl_xor_sync (FULL_MASK, nvalid, o);
+        ninvalid += __shfl_xor_sync (FULL_MASK, ninvalid, o);
+        stored   += __shfl_xor_sync (FULL_MASK, stored, o);
+        dropped  += __shfl_xor_sync (FULL_MASK, dropped, o);
+    }
+    if (lane == 0)
+    {
+        if (nvalid)   atomicAdd (&P.stats[0], nvalid);
+        if (ninvalid) atomicAdd (&P.stats[1], ninvalid);
+        if (stored)   atomicAdd (&P.stats[2], stored);
+        if (dropped)  atomicAdd (&P.stats[3], dropped);
+    }
+}
+
+static size_t k1_smem_bytes (int w) { return (size_t)w * K1_THREADS * 4 + 4 * (K1_QCAP * 2) * 4 + 4 * 32 * 8 + 4 * 4 + 16; }
+
+template<int W, bool HAS_N, int MODE>
+static cudaError_t k1_launch_t (const LaunchCtx& L, const K1Params& P)
+{
+    size_t smem = k1_smem_bytes (P.w);
+    cudaError_t e = cudaFuncSetAttribute (k1_superkmer_partition<W,HAS_N,MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_partition<W,HAS_N,MODE>, K1_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
+    uint64_t grid = (uint64_t)L.sm_count * per_sm;                 // persistent: a multiple of the SM count
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid == 0) return cudaSuccess;
+    k1_superkmer_partition<W,HAS_N,MODE><<<(unsigned)grid, K1_THREADS, smem, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
+cudaError_t launch_k1 (const LaunchCtx& L, const K1Params& P)
+{
+    const int W = (P.k < 32) ? 1 : 2;
+    const bool n = P.nmask != 0;
+    if (P.mode == K1_MODE_GATB)
+    {
+        if (W == 1) return n ? k1_launch_t<1,true,K1_MODE_GATB> (L, P) : k1_launch_t<1,false,K1_MODE_GATB> (L, P);
+        else        return n ? k1_launch_t<2,true,K1_MODE_GATB> (L, P) : k1_launch_t<2,false,K1_MODE_GATB> (L, P);
+    }
+    if (W == 1) return n ? k1_launch_t<1,true,K1_MODE_DEVICE> (L, P) : k1_launch_t<1,false,K1_MODE_DEVICE> (L, P);
+    else        return n ? k1_launch_t<2,true,K1_MODE_DEVICE> (L, P) : k1_launch_t<2,false,K1_MODE_DEVICE> (L, P);
+}

@@ -1,0 +1,423 @@
+// k2_count.cu -- k2a_fine_split + k2b_bucket_hash_count (+ global-memory fallback k2c_*).
+//
+// Replaces (paths relative to /root/reference/gatb-core/src/gatb/):
+//   ReadSuperKCommand::execute / hash-mode decode    kmer/impl/PartitionsCommand.cpp:944-1128, 420-501
+//   SortCommand + executeDump (sort, merge, count)   kmer/impl/PartitionsCommand.cpp:1400-1445, 1599-1805
+//   Hash16::insert (over-memory partitions)          tools/collections/impl/Hash16.hpp:198-230
+//   CountProcessorHistogram::process                 kmer/impl/CountProcessorHistogram.hpp:173 (Histogram::inc, Histogram.hpp:92)
+//   CountProcessorSoliditySum::check                 kmer/impl/CountProcessorSolidity.hpp:186
+//
+// k2a: one CTA per coarse bin; reads its records once (coalesced 16-byte loads) and scatters them to their fine bin,
+//      whose exact extent comes from the per-fine-bin counters k1 maintained (no histogram pass).
+// k2b: persistent CTAs pull fine bins from an atomic work counter; the bin's records are staged into shared memory
+//      with TMA bulk copies (cp.async.bulk + mbarrier), every k-mer of every record is rebuilt with bit tricks
+//      (common.cuh) and inserted into an open-addressed shared-memory table: 64-bit atomicCAS claims the key slot,
+//      a 32-bit shared atomicAdd counts.  The table scan then feeds the abundance histogram (shared-memory bins,
+//      flushed once per CTA) and appends the k-mers inside [emit_min, emit_max] to the output with warp-aggregated
+//      global atomics.  A bin whose distinct k-mers do not fit the table is deferred to k2c (global-memory table).
+#include "common.cuh"
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------------------ mbarrier / TMA
+__device__ __forceinline__ uint32_t smem_u32 (const void* p) { return (uint32_t)__cvta_generic_to_shared (p); }
+__device__ __forceinline__ void mbar_init (uint64_t* bar, uint32_t count)
+{ asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, uint32_t bytes)
+{ asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait (uint64_t* bar, uint32_t parity)
+{
+    asm volatile (
+        "{\n .reg .pred p;\n WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" :: "r"(smem_u32 (bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared (1D), completion on the mbarrier; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s (void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                  :: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ k2a
+template<int W>
+__global__ void __launch_bounds__(256) k2a_fine_split (const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                        const uint32_t* __restrict__ cursors, const uint32_t* __restrict__ fine_counts,
+                                                        uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc)
+{
+    __shared__ uint32_t s_off[128], s_cur[128], s_tmp[128];
+    const uint32_t b = blockIdx.x;
+    const int nf = 1 << fine_bits;
+    const int tid = threadIdx.x;
+    uint32_t n = min (cursors[b], cap);
+    if (tid < nf) { s_tmp[tid] = fine_counts[((uint64_t)b << fine_bits) + tid]; s_cur[tid] = 0; }
+    __syncthreads ();
+    if (tid < 32)
+    {   // exclusive scan of <=128 counters by one warp (4 per lane)
+        uint32_t v[4], sum = 0;
+        #pragma unroll
+        for (int i=0; i<4; i++) { int idx = tid*4 + i; v[i] = idx < nf ? s_tmp[idx] : 0; sum += v[i]; }
+        uint32_t incl = sum;
+        #pragma unroll
+        for (int o=1; o<32; o<<=1) { uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (tid >= o) incl += y; }
+        uint32_t run = incl - sum;
+        #pragma unroll
+        for (int i=0; i<4; i++) { int idx = tid*4 + i; if (idx < nf) { s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v[i]); } run += v[i]; }
+    }
+    __syncthreads ();
+    const uint64_t base = (uint64_t)b * cap;
+    for (uint32_t i = tid; i < n; i += blockDim.x)
+    {
+        if (W == 1)
+        {
+            uint4 rec = __ldg (&src[base + i]);
+            uint32_t f = rec.w >> (32 - FINE_BITS_W1);
+            uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+            dst[base + p] = rec;
+        }
+        else
+        {
+            uint4 r0 = __ldg (&src[2*(base + i)]), r1 = __ldg (&src[2*(base + i) + 1]);
+            uint32_t f = r1.w >> (32 - FINE_BITS_W2);
+            uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+            dst[2*(base + p)] = r0; dst[2*(base + p) + 1] = r1;
+        }
+    }
+}
+
+cudaError_t launch_k2a_split (const LaunchCtx& L, int W, const void* src, void* dst, const uint32_t* cursors,
+                              const uint32_t* fine_counts, uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc)
+{
+    if (nb1 == 0) return cudaSuccess;
+    if (W == 1) k2a_fine_split<1><<<nb1, 256, 0, L.stream>>> ((const uint4*)src, (uint4*)dst, cursors, fine_counts, cap, fine_bits, bin_desc);
+    else        k2a_fine_split<2><<<nb1, 256, 0, L.stream>>> ((const uint4*)src, (uint4*)dst, cursors, fine_counts, cap, fine_bits, bin_desc);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
+// ------------------------------------------------------------------------------------------------ record decoding
+// k-mer j of a record -> canonical value.  W=1: record = (lo,hi) 128 bits, stream bits at [2j, 2j+2k)
+__device__ __forceinline__ uint64_t rec_kmer_w1 (uint64_t lo, uint64_t hi, int j, int k)
+{
+    int s = 2*j;                                            // 0..54
+    uint64_t x = s ? ((lo >> s) | (hi << (64 - s))) : lo;
+    return canonical_from_stream64 (x & mask2k64 (k), k);
+}
+__device__ __forceinline__ u128 rec_kmer_w2 (const uint64_t* r, int j, int k)
+{
+    int s = 2*j, wi = s >> 6, sh = s & 63;                  // s in 0..118
+    uint64_t a = r[wi], b = wi+1 < 4 ? r[wi+1] : 0, c = wi+2 < 4 ? r[wi+2] : 0;
+    u128 x;
+    x.lo = sh ? ((a >> sh) | (b << (64 - sh))) : a;
+    x.hi = sh ? ((b >> sh) | (c << (64 - sh))) : b;
+    x.hi &= mask2k64 (k - 32);
+    return canonical_from_stream128 (x, k);
+}
+
+// multiply-shift slot hash: top 'log2' bits of key * odd constant
+__device__ __forceinline__ uint32_t slot_hash64 (uint64_t key, int log2)
+{ return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log2)); }
+__device__ __forceinline__ uint32_t slot_hash128 (u128 key, int log2)
+{ return slot_hash64 (key.lo ^ (key.hi * 0xC2B2AE3D27D4EB4FULL), log2); }
+
+#define EMPTY64 0xFFFFFFFFFFFFFFFFULL
+#define K2_THREADS 512
+#define K2_CHUNK   512        // records staged per TMA transfer
+#define K2_HB      1024       // histogram bins kept in shared memory
+#define K2_MAXPROBE 256
+
+// ---- insertion into an open-addressed table (shared or global memory) ------------------------------------------
+// W=1: the key word itself is claimed with a 64-bit CAS.
+__device__ __forceinline__ bool table_insert_w1 (unsigned long long* keys, uint32_t* cnts, int log2, uint64_t key, int maxprobe)
+{
+    const uint32_t tmask = (1u << log2) - 1;
+    uint32_t slot = slot_hash64 (key, log2);
+    for (int probe = 0; probe < maxprobe; probe++)
+    {
+        unsigned long long cur = keys[slot];
+        if (cur == EMPTY64) cur = atomicCAS (&keys[slot], EMPTY64, (unsigned long long)key);
+        if (cur == EMPTY64 || cur == key) { atomicAdd (&cnts[slot], 1u); return true; }
+        slot = (slot + 1) & tmask;
+    }
+    return false;
+}
+// W=2: the high word is claimed with a CAS from EMPTY to a LOCK value that is never a valid high half (k <= 63 keeps
+// bit 63 clear); the low word is then published and the high word released.  Readers spin while they see LOCK.
+#define LOCK64 0xFFFFFFFFFFFFFFFEULL
+template<bool GLOBAL>
+__device__ __forceinline__ bool table_insert_w2 (unsigned long long* klo, unsigned long long* khi, uint32_t* cnts, int log2, u128 key, int maxprobe)
+{
+    const uint32_t tmask = (1u << log2) - 1;
+    uint32_t slot = slot_hash128 (key, log2);
+    for (int probe = 0; probe < maxprobe; probe++)
+    {
+        for (;;)
+        {
+            unsigned long long h = *(volatile unsigned long long*)&khi[slot];
+            if (h == EMPTY64)
+            {
+                h = atomicCAS (&khi[slot], EMPTY64, LOCK64);
+                if (h == EMPTY64)
+                {   // we own the slot
+                    *(volatile unsigned long long*)&klo[slot] = key.lo;
+                    if (GLOBAL) __threadfence (); else __threadfence_block ();
+                    *(volatile unsigned long long*)&khi[slot] = key.hi;
+                    atomicAdd (&cnts[slot], 1u);
+                    return true;
+                }
+            }
+            if (h == LOCK64) continue;                       // another thread is publishing this slot
+            if (GLOBAL) __threadfence ();                    // order the high-word read before the low-word read
+            if (h == key.hi && *(volatile unsigned long long*)&klo[slot] == key.lo) { atomicAdd (&cnts[slot], 1u); return true; }
+            break;                                           // occupied by another key
+        }
+        slot = (slot + 1) & tmask;
+    }
+    return false;
+}
+
+// ---- consuming one table slot: histogram + statistics + emission -----------------------------------------------
+struct EmitState { unsigned long long distinct, solid; };
+
+__device__ __forceinline__ void consume_entry (const K2Params& P, bool occupied, uint64_t klo, uint64_t khi, uint32_t c,
+                                               uint32_t* s_hist, EmitState& st)
+{
+    bool emit = false;
+    if (occupied)
+    {
+        st.distinct++;
+        uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
+        if (s_hist && hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
+        if (c >= P.solid_min && c <= P.solid_max) st.solid++;
+        emit = (c >= P.emit_min && c <= P.emit_max);
+    }
+    unsigned ballot = __ballot_sync (__activemask (), emit);
+    if (emit)
+    {
+        int leader = __ffs (ballot) - 1, lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd (&P.counters[0], (unsigned long long)__popc (ballot));
+        base = __shfl_sync (ballot, base, leader);
+        unsigned long long pos = base + __popc (ballot & ((1u << lane) - 1));
+        if (pos < P.out_cap) { P.out_lo[pos] = klo; if (P.out_hi) P.out_hi[pos] = khi; P.out_cnt[pos] = c; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k2b
+template<int W>
+__global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Params P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = 1 << P.table_log2;
+    // layout: records [K2_CHUNK * 16W] | keys lo [T] (| keys hi [T]) | counts [T] | hist [K2_HB] | mbarrier
+    uint4* s_recs = (uint4*)smem_raw;
+    unsigned long long* s_klo = (unsigned long long*)(smem_raw + (size_t)K2_CHUNK * 16 * W);
+    unsigned long long* s_khi = (W == 2) ? s_klo + T : 0;
+    uint32_t* s_cnt  = (uint32_t*)(s_klo + (size_t)T * W);
+    uint32_t* s_hist = s_cnt + T;
+    uint64_t* s_bar  = (uint64_t*)(s_hist + K2_HB);
+    __shared__ uint32_t s_bin; __shared__ int s_ovf;
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < T; i += K2_THREADS) { if (W == 1) s_klo[i] = EMPTY64; else { s_khi[i] = EMPTY64; s_klo[i] = 0; } s_cnt[i] = 0; }
+    for (int i = tid; i < K2_HB; i += K2_THREADS) s_hist[i] = 0;
+    if (tid == 0) { mbar_init (s_bar, 1); s_ovf = 0; asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads ();
+    uint32_t parity = 0;
+    EmitState st; st.distinct = 0; st.solid = 0;
+    const int k = P.k;
+
+    for (;;)
+    {
+        if (tid == 0) s_bin = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
+        __syncthreads ();
+        const uint32_t bin = s_bin;
+        if (bin >= P.nbins) break;
+        const uint2 d = P.bin_desc[bin];
+        const uint32_t n = d.y;
+        if (n == 0) { __syncthreads (); continue; }
+        const uint4* base = (const uint4*)P.recs + ((uint64_t)(bin >> P.fine_bits) * P.cap + d.x) * W;
+
+        for (uint32_t c0 = 0; c0 < n; c0 += K2_CHUNK)
+        {
+            const uint32_t mrec = min ((uint32_t)K2_CHUNK, n - c0);
+            if (tid == 0)
+            {
+                fence_proxy_async ();                          // order earlier generic reads of the staging buffer
+                mbar_expect_tx (s_bar, mrec * 16 * W);
+                tma_bulk_g2s (s_recs, base + (uint64_t)c0 * W, mrec * 16 * W, s_bar);
+            }
+            mbar_wait (s_bar, parity); parity ^= 1;
+            for (uint32_t i = tid; i < mrec; i += K2_THREADS)
+            {
+                if (W == 1)
+                {
+                    uint4 r = s_recs[i];
+                    uint64_t lo = (uint64_t)r.x | ((uint64_t)r.y << 32), hi = (uint64_t)r.z | ((uint64_t)r.w << 32);
+                    const int len = (int)((hi >> REC_LEN_SHIFT_W1) & 31);
+                    hi &= (1ULL << REC_LEN_SHIFT_W1) - 1;
+                    for (int j = 0; j < len; j++)
+                        if (!table_insert_w1 (s_klo, s_cnt, P.table_log2, rec_kmer_w1 (lo, hi, j, k), K2_MAXPROBE)) s_ovf = 1;
+                }
+                else
+                {
+                    uint4 a = s_recs[2*i], b = s_recs[2*i+1];
+                    uint64_t r[4] = { (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
+                                      (uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32) };
+                    const int len = (int)((r[3] >> REC_LEN_SHIFT_W2) & 63);
+                    r[3] &= (1ULL << REC_LEN_SHIFT_W2) - 1;
+                    for (int j = 0; j < len; j++)
+                        if (!table_insert_w2<false> (s_klo, s_khi, s_cnt, P.table_log2, rec_kmer_w2 (r, j, k), K2_MAXPROBE)) s_ovf = 1;
+                }
+            }
+            __syncthreads ();                                 // staging buffer free for the next chunk; table complete
+            if (s_ovf) break;
+        }
+        const bool ovf = s_ovf != 0;
+        if (ovf && tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin; }
+        // ---- scan + clear the table ----
+        for (int i = tid; i < T; i += K2_THREADS)
+        {
+            uint64_t klo = s_klo[i], khi = (W == 2) ? s_khi[i] : 0;
+            uint32_t c = s_cnt[i];
+            bool occ = (W == 1) ? (klo != EMPTY64) : (khi != EMPTY64);
+            if (occ) { if (W == 1) s_klo[i] = EMPTY64; else { s_khi[i] = EMPTY64; } s_cnt[i] = 0; }
+            consume_entry (P, occ && !ovf, klo, khi, c, s_hist, st);
+        }
+        __syncthreads ();
+        if (tid == 0) s_ovf = 0;
+        // (the loop-top __syncthreads orders this reset before the next bin's inserts)
+    }
+    // ---- flush the shared histogram and the statistics ----
+    __syncthreads ();
+    for (int i = tid; i < K2_HB; i += K2_THREADS) { uint32_t v = s_hist[i]; if (v) atomicAdd (&P.histogram[i], (unsigned long long)v); }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { st.distinct += __shfl_xor_sync (FULL_MASK, st.distinct, o); st.solid += __shfl_xor_sync (FULL_MASK, st.solid, o); }
+    if ((tid & 31) == 0) { if (st.distinct) atomicAdd (&P.counters[1], st.distinct); if (st.solid) atomicAdd (&P.counters[2], st.solid); }
+}
+
+static size_t k2b_smem_bytes (int W, int table_log2)
+{ size_t T = (size_t)1 << table_log2; return (size_t)K2_CHUNK * 16 * W + T * 8 * W + T * 4 + K2_HB * 4 + 16; }
+
+cudaError_t launch_k2b_count (const LaunchCtx& L, const K2Params& P)
+{
+    if (P.nbins == 0) return cudaSuccess;
+    size_t smem = k2b_smem_bytes (P.W, P.table_log2);
+    const void* fn = (P.W == 1) ? (const void*)k2b_bucket_hash_count<1> : (const void*)k2b_bucket_hash_count<2>;
+    cudaError_t e = cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, fn, K2_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)L.sm_count * per_sm;
+    if (grid > P.nbins) grid = P.nbins;
+    if (P.W == 1) k2b_bucket_hash_count<1><<<(unsigned)grid, K2_THREADS, smem, L.stream>>> (P);
+    else          k2b_bucket_hash_count<2><<<(unsigned)grid, K2_THREADS, smem, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
+// ------------------------------------------------------------------------------------------------ k2c: global fallback
+// For the (rare) bins whose distinct k-mers exceed the shared-memory table: all of them share ONE global-memory table
+// (different bins hold disjoint k-mers), then the table is scanned like in k2b.
+template<int W>
+__global__ void __launch_bounds__(256) k2c_measure (const K2Params P, uint32_t n_ovf)
+{
+    unsigned long long sum = 0;
+    for (uint32_t o = blockIdx.x; o < n_ovf; o += gridDim.x)
+    {
+        const uint32_t bin = P.ovf_list[o];
+        const uint2 d = P.bin_desc[bin];
+        const uint4* base = (const uint4*)P.recs + ((uint64_t)(bin >> P.fine_bits) * P.cap + d.x) * W;
+        for (uint32_t i = threadIdx.x; i < d.y; i += blockDim.x)
+        {
+            uint4 last = __ldg (&base[(uint64_t)i * W + (W - 1)]);
+            uint64_t hi = (uint64_t)last.z | ((uint64_t)last.w << 32);
+            sum += (W == 1) ? ((hi >> REC_LEN_SHIFT_W1) & 31) : ((hi >> REC_LEN_SHIFT_W2) & 63);
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync (FULL_MASK, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd (&P.counters[5], sum);
+}
+
+template<int W>
+__global__ void __launch_bounds__(256) k2c_insert (const K2Params P, uint32_t n_ovf)
+{
+    const int k = P.k;
+    for (uint32_t o = blockIdx.y; o < n_ovf; o += gridDim.y)
+    {
+        const uint32_t bin = P.ovf_list[o];
+        const uint2 d = P.bin_desc[bin];
+        const uint4* base = (const uint4*)P.recs + ((uint64_t)(bin >> P.fine_bits) * P.cap + d.x) * W;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.y; i += gridDim.x * blockDim.x)
+        {
+            if (W == 1)
+            {
+                uint4 r = __ldg (&base[i]);
+                uint64_t lo = (uint64_t)r.x | ((uint64_t)r.y << 32), hi = (uint64_t)r.z | ((uint64_t)r.w << 32);
+                const int len = (int)((hi >> REC_LEN_SHIFT_W1) & 31);
+                hi &= (1ULL << REC_LEN_SHIFT_W1) - 1;
+                for (int j = 0; j < len; j++)
+                    table_insert_w1 ((unsigned long long*)P.g_lo, P.g_cnt, P.g_log2, rec_kmer_w1 (lo, hi, j, k), 1 << 30);
+            }
+            else
+            {
+                uint4 a = __ldg (&base[2*(uint64_t)i]), b = __ldg (&base[2*(uint64_t)i + 1]);
+                uint64_t r[4] = { (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
+                                  (uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32) };
+                const int len = (int)((r[3] >> REC_LEN_SHIFT_W2) & 63);
+                r[3] &= (1ULL << REC_LEN_SHIFT_W2) - 1;
+                for (int j = 0; j < len; j++)
+                    table_insert_w2<true> ((unsigned long long*)P.g_lo, (unsigned long long*)P.g_hi, P.g_cnt, P.g_log2, rec_kmer_w2 (r, j, k), 1 << 30);
+            }
+        }
+    }
+}
+
+template<int W>
+__global__ void __launch_bounds__(256) k2c_scan (const K2Params P)
+{
+    const uint64_t T = 1ULL << P.g_log2;
+    EmitState st; st.distinct = 0; st.solid = 0;
+    // every thread of a warp runs the same number of iterations (consume_entry uses warp collectives)
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t iters = (T + stride - 1) / stride;
+    for (uint64_t it = 0; it < iters; it++)
+    {
+        uint64_t i = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool occ = false; uint64_t klo = 0, khi = 0; uint32_t c = 0;
+        if (i < T)
+        {
+            klo = P.g_lo[i]; khi = (W == 2) ? P.g_hi[i] : 0; c = P.g_cnt[i];
+            occ = (W == 1) ? (klo != EMPTY64) : (khi != EMPTY64);
+        }
+        consume_entry (P, occ, klo, khi, c, 0, st);
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { st.distinct += __shfl_xor_sync (FULL_MASK, st.distinct, o); st.solid += __shfl_xor_sync (FULL_MASK, st.solid, o); }
+    if ((threadIdx.x & 31) == 0) { if (st.distinct) atomicAdd (&P.counters[1], st.distinct); if (st.solid) atomicAdd (&P.counters[2], st.solid); }
+}
+
+cudaError_t launch_k2c_measure (const LaunchCtx& L, const K2Params& P, uint32_t n_ovf)
+{
+    unsigned grid = n_ovf < 1024 ? n_ovf : 1024;
+    if (P.W == 1) k2c_measure<1><<<grid, 256, 0, L.stream>>> (P, n_ovf); else k2c_measure<2><<<grid, 256, 0, L.stream>>> (P, n_ovf);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+cudaError_t launch_k2c_insert (const LaunchCtx& L, const K2Params& P, uint32_t n_ovf)
+{
+    dim3 grid (n_ovf < 64 ? (unsigned)(L.sm_count * 8 / (n_ovf ? n_ovf : 1) + 1) : 8, n_ovf < 4096 ? n_ovf : 4096);
+    if (P.W == 1) k2c_insert<1><<<grid, 256, 0, L.stream>>> (P, n_ovf); else k2c_insert<2><<<grid, 256, 0, L.stream>>> (P, n_ovf);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+cudaError_t launch_k2c_scan (const LaunchCtx& L, const K2Params& P)
+{
+    unsigned grid = L.sm_count * 8;
+    if (P.W == 1) k2c_scan<1><<<grid, 256, 0, L.stream>>> (P); else k2c_scan<2><<<grid, 256, 0, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}

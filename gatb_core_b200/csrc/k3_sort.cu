@@ -1,0 +1,296 @@
+// k3_sort.cu -- k3: partition id of every emitted k-mer + ascending order inside each partition.
+//
+// Replaces (paths relative to /root/reference/gatb-core/src/gatb/):
+//   Repartitor::operator()                            kmer/impl/PartiInfo.hpp:323   (p = table[minimizer(kmer)])
+//   ModelMinimizer::computeNewMinimizerOriginal       kmer/impl/Model.hpp:1254-1287 (minimizer of one k-mer, GATB order)
+//   the ascending emission order of executeDump / Hash16::iterator(true)
+//                                                     kmer/impl/PartitionsCommand.cpp:1599-1805, 544
+//   CountProcessorDump::process (append to dsk/solid/<pass*nb_partitions+part>)   kmer/impl/CountProcessorDump.hpp:148
+//
+// k3a  one thread per emitted k-mer: GATB minimizer by rolling the forward/reverse m-mer along the k-mer (no table:
+//      lut value = min(mmer, revcomp) with the "AA" rule applied arithmetically), key = pass*nb_partitions + repart[min];
+//      bucket = key << t | (top t bits of the k-mer value); per-bucket population by global atomics.
+// scan exclusive prefix sum over buckets (u32 -> u64), tile scan + block-sum scan + add.
+// k3b  scatter into bucket order (atomic cursor per bucket).
+// k3c  one CTA per bucket: bitonic sort by k-mer value in shared memory, write to the final position.
+// k3d  buckets larger than the shared-memory budget: bitonic sort in global memory by one CTA (rare; skewed value ranges).
+#include "common.cuh"
+#include "kernels.h"
+
+#define K3_SORT_CAP 4096
+
+// minimizer (GATB lexicographic order with the AA rule) of one canonical k-mer value
+__device__ __forceinline__ uint32_t gatb_minimizer_w1 (uint64_t v, int k, int m, uint32_t mmask, uint32_t mask_ma1)
+{
+    uint32_t mm = (uint32_t)v & mmask;
+    uint32_t rc = (pair_reverse32 (mm) ^ 0xAAAAAAAAu) >> (32 - 2*m);
+    uint32_t best = gatb_mmer_key (min (mm, rc), mmask, mask_ma1);
+    const int top = 2*(m - 1);
+    for (int i = m; i < k; i++)
+    {
+        uint32_t nt = (uint32_t)(v >> (2*i)) & 3u;
+        mm = (mm >> 2) | (nt << top);
+        rc = ((rc << 2) | (nt ^ 2u)) & mmask;
+        best = min (best, gatb_mmer_key (min (mm, rc), mmask, mask_ma1));
+    }
+    return best;
+}
+__device__ __forceinline__ uint32_t gatb_minimizer_w2 (u128 v, int k, int m, uint32_t mmask, uint32_t mask_ma1)
+{
+    uint32_t mm = (uint32_t)v.lo & mmask;
+    uint32_t rc = (pair_reverse32 (mm) ^ 0xAAAAAAAAu) >> (32 - 2*m);
+    uint32_t best = gatb_mmer_key (min (mm, rc), mmask, mask_ma1);
+    const int top = 2*(m - 1);
+    for (int i = m; i < k; i++)
+    {
+        uint32_t nt = (uint32_t)((i < 32 ? v.lo >> (2*i) : v.hi >> (2*(i - 32)))) & 3u;
+        mm = (mm >> 2) | (nt << top);
+        rc = ((rc << 2) | (nt ^ 2u)) & mmask;
+        best = min (best, gatb_mmer_key (min (mm, rc), mmask, mask_ma1));
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(256) k3a_classify (const K3Params P)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    uint32_t key = 0, topbits = 0;
+    const int k = P.k, t = P.t_bits;
+    if (P.W == 1)
+    {
+        uint64_t v = P.in_lo[i];
+        if (P.n_keys > 1)
+        {
+            uint32_t mini = gatb_minimizer_w1 (v, k, P.m, P.mmask, P.mask_ma1);
+            key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
+        }
+        if (t) topbits = (uint32_t)(v >> (2*k - t));
+    }
+    else
+    {
+        u128 v; v.lo = P.in_lo[i]; v.hi = P.in_hi[i];
+        if (P.n_keys > 1)
+        {
+            uint32_t mini = gatb_minimizer_w2 (v, k, P.m, P.mmask, P.mask_ma1);
+            key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
+        }
+        if (t) { int s = 2*k - t; topbits = (uint32_t)(s >= 64 ? (v.hi >> (s - 64)) : ((v.lo >> s) | (v.hi << (64 - s)))); }
+    }
+    uint32_t b = (key << t) | topbits;
+    P.bucket_of[i] = b;
+    atomicAdd (&P.bucket_count[b], 1u);
+}
+
+__global__ void __launch_bounds__(256) k3b_scatter (const K3Params P)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint32_t b = P.bucket_of[i];
+    const uint64_t pos = P.bucket_off[b] + atomicAdd (&P.bucket_count[b], 1u);     // bucket_count was re-zeroed: it is the cursor now
+    P.tmp_lo[pos] = P.in_lo[i];
+    if (P.W == 2) P.tmp_hi[pos] = P.in_hi[i];
+    P.tmp_cnt[pos] = P.in_cnt[i];
+}
+
+// ---- bitonic sort of (key128, count) in shared memory ----------------------------------------------------------
+template<int W>
+__global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s_lo = (uint64_t*)smem_raw;
+    uint64_t* s_hi = (W == 2) ? s_lo + K3_SORT_CAP : 0;
+    uint32_t* s_c  = (uint32_t*)(s_lo + (size_t)K3_SORT_CAP * W);
+    for (uint32_t b = blockIdx.x; b < P.n_buckets; b += gridDim.x)
+    {
+        const uint64_t beg = P.bucket_off[b], end = P.bucket_off[b+1];
+        const uint64_t n64 = end - beg;
+        if (n64 == 0) continue;
+        if (n64 > K3_SORT_CAP)
+        {
+            if (threadIdx.x == 0) { unsigned long long idx = atomicAdd (&P.counters[0], 1ULL); P.big_list[idx] = b; }
+            continue;
+        }
+        const int n = (int)n64;
+        int np = 1; while (np < n) np <<= 1;
+        for (int i = threadIdx.x; i < np; i += blockDim.x)
+        {
+            if (i < n) { s_lo[i] = P.tmp_lo[beg + i]; if (W == 2) s_hi[i] = P.tmp_hi[beg + i]; s_c[i] = P.tmp_cnt[beg + i]; }
+            else       { s_lo[i] = ~0ULL; if (W == 2) s_hi[i] = ~0ULL; s_c[i] = 0; }
+        }
+        __syncthreads ();
+        // all-ascending bitonic network: each merge starts with a "flip" step (partner = mirror inside the block),
+        // then half-cleaners; +inf padding therefore never moves below index n
+        for (int size = 2; size <= np; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1)
+            {
+                const bool flip = (stride == (size >> 1));
+                for (int t = threadIdx.x; t < (np >> 1); t += blockDim.x)
+                {
+                    int lo_i, hi_i;
+                    if (flip) { int blk = t / stride, r = t - blk * stride; lo_i = blk * size + r; hi_i = blk * size + size - 1 - r; }
+                    else      { lo_i = 2*t - (t & (stride - 1)); hi_i = lo_i + stride; }
+                    uint64_t al = s_lo[lo_i], bl = s_lo[hi_i];
+                    uint64_t ah = (W == 2) ? s_hi[lo_i] : 0, bh = (W == 2) ? s_hi[hi_i] : 0;
+                    bool gt = (W == 2) ? (ah > bh || (ah == bh && al > bl)) : (al > bl);
+                    if (gt)
+                    {
+                        s_lo[lo_i] = bl; s_lo[hi_i] = al;
+                        if (W == 2) { s_hi[lo_i] = bh; s_hi[hi_i] = ah; }
+                        uint32_t c = s_c[lo_i]; s_c[lo_i] = s_c[hi_i]; s_c[hi_i] = c;
+                    }
+                }
+                __syncthreads ();
+            }
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        { P.out_lo[beg + i] = s_lo[i]; if (W == 2) P.out_hi[beg + i] = s_hi[i]; P.out_cnt[beg + i] = (int32_t)s_c[i]; }
+        __syncthreads ();
+    }
+}
+
+// ---- oversized buckets: bitonic network directly in global memory (virtual padding with +inf) -------------------
+template<int W>
+__global__ void __launch_bounds__(1024) k3d_sort_big (const K3Params P, uint32_t n_big)
+{
+    for (uint32_t q = blockIdx.x; q < n_big; q += gridDim.x)
+    {
+        const uint32_t b = (uint32_t)P.big_list[q];
+        const uint64_t beg = P.bucket_off[b], n = P.bucket_off[b+1] - beg;
+        uint64_t np = 1; while (np < n) np <<= 1;
+        uint64_t* lo = P.tmp_lo + beg; uint64_t* hi = (W == 2) ? P.tmp_hi + beg : 0; uint32_t* cn = P.tmp_cnt + beg;
+        for (uint64_t size = 2; size <= np; size <<= 1)
+            for (uint64_t stride = size >> 1; stride > 0; stride >>= 1)
+            {
+                const bool flip = (stride == (size >> 1));
+                for (uint64_t t = threadIdx.x; t < (np >> 1); t += blockDim.x)
+                {
+                    uint64_t lo_i, hi_i;
+                    if (flip) { uint64_t blk = t / stride, r = t - blk * stride; lo_i = blk * size + r; hi_i = blk * size + size - 1 - r; }
+                    else      { lo_i = 2*t - (t & (stride - 1)); hi_i = lo_i + stride; }
+                    if (hi_i >= n) continue;                    // partner is virtual +inf: ascending order already holds
+                    uint64_t al = lo[lo_i], bl = lo[hi_i];
+                    uint64_t ah = (W == 2) ? hi[lo_i] : 0, bh = (W == 2) ? hi[hi_i] : 0;
+                    bool gt = (W == 2) ? (ah > bh || (ah == bh && al > bl)) : (al > bl);
+                    if (gt)
+                    {
+                        lo[lo_i] = bl; lo[hi_i] = al;
+                        if (W == 2) { hi[lo_i] = bh; hi[hi_i] = ah; }
+                        uint32_t c = cn[lo_i]; cn[lo_i] = cn[hi_i]; cn[hi_i] = c;
+                    }
+                }
+                __syncthreads ();
+            }
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+        { P.out_lo[beg + i] = lo[i]; if (W == 2) P.out_hi[beg + i] = hi[i]; P.out_cnt[beg + i] = (int32_t)cn[i]; }
+        __syncthreads ();
+    }
+}
+
+cudaError_t launch_k3a_classify (const LaunchCtx& L, const K3Params& P)
+{
+    if (P.n == 0) return cudaSuccess;
+    k3a_classify<<<(unsigned)((P.n + 255) / 256), 256, 0, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+cudaError_t launch_k3b_scatter (const LaunchCtx& L, const K3Params& P)
+{
+    if (P.n == 0) return cudaSuccess;
+    k3b_scatter<<<(unsigned)((P.n + 255) / 256), 256, 0, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+cudaError_t launch_k3c_sort (const LaunchCtx& L, const K3Params& P)
+{
+    if (P.n == 0) return cudaSuccess;
+    size_t smem = (size_t)K3_SORT_CAP * (8 * P.W + 4);
+    const void* fn = P.W == 1 ? (const void*)k3c_sort<1> : (const void*)k3c_sort<2>;
+    cudaError_t e = cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = P.n_buckets < (unsigned)(L.sm_count * 32) ? P.n_buckets : (unsigned)(L.sm_count * 32);
+    if (P.W == 1) k3c_sort<1><<<grid, 256, smem, L.stream>>> (P); else k3c_sort<2><<<grid, 256, smem, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+cudaError_t launch_k3d_sort_big (const LaunchCtx& L, const K3Params& P, uint32_t n_big)
+{
+    if (n_big == 0) return cudaSuccess;
+    unsigned grid = n_big < (unsigned)L.sm_count ? n_big : (unsigned)L.sm_count;
+    if (P.W == 1) k3d_sort_big<1><<<grid, 1024, 0, L.stream>>> (P, n_big); else k3d_sort_big<2><<<grid, 1024, 0, L.stream>>> (P, n_big);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
+// ---- exclusive scan u32 -> u64 ----------------------------------------------------------------------------------
+#define SCAN_TILE 2048     // elements per block (256 threads x 8)
+__global__ void __launch_bounds__(256) scan_tile_sums (const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ sums)
+{
+    __shared__ unsigned long long s[8];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    unsigned long long v = 0;
+    for (int i = 0; i < 8; i++) { uint64_t idx = base + threadIdx.x + 256*i; if (idx < n) v += in[idx]; }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync (FULL_MASK, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads ();
+    if (threadIdx.x == 0) { unsigned long long t = 0; for (int i = 0; i < 8; i++) t += s[i]; sums[blockIdx.x] = t; }
+}
+// single block: exclusive scan of m values in place (m arbitrary; sequential over chunks of 1024)
+__global__ void __launch_bounds__(1024) scan_sums_inplace (uint64_t* sums, uint64_t m)
+{
+    __shared__ unsigned long long s_w[32]; __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads ();
+    for (uint64_t c0 = 0; c0 < m; c0 += 1024)
+    {
+        uint64_t idx = c0 + threadIdx.x;
+        unsigned long long v = idx < m ? sums[idx] : 0, incl = v;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) s_w[wid] = incl;
+        __syncthreads ();
+        if (wid == 0) { unsigned long long w = s_w[lane], wi = w; for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync (FULL_MASK, wi, o); if (lane >= o) wi += y; } s_w[lane] = wi - w; }
+        __syncthreads ();
+        unsigned long long excl = s_carry + s_w[wid] + incl - v;
+        if (idx < m) sums[idx] = excl;
+        __syncthreads ();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads ();
+    }
+}
+__global__ void __launch_bounds__(256) scan_tile_apply (const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ sums, uint64_t* __restrict__ out)
+{
+    // each thread owns 8 consecutive elements of the tile
+    __shared__ unsigned long long s_w[8];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * 8;
+    uint32_t v[8]; unsigned long long sum = 0;
+    for (int i = 0; i < 8; i++) { v[i] = base + i < n ? in[base + i] : 0; sum += v[i]; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long incl = sum;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_w[wid] = incl;
+    __syncthreads ();
+    unsigned long long woff = 0; for (int i = 0; i < wid; i++) woff += s_w[i];
+    unsigned long long run = sums[blockIdx.x] + woff + incl - sum;
+    for (int i = 0; i < 8; i++) { if (base + i < n) out[base + i] = run; run += v[i]; }
+    // the element one past the end receives the grand total
+    if (blockIdx.x == gridDim.x - 1)
+    {
+        __syncthreads ();
+        if (threadIdx.x == 255) out[n] = run;      // thread 255 of the last tile: run == total (elements past n are zero)
+    }
+}
+uint64_t scan_scratch_elems (uint64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
+// out has n+1 entries (out[n] = total)
+cudaError_t launch_scan_u32_to_u64 (const LaunchCtx& L, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch)
+{
+    if (n == 0) return cudaMemsetAsync (out, 0, sizeof(uint64_t), L.stream);
+    unsigned tiles = (unsigned)((n + SCAN_TILE - 1) / SCAN_TILE);
+    scan_tile_sums<<<tiles, 256, 0, L.stream>>> (in, n, scratch);
+    scan_sums_inplace<<<1, 1024, 0, L.stream>>> (scratch, tiles);
+    scan_tile_apply<<<tiles, 256, 0, L.stream>>> (in, n, scratch, out);
+    (*L.launches) += 3;
+    return cudaGetLastError ();
+}

@@ -1,0 +1,110 @@
+// kernels.h -- parameter blocks and host-side launchers of the sm_100a kernels (definitions in k*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// ----------------------------------------------------------------------------------------------------------------
+// Record format written by k1 and consumed by k2a/k2b (replaces the reference's SuperKmerBinFiles byte stream,
+// tools/storage/impl/Storage.cpp:310-589, by fixed-size HBM records so one aligned vector store/load moves one):
+//   W=1 (k<=31, Kmer<32>): 16 B.  bits [0,116)  = the k+nbK-1 nucleotides of the super-k-mer, stream order, 2 bits each
+//                                 bits [116,121) = nbK (1..28)           bits [121,128) = fine-bin id (7 bits)
+//   W=2 (k<=63, Kmer<64>): 32 B.  bits [0,244)  = nucleotides            bits [244,250) = nbK (1..60)
+//                                 bits [250,256) = fine-bin id (6 bits)
+// nbK <= maxs = min((8*sizeof(Type)-8)/2, 255) = 28 / 60 exactly as Sequence2SuperKmer.hpp:147.
+// ----------------------------------------------------------------------------------------------------------------
+enum { REC_LEN_SHIFT_W1 = 52, REC_FINE_SHIFT_W1 = 57, FINE_BITS_W1 = 7,
+       REC_LEN_SHIFT_W2 = 52, REC_FINE_SHIFT_W2 = 58, FINE_BITS_W2 = 6 };
+
+enum { K1_MODE_DEVICE = 0,   // hashed-order signature, device bins (the counting path)
+       K1_MODE_GATB   = 1 }; // GATB minimizer (lexicographic + AA rule), bins = pass*nb_partitions + repart[minimizer]
+
+struct K1Params
+{
+    const uint64_t* words;          // packed reads, 64-bit words
+    const uint64_t* offsets;        // [n_reads+1] nucleotide offsets, or NULL with read_len
+    const uint32_t* nmask;          // invalid-nucleotide bitmask or NULL
+    uint64_t n_reads;
+    int      read_len;
+    int      k, m, w, maxlen;       // m = size of the m-mers ranked; w = k-m+1; maxlen = max k-mers per record
+    uint32_t mmask, mask_ma1;
+    int      mode;
+    const uint16_t* repart;         // GATB mode
+    int      nb_partitions, nb_passes;
+    uint32_t nb1;                   // number of (coarse) bins
+    uint32_t cap;                   // records per bin
+    int      fine_bits;
+    void*    bins;                  // nb1*cap records
+    uint32_t* cursors;              // [nb1] demand per bin (may exceed cap)
+    uint32_t* fine_counts;          // [nb1<<fine_bits] stored records per fine bin, or NULL
+    unsigned long long* stats;      // [0] valid k-mers [1] invalid k-mers [2] records stored [3] records dropped (overflow)
+    int      count_only;            // 1: only count demand (cursors), store nothing
+};
+
+struct K2Params
+{
+    int      k, W;
+    const void* recs;               // fine-split records
+    const uint2* bin_desc;          // [nbins] {offset inside coarse region, record count}
+    uint32_t nbins;                 // nb1 << fine_bits
+    uint32_t cap; int fine_bits;
+    int      table_log2;            // log2 slots of the shared-memory table
+    uint32_t emit_min, emit_max;    // emit k-mers with emit_min <= count <= emit_max
+    uint32_t solid_min, solid_max;  // solidity range (stats only)
+    int      histo_max;
+    unsigned long long* histogram;  // [histo_max+1]
+    uint64_t* out_lo; uint64_t* out_hi; uint32_t* out_cnt; unsigned long long out_cap;
+    unsigned long long* counters;   // [0] emitted [1] distinct [2] solid [3] work counter [4] overflow bins [5] k-mers in overflow bins
+    uint32_t* ovf_list;             // [nbins] ids of bins whose table overflowed
+    // global-memory fallback table
+    uint64_t* g_lo; uint64_t* g_hi; uint32_t* g_cnt; int g_log2;
+};
+
+struct K3Params
+{
+    int k, m, W;
+    uint32_t mmask, mask_ma1;
+    const uint16_t* repart; int nb_partitions, nb_passes; uint32_t n_keys;
+    int t_bits;                     // value-range bits per key: bucket = key << t_bits | top t_bits of the k-mer
+    uint64_t n;
+    const uint64_t* in_lo; const uint64_t* in_hi; const uint32_t* in_cnt;
+    uint32_t* bucket_of;            // [n]
+    uint32_t* bucket_count;         // [n_buckets]   -> cursors during scatter
+    const uint64_t* bucket_off;     // [n_buckets+1]
+    uint64_t* tmp_lo; uint64_t* tmp_hi; uint32_t* tmp_cnt;     // scattered
+    uint64_t* out_lo; uint64_t* out_hi; int32_t* out_cnt;      // sorted
+    uint32_t n_buckets;
+    unsigned long long* big_list;   // buckets too large for shared memory
+    unsigned long long* counters;   // [0] number of big buckets
+};
+
+struct LaunchCtx { cudaStream_t stream; int sm_count; uint64_t* launches; };
+
+// k1_partition.cu
+cudaError_t launch_k1 (const LaunchCtx&, const K1Params&);
+// k2_count.cu
+cudaError_t launch_k2a_split (const LaunchCtx&, int W, const void* src, void* dst, const uint32_t* cursors,
+                              const uint32_t* fine_counts, uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc);
+cudaError_t launch_k2b_count (const LaunchCtx&, const K2Params&);
+cudaError_t launch_k2c_measure (const LaunchCtx&, const K2Params&, uint32_t n_ovf);
+cudaError_t launch_k2c_insert (const LaunchCtx&, const K2Params&, uint32_t n_ovf);
+cudaError_t launch_k2c_scan (const LaunchCtx&, const K2Params&);
+// k3_sort.cu
+cudaError_t launch_k3a_classify (const LaunchCtx&, const K3Params&);
+cudaError_t launch_k3b_scatter (const LaunchCtx&, const K3Params&);
+cudaError_t launch_k3c_sort (const LaunchCtx&, const K3Params&);
+cudaError_t launch_k3d_sort_big (const LaunchCtx&, const K3Params&, uint32_t n_big);
+cudaError_t launch_scan_u32_to_u64 (const LaunchCtx&, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch);
+uint64_t    scan_scratch_elems (uint64_t n);
+// gatb_serialize (k1 GATB mode -> reference byte streams)
+cudaError_t launch_serialize_sizes (const LaunchCtx&, int W, int k, const void* bins, const uint32_t* cursors, uint32_t nb1,
+                                    uint32_t cap, unsigned long long* key_bytes);
+cudaError_t launch_serialize_write (const LaunchCtx&, int W, int k, const void* bins, const uint32_t* cursors, uint32_t nb1,
+                                    uint32_t cap, const uint64_t* key_off, unsigned long long* key_cur, uint8_t* out);
+// bloom.cu
+cudaError_t launch_bloom_insert (const LaunchCtx&, int kind, int W, int k, int nb_hash, uint64_t tai, int pow2, uint64_t reduced,
+                                 const uint64_t* lo, const uint64_t* hi, uint64_t n, uint32_t* words);
+// synth.cu
+cudaError_t launch_synth_reads (const LaunchCtx&, uint64_t seed, uint64_t genome_len, uint64_t first_read, uint64_t n_reads,
+                                int L, uint8_t* packed);
+cudaError_t launch_pack_ascii (const LaunchCtx&, const char* ascii, uint64_t n, uint32_t* packed_words, uint32_t* nmask,
+                               unsigned long long* n_invalid);

@@ -1,0 +1,156 @@
+/* gatb_gpu.h -- C ABI of the B200-native k-mer counting path (libgatb_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of GATB-core: DSK / SortingCountAlgorithm (+ Bloom insertion of the
+ * solid k-mers).  Plain pointers and sizes only; no C++ or torch types.  The C++ host shim that keeps GATB's own
+ * API (gatb_core_b200/host/: Kmer<span>::Model*, SortingCountAlgorithm<span>, ICountProcessor<span>) and the Python
+ * harness (gatb_core_b200/__init__.py, ctypes) are both thin callers of these entry points.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/gatb-core/src/gatb/):
+ *   gatb_gpu_count / _dev     SortingCountAlgorithm<span>::execute            kmer/impl/SortingCountAlgorithm.cpp:636-781
+ *                             = fillPartitions (:1211-1344) + fillSolidKmers (:1384-1602) + the default
+ *                             ICountProcessor chain histogram -> solidity -> dump (kmer/api/ICountProcessor.hpp:91-183,
+ *                             kmer/impl/CountProcessorHistogram.hpp:173, CountProcessorSolidity.hpp:186, CountProcessorDump.hpp:148)
+ *   gatb_gpu_superkmers       Sequence2SuperKmer<span>::operator()            kmer/impl/Sequence2SuperKmer.hpp:138-159
+ *                             + FillPartitions<span,true>::processSuperkmer   kmer/impl/SortingCountAlgorithm.cpp:1081-1151
+ *                             + Kmer<span>::SuperKmer::save                   kmer/impl/Model.hpp:1386-1471
+ *   gatb_gpu_bloom_params     BloomAlgorithm<span>::execute sizing            kmer/impl/BloomAlgorithm.cpp:158-166
+ *   gatb_gpu_bloom / _dev     BloomBuilder<span>::build -> Bloom*::insert     kmer/impl/BloomBuilder.hpp:102-131,
+ *                                                                             tools/collections/impl/Bloom.hpp:394-412,445-459,555-588
+ *   gatb_gpu_histogram_cutoff Histogram::compute_threshold                    tools/misc/impl/Histogram.cpp:61-190
+ *
+ * Conventions
+ *   - nucleotides: A=0 C=1 T=2 G=3 (tools/misc/api/Data.hpp:185), a k-mer value holds its FIRST nucleotide in the most
+ *     significant position (kmer/impl/Model.hpp:636-657); canonical = min(forward, reverse complement).
+ *   - packed reads: 2 bits per nucleotide, nucleotide i of the stream in bits [2(i%4), 2(i%4)+2) of byte i/4; read r
+ *     occupies stream positions [read_offsets_nt[r], read_offsets_nt[r+1]).  Buffers must be 16-byte aligned and
+ *     readable for 16 bytes past the last nucleotide (gatb_gpu_count copies host input into such a buffer itself).
+ *   - n_mask (optional, may be NULL): 1 bit per stream position, bit (i%32) of 32-bit word i/32, set = the
+ *     nucleotide is not A/C/G/T (k-mers overlapping it are invalid and dropped, Sequence2SuperKmer.hpp:95-108).
+ *   - k-mers are returned as (lo, hi) 64-bit halves; hi arrays are NULL when kmer_size < 32 (Kmer<32>).
+ *   - every function returns 0 on success, non-zero on error; gatb_gpu_last_error() describes the last failure.
+ *     There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GATB_GPU_H
+#define GATB_GPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gatb_gpu_ctx gatb_gpu_ctx;
+
+/* Mirrors the fields of kmer/impl/Configuration.hpp:56-100 that decide the OUTPUT. */
+typedef struct gatb_gpu_params
+{
+    int32_t  kmer_size;          /* _kmerSize        1 <= m < k <= 63                                          */
+    int32_t  minimizer_size;     /* _minim_size      m <= 12 (size of the Repartitor table is 4^m)             */
+    int32_t  nb_partitions;      /* _nb_partitions                                                              */
+    int32_t  nb_passes;          /* _nb_passes       pass = minimizer % nb_passes (SortingCountAlgorithm.cpp:1083)*/
+    int32_t  abundance_min;      /* _abundance[0].getBegin()  (solid <=> min <= count <= max)                   */
+    int32_t  abundance_max;      /* _abundance[0].getEnd()    (default 2^31-1)                                  */
+    int32_t  histo_max;          /* _abundanceUserNb / -histo-max (default 10000)                               */
+    int32_t  minimizer_type;     /* _minimizerType   0 = lexicographic (supported); 1 = frequency (not yet)     */
+    int32_t  emit_all;           /* 1: return EVERY distinct k-mer (for custom ICountProcessor chains); 0: solid only */
+    int32_t  read_len;           /* >0: all reads have this length and read_offsets_nt may be NULL               */
+    int32_t  table_log2;         /* 0 = default; log2 slots of the per-bin shared-memory table (tests shrink it) */
+    int32_t  reserved[5];
+} gatb_gpu_params;
+
+enum { GATB_GPU_NSTATS = 16 };
+/* indices into gatb_gpu_result.stats */
+enum {
+    GATB_STAT_KMERS_VALID = 0,   /* kmers_nb_valid   (SortingCountAlgorithm.cpp:737)   */
+    GATB_STAT_KMERS_INVALID = 1, /* kmers_nb_invalid                                   */
+    GATB_STAT_DISTINCT = 2,      /* kmers_nb_distinct (CountProcessorSolidity.hpp:163) */
+    GATB_STAT_SOLID = 3,         /* kmers_nb_solid                                     */
+    GATB_STAT_RECORDS = 4,       /* super-k-mer records written by the partition kernel */
+    GATB_STAT_SEQUENCES = 5,
+    GATB_STAT_NUCLEOTIDES = 6,
+    GATB_STAT_BINS = 7,          /* device bins used                                    */
+    GATB_STAT_OVERFLOW_BINS = 8, /* bins counted through the global-memory fallback     */
+    GATB_STAT_RETRIES = 9,       /* partition-kernel re-runs after a bucket overflow    */
+    GATB_STAT_RECORD_BYTES = 10  /* bytes of super-k-mer records (S of SURVEY.md 8d)    */
+};
+
+typedef struct gatb_gpu_result
+{
+    uint64_t  n_keys;            /* nb_passes * nb_partitions; key = pass*nb_partitions + partition              */
+    uint64_t  n_items;           /* total k-mers returned                                                         */
+    uint64_t* part_offsets;      /* [n_keys+1] offsets into the arrays below; ascending k-mer order inside a key  */
+    uint64_t* kmers_lo;          /* [n_items]                                                                     */
+    uint64_t* kmers_hi;          /* [n_items] or NULL                                                             */
+    int32_t*  counts;            /* [n_items] CountNumber (system/api/types.hpp:49)                               */
+    uint64_t* histogram;         /* [histo_max+1], index clamped like Histogram::inc (tools/misc/impl/Histogram.hpp:92) */
+    uint64_t  stats[GATB_GPU_NSTATS];
+    double    seconds[8];        /* device time per stage: 0 h2d, 1 partition, 2 split, 3 count, 4 sort, 5 d2h, 6 total device */
+    int32_t   on_device;         /* 1: the arrays above are DEVICE pointers (gatb_gpu_count_dev), 0: host            */
+    int32_t   pad;
+    void*     owner;             /* internal */
+} gatb_gpu_result;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+gatb_gpu_ctx* gatb_gpu_create  (int device);         /* NULL when the device cannot be opened                     */
+void          gatb_gpu_destroy (gatb_gpu_ctx*);
+const char*   gatb_gpu_last_error (gatb_gpu_ctx*);   /* ctx may be NULL: error of gatb_gpu_create                 */
+void*         gatb_gpu_stream (gatb_gpu_ctx*);       /* the cudaStream_t every kernel of this ctx is launched on  */
+uint64_t      gatb_gpu_kernel_launches (gatb_gpu_ctx*); /* kernels launched by this ctx so far                    */
+int           gatb_gpu_sm_count (gatb_gpu_ctx*);
+
+/* ---- DSK: reads -> sorted (k-mer, count) per partition + histogram ------------------------------------------- */
+/* HOST buffers in, HOST arrays out (copies are part of the call). */
+int gatb_gpu_count (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* repart_table /* [4^m] or NULL when n_keys==1 */,
+                    const uint32_t* freq_order /* NULL */, const uint8_t* packed_reads, const uint64_t* read_offsets_nt,
+                    uint64_t n_reads, const uint32_t* n_mask, gatb_gpu_result* out);
+/* DEVICE buffers in, DEVICE arrays out (owned by ctx until gatb_gpu_result_free). repart_table is a HOST pointer. */
+int gatb_gpu_count_dev (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* repart_table, const uint32_t* freq_order,
+                        const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads,
+                        const uint32_t* d_n_mask, gatb_gpu_result* out);
+void gatb_gpu_result_free (gatb_gpu_ctx*, gatb_gpu_result*);
+
+/* ---- GATB-exact super-k-mer partitioning (rows A3-A6): per key, the record stream [u8 nbK][packed bytes]... that
+ *      the reference writes to its SuperKmerBinFiles (order of records inside a key is unspecified).
+ *      streams[key] is malloc'ed host memory (gatb_gpu_free_host); stats_out: [0] nb super-k-mers [1] nb k-mers
+ *      [2] valid k-mers [3] invalid k-mers. ---- */
+int gatb_gpu_superkmers (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* repart_table,
+                         const uint8_t* packed_reads, const uint64_t* read_offsets_nt, uint64_t n_reads,
+                         const uint32_t* n_mask, uint8_t** streams, uint64_t* stream_sizes, uint64_t* stats_out);
+void gatb_gpu_free_host (void*);
+
+/* ---- Bloom filter of solid k-mers ---------------------------------------------------------------------------- */
+enum { GATB_BLOOM_BASIC = 0, GATB_BLOOM_CACHE = 1, GATB_BLOOM_NEIGHBOR = 2 };
+/* bloom_size = (u64)((float)nb_solid * (float)rvalues[k][1]); nb_hash = floorf(0.7 * bits) */
+int gatb_gpu_bloom_params (int kmer_size, uint64_t nb_solid, uint64_t* bloom_size, int32_t* nb_hash);
+/* byte size of the array (1 + tai/8) and the value the reference reports as getBitSize() */
+int gatb_gpu_bloom_layout (int kind, uint64_t bloom_size, uint64_t* nbytes, uint64_t* bit_size);
+/* host k-mers in, host bytes out (out_bytes has nbytes from gatb_gpu_bloom_layout) */
+int gatb_gpu_bloom (gatb_gpu_ctx*, int kind, uint64_t bloom_size, int nb_hash, int kmer_size,
+                    const uint64_t* kmers_lo, const uint64_t* kmers_hi, uint64_t n, uint8_t* out_bytes);
+/* device k-mers in, device bytes out (d_out_bytes zeroed by the call; must be padded to a multiple of 4 bytes) */
+int gatb_gpu_bloom_dev (gatb_gpu_ctx*, int kind, uint64_t bloom_size, int nb_hash, int kmer_size,
+                        const uint64_t* d_kmers_lo, const uint64_t* d_kmers_hi, uint64_t n, uint8_t* d_out_bytes);
+
+/* ---- Histogram cutoff (host arithmetic on the small histogram; doubles like the reference) -------------------- */
+int gatb_gpu_histogram_cutoff (const uint64_t* histogram, int histo_max, int min_auto_threshold,
+                               uint32_t* cutoff, uint64_t* nb_solids, uint32_t* first_peak);
+
+/* ---- device utilities used by bench.py and the tests ---------------------------------------------------------- */
+void* gatb_gpu_malloc (gatb_gpu_ctx*, uint64_t bytes);       /* cudaMalloc on the ctx device                      */
+void  gatb_gpu_free   (gatb_gpu_ctx*, void*);
+int   gatb_gpu_memcpy_h2d (gatb_gpu_ctx*, void* dst, const void* src, uint64_t bytes);
+int   gatb_gpu_memcpy_d2h (gatb_gpu_ctx*, void* dst, const void* src, uint64_t bytes);
+int   gatb_gpu_synchronize (gatb_gpu_ctx*);
+/* Synthetic reads (DESIGN.md "Synthetic workload"; bit-identical to oracle/kmer_oracle.c orc_synth_reads + orc_pack_2bit):
+ * writes reads [first_read, first_read+n_reads) of length L, packed back to back, into d_packed. */
+int   gatb_gpu_synth_reads_dev (gatb_gpu_ctx*, uint64_t seed, uint64_t genome_len, uint64_t first_read,
+                                uint64_t n_reads, int L, uint8_t* d_packed);
+/* 2-bit packer for ASCII reads concatenated without separators (host in, host out; n_mask_out may be NULL):
+ * the device-side analogue of bank::Sequence -> Data::ConvertASCII (tools/misc/api/Data.hpp:185). */
+int   gatb_gpu_pack_ascii (gatb_gpu_ctx*, const char* ascii, uint64_t n, uint8_t* packed_out, uint32_t* n_mask_out,
+                           uint64_t* n_invalid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GATB_GPU_H */

@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle / committed reference fixtures /
+the reference's golden vectors.  Bit-exact everywhere (integer work)."""
+import numpy as np
+import pytest
+
+import fixtures
+from golden import reference_vectors as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import gatb_core_b200
+    g = gatb_core_b200.GatbGpu(0)
+    yield g
+    g.close()
+
+
+def pad(a, n=64):
+    return np.concatenate([a, np.zeros(n, a.dtype)])
+
+
+def pack_seqs(oracle, seqs):
+    """ASCII sequences -> (packed stream, offsets, n_mask or None) in the C-ABI layout."""
+    blob = b"".join(seqs)
+    codes = np.frombuffer(blob, np.uint8)
+    bad = ~np.isin(codes, np.frombuffer(b"ACGTacgt", np.uint8))
+    c2 = (codes >> 1) & 3
+    packed = pad(oracle.pack_2bit(c2.astype(np.uint8)))
+    offs = np.zeros(len(seqs) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    mask = None
+    if bad.any():
+        bits = np.zeros(((len(codes) + 31) // 32 + 2) * 32, np.uint8)
+        bits[:len(codes)] = bad
+        mask = np.packbits(bits.reshape(-1, 8), axis=1, bitorder="little").reshape(-1).view(np.uint32).copy()
+    return packed, offs, mask
+
+
+def rand_seq(rng, n, p_n=0.0):
+    s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy()
+    if p_n:
+        s[rng.random(n) < p_n] = ord("N")
+    return s.tobytes()
+
+
+def check_parts(got, want_parts, nkeys, words):
+    for key in range(nkeys):
+        lo, hi, cn = want_parts[key]
+        glo, ghi, gcn = got["parts"][key]
+        assert len(glo) == len(lo), (key, len(glo), len(lo))
+        assert (glo == lo).all() and (gcn == cn).all(), key
+        if words == 2:
+            assert (ghi == hi).all(), key
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_synth_generator_matches_oracle(gpu, oracle):
+    n, L = 3000, 150
+    for seed, first in ((1, 0), (42, 12345)):
+        codes = oracle.synth_reads(seed, 100000, first, n, L)
+        want = oracle.pack_2bit(codes)
+        d = gpu.malloc(len(want) + 64)
+        gpu.synth_reads_dev(seed, 100000, first, n, L, d)
+        got = np.zeros((len(want) + 3) // 4 * 4, np.uint8)
+        gpu.d2h(got, d)
+        gpu.free(d)
+        assert (got[:len(want)] == want).all()
+
+
+def test_pack_ascii_matches_reference_encoding(gpu, oracle):
+    rng = np.random.default_rng(0)
+    s = rand_seq(rng, 10007, 0.01) + b"acgtnRYK"
+    packed, mask, bad = gpu.pack_ascii(s)
+    want, offs, wmask = pack_seqs(oracle, [s])
+    n = (len(s) + 3) // 4
+    assert (packed[:n] == want[:n]).all()
+    assert bad == sum(c not in b"ACGTacgt" for c in s)
+    assert (mask[:len(wmask) - 2] == wmask[:len(wmask) - 2]).all()
+
+
+@pytest.mark.parametrize("name", fixtures.NAMES)
+@pytest.mark.parametrize("emit_all", [False, True])
+def test_dsk_against_reference_fixtures(gpu, oracle, name, emit_all):
+    fx = fixtures.Fixture(name, oracle)
+    packed, offs, mask = pack_seqs(oracle, fx.seqs)
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, nb_passes=fx.nb_passes,
+                             abundance_min=fx.abundance_min, emit_all=emit_all)
+    got = gpu.count(packed, offs, len(fx.seqs), params, repart=fx.repart, n_mask=mask)
+    nkeys = fx.nb_partitions * fx.nb_passes
+    want = {key: (fx.part(key) if emit_all else fx.solid(key)) for key in range(nkeys)}
+    check_parts(got, want, nkeys, fx.words)
+    assert (got["histogram"] == fx.z["histogram"]).all()
+    st = got["stats"]
+    assert [st["kmers_nb_valid"], st["kmers_nb_invalid"], st["kmers_nb_distinct"], st["kmers_nb_solid"]] == fx.z["stats"].tolist()
+    assert list(gpu.histogram_cutoff(got["histogram"])) == fx.z["cutoff"].tolist()
+
+
+@pytest.mark.parametrize("name", fixtures.NAMES)
+def test_fixed_length_fast_path_equals_offsets_path(gpu, oracle, name):
+    fx = fixtures.Fixture(name, oracle)
+    if len(fx.z["n_positions"]):
+        pytest.skip("fixture has invalid nucleotides")
+    packed, offs, _ = pack_seqs(oracle, fx.seqs)
+    p1 = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, abundance_min=2)
+    p2 = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, abundance_min=2, read_len=fx.L)
+    a = gpu.count(packed, offs, len(fx.seqs), p1, repart=fx.repart)
+    b = gpu.count(packed, None, len(fx.seqs), p2, repart=fx.repart)
+    check_parts(a, b["parts"], fx.nb_partitions, fx.words)
+
+
+@pytest.mark.parametrize("table_log2", [5, 7, 10])
+def test_small_tables_force_the_global_fallback(gpu, oracle, table_log2):
+    fx = fixtures.Fixture("dsk_k31_parts", oracle)
+    packed, offs, mask = pack_seqs(oracle, fx.seqs)
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, abundance_min=2, table_log2=table_log2)
+    got = gpu.count(packed, offs, len(fx.seqs), params, repart=fx.repart, n_mask=mask)
+    check_parts(got, {key: fx.solid(key) for key in range(fx.nb_partitions)}, fx.nb_partitions, 1)
+    assert (got["histogram"] == fx.z["histogram"]).all()
+
+
+def test_reference_golden_vectors_dsk(gpu, oracle):
+    # TestDSK.cpp:147-241 (solid counts) and :244-341 (exact set + checksum)
+    for seqs, k, nks, expected in G.DSK1_CASES:
+        m = min(8, k - 1)
+        packed, offs, mask = pack_seqs(oracle, [s.encode() for s in seqs])
+        got = gpu.count(packed, offs, len(seqs), gpu.make_params(k, m, abundance_min=nks))
+        assert got["stats"]["kmers_nb_solid"] == expected and got["n_items"] == expected, (k, nks)
+    packed, offs, mask = pack_seqs(oracle, [G.DSK2_SEQ.encode()])
+    got = gpu.count(packed, offs, 1, gpu.make_params(31, 10, abundance_min=1))
+    lo = got["parts"][0][0]
+    assert lo.tolist() == sorted(G.DSK2_SOLID)
+    assert sum(lo.tolist()) % 2 ** 64 == G.DSK2_CHECKSUM
+
+
+def test_edge_cases(gpu, oracle):
+    rng = np.random.default_rng(5)
+    k, m = 31, 10
+    cases = {
+        "empty": [],
+        "all_short": [b"ACGT" * 5, b"A" * 30, b""],
+        "exactly_k": [rand_seq(rng, k)],
+        "only_N": [b"N" * 100, b"ACGTN" * 40],
+        "identical_reads": [rand_seq(np.random.default_rng(1), 150)] * 3000,      # extreme skew: every record in a few bins
+        "poly_A": [b"A" * 500, b"T" * 500, b"AC" * 300],
+        "ragged": [rand_seq(rng, int(n), 0.02) for n in rng.integers(1, 700, 400)],
+        "long_read": [rand_seq(rng, 200000)],
+    }
+    for name, seqs in cases.items():
+        packed, offs, mask = pack_seqs(oracle, seqs) if seqs else (np.zeros(64, np.uint8), np.zeros(1, np.uint64), None)
+        want = oracle.dsk(seqs, k, m, np.zeros(4 ** m, np.uint16), 1, abundance_min=1) if seqs else None
+        got = gpu.count(packed, offs, len(seqs), gpu.make_params(k, m, abundance_min=1), n_mask=mask)
+        if want is None:
+            assert got["n_items"] == 0 and not got["histogram"].any()
+            continue
+        check_parts(got, want["solid"], 1, 1)
+        assert (got["histogram"] == want["histogram"]).all(), name
+        assert got["stats"]["kmers_nb_valid"] == int(want["stats"][0]) and got["stats"]["kmers_nb_invalid"] == int(want["stats"][1]), name
+
+
+@pytest.mark.parametrize("k,m,nparts,npass", [(31, 10, 7, 1), (21, 8, 3, 2), (63, 10, 5, 1), (12, 6, 2, 1), (40, 8, 4, 3)])
+def test_gatb_exact_superkmers(gpu, oracle, k, m, nparts, npass):
+    # rows A3-A6: same super-k-mers, same partition, same serialised bytes as the reference (multiset per key)
+    import oracle_lib
+    rng = np.random.default_rng(k + nparts)
+    seqs = [rand_seq(rng, int(rng.integers(20, 400)), 0.01 if i % 3 == 0 else 0.0) for i in range(300)]
+    seqs += [b"A" * 300, b"ACGTN" * 30, b"", b"N" * 100, b"ACGT"]
+    repart = rng.integers(0, nparts, 4 ** m).astype(np.uint16)
+    packed, offs, mask = pack_seqs(oracle, seqs)
+    params = gpu.make_params(k, m, nb_partitions=nparts, nb_passes=npass)
+    streams, stats = gpu.superkmers(packed, offs, len(seqs), params, repart=repart, n_mask=mask)
+    tot_sk = 0
+    for pass_ in range(npass):
+        want, wst = oracle.superkmers(seqs, k, m, repart, nparts, npass, pass_)
+        tot_sk += int(wst[0])
+        for p in range(nparts):
+            assert oracle_lib.split_records(streams[pass_ * nparts + p], k) == oracle_lib.split_records(want[p], k), (pass_, p)
+    assert int(stats[0]) == tot_sk
+
+
+@pytest.mark.parametrize("kind", ["basic", "cache", "neighbor"])
+@pytest.mark.parametrize("words,k", [(1, 21), (1, 31), (2, 63), (2, 33)])
+def test_bloom_bytes(gpu, oracle, kind, words, k):
+    rng = np.random.default_rng(words * 1000 + k)
+    n = 20000
+    full = [(int(rng.integers(0, 2 ** 63)) * (2 ** 65) + int(rng.integers(0, 2 ** 63)) * 4 + int(rng.integers(0, 4))) & (4 ** k - 1) for _ in range(n)]
+    lo = np.array([v & (2 ** 64 - 1) for v in full], np.uint64)
+    hi = np.array([v >> 64 for v in full], np.uint64) if words == 2 else None
+    for bit_size in (120000, 2 ** 17, 2 ** 17 - 8192, 12345):
+        got, gbits = gpu.bloom(kind, bit_size, 4, k, lo, hi)
+        want, wbits = oracle.bloom(kind, bit_size, 4, k, words, lo, hi)
+        assert gbits == wbits and len(got) == len(want)
+        assert (got == want).all(), (kind, bit_size)
+
+
+@pytest.mark.parametrize("name", fixtures.NAMES)
+def test_bloom_of_fixture_solid_kmers(gpu, oracle, name):
+    fx = fixtures.Fixture(name, oracle)
+    nkeys = fx.nb_partitions * fx.nb_passes
+    lo = np.concatenate([fx.solid(key)[0] for key in range(nkeys)])
+    hi = np.concatenate([fx.solid(key)[1] for key in range(nkeys)])
+    size, nh = gpu.bloom_params(fx.k, len(lo))
+    assert [size, nh] == fx.z["bloom_size"].tolist()
+    for kind in ("basic", "cache", "neighbor"):
+        got, bits = gpu.bloom(kind, size, nh, fx.k, lo, hi if fx.words == 2 else None)
+        assert bits == int(fx.z["bloom_%s_bitsize" % kind][0])
+        assert (got == fx.z["bloom_" + kind]).all(), kind
+
+
+def test_device_resident_api_and_size_independent_properties(gpu, oracle):
+    # 2e5 reads against the oracle, then 2e6 reads through invariants only
+    k, m, L = 31, 10, 150
+    for n, check_oracle in ((200000, True), (2000000, False)):
+        genome = n * L // 30
+        nbytes = (n * L + 3) // 4
+        d = gpu.malloc(nbytes + 64)
+        gpu.synth_reads_dev(42, genome, 0, n, L, d)
+        params = gpu.make_params(k, m, abundance_min=2, read_len=L)
+        res = gpu.count_dev(d, None, n, params)
+        got = gpu.result_to_host(res, params)
+        gpu.result_free(res)
+        gpu.free(d)
+        lo, hi, cn = got["parts"][0]
+        h = got["histogram"].astype(object)
+        assert (np.diff(lo.astype(object)) > 0).all() if len(lo) < 10 ** 6 else (lo[1:] > lo[:-1]).all()     # strictly ascending
+        assert sum(h) == got["stats"]["kmers_nb_distinct"]
+        assert sum(int(i) * int(v) for i, v in enumerate(h) if i < 10000) + 0 == got["stats"]["kmers_nb_valid"] or h[10000] > 0
+        assert got["stats"]["kmers_nb_valid"] == n * (L - k + 1)
+        assert (cn >= 2).all() and len(lo) == got["stats"]["kmers_nb_solid"]
+        if check_oracle:
+            codes = oracle.synth_reads(42, genome, 0, n, L).reshape(n, L)
+            want = oracle.dsk([oracle.codes_to_ascii(r) for r in codes], k, m, np.zeros(4 ** m, np.uint16), 1, abundance_min=2)
+            check_parts(got, want["solid"], 1, 1)
+            assert (got["histogram"] == want["histogram"]).all()
+
+
+def test_smoke_entry(gpu):
+    import __graft_entry__
+    __graft_entry__.smoke()
