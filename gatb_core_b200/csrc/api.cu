@@ -269,51 +269,60 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     uint64_t out_bound = total_kmers / emin + 1;                               // a k-mer emitted needs >= emin occurrences
     const size_t item_bytes = 8 * W + 4;
     uint64_t out_cap = ctx->slot_cap[S_COARSE] / item_bytes;
+    { uint64_t guess = total_kmers / 3 + 4096; if (out_cap < guess) out_cap = guess; }
     if (out_cap > out_bound) out_cap = out_bound;
     if (out_cap < 1) out_cap = 1;
-    uint64_t* u_lo = (uint64_t*)ctx->slot[S_COARSE];
-    uint64_t* u_hi = (W == 2) ? u_lo + out_cap : 0;
-    uint32_t* u_cnt = (uint32_t*)(u_lo + out_cap * W);
 
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
     if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
     if (ensure (ctx, S_OVFLIST, nbins * 4)) return 1;
     unsigned long long* d_cnt = (unsigned long long*)ctx->slot[S_COUNTERS];
-    CK (cudaMemsetAsync (ctx->slot[S_HISTO], 0, (size_t)(histo_max + 1) * 8, ctx->stream));
-    CK (cudaMemsetAsync (d_cnt, 0, 16 * 8, ctx->stream));
-
-    K2Params k2; memset (&k2, 0, sizeof(k2));
-    k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins;
-    k2.cap = (uint32_t)cap; k2.fine_bits = fine_bits; k2.table_log2 = table_log2;
-    k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
-    k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
-    k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
-    k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST];
-    CK (launch_k2b_count (L, k2));
     unsigned long long h_cnt[8];
-    CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK (cudaStreamSynchronize (ctx->stream));
-    const uint64_t n_ovf = h_cnt[4];
-    if (n_ovf)
-    {   // ---- k2c: bins that did not fit the shared-memory table share one global table ----
-        CK (launch_k2c_measure (L, k2, (uint32_t)n_ovf));
+    uint64_t n_ovf = 0;
+    uint64_t* u_lo = 0; uint64_t* u_hi = 0; uint32_t* u_cnt = 0;
+    K2Params k2;
+    for (int attempt = 0; ; attempt++)
+    {
+        if (ensure (ctx, S_COARSE, out_cap * item_bytes)) return 1;
+        u_lo = (uint64_t*)ctx->slot[S_COARSE];
+        u_hi = (W == 2) ? u_lo + out_cap : 0;
+        u_cnt = (uint32_t*)(u_lo + out_cap * W);
+        CK (cudaMemsetAsync (ctx->slot[S_HISTO], 0, (size_t)(histo_max + 1) * 8, ctx->stream));
+        CK (cudaMemsetAsync (d_cnt, 0, 16 * 8, ctx->stream));
+        memset (&k2, 0, sizeof(k2));
+        k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins;
+        k2.cap = (uint32_t)cap; k2.fine_bits = fine_bits; k2.table_log2 = table_log2;
+        k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
+        k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
+        k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
+        k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST];
+        CK (launch_k2b_count (L, k2));
         CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK (cudaStreamSynchronize (ctx->stream));
-        uint64_t occ = h_cnt[5]; int g_log2 = 10; while ((1ULL << g_log2) < 2 * occ) g_log2++;
-        if (g_log2 > 31) return fail (ctx, "fallback table too large (%llu k-mers in overflowing bins)", (unsigned long long)occ);
-        size_t gT = (size_t)1 << g_log2;
-        if (ensure (ctx, S_GTABLE, gT * (8 * W + 4))) return 1;
-        k2.g_lo = (uint64_t*)ctx->slot[S_GTABLE]; k2.g_hi = (W == 2) ? k2.g_lo + gT : 0; k2.g_cnt = (uint32_t*)(k2.g_lo + gT * W); k2.g_log2 = g_log2;
-        if (W == 1) CK (cudaMemsetAsync (k2.g_lo, 0xFF, gT * 8, ctx->stream));
-        else      { CK (cudaMemsetAsync (k2.g_lo, 0, gT * 8, ctx->stream)); CK (cudaMemsetAsync (k2.g_hi, 0xFF, gT * 8, ctx->stream)); }
-        CK (cudaMemsetAsync (k2.g_cnt, 0, gT * 4, ctx->stream));
-        CK (launch_k2c_insert (L, k2, (uint32_t)n_ovf));
-        CK (launch_k2c_scan (L, k2));
-        CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK (cudaStreamSynchronize (ctx->stream));
+        n_ovf = h_cnt[4];
+        if (n_ovf)
+        {   // ---- k2c: bins that did not fit the shared-memory table share one global table ----
+            CK (launch_k2c_measure (L, k2, (uint32_t)n_ovf));
+            CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+            uint64_t occ = h_cnt[5]; int g_log2 = 10; while ((1ULL << g_log2) < 2 * occ) g_log2++;
+            if (g_log2 > 31) return fail (ctx, "fallback table too large (%llu k-mers in overflowing bins)", (unsigned long long)occ);
+            size_t gT = (size_t)1 << g_log2;
+            if (ensure (ctx, S_GTABLE, gT * (8 * W + 4))) return 1;
+            k2.g_lo = (uint64_t*)ctx->slot[S_GTABLE]; k2.g_hi = (W == 2) ? k2.g_lo + gT : 0; k2.g_cnt = (uint32_t*)(k2.g_lo + gT * W); k2.g_log2 = g_log2;
+            if (W == 1) CK (cudaMemsetAsync (k2.g_lo, 0xFF, gT * 8, ctx->stream));
+            else      { CK (cudaMemsetAsync (k2.g_lo, 0, gT * 8, ctx->stream)); CK (cudaMemsetAsync (k2.g_hi, 0xFF, gT * 8, ctx->stream)); }
+            CK (cudaMemsetAsync (k2.g_cnt, 0, gT * 4, ctx->stream));
+            CK (launch_k2c_insert (L, k2, (uint32_t)n_ovf));
+            CK (launch_k2c_scan (L, k2));
+            CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+        }
+        if (h_cnt[0] <= out_cap) break;
+        if (attempt >= 1) return fail (ctx, "output capacity exceeded: %llu k-mers to emit, room for %llu", (unsigned long long)h_cnt[0], (unsigned long long)out_cap);
+        out_cap = h_cnt[0] + 16;               // the emission counter kept counting: it is the exact demand -> count again
     }
     const uint64_t n_items = h_cnt[0];
-    if (n_items > out_cap) return fail (ctx, "output capacity exceeded: %llu k-mers to emit, room for %llu", (unsigned long long)n_items, (unsigned long long)out_cap);
     cudaEventRecord (ctx->ev[4], ctx->stream);
 
     // ---- k3: partition id + ascending order ----
