@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- distinct k-mers counted / s on synthetic 150 bp reads (k=31, m=10, abundance-min 2): BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W              our CUDA path (one rank per GPU; torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...    the reference's own CPU implementation (rank 0 only)
+
+A "step" is one pass of the whole counting path (partition -> fine split -> hash count -> partition id + sort) over the
+workload.  `value` times it with the packed reads already resident in HBM; `e2e` times the public host-buffer call
+(gatb_gpu_count: pinned host reads in, host arrays out, H2D and D2H inside the timed region).
+Nothing here reads /root/reference at run time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K, M, L, ABUNDANCE_MIN, COVERAGE = 31, 10, 150, 2, 30
+SEED = 42
+METRIC = "distinct k-mers counted/sec (k=31, 150bp synthetic)"
+UNIT = "distinct k-mers/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        # median of the upper half of the samples ~ clock under load (idle samples between steps pull the median down)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(mx) if mx else None),
+                "reasons": reasons, "samples": len(sm)}
+
+
+def unpack_to_fasta(packed, n_reads, path):
+    codes = np.empty(n_reads * L, np.uint8)
+    p = packed[:(n_reads * L + 3) // 4]
+    for s in range(4):
+        codes[s::4] = ((p >> (2 * s)) & 3)[:len(codes[s::4])]
+    ascii_ = np.frombuffer(b"ACTG", np.uint8)[codes].reshape(n_reads, L)
+    with open(path, "wb") as f:
+        hdr = np.frombuffer(b">r\n", np.uint8)
+        block = np.empty((n_reads, 3 + L + 1), np.uint8)
+        block[:, :3] = hdr
+        block[:, 3:3 + L] = ascii_
+        block[:, -1] = ord("\n")
+        f.write(block.tobytes())
+
+
+class stdout_to_stderr:
+    """The reference prints progress notes on fd 1; keep bench's stdout to the single JSON line."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def cpu_reference_run(fasta, cores):
+    """Times the reference's (or, failing that, the oracle port's) DSK on a FASTA sample.  Returns (distinct, seconds, kind)."""
+    import oracle_lib
+    ref = oracle_lib.Reference()
+    if ref.available:
+        t0 = time.time()
+        with stdout_to_stderr():
+            res = ref.dsk(fasta, K, M, abundance_min=ABUNDANCE_MIN, nb_cores=cores)
+        wall = time.time() - t0
+        return res["nb_distinct"], wall, "reference"
+    orc = oracle_lib.Oracle()
+    seqs = [l.strip() for l in open(fasta, "rb") if not l.startswith(b">")]
+    t0 = time.time()
+    res = orc.dsk(seqs, K, M, np.zeros(4 ** M, np.uint16), 1, abundance_min=ABUNDANCE_MIN, nthreads=cores)
+    return int(res["stats"][2]), time.time() - t0, "port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib
+    orc = oracle_lib.Oracle()
+    n = args.ref_reads
+    cores = os.cpu_count() or 1
+    codes = orc.synth_reads(SEED, n * L // COVERAGE, 0, n, L)
+    packed = orc.pack_2bit(codes)
+    with tempfile.TemporaryDirectory() as tmp:
+        fa = os.path.join(tmp, "sample.fa")
+        unpack_to_fasta(packed, n, fa)
+        times, distinct, kind = [], 0, "port"
+        for i in range(args.warmup + args.steps):
+            distinct, sec, kind = cpu_reference_run(fa, cores)
+            if i >= args.warmup:
+                times.append(sec)
+    per_step = sum(times) / len(times)
+    value = distinct / per_step
+    sample = "%d reads x %d bp (same generator/seed as the GPU arm, %dx coverage), FASTA on local disk, parse + temp files included" % (n, L, COVERAGE)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "k=31, m=10, abundance-min=2, synthetic 150bp reads (bounded sample: %d reads per step)" % n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gatb_core_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        from gatb_core_b200 import multigpu
+        return multigpu.bench(args, rank, world, local)
+
+    gpu = gatb_core_b200.GatbGpu(local)
+    n = args.reads
+    genome = n * L // COVERAGE
+    nbytes = (n * L + 3) // 4
+    d_reads = gpu.malloc(nbytes + 64)
+    gpu.synth_reads_dev(SEED, genome, 0, n, L, d_reads)
+    gpu.synchronize()
+    params = gpu.make_params(K, M, abundance_min=ABUNDANCE_MIN, read_len=L)
+    stream = torch.cuda.ExternalStream(gpu.stream, device=torch.device("cuda", local))
+
+    def step():
+        res = gpu.count_dev(d_reads, None, n, params)
+        info = {"distinct": int(res.stats[2]), "solid": int(res.stats[3]), "valid": int(res.stats[0]), "records": int(res.stats[4]),
+                "items": int(res.n_items), "kernel_seconds": [float(x) for x in res.kernel_seconds], "bins": int(res.stats[7]),
+                "overflow_bins": int(res.stats[8]), "retries": int(res.stats[9])}
+        gpu.result_free(res)
+        return info
+
+    for _ in range(args.warmup):
+        info = step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    launches0 = gpu.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ksec = np.zeros(8)
+    for _ in range(args.steps):
+        info = step()
+        ksec += np.array(info["kernel_seconds"])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    launches = gpu.kernel_launches - launches0
+    total_s = e0.elapsed_time(e1) * 1e-3
+    per_step = total_s / args.steps
+    ksec /= args.steps
+
+    # ---- end to end through the host-buffer call: pinned host reads in, host arrays out ----
+    h_reads = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
+    gpu.d2h(h_reads.numpy()[:nbytes], d_reads)
+    gpu.free(d_reads)
+    host = h_reads.numpy()
+    e2e_times, d2h_bytes = [], 0
+    for i in range(2 + args.steps):
+        t0 = time.time()
+        out = gpu.L.gatb_gpu_count  # noqa (keep the raw call visible: this IS the public C entry point)
+        res = gatb_core_b200.Result()
+        rc = out(gpu.ctx, gatb_core_b200.C.byref(params), None, None, host.ctypes.data_as(gatb_core_b200.C.c_void_p), None, n, None,
+                 gatb_core_b200.C.byref(res))
+        if rc:
+            raise SystemExit(gpu.L.gatb_gpu_last_error(gpu.ctx).decode())
+        wall = time.time() - t0
+        if i >= 2:
+            e2e_times.append(max(wall, float(res.seconds[7])))
+        d2h_bytes = int(res.n_items) * 12 + (10001 + 2) * 8
+        gpu.result_free(res)
+    clocks = sampler.stop()
+    e2e_step = sum(e2e_times) / len(e2e_times)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes: DESIGN.md "Roofline accounting") ----
+    occ, distinct, records = info["valid"], info["distinct"], info["records"]
+    s_alg = records * (1 + (K - 1) / 4.0 + 0.375) + occ / 4.0        # sum over records of 1 + ceil((k+n-1)/4)
+    bytes_k1 = n * L / 4.0 + s_alg                                   # read 2-bit input once, write records once
+    bytes_k2 = s_alg + distinct * 12.0                               # read records once, write each distinct (kmer,count) once
+    peak, peak_src = measured_peak()
+    kernels = {"k1_superkmer_partition": (bytes_k1, ksec[0]), "k2b_bucket_hash_count": (bytes_k2, ksec[2])}
+    dom = max(kernels, key=lambda name: kernels[name][1])
+    dom_bytes, dom_sec = kernels[dom]
+    achieved = dom_bytes / dom_sec / 1e9
+    pair_bytes = n * L / 4.0 + 2 * s_alg + distinct * 12.0
+    pair_sec = ksec[0] + ksec[1] + ksec[2]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_sec * 1e3,
+                "pair": {"what": "partition + fine split + hash count vs A = N_nt/4 + 2S + D(W+4) (SURVEY.md 8d)",
+                         "algorithmic_bytes": pair_bytes, "ms": pair_sec * 1e3, "achieved": pair_bytes / pair_sec / 1e9,
+                         "frac": pair_bytes / pair_sec / 1e9 / peak, "frac_of_8TBps": pair_bytes / pair_sec / 1e9 / 8000.0},
+                "kernel_ms": {"k1_superkmer_partition": ksec[0] * 1e3, "k2a_fine_split": ksec[1] * 1e3,
+                              "k2b_bucket_hash_count": ksec[2] * 1e3, "k3_partition_id_sort": ksec[3] * 1e3}}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        ns = args.cpu_sample_reads
+        with tempfile.TemporaryDirectory() as tmp:
+            fa = os.path.join(tmp, "sample.fa")
+            # the first ns reads of a genome sized for ns reads (same coverage as the workload)
+            d_s = gpu.malloc((ns * L + 3) // 4 + 64)
+            gpu.synth_reads_dev(SEED, ns * L // COVERAGE, 0, ns, L, d_s)
+            hs = np.zeros((ns * L + 3) // 4, np.uint8)
+            gpu.d2h(hs, d_s)
+            gpu.free(d_s)
+            unpack_to_fasta(hs, ns, fa)
+            cores = os.cpu_count() or 1
+            dist_s, sec_s, kind = cpu_reference_run(fa, cores)
+        cpu = {"value": dist_s / sec_s, "unit": UNIT, "cores": cores, "kind": kind, "seconds": sec_s,
+               "sample": "%d reads x %d bp, same generator, %dx coverage; FASTA parse + temp files included" % (ns, L, COVERAGE)}
+
+    line = {"metric": METRIC, "value": distinct / per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": "k=31, %d synthetic 150bp reads, 1xB200, minimizer m=10, abundance-min=2" % n, "reads": n,
+                       "genome_nt": genome, "coverage": COVERAGE, "error_rate": 0.01,
+                       "l2": "inputs (%.1f GB packed reads, %.1f GB records) far exceed the 126 MB L2" % (nbytes / 1e9, records * 16 / 1e9)},
+            "input_bases_per_s": n * L / per_step, "kmer_occurrences_per_s": occ / per_step,
+            "distinct": distinct, "solid": info["solid"], "records": records, "bins": info["bins"],
+            "overflow_bins": info["overflow_bins"], "retries": info["retries"],
+            "e2e": {"value": distinct / e2e_step, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_step * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    gpu.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (BASELINE configs[1]: 1e8)")
+    ap.add_argument("--ref-reads", type=int, default=1_000_000, help="reads per step of the reference arm")
+    ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

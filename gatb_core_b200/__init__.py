@@ -39,7 +39,7 @@ class Params(C.Structure):
 class Result(C.Structure):
     _fields_ = [("n_keys", C.c_uint64), ("n_items", C.c_uint64), ("part_offsets", C.c_void_p), ("kmers_lo", C.c_void_p),
                 ("kmers_hi", C.c_void_p), ("counts", C.c_void_p), ("histogram", C.c_void_p),
-                ("stats", C.c_uint64 * NSTATS), ("seconds", C.c_double * 8), ("on_device", C.c_int32), ("pad", C.c_int32),
+                ("stats", C.c_uint64 * NSTATS), ("seconds", C.c_double * 8), ("kernel_seconds", C.c_double * 8), ("on_device", C.c_int32), ("pad", C.c_int32),
                 ("owner", C.c_void_p)]
 
 
@@ -195,7 +195,7 @@ class GatbGpu:
             parts[key] = (lo[a:b], hi[a:b], cn[a:b])
         stats = {name: int(res.stats[i]) for i, name in enumerate(STAT_NAMES)}
         return {"parts": parts, "part_offsets": offs, "histogram": hist, "stats": stats,
-                "seconds": [float(x) for x in res.seconds], "n_items": int(res.n_items)}
+                "seconds": [float(x) for x in res.seconds], "kernel_seconds": [float(x) for x in res.kernel_seconds], "n_items": int(res.n_items)}
 
     # ---- GATB-exact super-k-mers ---------------------------------------------------------------------------------
     def superkmers(self, packed, offsets, n_reads, params, repart=None, n_mask=None):

@@ -24,7 +24,7 @@ struct gatb_gpu_ctx
     int device; int sm_count; cudaStream_t stream; uint64_t launches;
     std::string error;
     void* slot[S_NSLOTS]; size_t slot_cap[S_NSLOTS];
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[8]; cudaEvent_t kev[16];
     void* pinned; size_t pinned_cap;
     const uint16_t* repart_host_cached; uint64_t repart_bytes_cached;
 };
@@ -52,6 +52,16 @@ static int ensure (gatb_gpu_ctx* ctx, int s, size_t bytes)
 static void release (gatb_gpu_ctx* ctx, int s)
 { if (ctx->slot[s]) { cudaStreamSynchronize (ctx->stream); cudaFree (ctx->slot[s]); ctx->slot[s] = 0; ctx->slot_cap[s] = 0; } }
 
+static void* pinned_ensure (gatb_gpu_ctx* ctx, size_t bytes)
+{
+    if (ctx->pinned_cap >= bytes) return ctx->pinned;
+    if (ctx->pinned) { cudaStreamSynchronize (ctx->stream); cudaFreeHost (ctx->pinned); ctx->pinned = 0; ctx->pinned_cap = 0; }
+    size_t want = bytes + bytes / 8 + 4096;
+    if (cudaHostAlloc (&ctx->pinned, want, cudaHostAllocDefault) != cudaSuccess) { ctx->pinned = 0; return 0; }
+    ctx->pinned_cap = want;
+    return ctx->pinned;
+}
+
 static LaunchCtx lctx (gatb_gpu_ctx* ctx) { LaunchCtx L; L.stream = ctx->stream; L.sm_count = ctx->sm_count; L.launches = &ctx->launches; return L; }
 
 extern "C" {
@@ -71,6 +81,7 @@ gatb_gpu_ctx* gatb_gpu_create (int device)
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail (0, "cudaStreamCreate: %s", cudaGetErrorString (e)); delete ctx; return 0; }
     for (int i = 0; i < 8; i++) cudaEventCreate (&ctx->ev[i]);
+    for (int i = 0; i < 16; i++) cudaEventCreate (&ctx->kev[i]);
     return ctx;
 }
 void gatb_gpu_destroy (gatb_gpu_ctx* ctx)
@@ -81,6 +92,7 @@ void gatb_gpu_destroy (gatb_gpu_ctx* ctx)
     for (int s = 0; s < S_NSLOTS; s++) if (ctx->slot[s]) cudaFree (ctx->slot[s]);
     if (ctx->pinned) cudaFreeHost (ctx->pinned);
     for (int i = 0; i < 8; i++) cudaEventDestroy (ctx->ev[i]);
+    for (int i = 0; i < 16; i++) cudaEventDestroy (ctx->kev[i]);
     cudaStreamDestroy (ctx->stream);
     delete ctx;
 }
@@ -244,7 +256,9 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         CK (cudaMemsetAsync (k1.cursors, 0, nb1 * 4, ctx->stream));
         CK (cudaMemsetAsync (k1.fine_counts, 0, nbins * 4, ctx->stream));
         CK (cudaMemsetAsync (d_stats, 0, 4 * 8, ctx->stream));
+        cudaEventRecord (ctx->kev[0], ctx->stream);
         if (n_reads) CK (launch_k1 (L, k1));
+        cudaEventRecord (ctx->kev[1], ctx->stream);
         CK (cudaMemcpyAsync (h_stats, d_stats, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK (cudaStreamSynchronize (ctx->stream));
         if (h_stats[3] == 0) break;
@@ -259,7 +273,9 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
 
     // ---- k2a: fine split ----
     if (ensure (ctx, S_FINE, nb1 * cap * rec_bytes)) return 1;
+    cudaEventRecord (ctx->kev[2], ctx->stream);
     CK (launch_k2a_split (L, W, ctx->slot[S_COARSE], ctx->slot[S_FINE], k1.cursors, k1.fine_counts, (uint32_t)nb1, (uint32_t)cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
+    cudaEventRecord (ctx->kev[3], ctx->stream);
     cudaEventRecord (ctx->ev[3], ctx->stream);
 
     // ---- k2b: count.  The coarse buffer is dead now: it becomes the unsorted output. ----
@@ -296,7 +312,9 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
         k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
         k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST];
+        cudaEventRecord (ctx->kev[4], ctx->stream);
         CK (launch_k2b_count (L, k2));
+        cudaEventRecord (ctx->kev[5], ctx->stream);
         CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK (cudaStreamSynchronize (ctx->stream));
         n_ovf = h_cnt[4];
@@ -365,11 +383,13 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     k3.out_lo = (uint64_t*)dr->lo; k3.out_hi = (uint64_t*)dr->hi; k3.out_cnt = (int32_t*)dr->cnt;
     k3.n_buckets = (uint32_t)n_buckets; k3.big_list = (unsigned long long*)ctx->slot[S_BIGLIST]; k3.counters = d_cnt + 8;
     CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
+    cudaEventRecord (ctx->kev[6], ctx->stream);
     CK (launch_k3a_classify (L, k3));
     CK (launch_scan_u32_to_u64 (L, k3.bucket_count, (uint64_t*)ctx->slot[S_BUCKETOFF], n_buckets, (uint64_t*)ctx->slot[S_SCAN]));
     CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
     CK (launch_k3b_scatter (L, k3));
     CK (launch_k3c_sort (L, k3));
+    cudaEventRecord (ctx->kev[7], ctx->stream);
     unsigned long long n_big = 0;
     CK (cudaMemcpyAsync (&n_big, d_cnt + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK (cudaStreamSynchronize (ctx->stream));
@@ -403,6 +423,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     cudaEventElapsedTime (&ms, ctx->ev[3], ctx->ev[4]); out->seconds[3] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[4], ctx->ev[5]); out->seconds[4] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[5]); out->seconds[6] = ms * 1e-3;
+    for (int i = 0; i < 4; i++) { cudaEventElapsedTime (&ms, ctx->kev[2*i], ctx->kev[2*i+1]); out->kernel_seconds[i] = ms * 1e-3; }
     return 0;
 }
 
@@ -431,7 +452,7 @@ void gatb_gpu_result_free (gatb_gpu_ctx* ctx, gatb_gpu_result* r)
     }
     else
     {
-        free (r->part_offsets); free (r->kmers_lo); free (r->kmers_hi); free (r->counts); free (r->histogram);
+        /* host arrays point into the context's pinned staging buffer: nothing to free */
     }
     memset (r, 0, sizeof(*r));
 }
@@ -473,10 +494,17 @@ int gatb_gpu_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t*
     const int W = p->kmer_size < 32 ? 1 : 2;
     gatb_gpu_result h = dres; h.on_device = 0; h.owner = 0;
     uint64_t n = dres.n_items, na = n ? n : 1;
-    h.part_offsets = (uint64_t*) malloc ((dres.n_keys + 1) * 8);
-    h.kmers_lo = (uint64_t*) malloc (na * 8); h.kmers_hi = (W == 2) ? (uint64_t*) malloc (na * 8) : 0;
-    h.counts = (int32_t*) malloc (na * 4); h.histogram = (uint64_t*) malloc ((size_t)(p->histo_max + 1) * 8);
-    if (!h.part_offsets || !h.kmers_lo || !h.counts || !h.histogram || (W == 2 && !h.kmers_hi)) { gatb_gpu_result_free (ctx, &dres); return fail (ctx, "host allocation of the result failed"); }
+    // host arrays live in one pinned staging buffer owned by the context (valid until the next count on this context
+    // or gatb_gpu_result_free): pinned memory lets the copies run at full PCIe rate
+    const size_t hist_bytes = (size_t)(p->histo_max + 1) * 8, off_bytes = (dres.n_keys + 1) * 8;
+    size_t need = off_bytes + hist_bytes + na * 8 * W + na * 4 + 256;
+    uint8_t* pin = (uint8_t*) pinned_ensure (ctx, need);
+    if (!pin) { gatb_gpu_result_free (ctx, &dres); return fail (ctx, "pinned host allocation of the result (%zu bytes) failed", need); }
+    h.kmers_lo = (uint64_t*)pin; pin += na * 8;
+    h.kmers_hi = 0; if (W == 2) { h.kmers_hi = (uint64_t*)pin; pin += na * 8; }
+    h.part_offsets = (uint64_t*)pin; pin += off_bytes;
+    h.histogram = (uint64_t*)pin; pin += hist_bytes;
+    h.counts = (int32_t*)pin;
     CK (cudaMemcpyAsync (h.part_offsets, dres.part_offsets, (dres.n_keys + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (n)
     {

@@ -84,7 +84,10 @@ typedef struct gatb_gpu_result
     int32_t*  counts;            /* [n_items] CountNumber (system/api/types.hpp:49)                               */
     uint64_t* histogram;         /* [histo_max+1], index clamped like Histogram::inc (tools/misc/impl/Histogram.hpp:92) */
     uint64_t  stats[GATB_GPU_NSTATS];
-    double    seconds[8];        /* device time per stage: 0 h2d, 1 partition, 2 split, 3 count, 4 sort, 5 d2h, 6 total device */
+    double    seconds[8];        /* stream time per stage (CUDA events): 0 h2d, 1 partition, 2 split, 3 count, 4 sort, 5 d2h,
+                                    6 device total, 7 end to end */
+    double    kernel_seconds[8]; /* kernel-only durations: 0 k1_superkmer_partition, 1 k2a_fine_split, 2 k2b_bucket_hash_count,
+                                    3 k3 (classify + scan + scatter + sort) */
     int32_t   on_device;         /* 1: the arrays above are DEVICE pointers (gatb_gpu_count_dev), 0: host            */
     int32_t   pad;
     void*     owner;             /* internal */
@@ -99,7 +102,8 @@ uint64_t      gatb_gpu_kernel_launches (gatb_gpu_ctx*); /* kernels launched by t
 int           gatb_gpu_sm_count (gatb_gpu_ctx*);
 
 /* ---- DSK: reads -> sorted (k-mer, count) per partition + histogram ------------------------------------------- */
-/* HOST buffers in, HOST arrays out (copies are part of the call). */
+/* HOST buffers in, HOST arrays out (copies are part of the call).  The returned host arrays live in a pinned staging
+ * buffer owned by the context: they stay valid until the next gatb_gpu_count on this context or gatb_gpu_result_free. */
 int gatb_gpu_count (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* repart_table /* [4^m] or NULL when n_keys==1 */,
                     const uint32_t* freq_order /* NULL */, const uint8_t* packed_reads, const uint64_t* read_offsets_nt,
                     uint64_t n_reads, const uint32_t* n_mask, gatb_gpu_result* out);

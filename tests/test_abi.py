@@ -27,7 +27,7 @@ def test_header_and_exports_agree():
 def test_struct_layout_matches_header():
     # gatb_gpu_params: 11 named int32 + 5 reserved; gatb_gpu_result: see header
     assert gatb_core_b200.C.sizeof(gatb_core_b200.Params) == 16 * 4
-    assert gatb_core_b200.C.sizeof(gatb_core_b200.Result) == 8 * 7 + 16 * 8 + 8 * 8 + 4 + 4 + 8
+    assert gatb_core_b200.C.sizeof(gatb_core_b200.Result) == 8 * 7 + 16 * 8 + 8 * 8 + 8 * 8 + 4 + 4 + 8
 
 
 def test_host_only_entry_points():
