@@ -220,8 +220,8 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     if (max_len >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported by the partition kernel yet (longest: %llu)", (unsigned long long)max_len);
 
     // ---- device binning geometry ----
-    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : 13;
-    if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
+    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : 12;
+    if (table_log2 < 5 || table_log2 > 12) return fail (ctx, "table_log2 must be in [5,12]");
     const uint64_t T = 1ULL << table_log2;
     const uint64_t occ_per_bin = (T * 55) / 100;
     const int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
@@ -287,7 +287,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     uint64_t out_cap = ctx->slot_cap[S_COARSE] / item_bytes;
     { uint64_t guess = total_kmers / 3 + 4096; if (out_cap < guess) out_cap = guess; }
     if (out_cap > out_bound) out_cap = out_bound;
-    if (out_cap < 1) out_cap = 1;
+    out_cap += (uint64_t)(ctx->sm_count * 4 + 8) * 8192;          // every CTA of k2b reserves output in blocks of 8192 slots
 
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
     if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
@@ -338,9 +338,10 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         }
         if (h_cnt[0] <= out_cap) break;
         if (attempt >= 1) return fail (ctx, "output capacity exceeded: %llu k-mers to emit, room for %llu", (unsigned long long)h_cnt[0], (unsigned long long)out_cap);
-        out_cap = h_cnt[0] + 16;               // the emission counter kept counting: it is the exact demand -> count again
+        out_cap = h_cnt[0] + (uint64_t)(ctx->sm_count * 4 + 8) * 8192;   // the cursor kept counting: it bounds the demand -> count again
     }
-    const uint64_t n_items = h_cnt[0];
+    const uint64_t n_items = h_cnt[6];          // k-mers emitted
+    const uint64_t n_range = h_cnt[0];          // extent of the unsorted array (block reservations leave EMPTY holes)
     cudaEventRecord (ctx->ev[4], ctx->stream);
 
     // ---- k3: partition id + ascending order ----
@@ -358,7 +359,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     { cudaFree (d_sorted); delete dr; return fail (ctx, "cudaMalloc of the result tables failed"); }
     dr->offs = d_offs; dr->histo = d_hist;
 
-    if (ensure (ctx, S_BUCKETOF, n_alloc * 4)) return 1;
+    if (ensure (ctx, S_BUCKETOF, (n_range + 1) * 4)) return 1;
     if (ensure (ctx, S_BUCKETCNT, n_buckets * 4)) return 1;
     if (ensure (ctx, S_BUCKETOFF, (n_buckets + 1) * 8)) return 1;
     if (ensure (ctx, S_SCAN, scan_scratch_elems (n_buckets) * 8)) return 1;
@@ -375,7 +376,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     k3.k = k; k3.m = p->minimizer_size; k3.W = W;
     k3.mmask = (1u << (2 * p->minimizer_size)) - 1; k3.mask_ma1 = gatb_mask_ma1 (p->minimizer_size);
     k3.repart = (const uint16_t*)ctx->slot[S_REPART]; k3.nb_partitions = p->nb_partitions; k3.nb_passes = p->nb_passes; k3.n_keys = (uint32_t)n_keys;
-    k3.t_bits = t_bits; k3.n = n_items;
+    k3.t_bits = t_bits; k3.n = n_range;
     k3.in_lo = u_lo; k3.in_hi = u_hi; k3.in_cnt = u_cnt;
     k3.bucket_of = (uint32_t*)ctx->slot[S_BUCKETOF]; k3.bucket_count = (uint32_t*)ctx->slot[S_BUCKETCNT];
     k3.bucket_off = (const uint64_t*)ctx->slot[S_BUCKETOFF];

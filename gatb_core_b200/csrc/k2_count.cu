@@ -122,11 +122,19 @@ __device__ __forceinline__ uint32_t slot_hash128 (u128 key, int log2)
 
 #define EMPTY64 0xFFFFFFFFFFFFFFFFULL
 #define K2_THREADS 512
-#define K2_CHUNK   512        // records staged per TMA transfer
-#define K2_HB      1024       // histogram bins kept in shared memory
-#define K2_MAXPROBE 256
+#define K2_HB      256        // histogram bins kept in shared memory (larger abundances go to global atomics)
+#define K2_MAXPROBE 512
+#define K2_ROUNDS  6          // table-scan rounds: occupied-slot list capacity (3T/4) <= K2_ROUNDS * K2_THREADS  => T <= 4096
+#define K2_OUT_BLOCK 8192     // output slots a CTA reserves with one global atomic
+template<int W> struct K2Cfg;
+template<> struct K2Cfg<1> { enum { CH = 128, MAXLEN = 28, JBITS = 5 }; };   // records per staged chunk, k-mers per record
+template<> struct K2Cfg<2> { enum { CH = 64,  MAXLEN = 60, JBITS = 6 }; };
 
-// ---- insertion into an open-addressed table (shared or global memory) ------------------------------------------
+// cheap slot hash for the shared-memory table: two 32-bit multiplies
+__device__ __forceinline__ uint32_t smem_slot64 (uint64_t key, int log2)
+{ uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u); h ^= h >> 15; return (h * 0x2C1B3C6Du) >> (32 - log2); }
+
+// ---- insertion into an open-addressed table in GLOBAL memory (fallback path) -----------------------------------
 // W=1: the key word itself is claimed with a 64-bit CAS.
 __device__ __forceinline__ bool table_insert_w1 (unsigned long long* keys, uint32_t* cnts, int log2, uint64_t key, int maxprobe)
 {
@@ -145,10 +153,9 @@ __device__ __forceinline__ bool table_insert_w1 (unsigned long long* keys, uint3
 // bit 63 clear); the low word is then published and the high word released.  Readers spin while they see LOCK.
 #define LOCK64 0xFFFFFFFFFFFFFFFEULL
 template<bool GLOBAL>
-__device__ __forceinline__ bool table_insert_w2 (unsigned long long* klo, unsigned long long* khi, uint32_t* cnts, int log2, u128 key, int maxprobe)
+__device__ __forceinline__ int table_insert_w2 (unsigned long long* klo, unsigned long long* khi, uint32_t* cnts, int log2, uint32_t slot, u128 key, int maxprobe)
 {
     const uint32_t tmask = (1u << log2) - 1;
-    uint32_t slot = slot_hash128 (key, log2);
     for (int probe = 0; probe < maxprobe; probe++)
     {
         for (;;)
@@ -163,37 +170,37 @@ __device__ __forceinline__ bool table_insert_w2 (unsigned long long* klo, unsign
                     if (GLOBAL) __threadfence (); else __threadfence_block ();
                     *(volatile unsigned long long*)&khi[slot] = key.hi;
                     atomicAdd (&cnts[slot], 1u);
-                    return true;
+                    return (int)slot | 0x40000000;           // new key
                 }
             }
             if (h == LOCK64) continue;                       // another thread is publishing this slot
             if (GLOBAL) __threadfence ();                    // order the high-word read before the low-word read
-            if (h == key.hi && *(volatile unsigned long long*)&klo[slot] == key.lo) { atomicAdd (&cnts[slot], 1u); return true; }
+            if (h == key.hi && *(volatile unsigned long long*)&klo[slot] == key.lo) { atomicAdd (&cnts[slot], 1u); return (int)slot; }
             break;                                           // occupied by another key
         }
         slot = (slot + 1) & tmask;
     }
-    return false;
+    return -1;
 }
 
-// ---- consuming one table slot: histogram + statistics + emission -----------------------------------------------
-struct EmitState { unsigned long long distinct, solid; };
+// ---- consuming one table slot of the GLOBAL fallback table: histogram + statistics + emission -------------------
+struct EmitState { unsigned long long distinct, solid, emitted; };
 
-__device__ __forceinline__ void consume_entry (const K2Params& P, bool occupied, uint64_t klo, uint64_t khi, uint32_t c,
-                                               uint32_t* s_hist, EmitState& st)
+__device__ __forceinline__ void consume_entry (const K2Params& P, bool occupied, uint64_t klo, uint64_t khi, uint32_t c, EmitState& st)
 {
     bool emit = false;
     if (occupied)
     {
         st.distinct++;
         uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
-        if (s_hist && hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
+        atomicAdd (&P.histogram[hb], 1ULL);
         if (c >= P.solid_min && c <= P.solid_max) st.solid++;
         emit = (c >= P.emit_min && c <= P.emit_max);
     }
     unsigned ballot = __ballot_sync (__activemask (), emit);
     if (emit)
     {
+        st.emitted++;
         int leader = __ffs (ballot) - 1, lane = threadIdx.x & 31;
         unsigned long long base = 0;
         if (lane == leader) base = atomicAdd (&P.counters[0], (unsigned long long)__popc (ballot));
@@ -204,27 +211,42 @@ __device__ __forceinline__ void consume_entry (const K2Params& P, bool occupied,
 }
 
 // ------------------------------------------------------------------------------------------------ k2b
+// Shared-memory layout (T = table slots, CH/MAXLEN from K2Cfg<W>):
+//   records  CH * 16W bytes      staged by TMA
+//   owner    CH * MAXLEN u16     k-mer g of the chunk -> (record << JBITS | index in record)
+//   keys     T * 8W, counts T * 4
+//   occ      3T/4 u16            slots claimed for this bin, in claim order (the table scan walks this list, not T slots)
+//   hist     K2_HB u32
 template<int W>
 __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Params P)
 {
+    typedef K2Cfg<W> Cfg;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = 1 << P.table_log2;
-    // layout: records [K2_CHUNK * 16W] | keys lo [T] (| keys hi [T]) | counts [T] | hist [K2_HB] | mbarrier
+    const int OCC_CAP = (T * 3) / 4;
     uint4* s_recs = (uint4*)smem_raw;
-    unsigned long long* s_klo = (unsigned long long*)(smem_raw + (size_t)K2_CHUNK * 16 * W);
+    uint16_t* s_owner = (uint16_t*)(smem_raw + (size_t)Cfg::CH * 16 * W);
+    unsigned long long* s_klo = (unsigned long long*)(smem_raw + (size_t)Cfg::CH * 16 * W + (size_t)Cfg::CH * Cfg::MAXLEN * 2);
     unsigned long long* s_khi = (W == 2) ? s_klo + T : 0;
     uint32_t* s_cnt  = (uint32_t*)(s_klo + (size_t)T * W);
-    uint32_t* s_hist = s_cnt + T;
-    uint64_t* s_bar  = (uint64_t*)(s_hist + K2_HB);
-    __shared__ uint32_t s_bin; __shared__ int s_ovf;
+    uint16_t* s_occ  = (uint16_t*)(s_cnt + T);
+    uint32_t* s_hist = (uint32_t*)(s_occ + OCC_CAP + (OCC_CAP & 1));
+    uint64_t* s_bar  = (uint64_t*)(s_hist + K2_HB + (K2_HB & 1));
+    __shared__ uint32_t s_bin, s_wsum[8], s_total, s_nocc, s_nemit;
+    __shared__ int s_ovf;
+    __shared__ unsigned long long s_out_pos, s_out_end, s_gbase, s_hole_b, s_hole_e;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < T; i += K2_THREADS) { if (W == 1) s_klo[i] = EMPTY64; else { s_khi[i] = EMPTY64; s_klo[i] = 0; } s_cnt[i] = 0; }
     for (int i = tid; i < K2_HB; i += K2_THREADS) s_hist[i] = 0;
-    if (tid == 0) { mbar_init (s_bar, 1); s_ovf = 0; asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0)
+    {
+        mbar_init (s_bar, 1); asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_ovf = 0; s_nocc = 0; s_nemit = 0; s_out_pos = 0; s_out_end = 0; s_hole_b = 0; s_hole_e = 0;
+    }
     __syncthreads ();
     uint32_t parity = 0;
-    EmitState st; st.distinct = 0; st.solid = 0;
+    unsigned long long n_distinct = 0, n_solid = 0, n_emitted = 0;
     const int k = P.k;
 
     for (;;)
@@ -238,9 +260,9 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
         if (n == 0) { __syncthreads (); continue; }
         const uint4* base = (const uint4*)P.recs + ((uint64_t)(bin >> P.fine_bits) * P.cap + d.x) * W;
 
-        for (uint32_t c0 = 0; c0 < n; c0 += K2_CHUNK)
+        for (uint32_t c0 = 0; c0 < n; c0 += Cfg::CH)
         {
-            const uint32_t mrec = min ((uint32_t)K2_CHUNK, n - c0);
+            const uint32_t mrec = min ((uint32_t)Cfg::CH, n - c0);
             if (tid == 0)
             {
                 fence_proxy_async ();                          // order earlier generic reads of the staging buffer
@@ -248,56 +270,181 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
                 tma_bulk_g2s (s_recs, base + (uint64_t)c0 * W, mrec * 16 * W, s_bar);
             }
             mbar_wait (s_bar, parity); parity ^= 1;
-            for (uint32_t i = tid; i < mrec; i += K2_THREADS)
+            // ---- phase A: expand records into one entry per k-mer ----
+            int len = 0; uint32_t incl = 0;
+            if (tid < Cfg::CH)
             {
+                if ((uint32_t)tid < mrec)
+                {
+                    uint32_t top = s_recs[(size_t)tid * W + (W - 1)].w;                         // high 32 bits of the record
+                    len = (W == 1) ? (int)((top >> (REC_LEN_SHIFT_W1 - 32)) & 31) : (int)((top >> (REC_LEN_SHIFT_W2 - 32)) & 63);
+                }
+                incl = (uint32_t)len;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
+                if (lane == 31) s_wsum[wid] = incl;
+            }
+            __syncthreads ();
+            if (tid < Cfg::CH)
+            {
+                uint32_t excl = incl - (uint32_t)len;
+                for (int q = 0; q < wid; q++) excl += s_wsum[q];
+                for (int j = 0; j < len; j++) s_owner[excl + j] = (uint16_t)((tid << Cfg::JBITS) | j);
+                if (tid == Cfg::CH - 1) s_total = excl + (uint32_t)len;
+            }
+            __syncthreads ();
+            // ---- phase B: one thread per k-mer ----
+            const uint32_t total = s_total;
+            for (uint32_t g = tid; g < total; g += K2_THREADS)
+            {
+                const uint32_t o = s_owner[g];
+                const uint32_t ri = o >> Cfg::JBITS; const int j = (int)(o & ((1u << Cfg::JBITS) - 1));
                 if (W == 1)
                 {
-                    uint4 r = s_recs[i];
-                    uint64_t lo = (uint64_t)r.x | ((uint64_t)r.y << 32), hi = (uint64_t)r.z | ((uint64_t)r.w << 32);
-                    const int len = (int)((hi >> REC_LEN_SHIFT_W1) & 31);
-                    hi &= (1ULL << REC_LEN_SHIFT_W1) - 1;
-                    for (int j = 0; j < len; j++)
-                        if (!table_insert_w1 (s_klo, s_cnt, P.table_log2, rec_kmer_w1 (lo, hi, j, k), K2_MAXPROBE)) s_ovf = 1;
+                    uint4 r = s_recs[ri];
+                    uint64_t lo = (uint64_t)r.x | ((uint64_t)r.y << 32), hi = ((uint64_t)r.z | ((uint64_t)r.w << 32)) & ((1ULL << REC_LEN_SHIFT_W1) - 1);
+                    const uint64_t key = rec_kmer_w1 (lo, hi, j, k);
+                    uint32_t slot = smem_slot64 (key, P.table_log2);
+                    bool done = false;
+                    for (int probe = 0; probe < K2_MAXPROBE && !done; probe++)
+                    {
+                        unsigned long long cur = s_klo[slot];
+                        if (cur == EMPTY64)
+                        {
+                            cur = atomicCAS (&s_klo[slot], EMPTY64, (unsigned long long)key);
+                            if (cur == EMPTY64)
+                            {   // new distinct k-mer: remember its slot
+                                uint32_t q = atomicAdd (&s_nocc, 1u);
+                                if (q < (uint32_t)OCC_CAP) s_occ[q] = (uint16_t)slot; else s_ovf = 1;
+                                cur = key;
+                            }
+                        }
+                        if (cur == key) { atomicAdd (&s_cnt[slot], 1u); done = true; }
+                        else slot = (slot + 1) & (T - 1);
+                    }
+                    if (!done) s_ovf = 1;
                 }
                 else
                 {
-                    uint4 a = s_recs[2*i], b = s_recs[2*i+1];
+                    uint4 a = s_recs[2*ri], b = s_recs[2*ri+1];
                     uint64_t r[4] = { (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
-                                      (uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32) };
-                    const int len = (int)((r[3] >> REC_LEN_SHIFT_W2) & 63);
-                    r[3] &= (1ULL << REC_LEN_SHIFT_W2) - 1;
-                    for (int j = 0; j < len; j++)
-                        if (!table_insert_w2<false> (s_klo, s_khi, s_cnt, P.table_log2, rec_kmer_w2 (r, j, k), K2_MAXPROBE)) s_ovf = 1;
+                                      (uint64_t)b.x | ((uint64_t)b.y << 32), ((uint64_t)b.z | ((uint64_t)b.w << 32)) & ((1ULL << REC_LEN_SHIFT_W2) - 1) };
+                    const u128 key = rec_kmer_w2 (r, j, k);
+                    uint32_t slot = smem_slot64 (key.lo ^ (key.hi * 0xC2B2AE3D27D4EB4FULL), P.table_log2);
+                    int res = table_insert_w2<false> (s_klo, s_khi, s_cnt, P.table_log2, slot, key, K2_MAXPROBE);
+                    if (res < 0) s_ovf = 1;
+                    else if (res & 0x40000000)
+                    {
+                        uint32_t q = atomicAdd (&s_nocc, 1u);
+                        if (q < (uint32_t)OCC_CAP) s_occ[q] = (uint16_t)(res & 0xFFFF); else s_ovf = 1;
+                    }
                 }
             }
-            __syncthreads ();                                 // staging buffer free for the next chunk; table complete
+            __syncthreads ();                                 // staging buffers free for the next chunk; inserts of this chunk done
             if (s_ovf) break;
         }
         const bool ovf = s_ovf != 0;
-        if (ovf && tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin; }
-        // ---- scan + clear the table ----
-        for (int i = tid; i < T; i += K2_THREADS)
+        // ---- table scan over the claimed slots only: histogram, statistics, emission; slots are cleared on the way ----
+        if (ovf)
+        {   // the bin goes to the global-memory fallback (k2c): wipe the whole table
+            if (tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin; }
+            for (int i = tid; i < T; i += K2_THREADS) { if (W == 1) s_klo[i] = EMPTY64; else s_khi[i] = EMPTY64; s_cnt[i] = 0; }
+            __syncthreads ();
+            if (tid == 0) { s_ovf = 0; s_nocc = 0; s_nemit = 0; }
+            continue;                                          // (loop-top __syncthreads orders the reset)
+        }
+        const uint32_t nocc = s_nocc;
+        uint64_t e_lo[K2_ROUNDS], e_hi[(W == 2) ? K2_ROUNDS : 1]; uint32_t e_c[K2_ROUNDS], e_pos[K2_ROUNDS];
+        #pragma unroll
+        for (int r = 0; r < K2_ROUNDS; r++)
         {
-            uint64_t klo = s_klo[i], khi = (W == 2) ? s_khi[i] : 0;
-            uint32_t c = s_cnt[i];
-            bool occ = (W == 1) ? (klo != EMPTY64) : (khi != EMPTY64);
-            if (occ) { if (W == 1) s_klo[i] = EMPTY64; else { s_khi[i] = EMPTY64; } s_cnt[i] = 0; }
-            consume_entry (P, occ && !ovf, klo, khi, c, s_hist, st);
+            const uint32_t q = (uint32_t)r * K2_THREADS + tid;
+            bool emit = false; e_c[r] = 0; e_pos[r] = 0xFFFFFFFFu;
+            if ((uint32_t)r * K2_THREADS < nocc)              // uniform per CTA
+            {
+                if (q < nocc)
+                {
+                    const uint32_t slot = s_occ[q];
+                    const uint32_t c = s_cnt[slot];
+                    e_lo[r] = s_klo[slot]; if (W == 2) e_hi[r] = s_khi[slot];
+                    if (W == 1) s_klo[slot] = EMPTY64; else s_khi[slot] = EMPTY64;
+                    s_cnt[slot] = 0;
+                    e_c[r] = c;
+                    n_distinct++;
+                    const uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
+                    if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
+                    if (c >= P.solid_min && c <= P.solid_max) n_solid++;
+                    emit = (c >= P.emit_min && c <= P.emit_max);
+                }
+                const unsigned ballot = __ballot_sync (FULL_MASK, emit);
+                if (ballot)
+                {
+                    uint32_t wbase = 0;
+                    if (lane == 0) wbase = atomicAdd (&s_nemit, (uint32_t)__popc (ballot));
+                    wbase = __shfl_sync (FULL_MASK, wbase, 0);
+                    if (emit) e_pos[r] = wbase + __popc (ballot & ((1u << lane) - 1));
+                }
+            }
         }
         __syncthreads ();
-        if (tid == 0) s_ovf = 0;
-        // (the loop-top __syncthreads orders this reset before the next bin's inserts)
+        if (tid == 0)
+        {
+            const uint32_t ne = s_nemit;
+            s_hole_b = s_hole_e = 0;
+            if (ne)
+            {
+                if (s_out_pos + ne > s_out_end)
+                {   // the rest of the current block becomes holes (EMPTY keys, skipped by k3a); reserve a new block
+                    s_hole_b = s_out_pos; s_hole_e = s_out_end;
+                    const unsigned long long grab = ne > K2_OUT_BLOCK ? ne : K2_OUT_BLOCK;
+                    const unsigned long long b0 = atomicAdd (&P.counters[0], grab);
+                    s_out_pos = b0; s_out_end = b0 + grab;
+                }
+                s_gbase = s_out_pos; s_out_pos += ne;
+            }
+            s_nemit = 0; s_nocc = 0;
+        }
+        __syncthreads ();
+        {
+            const unsigned long long gb = s_gbase;
+            #pragma unroll
+            for (int r = 0; r < K2_ROUNDS; r++)
+                if (e_pos[r] != 0xFFFFFFFFu)
+                {
+                    const unsigned long long pos = gb + e_pos[r];
+                    n_emitted++;
+                    if (pos < P.out_cap) { P.out_lo[pos] = e_lo[r]; if (W == 2) P.out_hi[pos] = e_hi[r]; P.out_cnt[pos] = e_c[r]; }
+                }
+            for (unsigned long long h = s_hole_b + tid; h < s_hole_e; h += K2_THREADS)
+                if (h < P.out_cap) { if (W == 1) P.out_lo[h] = EMPTY64; else P.out_hi[h] = EMPTY64; }
+        }
+        // (the loop-top __syncthreads separates these reads of s_gbase/s_hole_* from the next bin's writes)
     }
-    // ---- flush the shared histogram and the statistics ----
+    // ---- holes at the end of the last block, shared histogram, statistics ----
     __syncthreads ();
+    for (unsigned long long h = s_out_pos + tid; h < s_out_end; h += K2_THREADS)
+        if (h < P.out_cap) { if (W == 1) P.out_lo[h] = EMPTY64; else P.out_hi[h] = EMPTY64; }
     for (int i = tid; i < K2_HB; i += K2_THREADS) { uint32_t v = s_hist[i]; if (v) atomicAdd (&P.histogram[i], (unsigned long long)v); }
     #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { st.distinct += __shfl_xor_sync (FULL_MASK, st.distinct, o); st.solid += __shfl_xor_sync (FULL_MASK, st.solid, o); }
-    if ((tid & 31) == 0) { if (st.distinct) atomicAdd (&P.counters[1], st.distinct); if (st.solid) atomicAdd (&P.counters[2], st.solid); }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        n_distinct += __shfl_xor_sync (FULL_MASK, n_distinct, o); n_solid += __shfl_xor_sync (FULL_MASK, n_solid, o);
+        n_emitted += __shfl_xor_sync (FULL_MASK, n_emitted, o);
+    }
+    if (lane == 0)
+    {
+        if (n_distinct) atomicAdd (&P.counters[1], n_distinct);
+        if (n_solid)    atomicAdd (&P.counters[2], n_solid);
+        if (n_emitted)  atomicAdd (&P.counters[6], n_emitted);
+    }
 }
 
 static size_t k2b_smem_bytes (int W, int table_log2)
-{ size_t T = (size_t)1 << table_log2; return (size_t)K2_CHUNK * 16 * W + T * 8 * W + T * 4 + K2_HB * 4 + 16; }
+{
+    size_t T = (size_t)1 << table_log2, occ = (T * 3) / 4; occ += occ & 1;
+    size_t CH = (W == 1) ? K2Cfg<1>::CH : K2Cfg<2>::CH, ML = (W == 1) ? K2Cfg<1>::MAXLEN : K2Cfg<2>::MAXLEN;
+    return CH * 16 * W + CH * ML * 2 + T * 8 * W + T * 4 + occ * 2 + K2_HB * 4 + 16;
+}
 
 cudaError_t launch_k2b_count (const LaunchCtx& L, const K2Params& P)
 {
@@ -317,6 +464,7 @@ cudaError_t launch_k2b_count (const LaunchCtx& L, const K2Params& P)
     (*L.launches)++;
     return cudaGetLastError ();
 }
+unsigned k2b_max_grid (const LaunchCtx& L) { return (unsigned)L.sm_count * 4; }
 
 // ------------------------------------------------------------------------------------------------ k2c: global fallback
 // For the (rare) bins whose distinct k-mers exceed the shared-memory table: all of them share ONE global-memory table
@@ -370,7 +518,7 @@ __global__ void __launch_bounds__(256) k2c_insert (const K2Params P, uint32_t n_
                 const int len = (int)((r[3] >> REC_LEN_SHIFT_W2) & 63);
                 r[3] &= (1ULL << REC_LEN_SHIFT_W2) - 1;
                 for (int j = 0; j < len; j++)
-                    table_insert_w2<true> ((unsigned long long*)P.g_lo, (unsigned long long*)P.g_hi, P.g_cnt, P.g_log2, rec_kmer_w2 (r, j, k), 1 << 30);
+                    { u128 key = rec_kmer_w2 (r, j, k); table_insert_w2<true> ((unsigned long long*)P.g_lo, (unsigned long long*)P.g_hi, P.g_cnt, P.g_log2, slot_hash128 (key, P.g_log2), key, 1 << 30); }
             }
         }
     }
@@ -380,7 +528,7 @@ template<int W>
 __global__ void __launch_bounds__(256) k2c_scan (const K2Params P)
 {
     const uint64_t T = 1ULL << P.g_log2;
-    EmitState st; st.distinct = 0; st.solid = 0;
+    EmitState st; st.distinct = 0; st.solid = 0; st.emitted = 0;
     // every thread of a warp runs the same number of iterations (consume_entry uses warp collectives)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t iters = (T + stride - 1) / stride;
@@ -393,11 +541,11 @@ __global__ void __launch_bounds__(256) k2c_scan (const K2Params P)
             klo = P.g_lo[i]; khi = (W == 2) ? P.g_hi[i] : 0; c = P.g_cnt[i];
             occ = (W == 1) ? (klo != EMPTY64) : (khi != EMPTY64);
         }
-        consume_entry (P, occ, klo, khi, c, 0, st);
+        consume_entry (P, occ, klo, khi, c, st);
     }
     #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { st.distinct += __shfl_xor_sync (FULL_MASK, st.distinct, o); st.solid += __shfl_xor_sync (FULL_MASK, st.solid, o); }
-    if ((threadIdx.x & 31) == 0) { if (st.distinct) atomicAdd (&P.counters[1], st.distinct); if (st.solid) atomicAdd (&P.counters[2], st.solid); }
+    for (int o = 16; o > 0; o >>= 1) { st.distinct += __shfl_xor_sync (FULL_MASK, st.distinct, o); st.solid += __shfl_xor_sync (FULL_MASK, st.solid, o); st.emitted += __shfl_xor_sync (FULL_MASK, st.emitted, o); }
+    if ((threadIdx.x & 31) == 0) { if (st.distinct) atomicAdd (&P.counters[1], st.distinct); if (st.solid) atomicAdd (&P.counters[2], st.solid); if (st.emitted) atomicAdd (&P.counters[6], st.emitted); }
 }
 
 cudaError_t launch_k2c_measure (const LaunchCtx& L, const K2Params& P, uint32_t n_ovf)

@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(256) k3a_classify (const K3Params P)
     if (i >= P.n) return;
     uint32_t key = 0, topbits = 0;
     const int k = P.k, t = P.t_bits;
+    // holes left by k2b's block-wise output reservation carry an all-ones key: skip them
+    if ((P.W == 1 ? P.in_lo[i] : P.in_hi[i]) == 0xFFFFFFFFFFFFFFFFULL) { P.bucket_of[i] = 0xFFFFFFFFu; return; }
     if (P.W == 1)
     {
         uint64_t v = P.in_lo[i];
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) k3b_scatter (const K3Params P)
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint32_t b = P.bucket_of[i];
+    if (b == 0xFFFFFFFFu) return;
     const uint64_t pos = P.bucket_off[b] + atomicAdd (&P.bucket_count[b], 1u);     // bucket_count was re-zeroed: it is the cursor now
     P.tmp_lo[pos] = P.in_lo[i];
     if (P.W == 2) P.tmp_hi[pos] = P.in_hi[i];

@@ -53,7 +53,7 @@ struct K2Params
     int      histo_max;
     unsigned long long* histogram;  // [histo_max+1]
     uint64_t* out_lo; uint64_t* out_hi; uint32_t* out_cnt; unsigned long long out_cap;
-    unsigned long long* counters;   // [0] emitted [1] distinct [2] solid [3] work counter [4] overflow bins [5] k-mers in overflow bins
+    unsigned long long* counters;   // [0] output cursor (incl. holes) [1] distinct [2] solid [3] work counter [4] overflow bins [5] k-mers in overflow bins [6] emitted
     uint32_t* ovf_list;             // [nbins] ids of bins whose table overflowed
     // global-memory fallback table
     uint64_t* g_lo; uint64_t* g_hi; uint32_t* g_cnt; int g_log2;
