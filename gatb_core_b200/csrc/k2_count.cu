@@ -211,219 +211,237 @@ __device__ __forceinline__ void consume_entry (const K2Params& P, bool occupied,
 }
 
 // ------------------------------------------------------------------------------------------------ k2b
-// Shared-memory layout (T = table slots, CH/MAXLEN from K2Cfg<W>):
-//   records  CH * 16W bytes      staged by TMA
-//   owner    CH * MAXLEN u16     k-mer g of the chunk -> (record << JBITS | index in record)
-//   keys     T * 8W, counts T * 4
-//   occ      3T/4 u16            slots claimed for this bin, in claim order (the table scan walks this list, not T slots)
-//   hist     K2_HB u32
+// Persistent CTAs; per fine bin:
+//   * the bin's records arrive in shared memory by TMA bulk copy into one of two staging buffers; thread 0 fetches the
+//     NEXT bin from the work counter and starts its copy before the current bin is processed (latency hidden);
+//   * insert phase, warp-autonomous (no block barrier): a warp takes 32 records (lane <-> record), prefix-sums their
+//     k-mer counts with shuffles and then walks the k-mers 32 at a time (lane <-> k-mer).  The k-mer -> record map of a
+//     32-wide window is one __reduce_or_sync of "head" bits plus a popc; the record comes back from shared memory with
+//     one 16-byte load and the k-mer is rebuilt with bit tricks (common.cuh).  Insert = LDS.64 probe, 64-bit atomicCAS
+//     only on an empty slot, shared atomicAdd on the count; a slot claimed for the first time is appended to the bin's
+//     claimed-slot list;
+//   * scan phase: the claimed-slot list (not the T slots) is walked: histogram in shared memory, statistics, slots
+//     cleared, and k-mers in the emission range appended to a per-WARP output block (one global atomic per 2048
+//     emitted k-mers; unused tails are marked EMPTY and skipped by k3a).
+// Block barriers per bin: one after the inserts, one after the scan.
+// Shared-memory layout (T = table slots): staging 2 x CHR records | keys T*8W | counts T*4 | claimed 3T/4 u16 | hist
 template<int W>
 __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Params P)
 {
-    typedef K2Cfg<W> Cfg;
+    constexpr int CHR = (W == 1) ? 512 : 256;              // records per staging buffer (8 KB)
+    constexpr int NWARP = K2_THREADS / 32;
+    constexpr unsigned WBLOCK = 2048;                      // output slots a warp reserves at a time
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = 1 << P.table_log2;
     const int OCC_CAP = (T * 3) / 4;
-    uint4* s_recs = (uint4*)smem_raw;
-    uint16_t* s_owner = (uint16_t*)(smem_raw + (size_t)Cfg::CH * 16 * W);
-    unsigned long long* s_klo = (unsigned long long*)(smem_raw + (size_t)Cfg::CH * 16 * W + (size_t)Cfg::CH * Cfg::MAXLEN * 2);
+    uint4* s_recs = (uint4*)smem_raw;                                        // [2][CHR*W]
+    unsigned long long* s_klo = (unsigned long long*)(smem_raw + (size_t)2 * CHR * 16 * W);
     unsigned long long* s_khi = (W == 2) ? s_klo + T : 0;
     uint32_t* s_cnt  = (uint32_t*)(s_klo + (size_t)T * W);
     uint16_t* s_occ  = (uint16_t*)(s_cnt + T);
     uint32_t* s_hist = (uint32_t*)(s_occ + OCC_CAP + (OCC_CAP & 1));
-    uint64_t* s_bar  = (uint64_t*)(s_hist + K2_HB + (K2_HB & 1));
-    __shared__ uint32_t s_bin, s_wsum[8], s_total, s_nocc, s_nemit;
+    uint64_t* s_bar  = (uint64_t*)(s_hist + K2_HB + (K2_HB & 1));             // [2]
+    __shared__ uint32_t s_bin[2], s_n[2], s_nocc[2];
+    __shared__ unsigned long long s_base[2];
     __shared__ int s_ovf;
-    __shared__ unsigned long long s_out_pos, s_out_end, s_gbase, s_hole_b, s_hole_e;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = P.k;
     for (int i = tid; i < T; i += K2_THREADS) { if (W == 1) s_klo[i] = EMPTY64; else { s_khi[i] = EMPTY64; s_klo[i] = 0; } s_cnt[i] = 0; }
     for (int i = tid; i < K2_HB; i += K2_THREADS) s_hist[i] = 0;
+
+    // thread 0 only: take the next bin from the work counter and start the TMA copy of its first chunk
+    auto fetch = [&] (int st)
+    {
+        uint32_t bin; uint2 d = make_uint2 (0, 0);
+        for (;;)
+        {   // skip empty bins here so that the CTA never synchronises for nothing
+            bin = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
+            if (bin >= P.nbins) break;
+            d = P.bin_desc[bin];
+            if (d.y) break;
+        }
+        s_bin[st] = bin; s_nocc[st] = 0;
+        if (bin < P.nbins)
+        {
+            const unsigned long long base = ((unsigned long long)(bin >> P.fine_bits) * P.cap + d.x);
+            s_n[st] = d.y; s_base[st] = base;
+            const uint32_t mrec = min ((uint32_t)CHR, d.y);
+            fence_proxy_async ();
+            mbar_expect_tx (&s_bar[st], mrec * 16 * W);
+            tma_bulk_g2s (s_recs + (size_t)st * CHR * W, (const uint4*)P.recs + base * W, mrec * 16 * W, &s_bar[st]);
+        }
+    };
     if (tid == 0)
     {
-        mbar_init (s_bar, 1); asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_ovf = 0; s_nocc = 0; s_nemit = 0; s_out_pos = 0; s_out_end = 0; s_hole_b = 0; s_hole_e = 0;
+        mbar_init (&s_bar[0], 1); mbar_init (&s_bar[1], 1);
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_ovf = 0;
+        fetch (0);
     }
     __syncthreads ();
-    uint32_t parity = 0;
+    uint32_t par0 = 0, par1 = 0;
     unsigned long long n_distinct = 0, n_solid = 0, n_emitted = 0;
-    const int k = P.k;
+    unsigned long long out_pos = 0, out_end = 0;           // this warp's output block (warp-uniform)
+    int st = 0;
 
     for (;;)
     {
-        if (tid == 0) s_bin = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
-        __syncthreads ();
-        const uint32_t bin = s_bin;
+        const uint32_t bin = s_bin[st];
         if (bin >= P.nbins) break;
-        const uint2 d = P.bin_desc[bin];
-        const uint32_t n = d.y;
-        if (n == 0) { __syncthreads (); continue; }
-        const uint4* base = (const uint4*)P.recs + ((uint64_t)(bin >> P.fine_bits) * P.cap + d.x) * W;
+        const uint32_t n = s_n[st];
+        const unsigned long long base = s_base[st];
+        if (tid == 0) fetch (st ^ 1);                       // prefetch the next bin into the other staging buffer
+        const uint4* recs = s_recs + (size_t)st * CHR * W;
 
-        for (uint32_t c0 = 0; c0 < n; c0 += Cfg::CH)
+        for (uint32_t c0 = 0; c0 < n; c0 += CHR)
         {
-            const uint32_t mrec = min ((uint32_t)Cfg::CH, n - c0);
-            if (tid == 0)
-            {
-                fence_proxy_async ();                          // order earlier generic reads of the staging buffer
-                mbar_expect_tx (s_bar, mrec * 16 * W);
-                tma_bulk_g2s (s_recs, base + (uint64_t)c0 * W, mrec * 16 * W, s_bar);
-            }
-            mbar_wait (s_bar, parity); parity ^= 1;
-            // ---- phase A: expand records into one entry per k-mer ----
-            int len = 0; uint32_t incl = 0;
-            if (tid < Cfg::CH)
-            {
-                if ((uint32_t)tid < mrec)
+            const uint32_t mrec = min ((uint32_t)CHR, n - c0);
+            if (c0)
+            {   // bins larger than one staging buffer (rare): reload the same buffer
+                __syncthreads ();
+                if (tid == 0)
                 {
-                    uint32_t top = s_recs[(size_t)tid * W + (W - 1)].w;                         // high 32 bits of the record
+                    fence_proxy_async ();
+                    mbar_expect_tx (&s_bar[st], mrec * 16 * W);
+                    tma_bulk_g2s ((void*)recs, (const uint4*)P.recs + (base + c0) * W, mrec * 16 * W, &s_bar[st]);
+                }
+            }
+            if (st == 0) { mbar_wait (&s_bar[0], par0); par0 ^= 1; } else { mbar_wait (&s_bar[1], par1); par1 ^= 1; }
+
+            // ---- insert phase: warp-autonomous ----
+            for (uint32_t g0 = wid * 32; g0 < mrec; g0 += NWARP * 32)
+            {
+                const uint32_t ri = g0 + lane;
+                int len = 0;
+                if (ri < mrec)
+                {
+                    const uint32_t top = recs[(size_t)ri * W + (W - 1)].w;
                     len = (W == 1) ? (int)((top >> (REC_LEN_SHIFT_W1 - 32)) & 31) : (int)((top >> (REC_LEN_SHIFT_W2 - 32)) & 63);
                 }
-                incl = (uint32_t)len;
+                uint32_t incl = (uint32_t)len;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
-                if (lane == 31) s_wsum[wid] = incl;
-            }
-            __syncthreads ();
-            if (tid < Cfg::CH)
-            {
-                uint32_t excl = incl - (uint32_t)len;
-                for (int q = 0; q < wid; q++) excl += s_wsum[q];
-                for (int j = 0; j < len; j++) s_owner[excl + j] = (uint16_t)((tid << Cfg::JBITS) | j);
-                if (tid == Cfg::CH - 1) s_total = excl + (uint32_t)len;
-            }
-            __syncthreads ();
-            // ---- phase B: one thread per k-mer ----
-            const uint32_t total = s_total;
-            for (uint32_t g = tid; g < total; g += K2_THREADS)
-            {
-                const uint32_t o = s_owner[g];
-                const uint32_t ri = o >> Cfg::JBITS; const int j = (int)(o & ((1u << Cfg::JBITS) - 1));
-                if (W == 1)
+                const uint32_t excl = incl - (uint32_t)len;
+                const uint32_t total = __shfl_sync (FULL_MASK, incl, 31);
+                uint32_t r0 = 0;                                            // records that start before the window
+                for (uint32_t wb = 0; wb < total; wb += 32)
                 {
-                    uint4 r = s_recs[ri];
-                    uint64_t lo = (uint64_t)r.x | ((uint64_t)r.y << 32), hi = ((uint64_t)r.z | ((uint64_t)r.w << 32)) & ((1ULL << REC_LEN_SHIFT_W1) - 1);
-                    const uint64_t key = rec_kmer_w1 (lo, hi, j, k);
-                    uint32_t slot = smem_slot64 (key, P.table_log2);
-                    bool done = false;
-                    for (int probe = 0; probe < K2_MAXPROBE && !done; probe++)
+                    const uint32_t h = excl - wb;                           // head position inside the window (unsigned wrap = outside)
+                    const uint32_t M = __reduce_or_sync (FULL_MASK, (len > 0 && h < 32u) ? (1u << h) : 0u);
+                    const uint32_t gk = wb + lane;
+                    uint32_t r = r0 + __popc (M & (0xFFFFFFFFu >> (31 - lane))) - 1;
+                    r0 += __popc (M);
+                    const uint32_t ex = __shfl_sync (FULL_MASK, excl, r & 31);
+                    if (gk < total)
                     {
-                        unsigned long long cur = s_klo[slot];
-                        if (cur == EMPTY64)
+                        const int j = (int)(gk - ex);
+                        const uint32_t rr = g0 + r;
+                        if (W == 1)
                         {
-                            cur = atomicCAS (&s_klo[slot], EMPTY64, (unsigned long long)key);
-                            if (cur == EMPTY64)
-                            {   // new distinct k-mer: remember its slot
-                                uint32_t q = atomicAdd (&s_nocc, 1u);
-                                if (q < (uint32_t)OCC_CAP) s_occ[q] = (uint16_t)slot; else s_ovf = 1;
-                                cur = key;
+                            const uint4 q = recs[rr];
+                            const uint64_t lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+                            const uint64_t hi = ((uint64_t)q.z | ((uint64_t)q.w << 32)) & ((1ULL << REC_LEN_SHIFT_W1) - 1);
+                            const uint64_t key = rec_kmer_w1 (lo, hi, j, k);
+                            uint32_t slot = smem_slot64 (key, P.table_log2);
+                            int probe = 0;
+                            for (;;)
+                            {
+                                unsigned long long cur = s_klo[slot];
+                                if (cur == key) { atomicAdd (&s_cnt[slot], 1u); break; }
+                                if (cur == EMPTY64)
+                                {
+                                    cur = atomicCAS (&s_klo[slot], EMPTY64, (unsigned long long)key);
+                                    if (cur == EMPTY64)
+                                    {   // first occurrence in this bin: remember the slot
+                                        const uint32_t qn = atomicAdd (&s_nocc[st], 1u);
+                                        if (qn < (uint32_t)OCC_CAP) s_occ[qn] = (uint16_t)slot; else s_ovf = 1;
+                                        atomicAdd (&s_cnt[slot], 1u); break;
+                                    }
+                                    if (cur == key) { atomicAdd (&s_cnt[slot], 1u); break; }
+                                }
+                                slot = (slot + 1) & (T - 1);
+                                if (++probe >= K2_MAXPROBE) { s_ovf = 1; break; }
                             }
                         }
-                        if (cur == key) { atomicAdd (&s_cnt[slot], 1u); done = true; }
-                        else slot = (slot + 1) & (T - 1);
-                    }
-                    if (!done) s_ovf = 1;
-                }
-                else
-                {
-                    uint4 a = s_recs[2*ri], b = s_recs[2*ri+1];
-                    uint64_t r[4] = { (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
-                                      (uint64_t)b.x | ((uint64_t)b.y << 32), ((uint64_t)b.z | ((uint64_t)b.w << 32)) & ((1ULL << REC_LEN_SHIFT_W2) - 1) };
-                    const u128 key = rec_kmer_w2 (r, j, k);
-                    uint32_t slot = smem_slot64 (key.lo ^ (key.hi * 0xC2B2AE3D27D4EB4FULL), P.table_log2);
-                    int res = table_insert_w2<false> (s_klo, s_khi, s_cnt, P.table_log2, slot, key, K2_MAXPROBE);
-                    if (res < 0) s_ovf = 1;
-                    else if (res & 0x40000000)
-                    {
-                        uint32_t q = atomicAdd (&s_nocc, 1u);
-                        if (q < (uint32_t)OCC_CAP) s_occ[q] = (uint16_t)(res & 0xFFFF); else s_ovf = 1;
+                        else
+                        {
+                            const uint4 a = recs[2*rr], b = recs[2*rr+1];
+                            uint64_t rw[4] = { (uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
+                                               (uint64_t)b.x | ((uint64_t)b.y << 32), ((uint64_t)b.z | ((uint64_t)b.w << 32)) & ((1ULL << REC_LEN_SHIFT_W2) - 1) };
+                            const u128 key = rec_kmer_w2 (rw, j, k);
+                            const uint32_t slot = smem_slot64 (key.lo ^ (key.hi * 0xC2B2AE3D27D4EB4FULL), P.table_log2);
+                            const int res = table_insert_w2<false> (s_klo, s_khi, s_cnt, P.table_log2, slot, key, K2_MAXPROBE);
+                            if (res < 0) s_ovf = 1;
+                            else if (res & 0x40000000)
+                            {
+                                const uint32_t qn = atomicAdd (&s_nocc[st], 1u);
+                                if (qn < (uint32_t)OCC_CAP) s_occ[qn] = (uint16_t)(res & 0xFFFF); else s_ovf = 1;
+                            }
+                        }
                     }
                 }
             }
-            __syncthreads ();                                 // staging buffers free for the next chunk; inserts of this chunk done
-            if (s_ovf) break;
         }
+        __syncthreads ();                                     // all inserts of the bin are done
         const bool ovf = s_ovf != 0;
-        // ---- table scan over the claimed slots only: histogram, statistics, emission; slots are cleared on the way ----
         if (ovf)
         {   // the bin goes to the global-memory fallback (k2c): wipe the whole table
             if (tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin; }
             for (int i = tid; i < T; i += K2_THREADS) { if (W == 1) s_klo[i] = EMPTY64; else s_khi[i] = EMPTY64; s_cnt[i] = 0; }
             __syncthreads ();
-            if (tid == 0) { s_ovf = 0; s_nocc = 0; s_nemit = 0; }
-            continue;                                          // (loop-top __syncthreads orders the reset)
+            if (tid == 0) s_ovf = 0;
+            __syncthreads ();
+            st ^= 1;
+            continue;
         }
-        const uint32_t nocc = s_nocc;
-        uint64_t e_lo[K2_ROUNDS], e_hi[(W == 2) ? K2_ROUNDS : 1]; uint32_t e_c[K2_ROUNDS], e_pos[K2_ROUNDS];
-        #pragma unroll
-        for (int r = 0; r < K2_ROUNDS; r++)
+        // ---- scan phase over the claimed slots: warp-autonomous ----
+        const uint32_t nocc = s_nocc[st];
+        for (uint32_t q0 = wid * 32; q0 < nocc; q0 += NWARP * 32)
         {
-            const uint32_t q = (uint32_t)r * K2_THREADS + tid;
-            bool emit = false; e_c[r] = 0; e_pos[r] = 0xFFFFFFFFu;
-            if ((uint32_t)r * K2_THREADS < nocc)              // uniform per CTA
+            const uint32_t q = q0 + lane;
+            bool emit = false; uint64_t klo = 0, khi = 0; uint32_t c = 0;
+            if (q < nocc)
             {
-                if (q < nocc)
-                {
-                    const uint32_t slot = s_occ[q];
-                    const uint32_t c = s_cnt[slot];
-                    e_lo[r] = s_klo[slot]; if (W == 2) e_hi[r] = s_khi[slot];
-                    if (W == 1) s_klo[slot] = EMPTY64; else s_khi[slot] = EMPTY64;
-                    s_cnt[slot] = 0;
-                    e_c[r] = c;
-                    n_distinct++;
-                    const uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
-                    if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
-                    if (c >= P.solid_min && c <= P.solid_max) n_solid++;
-                    emit = (c >= P.emit_min && c <= P.emit_max);
-                }
-                const unsigned ballot = __ballot_sync (FULL_MASK, emit);
-                if (ballot)
-                {
-                    uint32_t wbase = 0;
-                    if (lane == 0) wbase = atomicAdd (&s_nemit, (uint32_t)__popc (ballot));
-                    wbase = __shfl_sync (FULL_MASK, wbase, 0);
-                    if (emit) e_pos[r] = wbase + __popc (ballot & ((1u << lane) - 1));
-                }
+                const uint32_t slot = s_occ[q];
+                c = s_cnt[slot]; klo = s_klo[slot]; if (W == 2) khi = s_khi[slot];
+                if (W == 1) s_klo[slot] = EMPTY64; else s_khi[slot] = EMPTY64;
+                s_cnt[slot] = 0;
+                n_distinct++;
+                const uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
+                if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
+                if (c >= P.solid_min && c <= P.solid_max) n_solid++;
+                emit = (c >= P.emit_min && c <= P.emit_max);
             }
-        }
-        __syncthreads ();
-        if (tid == 0)
-        {
-            const uint32_t ne = s_nemit;
-            s_hole_b = s_hole_e = 0;
-            if (ne)
+            const unsigned ballot = __ballot_sync (FULL_MASK, emit);
+            if (ballot)
             {
-                if (s_out_pos + ne > s_out_end)
-                {   // the rest of the current block becomes holes (EMPTY keys, skipped by k3a); reserve a new block
-                    s_hole_b = s_out_pos; s_hole_e = s_out_end;
-                    const unsigned long long grab = ne > K2_OUT_BLOCK ? ne : K2_OUT_BLOCK;
-                    const unsigned long long b0 = atomicAdd (&P.counters[0], grab);
-                    s_out_pos = b0; s_out_end = b0 + grab;
+                const unsigned ne = __popc (ballot);
+                if (out_pos + ne > out_end)
+                {   // rest of the block -> holes; reserve a new block
+                    for (unsigned long long hpos = out_pos + lane; hpos < out_end; hpos += 32)
+                        if (hpos < P.out_cap) { if (W == 1) P.out_lo[hpos] = EMPTY64; else P.out_hi[hpos] = EMPTY64; }
+                    unsigned long long b0 = 0;
+                    if (lane == 0) b0 = atomicAdd (&P.counters[0], (unsigned long long)WBLOCK);
+                    b0 = __shfl_sync (FULL_MASK, b0, 0);
+                    out_pos = b0; out_end = b0 + WBLOCK;
                 }
-                s_gbase = s_out_pos; s_out_pos += ne;
-            }
-            s_nemit = 0; s_nocc = 0;
-        }
-        __syncthreads ();
-        {
-            const unsigned long long gb = s_gbase;
-            #pragma unroll
-            for (int r = 0; r < K2_ROUNDS; r++)
-                if (e_pos[r] != 0xFFFFFFFFu)
+                if (emit)
                 {
-                    const unsigned long long pos = gb + e_pos[r];
+                    const unsigned long long pos = out_pos + __popc (ballot & ((1u << lane) - 1));
                     n_emitted++;
-                    if (pos < P.out_cap) { P.out_lo[pos] = e_lo[r]; if (W == 2) P.out_hi[pos] = e_hi[r]; P.out_cnt[pos] = e_c[r]; }
+                    if (pos < P.out_cap) { P.out_lo[pos] = klo; if (W == 2) P.out_hi[pos] = khi; P.out_cnt[pos] = c; }
                 }
-            for (unsigned long long h = s_hole_b + tid; h < s_hole_e; h += K2_THREADS)
-                if (h < P.out_cap) { if (W == 1) P.out_lo[h] = EMPTY64; else P.out_hi[h] = EMPTY64; }
+                out_pos += ne;
+            }
         }
-        // (the loop-top __syncthreads separates these reads of s_gbase/s_hole_* from the next bin's writes)
+        __syncthreads ();                                     // table clean again before the next bin's inserts
+        st ^= 1;
     }
-    // ---- holes at the end of the last block, shared histogram, statistics ----
+    // ---- holes at the end of each warp's last block, shared histogram, statistics ----
+    for (unsigned long long hpos = out_pos + lane; hpos < out_end; hpos += 32)
+        if (hpos < P.out_cap) { if (W == 1) P.out_lo[hpos] = EMPTY64; else P.out_hi[hpos] = EMPTY64; }
     __syncthreads ();
-    for (unsigned long long h = s_out_pos + tid; h < s_out_end; h += K2_THREADS)
-        if (h < P.out_cap) { if (W == 1) P.out_lo[h] = EMPTY64; else P.out_hi[h] = EMPTY64; }
     for (int i = tid; i < K2_HB; i += K2_THREADS) { uint32_t v = s_hist[i]; if (v) atomicAdd (&P.histogram[i], (unsigned long long)v); }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -442,8 +460,8 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
 static size_t k2b_smem_bytes (int W, int table_log2)
 {
     size_t T = (size_t)1 << table_log2, occ = (T * 3) / 4; occ += occ & 1;
-    size_t CH = (W == 1) ? K2Cfg<1>::CH : K2Cfg<2>::CH, ML = (W == 1) ? K2Cfg<1>::MAXLEN : K2Cfg<2>::MAXLEN;
-    return CH * 16 * W + CH * ML * 2 + T * 8 * W + T * 4 + occ * 2 + K2_HB * 4 + 16;
+    size_t CHR = (W == 1) ? 512 : 256;
+    return 2 * CHR * 16 * W + T * 8 * W + T * 4 + occ * 2 + K2_HB * 4 + 32;
 }
 
 cudaError_t launch_k2b_count (const LaunchCtx& L, const K2Params& P)
