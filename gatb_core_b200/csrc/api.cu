@@ -220,8 +220,8 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     if (max_len >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported by the partition kernel yet (longest: %llu)", (unsigned long long)max_len);
 
     // ---- device binning geometry ----
-    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : 12;
-    if (table_log2 < 5 || table_log2 > 12) return fail (ctx, "table_log2 must be in [5,12]");
+    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : 11;
+    if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
     const uint64_t T = 1ULL << table_log2;
     const uint64_t occ_per_bin = (T * 55) / 100;
     const int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
@@ -287,7 +287,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     uint64_t out_cap = ctx->slot_cap[S_COARSE] / item_bytes;
     { uint64_t guess = total_kmers / 3 + 4096; if (out_cap < guess) out_cap = guess; }
     if (out_cap > out_bound) out_cap = out_bound;
-    out_cap += (uint64_t)(ctx->sm_count * 4 + 8) * 16 * 2048;     // every warp of k2b reserves output in blocks of 2048 slots
+    out_cap += (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;     // every warp of k2b reserves output in blocks of 2048 slots
 
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
     if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
@@ -338,7 +338,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         }
         if (h_cnt[0] <= out_cap) break;
         if (attempt >= 1) return fail (ctx, "output capacity exceeded: %llu k-mers to emit, room for %llu", (unsigned long long)h_cnt[0], (unsigned long long)out_cap);
-        out_cap = h_cnt[0] + (uint64_t)(ctx->sm_count * 4 + 8) * 16 * 2048;   // the cursor kept counting: it bounds the demand -> count again
+        out_cap = h_cnt[0] + (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;   // the cursor kept counting: it bounds the demand -> count again
     }
     const uint64_t n_items = h_cnt[6];          // k-mers emitted
     const uint64_t n_range = h_cnt[0];          // extent of the unsorted array (block reservations leave EMPTY holes)

@@ -121,7 +121,7 @@ __device__ __forceinline__ uint32_t slot_hash128 (u128 key, int log2)
 { return slot_hash64 (key.lo ^ (key.hi * 0xC2B2AE3D27D4EB4FULL), log2); }
 
 #define EMPTY64 0xFFFFFFFFFFFFFFFFULL
-#define K2_THREADS 512
+#define K2_THREADS 256
 #define K2_HB      256        // histogram bins kept in shared memory (larger abundances go to global atomics)
 #define K2_MAXPROBE 512
 #define K2_ROUNDS  6          // table-scan rounds: occupied-slot list capacity (3T/4) <= K2_ROUNDS * K2_THREADS  => T <= 4096
@@ -228,7 +228,8 @@ __device__ __forceinline__ void consume_entry (const K2Params& P, bool occupied,
 template<int W>
 __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Params P)
 {
-    constexpr int CHR = (W == 1) ? 512 : 256;              // records per staging buffer (8 KB)
+    constexpr int CHR = (W == 1) ? 256 : 128;              // records per staging buffer (4 KB)
+    constexpr int GRP = 16;                                // records a warp expands at a time (lanes 0..GRP-1 hold one each)
     constexpr int NWARP = K2_THREADS / 32;
     constexpr unsigned WBLOCK = 2048;                      // output slots a warp reserves at a time
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -310,11 +311,11 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
             if (st == 0) { mbar_wait (&s_bar[0], par0); par0 ^= 1; } else { mbar_wait (&s_bar[1], par1); par1 ^= 1; }
 
             // ---- insert phase: warp-autonomous ----
-            for (uint32_t g0 = wid * 32; g0 < mrec; g0 += NWARP * 32)
+            for (uint32_t g0 = wid * GRP; g0 < mrec; g0 += NWARP * GRP)
             {
                 const uint32_t ri = g0 + lane;
                 int len = 0;
-                if (ri < mrec)
+                if (lane < GRP && ri < mrec)
                 {
                     const uint32_t top = recs[(size_t)ri * W + (W - 1)].w;
                     len = (W == 1) ? (int)((top >> (REC_LEN_SHIFT_W1 - 32)) & 31) : (int)((top >> (REC_LEN_SHIFT_W2 - 32)) & 63);
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
 static size_t k2b_smem_bytes (int W, int table_log2)
 {
     size_t T = (size_t)1 << table_log2, occ = (T * 3) / 4; occ += occ & 1;
-    size_t CHR = (W == 1) ? 512 : 256;
+    size_t CHR = (W == 1) ? 256 : 128;
     return 2 * CHR * 16 * W + T * 8 * W + T * 4 + occ * 2 + K2_HB * 4 + 32;
 }
 

@@ -54,7 +54,7 @@ typedef struct gatb_gpu_params
     int32_t  minimizer_type;     /* _minimizerType   0 = lexicographic (supported); 1 = frequency (not yet)     */
     int32_t  emit_all;           /* 1: return EVERY distinct k-mer (for custom ICountProcessor chains); 0: solid only */
     int32_t  read_len;           /* >0: all reads have this length and read_offsets_nt may be NULL               */
-    int32_t  table_log2;         /* 0 = default (12); log2 slots of the per-bin shared-memory table, 5..12 */
+    int32_t  table_log2;         /* 0 = default (11); log2 slots of the per-bin shared-memory table, 5..13 */
     int32_t  reserved[5];
 } gatb_gpu_params;
 
