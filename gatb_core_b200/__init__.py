@@ -22,7 +22,8 @@ EXPORTS = ["gatb_gpu_create", "gatb_gpu_destroy", "gatb_gpu_last_error", "gatb_g
            "gatb_gpu_sm_count", "gatb_gpu_count", "gatb_gpu_count_dev", "gatb_gpu_result_free", "gatb_gpu_superkmers",
            "gatb_gpu_free_host", "gatb_gpu_bloom_params", "gatb_gpu_bloom_layout", "gatb_gpu_bloom", "gatb_gpu_bloom_dev",
            "gatb_gpu_histogram_cutoff", "gatb_gpu_malloc", "gatb_gpu_free", "gatb_gpu_memcpy_h2d", "gatb_gpu_memcpy_d2h",
-           "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii"]
+           "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii", "gatb_gpu_plan",
+           "gatb_gpu_partition_into", "gatb_gpu_count_bins"]
 
 
 class GatbGpuError(RuntimeError):
@@ -41,6 +42,13 @@ class Result(C.Structure):
                 ("kmers_hi", C.c_void_p), ("counts", C.c_void_p), ("histogram", C.c_void_p),
                 ("stats", C.c_uint64 * NSTATS), ("seconds", C.c_double * 8), ("kernel_seconds", C.c_double * 8), ("on_device", C.c_int32), ("pad", C.c_int32),
                 ("owner", C.c_void_p)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("total_kmers", C.c_uint64), ("nb1", C.c_uint32), ("cap", C.c_uint32), ("fine_bits", C.c_int32),
+                ("table_log2", C.c_int32), ("m_device", C.c_int32), ("w", C.c_int32), ("maxlen", C.c_int32),
+                ("words", C.c_int32), ("n_ranks", C.c_uint32), ("bins_per_rank", C.c_uint32), ("record_bytes", C.c_uint32),
+                ("pad", C.c_uint32)]
 
 
 def load_library():
@@ -77,6 +85,10 @@ def load_library():
     L.gatb_gpu_synchronize.argtypes = [VP]
     L.gatb_gpu_synth_reads_dev.argtypes = [VP, U64, U64, U64, U64, I32, VP]
     L.gatb_gpu_pack_ascii.argtypes = [VP, C.c_char_p, U64, VP, VP, C.POINTER(U64)]
+    L.gatb_gpu_plan.argtypes = [VP, C.POINTER(Params), U64, U64, I32, C.POINTER(Geometry)]
+    L.gatb_gpu_partition_into.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), VP, VP, U64, VP, VP, VP, VP, VP]
+    L.gatb_gpu_count_bins.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), I32, C.POINTER(VP), C.POINTER(VP), VP,
+                                      C.c_uint32, VP, U64, C.POINTER(Result)]
     return L
 
 
@@ -196,6 +208,30 @@ class GatbGpu:
         stats = {name: int(res.stats[i]) for i, name in enumerate(STAT_NAMES)}
         return {"parts": parts, "part_offsets": offs, "histogram": hist, "stats": stats,
                 "seconds": [float(x) for x in res.seconds], "kernel_seconds": [float(x) for x in res.kernel_seconds], "n_items": int(res.n_items)}
+
+    # ---- staged path (multi-GPU) --------------------------------------------------------------------------------
+    def plan(self, params, total_kmers, n_reads, n_ranks):
+        g = Geometry()
+        self._check(self.L.gatb_gpu_plan(self.ctx, C.byref(params), total_kmers, n_reads, n_ranks, C.byref(g)))
+        return g
+
+    def partition_into(self, params, geom, d_packed, d_offsets, n_reads, d_bins, d_cursors, d_fine_counts, d_n_mask=None):
+        """k1 into caller-provided device buffers (ints).  Returns [valid, invalid, stored, dropped]."""
+        st = np.zeros(4, np.uint64)
+        self._check(self.L.gatb_gpu_partition_into(self.ctx, C.byref(params), C.byref(geom), _ptr(d_packed), _ptr(d_offsets),
+                                                   n_reads, _ptr(d_n_mask), _ptr(d_bins), _ptr(d_cursors), _ptr(d_fine_counts), _ptr(st)))
+        return [int(x) for x in st]
+
+    def count_bins(self, params, geom, src_bins, src_cursors, d_fine_total, nb1_local, kmers_bound, repart=None):
+        """Counts nb1_local coarse bins gathered from len(src_bins) sources (device pointers).  Returns a device Result."""
+        n = len(src_bins)
+        a = (C.c_void_p * n)(*src_bins)
+        b = (C.c_void_p * n)(*src_cursors)
+        res = Result()
+        rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
+        self._check(self.L.gatb_gpu_count_bins(self.ctx, C.byref(params), C.byref(geom), n, a, b, _ptr(d_fine_total), nb1_local,
+                                               _ptr(rp), kmers_bound, C.byref(res)))
+        return res
 
     # ---- GATB-exact super-k-mers ---------------------------------------------------------------------------------
     def superkmers(self, packed, offsets, n_reads, params, repart=None, n_mask=None):

@@ -17,7 +17,7 @@ static std::string g_create_error;
 
 // device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
 enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_FINECNT, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
-            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_NSLOTS };
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_NSLOTS };
 
 struct gatb_gpu_ctx
 {
@@ -174,7 +174,7 @@ static int pick_device_m (int k, uint64_t nbins_fine)
     return m;
 }
 
-// total number of k-mer positions (device reduction is overkill for a bound: offsets are small or read_len fixed)
+// total number of k-mer positions of a batch of reads
 __global__ void k_count_kmers (const uint64_t* offsets, uint64_t n_reads, int k, unsigned long long* out /* [0] kmers [1] nt [2] maxlen */)
 {
     unsigned long long km = 0, nt = 0, mx = 0;
@@ -188,106 +188,140 @@ __global__ void k_count_kmers (const uint64_t* offsets, uint64_t n_reads, int k,
     if ((threadIdx.x & 31) == 0) { atomicAdd (&out[0], km); atomicAdd (&out[1], nt); atomicMax (&out[2], mx); }
 }
 
-static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_host,
-                           const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
-                           gatb_gpu_result* out)
+// tot[b] = sum over sources of min(cursor_s[b], cap)
+struct CursorList { const uint32_t* cur[GATB_GPU_MAX_SOURCES]; int n; };
+__global__ void k_sum_cursors (CursorList C, uint32_t nb1, uint32_t cap, uint32_t* tot)
 {
-    LaunchCtx L = lctx (ctx);
-    const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
-    const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
-    const int histo_max = p->histo_max;
-    cudaEventRecord (ctx->ev[1], ctx->stream);
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb1) return;
+    uint32_t t = 0;
+    for (int s = 0; s < C.n; s++) t += min (C.cur[s][b], cap);
+    tot[b] = t;
+}
 
-    // ---- workload size ----
-    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
-    unsigned long long* d_stats = (unsigned long long*)ctx->slot[S_STATS];
-    uint64_t total_kmers = 0, total_nt = 0, max_len = 0;
+static int workload_size (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint64_t* d_offsets, uint64_t n_reads,
+                          uint64_t* total_kmers, uint64_t* total_nt, uint64_t* max_len)
+{
+    const int k = p->kmer_size;
     if (!d_offsets)
     {
         if (p->read_len <= 0) return fail (ctx, "read_offsets_nt is NULL and read_len <= 0");
-        total_nt = n_reads * (uint64_t)p->read_len; max_len = p->read_len;
-        total_kmers = p->read_len >= k ? n_reads * (uint64_t)(p->read_len - k + 1) : 0;
+        *total_nt = n_reads * (uint64_t)p->read_len; *max_len = p->read_len;
+        *total_kmers = p->read_len >= k ? n_reads * (uint64_t)(p->read_len - k + 1) : 0;
+        return 0;
     }
-    else
-    {
-        CK (cudaMemsetAsync (d_stats + 32, 0, 3 * 8, ctx->stream));
-        if (n_reads) { k_count_kmers<<<ctx->sm_count * 4, 256, 0, ctx->stream>>> (d_offsets, n_reads, k, d_stats + 32); ctx->launches++; }
-        unsigned long long h[3];
-        CK (cudaMemcpyAsync (h, d_stats + 32, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK (cudaStreamSynchronize (ctx->stream));
-        total_kmers = h[0]; total_nt = h[1]; max_len = h[2];
-    }
-    if (max_len >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported by the partition kernel yet (longest: %llu)", (unsigned long long)max_len);
+    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
+    unsigned long long* d_stats = (unsigned long long*)ctx->slot[S_STATS];
+    CK (cudaMemsetAsync (d_stats + 32, 0, 3 * 8, ctx->stream));
+    if (n_reads) { k_count_kmers<<<ctx->sm_count * 4, 256, 0, ctx->stream>>> (d_offsets, n_reads, k, d_stats + 32); ctx->launches++; }
+    unsigned long long h[3];
+    CK (cudaMemcpyAsync (h, d_stats + 32, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    *total_kmers = h[0]; *total_nt = h[1]; *max_len = h[2];
+    return 0;
+}
 
-    // ---- device binning geometry ----
+// ---- geometry of the device binning: must be identical on every rank of a multi-GPU run ----------------------------
+static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t total_kmers, uint64_t n_reads, int n_ranks, gatb_gpu_geometry* g)
+{
+    const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
     const int table_log2 = p->table_log2 > 0 ? p->table_log2 : 11;
     if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
+    if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_SOURCES) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_SOURCES);
     const uint64_t T = 1ULL << table_log2;
     const uint64_t occ_per_bin = (T * 55) / 100;
     const int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
     uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
     uint64_t nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits; if (nb1 < 1) nb1 = 1;
-    if (nb1 > (1ULL << 24)) return fail (ctx, "input too large for one device (%llu coarse bins)", (unsigned long long)nb1);
-    const uint64_t nbins = nb1 << fine_bits;
-    const int mg = pick_device_m (k, nbins);
+    nb1 = (nb1 + n_ranks - 1) / n_ranks * n_ranks;                              // every rank owns nb1/n_ranks consecutive coarse bins
+    if (nb1 > (1ULL << 24)) return fail (ctx, "input too large (%llu coarse bins)", (unsigned long long)nb1);
+    const int mg = pick_device_m (k, nb1 << fine_bits);
     const int w = k - mg + 1;
-    const int maxlen = (W == 1) ? 28 : 60;                                      // Sequence2SuperKmer.hpp:147
-    double est_records = (double)total_kmers * 2.0 / (w + 1) * 1.10 + (double)n_reads * 0.5 + 64;
+    // records a rank produces for one coarse bin ~ (its k-mers * 2/(w+1)) / nb1
+    double local_kmers = (double)total_kmers / n_ranks, local_reads = (double)n_reads / n_ranks;
+    double est_records = local_kmers * 2.0 / (w + 1) * 1.10 + local_reads * 0.5 + 64;
     uint64_t cap = (uint64_t)(est_records / nb1 * 1.30) + 64; cap = (cap + 7) & ~7ULL;
-    const size_t rec_bytes = 16 * W;
+    memset (g, 0, sizeof(*g));
+    g->total_kmers = total_kmers; g->nb1 = (uint32_t)nb1; g->cap = (uint32_t)cap; g->fine_bits = fine_bits; g->table_log2 = table_log2;
+    g->m_device = mg; g->w = w; g->maxlen = (W == 1) ? 28 : 60; g->words = W;                  // maxlen: Sequence2SuperKmer.hpp:147
+    g->n_ranks = n_ranks; g->bins_per_rank = (uint32_t)(nb1 / n_ranks); g->record_bytes = 16 * W;
+    return 0;
+}
 
+// ---- stage 1: k1 into caller-provided buffers (no retry here).  h_stats: valid, invalid, stored, dropped ------------
+static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
+                           const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
+                           void* d_bins, uint32_t* d_cursors, uint32_t* d_fine_counts, unsigned long long* h_stats)
+{
+    LaunchCtx L = lctx (ctx);
+    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
+    unsigned long long* d_stats = (unsigned long long*)ctx->slot[S_STATS];
+    const uint64_t nbins = (uint64_t)g->nb1 << g->fine_bits;
+    if ((uint64_t)g->cap * g->nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %u x %u bins)", g->cap, g->nb1);
     K1Params k1; memset (&k1, 0, sizeof(k1));
     k1.words = (const uint64_t*)d_reads; k1.offsets = d_offsets; k1.nmask = d_nmask; k1.n_reads = n_reads; k1.read_len = p->read_len;
-    k1.k = k; k1.m = mg; k1.w = w; k1.maxlen = maxlen;
-    k1.mmask = (mg >= 16) ? 0xFFFFFFFFu : ((1u << (2*mg)) - 1); k1.mask_ma1 = 0;
-    k1.mode = K1_MODE_DEVICE; k1.nb1 = (uint32_t)nb1; k1.fine_bits = fine_bits; k1.count_only = 0;
+    k1.k = p->kmer_size; k1.m = g->m_device; k1.w = g->w; k1.maxlen = g->maxlen;
+    k1.mmask = (g->m_device >= 16) ? 0xFFFFFFFFu : ((1u << (2 * g->m_device)) - 1); k1.mask_ma1 = 0;
+    k1.mode = K1_MODE_DEVICE; k1.nb1 = g->nb1; k1.fine_bits = g->fine_bits; k1.count_only = 0;
+    k1.bins = d_bins; k1.cap = g->cap; k1.cursors = d_cursors; k1.fine_counts = d_fine_counts; k1.stats = d_stats;
+    CK (cudaMemsetAsync (d_cursors, 0, (size_t)g->nb1 * 4, ctx->stream));
+    CK (cudaMemsetAsync (d_fine_counts, 0, nbins * 4, ctx->stream));
+    CK (cudaMemsetAsync (d_stats, 0, 4 * 8, ctx->stream));
+    cudaEventRecord (ctx->kev[0], ctx->stream);
+    if (n_reads) CK (launch_k1 (L, k1));
+    cudaEventRecord (ctx->kev[1], ctx->stream);
+    CK (cudaMemcpyAsync (h_stats, d_stats, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    return 0;
+}
 
-    if (ensure (ctx, S_CURSORS, nb1 * 4)) return 1;
-    if (ensure (ctx, S_FINECNT, nbins * 4)) return 1;
+// ---- stages 2-4: fine split of nb1_local coarse bins gathered from n_src sources, count, partition id + sort --------
+static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
+                            const void* const* d_src_bins, const uint32_t* const* d_src_cursors, const uint32_t* d_fine_counts_total,
+                            uint32_t nb1_local, const uint16_t* repart_host, uint64_t total_kmers_bound, gatb_gpu_result* out)
+{
+    LaunchCtx L = lctx (ctx);
+    const int k = p->kmer_size, W = g->words;
+    const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
+    const int histo_max = p->histo_max, fine_bits = g->fine_bits, table_log2 = g->table_log2;
+    const uint64_t nbins = (uint64_t)nb1_local << fine_bits;
+    const uint32_t cap = g->cap;
+    const size_t rec_bytes = 16 * W;
+    if (n_src < 1 || n_src > GATB_GPU_MAX_SOURCES) return fail (ctx, "n_src must be in [1,%d]", GATB_GPU_MAX_SOURCES);
+
+    // ---- compact layout of the fine-split copy: coarse_off = exclusive scan of the gathered record counts ----
+    if (ensure (ctx, S_TOTCUR, (size_t)nb1_local * 4)) return 1;
+    if (ensure (ctx, S_COARSEOFF, ((size_t)nb1_local + 1) * 8)) return 1;
+    if (ensure (ctx, S_SCAN, scan_scratch_elems (nb1_local > (n_keys << 24) ? nb1_local : (n_keys << 24)) * 8)) return 1;
     if (ensure (ctx, S_BINDESC, nbins * 8)) return 1;
-    uint64_t retries = 0;
-    unsigned long long h_stats[4];
-    for (;;)
-    {
-        if (cap * nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %llu x %llu bins)", (unsigned long long)cap, (unsigned long long)nb1);
-        if (ensure (ctx, S_COARSE, nb1 * cap * rec_bytes)) return 1;
-        k1.bins = ctx->slot[S_COARSE]; k1.cap = (uint32_t)cap;
-        k1.cursors = (uint32_t*)ctx->slot[S_CURSORS]; k1.fine_counts = (uint32_t*)ctx->slot[S_FINECNT]; k1.stats = d_stats;
-        CK (cudaMemsetAsync (k1.cursors, 0, nb1 * 4, ctx->stream));
-        CK (cudaMemsetAsync (k1.fine_counts, 0, nbins * 4, ctx->stream));
-        CK (cudaMemsetAsync (d_stats, 0, 4 * 8, ctx->stream));
-        cudaEventRecord (ctx->kev[0], ctx->stream);
-        if (n_reads) CK (launch_k1 (L, k1));
-        cudaEventRecord (ctx->kev[1], ctx->stream);
-        CK (cudaMemcpyAsync (h_stats, d_stats, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK (cudaStreamSynchronize (ctx->stream));
-        if (h_stats[3] == 0) break;
-        // a bin overflowed: the cursors hold the true demand -> size for the largest and run again
-        std::vector<uint32_t> cur (nb1);
-        CK (cudaMemcpy (cur.data (), k1.cursors, nb1 * 4, cudaMemcpyDeviceToHost));
-        uint32_t mx = 0; for (uint64_t i = 0; i < nb1; i++) if (cur[i] > mx) mx = cur[i];
-        cap = ((uint64_t)mx + 7) & ~7ULL;
-        if (++retries > 3) return fail (ctx, "partition kernel still overflows after %llu retries", (unsigned long long)retries);
-    }
+    CursorList CL; CL.n = n_src; for (int s = 0; s < n_src; s++) CL.cur[s] = d_src_cursors[s];
+    k_sum_cursors<<<(nb1_local + 255) / 256, 256, 0, ctx->stream>>> (CL, nb1_local, cap, (uint32_t*)ctx->slot[S_TOTCUR]); ctx->launches++;
+    CK (launch_scan_u32_to_u64 (L, (const uint32_t*)ctx->slot[S_TOTCUR], (uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, (uint64_t*)ctx->slot[S_SCAN]));
+    uint64_t n_records = 0;
+    CK (cudaMemcpyAsync (&n_records, (const uint64_t*)ctx->slot[S_COARSEOFF] + nb1_local, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
     cudaEventRecord (ctx->ev[2], ctx->stream);
 
     // ---- k2a: fine split ----
-    if (ensure (ctx, S_FINE, nb1 * cap * rec_bytes)) return 1;
+    if (ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
+    K2aSrc S2; S2.n = n_src; for (int s = 0; s < n_src; s++) { S2.bins[s] = (const uint4*)d_src_bins[s]; S2.cursors[s] = d_src_cursors[s]; }
     cudaEventRecord (ctx->kev[2], ctx->stream);
-    CK (launch_k2a_split (L, W, ctx->slot[S_COARSE], ctx->slot[S_FINE], k1.cursors, k1.fine_counts, (uint32_t)nb1, (uint32_t)cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
+    CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], d_fine_counts_total, nb1_local, cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
     cudaEventRecord (ctx->kev[3], ctx->stream);
     cudaEventRecord (ctx->ev[3], ctx->stream);
 
-    // ---- k2b: count.  The coarse buffer is dead now: it becomes the unsorted output. ----
+    // ---- k2b: count.  When the single source is the context's own coarse buffer it is dead now and becomes the output. ----
     const uint32_t amin = p->abundance_min < 1 ? 1 : (uint32_t)p->abundance_min;
     const uint32_t amax = p->abundance_max < 0 ? 0x7fffffffu : (uint32_t)p->abundance_max;
     const uint32_t emin = p->emit_all ? 1u : amin, emax = p->emit_all ? 0xffffffffu : amax;
-    uint64_t out_bound = total_kmers / emin + 1;                               // a k-mer emitted needs >= emin occurrences
+    const int S_OUT = (n_src == 1 && d_src_bins[0] == ctx->slot[S_COARSE]) ? S_COARSE : S_UNSORTED;
+    uint64_t out_bound = total_kmers_bound / emin + 1;                         // a k-mer emitted needs >= emin occurrences
     const size_t item_bytes = 8 * W + 4;
-    uint64_t out_cap = ctx->slot_cap[S_COARSE] / item_bytes;
-    { uint64_t guess = total_kmers / 3 + 4096; if (out_cap < guess) out_cap = guess; }
+    const uint64_t block_slack = (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;  // every warp of k2b reserves output in blocks of 2048 slots
+    uint64_t out_cap = ctx->slot_cap[S_OUT] / item_bytes;
+    { uint64_t guess = total_kmers_bound / 3 + 4096; if (out_cap < guess) out_cap = guess; }
     if (out_cap > out_bound) out_cap = out_bound;
-    out_cap += (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;     // every warp of k2b reserves output in blocks of 2048 slots
+    out_cap += block_slack;
 
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
     if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
@@ -299,15 +333,15 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     K2Params k2;
     for (int attempt = 0; ; attempt++)
     {
-        if (ensure (ctx, S_COARSE, out_cap * item_bytes)) return 1;
-        u_lo = (uint64_t*)ctx->slot[S_COARSE];
+        if (ensure (ctx, S_OUT, out_cap * item_bytes)) return 1;
+        u_lo = (uint64_t*)ctx->slot[S_OUT];
         u_hi = (W == 2) ? u_lo + out_cap : 0;
         u_cnt = (uint32_t*)(u_lo + out_cap * W);
         CK (cudaMemsetAsync (ctx->slot[S_HISTO], 0, (size_t)(histo_max + 1) * 8, ctx->stream));
         CK (cudaMemsetAsync (d_cnt, 0, 16 * 8, ctx->stream));
         memset (&k2, 0, sizeof(k2));
         k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins;
-        k2.cap = (uint32_t)cap; k2.fine_bits = fine_bits; k2.table_log2 = table_log2;
+        k2.coarse_off = (const uint64_t*)ctx->slot[S_COARSEOFF]; k2.fine_bits = fine_bits; k2.table_log2 = table_log2;
         k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
         k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
         k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
@@ -338,7 +372,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         }
         if (h_cnt[0] <= out_cap) break;
         if (attempt >= 1) return fail (ctx, "output capacity exceeded: %llu k-mers to emit, room for %llu", (unsigned long long)h_cnt[0], (unsigned long long)out_cap);
-        out_cap = h_cnt[0] + (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;   // the cursor kept counting: it bounds the demand -> count again
+        out_cap = h_cnt[0] + block_slack;                     // the cursor kept counting: it bounds the demand -> count again
     }
     const uint64_t n_items = h_cnt[6];          // k-mers emitted
     const uint64_t n_range = h_cnt[0];          // extent of the unsorted array (block reservations leave EMPTY holes)
@@ -403,7 +437,6 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         CK (cudaStreamSynchronize (ctx->stream));
         CK (cudaMemcpyAsync (d_offs, offs.data (), (n_keys + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK (cudaMemcpyAsync (d_hist, ctx->slot[S_HISTO], (size_t)(histo_max + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        CK (cudaStreamSynchronize (ctx->stream));
     }
     cudaEventRecord (ctx->ev[5], ctx->stream);
     CK (cudaStreamSynchronize (ctx->stream));
@@ -413,18 +446,55 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     out->n_keys = n_keys; out->n_items = n_items; out->on_device = 1; out->owner = dr;
     out->part_offsets = (uint64_t*)dr->offs; out->kmers_lo = (uint64_t*)dr->lo; out->kmers_hi = (uint64_t*)dr->hi;
     out->counts = (int32_t*)dr->cnt; out->histogram = (uint64_t*)dr->histo;
-    out->stats[GATB_STAT_KMERS_VALID] = h_stats[0]; out->stats[GATB_STAT_KMERS_INVALID] = h_stats[1];
     out->stats[GATB_STAT_DISTINCT] = h_cnt[1]; out->stats[GATB_STAT_SOLID] = h_cnt[2];
-    out->stats[GATB_STAT_RECORDS] = h_stats[2]; out->stats[GATB_STAT_SEQUENCES] = n_reads; out->stats[GATB_STAT_NUCLEOTIDES] = total_nt;
-    out->stats[GATB_STAT_BINS] = nbins; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf; out->stats[GATB_STAT_RETRIES] = retries;
-    out->stats[GATB_STAT_RECORD_BYTES] = h_stats[2] * rec_bytes;
+    out->stats[GATB_STAT_RECORDS] = n_records; out->stats[GATB_STAT_BINS] = nbins; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf;
+    out->stats[GATB_STAT_RECORD_BYTES] = n_records * rec_bytes;
     float ms;
-    cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[2]); out->seconds[1] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[2], ctx->ev[3]); out->seconds[2] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[3], ctx->ev[4]); out->seconds[3] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[4], ctx->ev[5]); out->seconds[4] = ms * 1e-3;
+    for (int i = 1; i < 4; i++) { cudaEventElapsedTime (&ms, ctx->kev[2*i], ctx->kev[2*i+1]); out->kernel_seconds[i] = ms * 1e-3; }
+    return 0;
+}
+
+static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_host,
+                           const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
+                           gatb_gpu_result* out)
+{
+    cudaEventRecord (ctx->ev[1], ctx->stream);
+    uint64_t total_kmers = 0, total_nt = 0, max_len = 0;
+    if (workload_size (ctx, p, d_offsets, n_reads, &total_kmers, &total_nt, &max_len)) return 1;
+    if (max_len >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported by the partition kernel yet (longest: %llu)", (unsigned long long)max_len);
+    gatb_gpu_geometry g;
+    if (plan_geometry (ctx, p, total_kmers, n_reads, 1, &g)) return 1;
+    const uint64_t nbins = (uint64_t)g.nb1 << g.fine_bits;
+    if (ensure (ctx, S_CURSORS, (size_t)g.nb1 * 4)) return 1;
+    if (ensure (ctx, S_FINECNT, nbins * 4)) return 1;
+    uint64_t retries = 0;
+    unsigned long long h_stats[4];
+    for (;;)
+    {
+        if ((uint64_t)g.cap * g.nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %u x %u bins)", g.cap, g.nb1);
+        if (ensure (ctx, S_COARSE, (size_t)g.nb1 * g.cap * g.record_bytes)) return 1;
+        if (partition_impl (ctx, p, &g, d_reads, d_offsets, n_reads, d_nmask, ctx->slot[S_COARSE], (uint32_t*)ctx->slot[S_CURSORS],
+                            (uint32_t*)ctx->slot[S_FINECNT], h_stats)) return 1;
+        if (h_stats[3] == 0) break;
+        // a bin overflowed: the cursors hold the true demand -> size for the largest and run again
+        std::vector<uint32_t> cur (g.nb1);
+        CK (cudaMemcpy (cur.data (), ctx->slot[S_CURSORS], (size_t)g.nb1 * 4, cudaMemcpyDeviceToHost));
+        uint32_t mx = 0; for (uint64_t i = 0; i < g.nb1; i++) if (cur[i] > mx) mx = cur[i];
+        g.cap = (uint32_t)(((uint64_t)mx + 7) & ~7ULL);
+        if (++retries > 3) return fail (ctx, "partition kernel still overflows after %llu retries", (unsigned long long)retries);
+    }
+    const void* src_bins[1] = { ctx->slot[S_COARSE] };
+    const uint32_t* src_cur[1] = { (const uint32_t*)ctx->slot[S_CURSORS] };
+    if (count_bins_impl (ctx, p, &g, 1, src_bins, src_cur, (const uint32_t*)ctx->slot[S_FINECNT], g.nb1, repart_host, total_kmers, out)) return 1;
+    out->stats[GATB_STAT_KMERS_VALID] = h_stats[0]; out->stats[GATB_STAT_KMERS_INVALID] = h_stats[1];
+    out->stats[GATB_STAT_SEQUENCES] = n_reads; out->stats[GATB_STAT_NUCLEOTIDES] = total_nt; out->stats[GATB_STAT_RETRIES] = retries;
+    float ms;
+    cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[2]); out->seconds[1] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[5]); out->seconds[6] = ms * 1e-3;
-    for (int i = 0; i < 4; i++) { cudaEventElapsedTime (&ms, ctx->kev[2*i], ctx->kev[2*i+1]); out->kernel_seconds[i] = ms * 1e-3; }
+    cudaEventElapsedTime (&ms, ctx->kev[0], ctx->kev[1]); out->kernel_seconds[0] = ms * 1e-3;
     return 0;
 }
 
@@ -440,6 +510,39 @@ int gatb_gpu_count_dev (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint1
     if (check_params (ctx, p, repart_table)) return 1;
     (void)freq_order;
     return count_dev_impl (ctx, p, repart_table, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, out);
+}
+
+// ---- staged entry points for multi-GPU runs (one process per GPU; the exchange between the stages is the caller's) ----
+int gatb_gpu_plan (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t total_kmers, uint64_t n_reads, int n_ranks, gatb_gpu_geometry* g)
+{
+    if (!ctx) return 1;
+    if (check_params (ctx, p, (const uint16_t*)1)) return 1;
+    return plan_geometry (ctx, p, total_kmers, n_reads, n_ranks, g);
+}
+int gatb_gpu_partition_into (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
+                             const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads, const uint32_t* d_n_mask,
+                             void* d_bins, uint32_t* d_cursors, uint32_t* d_fine_counts, uint64_t* stats4)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (check_params (ctx, p, (const uint16_t*)1)) return 1;
+    unsigned long long h[4];
+    if (partition_impl (ctx, p, g, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, d_bins, d_cursors, d_fine_counts, h)) return 1;
+    for (int i = 0; i < 4; i++) stats4[i] = h[i];
+    return 0;
+}
+int gatb_gpu_count_bins (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
+                         const void* const* d_src_bins, const uint32_t* const* d_src_cursors, const uint32_t* d_fine_counts_total,
+                         uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, gatb_gpu_result* out)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (!out) return fail (ctx, "out is NULL");
+    if (check_params (ctx, p, repart_table)) return 1;
+    cudaEventRecord (ctx->ev[1], ctx->stream);
+    if (count_bins_impl (ctx, p, g, n_src, d_src_bins, d_src_cursors, d_fine_counts_total, nb1_local, repart_table, kmers_bound, out)) return 1;
+    float ms; cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[5]); out->seconds[6] = ms * 1e-3;
+    return 0;
 }
 
 void gatb_gpu_result_free (gatb_gpu_ctx* ctx, gatb_gpu_result* r)

@@ -41,15 +41,14 @@ __device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.prox
 
 // ------------------------------------------------------------------------------------------------ k2a
 template<int W>
-__global__ void __launch_bounds__(256) k2a_fine_split (const uint4* __restrict__ src, uint4* __restrict__ dst,
-                                                        const uint32_t* __restrict__ cursors, const uint32_t* __restrict__ fine_counts,
-                                                        uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc)
+__global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __restrict__ dst, const uint64_t* __restrict__ coarse_off,
+                                                        const uint32_t* __restrict__ fine_counts, uint32_t cap, int fine_bits,
+                                                        uint2* __restrict__ bin_desc)
 {
     __shared__ uint32_t s_off[128], s_cur[128], s_tmp[128];
     const uint32_t b = blockIdx.x;
     const int nf = 1 << fine_bits;
     const int tid = threadIdx.x;
-    uint32_t n = min (cursors[b], cap);
     if (tid < nf) { s_tmp[tid] = fine_counts[((uint64_t)b << fine_bits) + tid]; s_cur[tid] = 0; }
     __syncthreads ();
     if (tid < 32)
@@ -65,32 +64,37 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const uint4* __restrict__
         for (int i=0; i<4; i++) { int idx = tid*4 + i; if (idx < nf) { s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v[i]); } run += v[i]; }
     }
     __syncthreads ();
-    const uint64_t base = (uint64_t)b * cap;
-    for (uint32_t i = tid; i < n; i += blockDim.x)
+    const uint64_t dbase = coarse_off[b];
+    for (int s = 0; s < S.n; s++)
     {
-        if (W == 1)
+        const uint32_t n = min (S.cursors[s][b], cap);
+        const uint4* __restrict__ src = S.bins[s] + (uint64_t)b * cap * W;
+        for (uint32_t i = tid; i < n; i += blockDim.x)
         {
-            uint4 rec = __ldg (&src[base + i]);
-            uint32_t f = rec.w >> (32 - FINE_BITS_W1);
-            uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
-            dst[base + p] = rec;
-        }
-        else
-        {
-            uint4 r0 = __ldg (&src[2*(base + i)]), r1 = __ldg (&src[2*(base + i) + 1]);
-            uint32_t f = r1.w >> (32 - FINE_BITS_W2);
-            uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
-            dst[2*(base + p)] = r0; dst[2*(base + p) + 1] = r1;
+            if (W == 1)
+            {
+                uint4 rec = __ldg (&src[i]);
+                uint32_t f = rec.w >> (32 - FINE_BITS_W1);
+                uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+                dst[dbase + p] = rec;
+            }
+            else
+            {
+                uint4 r0 = __ldg (&src[2*(uint64_t)i]), r1 = __ldg (&src[2*(uint64_t)i + 1]);
+                uint32_t f = r1.w >> (32 - FINE_BITS_W2);
+                uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+                dst[2*(dbase + p)] = r0; dst[2*(dbase + p) + 1] = r1;
+            }
         }
     }
 }
 
-cudaError_t launch_k2a_split (const LaunchCtx& L, int W, const void* src, void* dst, const uint32_t* cursors,
+cudaError_t launch_k2a_split (const LaunchCtx& L, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
                               const uint32_t* fine_counts, uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc)
 {
     if (nb1 == 0) return cudaSuccess;
-    if (W == 1) k2a_fine_split<1><<<nb1, 256, 0, L.stream>>> ((const uint4*)src, (uint4*)dst, cursors, fine_counts, cap, fine_bits, bin_desc);
-    else        k2a_fine_split<2><<<nb1, 256, 0, L.stream>>> ((const uint4*)src, (uint4*)dst, cursors, fine_counts, cap, fine_bits, bin_desc);
+    if (W == 1) k2a_fine_split<1><<<nb1, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, fine_counts, cap, fine_bits, bin_desc);
+    else        k2a_fine_split<2><<<nb1, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, fine_counts, cap, fine_bits, bin_desc);
     (*L.launches)++;
     return cudaGetLastError ();
 }
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
         s_bin[st] = bin; s_nocc[st] = 0;
         if (bin < P.nbins)
         {
-            const unsigned long long base = ((unsigned long long)(bin >> P.fine_bits) * P.cap + d.x);
+            const unsigned long long base = P.coarse_off[bin >> P.fine_bits] + d.x;
             s_n[st] = d.y; s_base[st] = base;
             const uint32_t mrec = min ((uint32_t)CHR, d.y);
             fence_proxy_async ();
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(256) k2c_measure (const K2Params P, uint32_t n
     {
         const uint32_t bin = P.ovf_list[o];
         const uint2 d = P.bin_desc[bin];
-        const uint4* base = (const uint4*)P.recs + ((uint64_t)(bin >> P.fine_bits) * P.cap + d.x) * W;
+        const uint4* base = (const uint4*)P.recs + (P.coarse_off[bin >> P.fine_bits] + d.x) * W;
         for (uint32_t i = threadIdx.x; i < d.y; i += blockDim.x)
         {
             uint4 last = __ldg (&base[(uint64_t)i * W + (W - 1)]);
@@ -517,7 +521,7 @@ __global__ void __launch_bounds__(256) k2c_insert (const K2Params P, uint32_t n_
     {
         const uint32_t bin = P.ovf_list[o];
         const uint2 d = P.bin_desc[bin];
-        const uint4* base = (const uint4*)P.recs + ((uint64_t)(bin >> P.fine_bits) * P.cap + d.x) * W;
+        const uint4* base = (const uint4*)P.recs + (P.coarse_off[bin >> P.fine_bits] + d.x) * W;
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.y; i += gridDim.x * blockDim.x)
         {
             if (W == 1)

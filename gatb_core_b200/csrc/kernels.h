@@ -46,7 +46,8 @@ struct K2Params
     const void* recs;               // fine-split records
     const uint2* bin_desc;          // [nbins] {offset inside coarse region, record count}
     uint32_t nbins;                 // nb1 << fine_bits
-    uint32_t cap; int fine_bits;
+    const uint64_t* coarse_off;     // [nb1+1] first record of each coarse bin in the fine-split copy
+    int fine_bits;
     int      table_log2;            // log2 slots of the shared-memory table
     uint32_t emit_min, emit_max;    // emit k-mers with emit_min <= count <= emit_max
     uint32_t solid_min, solid_max;  // solidity range (stats only)
@@ -82,7 +83,8 @@ struct LaunchCtx { cudaStream_t stream; int sm_count; uint64_t* launches; };
 // k1_partition.cu
 cudaError_t launch_k1 (const LaunchCtx&, const K1Params&);
 // k2_count.cu
-cudaError_t launch_k2a_split (const LaunchCtx&, int W, const void* src, void* dst, const uint32_t* cursors,
+struct K2aSrc { const uint4* bins[8]; const uint32_t* cursors[8]; int n; };     // the same coarse bins gathered from n sources
+cudaError_t launch_k2a_split (const LaunchCtx&, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
                               const uint32_t* fine_counts, uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc);
 cudaError_t launch_k2b_count (const LaunchCtx&, const K2Params&);
 cudaError_t launch_k2c_measure (const LaunchCtx&, const K2Params&, uint32_t n_ovf);

@@ -58,7 +58,7 @@ typedef struct gatb_gpu_params
     int32_t  reserved[5];
 } gatb_gpu_params;
 
-enum { GATB_GPU_NSTATS = 16 };
+enum { GATB_GPU_NSTATS = 16, GATB_GPU_MAX_SOURCES = 8 };
 /* indices into gatb_gpu_result.stats */
 enum {
     GATB_STAT_KMERS_VALID = 0,   /* kmers_nb_valid   (SortingCountAlgorithm.cpp:737)   */
@@ -112,6 +112,33 @@ int gatb_gpu_count_dev (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* r
                         const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads,
                         const uint32_t* d_n_mask, gatb_gpu_result* out);
 void gatb_gpu_result_free (gatb_gpu_ctx*, gatb_gpu_result*);
+
+/* ---- the same path in stages, for multi-GPU runs (one process per GPU) -------------------------------------------
+ * The device binning: every rank partitions ITS reads into nb1 coarse bins with the SAME geometry;
+ * coarse bin b is owned by rank b / bins_per_rank; the caller moves each bin region to its owner (one all-to-all of
+ * [bins_per_rank][cap] records + cursors + fine counters) and the owner counts the bins it gathered from all sources.
+ * Replaces the reference's only exchange medium, the SuperKmerBinFiles temp files (tools/storage/impl/Storage.cpp:310-347). */
+typedef struct gatb_gpu_geometry
+{
+    uint64_t total_kmers;       /* k-mer positions of the WHOLE job (all ranks)                                          */
+    uint32_t nb1;               /* coarse bins (multiple of n_ranks)                                                     */
+    uint32_t cap;               /* record slots per coarse bin in a rank's partition buffer                              */
+    int32_t  fine_bits;         /* fine bins per coarse bin = 1 << fine_bits                                             */
+    int32_t  table_log2;
+    int32_t  m_device, w, maxlen, words;
+    uint32_t n_ranks, bins_per_rank, record_bytes, pad;
+} gatb_gpu_geometry;
+int gatb_gpu_plan (gatb_gpu_ctx*, const gatb_gpu_params*, uint64_t total_kmers, uint64_t n_reads, int n_ranks, gatb_gpu_geometry* out);
+/* k1 into caller buffers: d_bins [nb1*cap records], d_cursors [nb1] (demand; > cap means overflow), d_fine_counts
+ * [nb1 << fine_bits]; stats4 (host): valid k-mers, invalid k-mers, records stored, records dropped. */
+int gatb_gpu_partition_into (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_geometry*,
+                             const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads, const uint32_t* d_n_mask,
+                             void* d_bins, uint32_t* d_cursors, uint32_t* d_fine_counts, uint64_t* stats4);
+/* counts nb1_local coarse bins gathered from n_src sources: d_src_bins[s] = [nb1_local*cap records], d_src_cursors[s] =
+ * [nb1_local]; d_fine_counts_total = [nb1_local << fine_bits] summed over the sources; kmers_bound >= k-mers in these bins. */
+int gatb_gpu_count_bins (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_geometry*, int n_src,
+                         const void* const* d_src_bins, const uint32_t* const* d_src_cursors, const uint32_t* d_fine_counts_total,
+                         uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, gatb_gpu_result* out);
 
 /* ---- GATB-exact super-k-mer partitioning (rows A3-A6): per key, the record stream [u8 nbK][packed bytes]... that
  *      the reference writes to its SuperKmerBinFiles (order of records inside a key is unspecified).

@@ -238,3 +238,28 @@ def test_device_resident_api_and_size_independent_properties(gpu, oracle):
 def test_smoke_entry(gpu):
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_staged_multi_gpu_path_on_one_rank(gpu, oracle):
+    # the staged entry points (plan / partition_into / exchange / count_bins) with world = 1 must equal the one-shot call
+    import torch
+    from gatb_core_b200 import multigpu
+    fx = fixtures.Fixture("dsk_k31_parts", oracle)
+    packed, offs, mask = pack_seqs(oracle, fx.seqs)
+    if mask is not None:                                      # staged path without the N mask: use clean reads
+        seqs = [s.replace(b"N", b"A") for s in fx.seqs]
+        packed, offs, mask = pack_seqs(oracle, seqs)
+    else:
+        seqs = fx.seqs
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, abundance_min=2)
+    want = gpu.count(packed, offs, len(seqs), params, repart=fx.repart)
+    d_reads = torch.from_numpy(packed).cuda()
+    d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+    total_kmers = sum(max(len(s) - fx.k + 1, 0) for s in seqs)
+    res, stats = multigpu.count_distributed(gpu, params, d_reads.data_ptr(), len(seqs), len(seqs), total_kmers, 0, 1,
+                                            repart=fx.repart, d_offsets=d_offs.data_ptr())
+    got = gpu.result_to_host(res, params)
+    gpu.result_free(res)
+    check_parts(got, want["parts"], fx.nb_partitions, 1)
+    assert (got["histogram"] == want["histogram"]).all()
+    assert stats["kmers_nb_distinct"] == want["stats"]["kmers_nb_distinct"]

@@ -1,0 +1,84 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo processes exercise the all-to-all plumbing
+(gatb_core_b200.multigpu.exchange_bins) and the merge of per-rank sorted runs.  No CUDA kernels run here."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gatb_core_b200 import multigpu
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bpr, cap, rb, fb = 3, 4, 16, 2
+        nb1 = bpr * world
+        # record (b, i) of source `rank` carries the bytes [rank, b, i, 0...]
+        bins = torch.zeros(nb1, cap, rb, dtype=torch.uint8)
+        for b in range(nb1):
+            for i in range(cap):
+                bins[b, i, 0], bins[b, i, 1], bins[b, i, 2] = rank, b, i
+        cursors = torch.tensor([(b + rank) % (cap + 1) for b in range(nb1)], dtype=torch.int32)
+        fine = torch.arange(nb1 << fb, dtype=torch.int32) * (rank + 1)
+        rbins, rcur, rfine = multigpu.exchange_bins(bins.view(-1), cursors, fine, world)
+        ok = rbins.shape == (world, bpr * cap * rb) and rcur.shape == (world, bpr) and rfine.shape == (world, bpr << fb)
+        for s in range(world):
+            piece = rbins[s].view(bpr, cap, rb)
+            for lb in range(bpr):
+                gb = rank * bpr + lb                                  # global id of the bin this rank owns
+                assert multigpu.owner_of_bin(gb, bpr) == rank
+                ok &= bool((piece[lb, :, 0] == s).all() and (piece[lb, :, 1] == gb).all())
+                ok &= int(rcur[s, lb]) == (gb + s) % (cap + 1)
+            want_fine = torch.arange(nb1 << fb, dtype=torch.int32).view(world, -1)[rank] * (s + 1)
+            ok &= bool((rfine[s] == want_fine).all())
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_bins_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_exchange_bins_world1_is_identity():
+    bins = torch.arange(4 * 3 * 16, dtype=torch.uint8)
+    cur = torch.tensor([1, 2, 3, 0], dtype=torch.int32)
+    fine = torch.arange(16, dtype=torch.int32)
+    a, b, c = multigpu.exchange_bins(bins, cur, fine, 1)
+    assert (a.view(-1) == bins).all() and (b.view(-1) == cur).all() and (c.view(-1) == fine).all()
+
+
+def test_merge_sorted_runs():
+    rng = np.random.default_rng(0)
+    full = np.unique(rng.integers(0, 2 ** 62, 5000, dtype=np.uint64))
+    hi = rng.integers(0, 4, len(full)).astype(np.uint64)
+    order = np.lexsort((full, hi))
+    full, hi = full[order], hi[order]
+    cn = rng.integers(1, 100, len(full)).astype(np.int32)
+    owner = rng.integers(0, 3, len(full))
+    runs = [(full[owner == r], hi[owner == r], cn[owner == r]) for r in range(3)]
+    lo2, hi2, cn2 = multigpu.merge_sorted_runs(runs)
+    assert (lo2 == full).all() and (hi2 == hi).all() and (cn2 == cn).all()
