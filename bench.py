@@ -159,8 +159,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if world > 1:
+    if world > 1 or args.staged:
         from gatb_core_b200 import multigpu
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
         return multigpu.bench(args, rank, world, local)
 
     gpu = gatb_core_b200.GatbGpu(local)
@@ -286,6 +290,7 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=1_000_000, help="reads per step of the reference arm")
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--staged", action="store_true", help="N=1 through the staged multi-GPU code path (debugging aid)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

@@ -17,7 +17,7 @@ static std::string g_create_error;
 
 // device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
 enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_FINECNT, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
-            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_NSLOTS };
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_NSLOTS };
 
 struct gatb_gpu_ctx
 {
@@ -383,14 +383,14 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     { uint64_t per_key = n_items / n_keys + 1; while (t_bits < 2*k && t_bits < 24 && (per_key >> t_bits) > 1024) t_bits++; }
     while (t_bits > 0 && (n_keys << t_bits) > (1ULL << 30)) t_bits--;
     const uint64_t n_buckets = n_keys << t_bits;
-    DevResult* dr = new DevResult (); memset (dr, 0, sizeof(*dr));
+    // result arrays live in context-owned slots (valid until the next count on this context): no per-call cudaMalloc
+    DevResult drs; DevResult* dr = &drs; memset (dr, 0, sizeof(*dr));
     uint64_t n_alloc = n_items ? n_items : 1;
-    void* d_sorted = 0;
-    { cudaError_t e = cudaMalloc (&d_sorted, n_alloc * item_bytes + 64); if (e != cudaSuccess) { delete dr; return fail (ctx, "cudaMalloc of the result arrays (%llu items) failed: %s", (unsigned long long)n_items, cudaGetErrorString (e)); } }
+    if (ensure (ctx, S_SORTED, n_alloc * item_bytes + 64)) return 1;
+    if (ensure (ctx, S_RESMISC, (n_keys + 1) * 8 + (size_t)(histo_max + 1) * 8 + 64)) return 1;
+    void* d_sorted = ctx->slot[S_SORTED];
     dr->lo = d_sorted; dr->hi = (W == 2) ? (void*)((uint64_t*)d_sorted + n_alloc) : 0; dr->cnt = (void*)((uint64_t*)d_sorted + n_alloc * W);
-    void* d_offs = 0; void* d_hist = 0;
-    if (cudaMalloc (&d_offs, (n_keys + 1) * 8) != cudaSuccess || cudaMalloc (&d_hist, (size_t)(histo_max + 1) * 8) != cudaSuccess)
-    { cudaFree (d_sorted); delete dr; return fail (ctx, "cudaMalloc of the result tables failed"); }
+    void* d_offs = ctx->slot[S_RESMISC]; void* d_hist = (void*)((uint64_t*)ctx->slot[S_RESMISC] + (n_keys + 1));
     dr->offs = d_offs; dr->histo = d_hist;
 
     if (ensure (ctx, S_BUCKETOF, (n_range + 1) * 4)) return 1;
@@ -443,7 +443,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
 
     // ---- result ----
     memset (out, 0, sizeof(*out));
-    out->n_keys = n_keys; out->n_items = n_items; out->on_device = 1; out->owner = dr;
+    out->n_keys = n_keys; out->n_items = n_items; out->on_device = 1; out->owner = 0;
     out->part_offsets = (uint64_t*)dr->offs; out->kmers_lo = (uint64_t*)dr->lo; out->kmers_hi = (uint64_t*)dr->hi;
     out->counts = (int32_t*)dr->cnt; out->histogram = (uint64_t*)dr->histo;
     out->stats[GATB_STAT_DISTINCT] = h_cnt[1]; out->stats[GATB_STAT_SOLID] = h_cnt[2];
@@ -549,15 +549,8 @@ void gatb_gpu_result_free (gatb_gpu_ctx* ctx, gatb_gpu_result* r)
 {
     if (!r) return;
     if (ctx) cudaSetDevice (ctx->device);
-    if (r->on_device)
-    {
-        DevResult* dr = (DevResult*)r->owner;
-        if (dr) { cudaFree (dr->lo); cudaFree (dr->offs); cudaFree (dr->histo); delete dr; }
-    }
-    else
-    {
-        /* host arrays point into the context's pinned staging buffer: nothing to free */
-    }
+    /* device arrays live in context slots, host arrays in the context's pinned staging buffer: nothing to free;
+       both stay valid until the next count on the same context */
     memset (r, 0, sizeof(*r));
 }
 

@@ -88,10 +88,17 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
     src_bins = [recv_bins[s].data_ptr() for s in range(world)]
     src_cur = [recv_cur[s].data_ptr() for s in range(world)]
     gathered = int(recv_cur.clamp(max=geom.cap).sum().item())
-    kmers_bound = gathered * geom.maxlen                   # k-mers in the bins this rank owns (upper bound)
+    tot = torch.tensor([st[0], st[2]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    avg_len = float(tot[0].item()) / max(float(tot[1].item()), 1.0)       # k-mers per record, whole job
+    # k-mers in the bins this rank owns: estimate with 25 % head-room, never above the hard bound
+    kmers_bound = int(min(gathered * geom.maxlen, gathered * avg_len * 1.25 + 65536))
     t0 = time.time()
     res = gpu.count_bins(params, geom, src_bins, src_cur, fine_total.data_ptr(), bpr, kmers_bound, repart=repart)
     t["count"] = time.time() - t0
+    t["count_kernels"] = [float(x) for x in res.kernel_seconds][:4]
+    t["count_stages"] = [float(x) for x in res.seconds][:7]
     sums = torch.tensor([st[0], st[1], int(res.stats[2]), int(res.stats[3]), st[2], int(res.n_items)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(sums)
@@ -101,6 +108,34 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
     if timers is not None:
         timers.update(t)
     return res, stats
+
+
+_PINNED = {}
+
+
+def result_to_pinned(gpu, res, params):
+    """Device Result -> pinned host tensors (cached, grow-only) with one copy per array; returns numpy views."""
+    W = 1 if params.kmer_size < 32 else 2
+    n, nk = int(res.n_items), int(res.n_keys)
+
+    def buf(name, count, dtype):
+        t = _PINNED.get(name)
+        if t is None or t.numel() < max(count, 1):
+            t = torch.empty(max(count, 1) + max(count, 1) // 8, dtype=dtype, pin_memory=True)
+            _PINNED[name] = t
+        return t[:count].numpy()
+    out = {"part_offsets": buf("offs", nk + 1, torch.int64), "histogram": buf("hist", params.histo_max + 1, torch.int64),
+           "kmers_lo": buf("lo", n, torch.int64), "counts": buf("cnt", n, torch.int32)}
+    gpu.d2h(out["part_offsets"], res.part_offsets)
+    gpu.d2h(out["histogram"], res.histogram)
+    if n:
+        gpu.d2h(out["kmers_lo"], res.kmers_lo)
+        gpu.d2h(out["counts"], res.counts)
+        if W == 2:
+            out["kmers_hi"] = buf("hi", n, torch.int64)
+            gpu.d2h(out["kmers_hi"], res.kmers_hi)
+    out["n_items"] = n
+    return out
 
 
 def bench(args, rank, world, local):
@@ -157,9 +192,13 @@ def bench(args, rank, world, local):
         t0 = time.time()
         reads.copy_(h_reads, non_blocking=True)
         torch.cuda.synchronize()
+        t1 = time.time()
         res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world)
-        host = gpu.result_to_host(res, params)
+        t2 = time.time()
+        host = result_to_pinned(gpu, res, params)
         gpu.result_free(res)
+        if rank == 0 and os.environ.get("GATB_BENCH_DEBUG"):
+            print("e2e step %d: h2d %.1f ms, count %.1f ms, d2h %.1f ms" % (i, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.time() - t2) * 1e3), file=__import__("sys").stderr)
         d2h_bytes = int(host["n_items"]) * 12 + (10001 + 2) * 8
         el2 = torch.tensor([time.time() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(el2, op=dist.ReduceOp.MAX)

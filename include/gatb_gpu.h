@@ -107,7 +107,7 @@ int           gatb_gpu_sm_count (gatb_gpu_ctx*);
 int gatb_gpu_count (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* repart_table /* [4^m] or NULL when n_keys==1 */,
                     const uint32_t* freq_order /* NULL */, const uint8_t* packed_reads, const uint64_t* read_offsets_nt,
                     uint64_t n_reads, const uint32_t* n_mask, gatb_gpu_result* out);
-/* DEVICE buffers in, DEVICE arrays out (owned by ctx until gatb_gpu_result_free). repart_table is a HOST pointer. */
+/* DEVICE buffers in, DEVICE arrays out (owned by the context, valid until its next count call). repart_table is a HOST pointer. */
 int gatb_gpu_count_dev (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* repart_table, const uint32_t* freq_order,
                         const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads,
                         const uint32_t* d_n_mask, gatb_gpu_result* out);
