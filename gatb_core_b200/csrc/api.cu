@@ -354,6 +354,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         n_ovf = h_cnt[4];
         if (n_ovf)
         {   // ---- k2c: bins that did not fit the shared-memory table share one global table ----
+            cudaEventRecord (ctx->kev[8], ctx->stream);
             CK (launch_k2c_measure (L, k2, (uint32_t)n_ovf));
             CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK (cudaStreamSynchronize (ctx->stream));
@@ -367,6 +368,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
             CK (cudaMemsetAsync (k2.g_cnt, 0, gT * 4, ctx->stream));
             CK (launch_k2c_insert (L, k2, (uint32_t)n_ovf));
             CK (launch_k2c_scan (L, k2));
+            cudaEventRecord (ctx->kev[9], ctx->stream);
             CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK (cudaStreamSynchronize (ctx->stream));
         }
@@ -454,6 +456,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     cudaEventElapsedTime (&ms, ctx->ev[3], ctx->ev[4]); out->seconds[3] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[4], ctx->ev[5]); out->seconds[4] = ms * 1e-3;
     for (int i = 1; i < 4; i++) { cudaEventElapsedTime (&ms, ctx->kev[2*i], ctx->kev[2*i+1]); out->kernel_seconds[i] = ms * 1e-3; }
+    if (n_ovf) { cudaEventElapsedTime (&ms, ctx->kev[8], ctx->kev[9]); out->kernel_seconds[4] = ms * 1e-3; out->stats[11] = h_cnt[5]; }
     return 0;
 }
 

@@ -97,8 +97,11 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
     t0 = time.time()
     res = gpu.count_bins(params, geom, src_bins, src_cur, fine_total.data_ptr(), bpr, kmers_bound, repart=repart)
     t["count"] = time.time() - t0
-    t["count_kernels"] = [float(x) for x in res.kernel_seconds][:4]
+    t["count_kernels"] = [float(x) for x in res.kernel_seconds][:5]
+    t["overflow_kmers"] = int(res.stats[11])
     t["count_stages"] = [float(x) for x in res.seconds][:7]
+    t["overflow_bins"] = int(res.stats[8])
+    t["bins"] = int(res.stats[7])
     sums = torch.tensor([st[0], st[1], int(res.stats[2]), int(res.stats[3]), st[2], int(res.n_items)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(sums)
