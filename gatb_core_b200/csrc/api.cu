@@ -318,10 +318,10 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     uint64_t out_bound = total_kmers_bound / emin + 1;                         // a k-mer emitted needs >= emin occurrences
     const size_t item_bytes = 8 * W + 4;
     const uint64_t block_slack = (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;  // every warp of k2b reserves output in blocks of 2048 slots
-    uint64_t out_cap = ctx->slot_cap[S_OUT] / item_bytes;
-    { uint64_t guess = total_kmers_bound / 3 + 4096; if (out_cap < guess) out_cap = guess; }
+    uint64_t out_cap = total_kmers_bound / 8 + 4096;                           // first guess; the retry below corrects it
     if (out_cap > out_bound) out_cap = out_bound;
     out_cap += block_slack;
+    if (out_cap < ctx->slot_cap[S_OUT] / item_bytes) out_cap = ctx->slot_cap[S_OUT] / item_bytes;   // never shrink: no re-allocation per call
 
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
     if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
