@@ -25,6 +25,7 @@ struct gatb_gpu_ctx
     std::string error;
     void* slot[S_NSLOTS]; size_t slot_cap[S_NSLOTS];
     cudaEvent_t ev[8]; cudaEvent_t kev[16];
+    cudaStream_t copy_stream; cudaEvent_t cev[40];
     void* pinned; size_t pinned_cap;
     const uint16_t* repart_host_cached; uint64_t repart_bytes_cached;
 };
@@ -82,6 +83,8 @@ gatb_gpu_ctx* gatb_gpu_create (int device)
     if ((e = cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail (0, "cudaStreamCreate: %s", cudaGetErrorString (e)); delete ctx; return 0; }
     for (int i = 0; i < 8; i++) cudaEventCreate (&ctx->ev[i]);
     for (int i = 0; i < 16; i++) cudaEventCreate (&ctx->kev[i]);
+    cudaStreamCreateWithFlags (&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 40; i++) cudaEventCreateWithFlags (&ctx->cev[i], cudaEventDisableTiming);
     return ctx;
 }
 void gatb_gpu_destroy (gatb_gpu_ctx* ctx)
@@ -93,6 +96,8 @@ void gatb_gpu_destroy (gatb_gpu_ctx* ctx)
     if (ctx->pinned) cudaFreeHost (ctx->pinned);
     for (int i = 0; i < 8; i++) cudaEventDestroy (ctx->ev[i]);
     for (int i = 0; i < 16; i++) cudaEventDestroy (ctx->kev[i]);
+    for (int i = 0; i < 40; i++) cudaEventDestroy (ctx->cev[i]);
+    cudaStreamDestroy (ctx->copy_stream);
     cudaStreamDestroy (ctx->stream);
     delete ctx;
 }
@@ -249,9 +254,13 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
 }
 
 // ---- stage 1: k1 into caller-provided buffers (no retry here).  h_stats: valid, invalid, stored, dropped ------------
+// chunks of reads whose host->device copy is still in flight on the copy stream: k1 of chunk c waits for ready[c]
+struct ReadChunks { int n; uint64_t first[17]; cudaEvent_t* ready; };
+
 static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
                            const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
-                           void* d_bins, uint32_t* d_cursors, uint32_t* d_fine_counts, unsigned long long* h_stats)
+                           void* d_bins, uint32_t* d_cursors, uint32_t* d_fine_counts, unsigned long long* h_stats,
+                           const ReadChunks* chunks = 0)
 {
     LaunchCtx L = lctx (ctx);
     if (ensure (ctx, S_STATS, 64 * 8)) return 1;
@@ -268,7 +277,16 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
     CK (cudaMemsetAsync (d_fine_counts, 0, nbins * 4, ctx->stream));
     CK (cudaMemsetAsync (d_stats, 0, 4 * 8, ctx->stream));
     cudaEventRecord (ctx->kev[0], ctx->stream);
-    if (n_reads) CK (launch_k1 (L, k1));
+    if (chunks && chunks->n > 1)
+    {
+        for (int c = 0; c < chunks->n; c++)
+        {
+            if (chunks->ready) CK (cudaStreamWaitEvent (ctx->stream, chunks->ready[c], 0));
+            k1.first_read = chunks->first[c]; k1.n_reads = chunks->first[c+1] - chunks->first[c];
+            if (k1.n_reads) CK (launch_k1 (L, k1));
+        }
+    }
+    else if (n_reads) CK (launch_k1 (L, k1));
     cudaEventRecord (ctx->kev[1], ctx->stream);
     CK (cudaMemcpyAsync (h_stats, d_stats, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK (cudaStreamSynchronize (ctx->stream));
@@ -278,7 +296,8 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
 // ---- stages 2-4: fine split of nb1_local coarse bins gathered from n_src sources, count, partition id + sort --------
 static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
                             const void* const* d_src_bins, const uint32_t* const* d_src_cursors, const uint32_t* d_fine_counts_total,
-                            uint32_t nb1_local, const uint16_t* repart_host, uint64_t total_kmers_bound, gatb_gpu_result* out)
+                            uint32_t nb1_local, const uint16_t* repart_host, uint64_t total_kmers_bound, gatb_gpu_result* out,
+                            bool to_host = false)
 {
     LaunchCtx L = lctx (ctx);
     const int k = p->kmer_size, W = g->words;
@@ -425,12 +444,56 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     CK (launch_scan_u32_to_u64 (L, k3.bucket_count, (uint64_t*)ctx->slot[S_BUCKETOFF], n_buckets, (uint64_t*)ctx->slot[S_SCAN]));
     CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
     CK (launch_k3b_scatter (L, k3));
-    CK (launch_k3c_sort (L, k3));
+    // host sink: the sorted arrays leave in chunks of buckets while the next chunk is being sorted
+    uint8_t* pin = 0; uint64_t* h_lo = 0; uint64_t* h_hi = 0; int32_t* h_cnt32 = 0; uint64_t* h_offs = 0; uint64_t* h_hist = 0;
+    const int n_chunks = (to_host && n_items > (1u << 20)) ? 8 : 1;
+    std::vector<uint64_t> chunk_bucket (n_chunks + 1), chunk_off (n_chunks + 1);
+    for (int c = 0; c <= n_chunks; c++) chunk_bucket[c] = n_buckets * c / n_chunks;
+    if (to_host)
+    {
+        const size_t hist_bytes = (size_t)(histo_max + 1) * 8, off_bytes = (n_keys + 1) * 8;
+        const size_t need = off_bytes + hist_bytes + n_alloc * 8 * W + n_alloc * 4 + 256;
+        pin = (uint8_t*) pinned_ensure (ctx, need);
+        if (!pin) return fail (ctx, "pinned host allocation of the result (%zu bytes) failed", need);
+        h_lo = (uint64_t*)pin; pin += n_alloc * 8;
+        if (W == 2) { h_hi = (uint64_t*)pin; pin += n_alloc * 8; }
+        h_offs = (uint64_t*)pin; pin += off_bytes; h_hist = (uint64_t*)pin; pin += hist_bytes; h_cnt32 = (int32_t*)pin;
+        for (int c = 0; c <= n_chunks; c++)
+            CK (cudaMemcpyAsync (&chunk_off[c], (const uint64_t*)ctx->slot[S_BUCKETOFF] + chunk_bucket[c], 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+    }
+    for (int c = 0; c < n_chunks; c++)
+    {
+        k3.bucket_begin = (uint32_t)chunk_bucket[c]; k3.bucket_end = (uint32_t)chunk_bucket[c+1];
+        CK (launch_k3c_sort (L, k3));
+        if (to_host)
+        {
+            CK (cudaEventRecord (ctx->cev[20 + c], ctx->stream));
+            CK (cudaStreamWaitEvent (ctx->copy_stream, ctx->cev[20 + c], 0));
+            const uint64_t a0 = chunk_off[c], cnt = chunk_off[c+1] - chunk_off[c];
+            if (cnt)
+            {
+                CK (cudaMemcpyAsync (h_lo + a0, (const uint64_t*)dr->lo + a0, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                if (W == 2) CK (cudaMemcpyAsync (h_hi + a0, (const uint64_t*)dr->hi + a0, cnt * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                CK (cudaMemcpyAsync (h_cnt32 + a0, (const int32_t*)dr->cnt + a0, cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
+        }
+    }
     cudaEventRecord (ctx->kev[7], ctx->stream);
     unsigned long long n_big = 0;
     CK (cudaMemcpyAsync (&n_big, d_cnt + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK (cudaStreamSynchronize (ctx->stream));
-    if (n_big) CK (launch_k3d_sort_big (L, k3, (uint32_t)n_big));
+    if (n_big)
+    {
+        CK (launch_k3d_sort_big (L, k3, (uint32_t)n_big));
+        if (to_host && n_items)
+        {   // rare: oversized buckets were sorted after their chunk left; send the arrays again
+            CK (cudaStreamSynchronize (ctx->copy_stream));
+            CK (cudaMemcpyAsync (h_lo, dr->lo, n_items * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (W == 2) CK (cudaMemcpyAsync (h_hi, dr->hi, n_items * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaMemcpyAsync (h_cnt32, dr->cnt, n_items * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
     // part_offsets[key] = bucket_off[key << t_bits]
     {
         std::vector<uint64_t> offs (n_keys + 1);
@@ -439,6 +502,12 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         CK (cudaStreamSynchronize (ctx->stream));
         CK (cudaMemcpyAsync (d_offs, offs.data (), (n_keys + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK (cudaMemcpyAsync (d_hist, ctx->slot[S_HISTO], (size_t)(histo_max + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (to_host)
+        {
+            memcpy (h_offs, offs.data (), (n_keys + 1) * 8);
+            CK (cudaMemcpyAsync (h_hist, ctx->slot[S_HISTO], (size_t)(histo_max + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->copy_stream));
+        }
     }
     cudaEventRecord (ctx->ev[5], ctx->stream);
     CK (cudaStreamSynchronize (ctx->stream));
@@ -448,6 +517,11 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     out->n_keys = n_keys; out->n_items = n_items; out->on_device = 1; out->owner = 0;
     out->part_offsets = (uint64_t*)dr->offs; out->kmers_lo = (uint64_t*)dr->lo; out->kmers_hi = (uint64_t*)dr->hi;
     out->counts = (int32_t*)dr->cnt; out->histogram = (uint64_t*)dr->histo;
+    if (to_host)
+    {
+        out->on_device = 0;
+        out->part_offsets = h_offs; out->kmers_lo = h_lo; out->kmers_hi = h_hi; out->counts = h_cnt32; out->histogram = h_hist;
+    }
     out->stats[GATB_STAT_DISTINCT] = h_cnt[1]; out->stats[GATB_STAT_SOLID] = h_cnt[2];
     out->stats[GATB_STAT_RECORDS] = n_records; out->stats[GATB_STAT_BINS] = nbins; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf;
     out->stats[GATB_STAT_RECORD_BYTES] = n_records * rec_bytes;
@@ -462,7 +536,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
 
 static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_host,
                            const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
-                           gatb_gpu_result* out)
+                           gatb_gpu_result* out, const ReadChunks* chunks = 0, bool to_host = false)
 {
     cudaEventRecord (ctx->ev[1], ctx->stream);
     uint64_t total_kmers = 0, total_nt = 0, max_len = 0;
@@ -480,7 +554,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         if ((uint64_t)g.cap * g.nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %u x %u bins)", g.cap, g.nb1);
         if (ensure (ctx, S_COARSE, (size_t)g.nb1 * g.cap * g.record_bytes)) return 1;
         if (partition_impl (ctx, p, &g, d_reads, d_offsets, n_reads, d_nmask, ctx->slot[S_COARSE], (uint32_t*)ctx->slot[S_CURSORS],
-                            (uint32_t*)ctx->slot[S_FINECNT], h_stats)) return 1;
+                            (uint32_t*)ctx->slot[S_FINECNT], h_stats, chunks)) return 1;
         if (h_stats[3] == 0) break;
         // a bin overflowed: the cursors hold the true demand -> size for the largest and run again
         std::vector<uint32_t> cur (g.nb1);
@@ -491,7 +565,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     }
     const void* src_bins[1] = { ctx->slot[S_COARSE] };
     const uint32_t* src_cur[1] = { (const uint32_t*)ctx->slot[S_CURSORS] };
-    if (count_bins_impl (ctx, p, &g, 1, src_bins, src_cur, (const uint32_t*)ctx->slot[S_FINECNT], g.nb1, repart_host, total_kmers, out)) return 1;
+    if (count_bins_impl (ctx, p, &g, 1, src_bins, src_cur, (const uint32_t*)ctx->slot[S_FINECNT], g.nb1, repart_host, total_kmers, out, to_host)) return 1;
     out->stats[GATB_STAT_KMERS_VALID] = h_stats[0]; out->stats[GATB_STAT_KMERS_INVALID] = h_stats[1];
     out->stats[GATB_STAT_SEQUENCES] = n_reads; out->stats[GATB_STAT_NUCLEOTIDES] = total_nt; out->stats[GATB_STAT_RETRIES] = retries;
     float ms;
@@ -566,12 +640,12 @@ int gatb_gpu_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t*
     if (!out) return fail (ctx, "out is NULL");
     if (check_params (ctx, p, repart_table)) return 1;
     if (!read_offsets_nt && p->read_len <= 0) return fail (ctx, "read_offsets_nt is NULL and read_len <= 0");
+    (void)freq_order;
     cudaEventRecord (ctx->ev[0], ctx->stream);
     const uint64_t total_nt = read_offsets_nt ? read_offsets_nt[n_reads] : n_reads * (uint64_t)p->read_len;
     const uint64_t bytes = (total_nt + 3) / 4;
     if (ensure (ctx, S_READS, bytes + 64)) return 1;
-    CK (cudaMemsetAsync ((uint8_t*)ctx->slot[S_READS] + (bytes & ~15ULL), 0, (bytes & 15) + 48, ctx->stream));     // zero the padding
-    CK (cudaMemcpyAsync (ctx->slot[S_READS], packed_reads, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d_reads = (uint8_t*)ctx->slot[S_READS];
     const uint64_t* d_off = 0; const uint32_t* d_mask = 0;
     if (read_offsets_nt)
     {
@@ -587,39 +661,30 @@ int gatb_gpu_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t*
         CK (cudaMemcpyAsync (ctx->slot[S_NMASK], n_mask, mw * 4, cudaMemcpyHostToDevice, ctx->stream));
         d_mask = (const uint32_t*)ctx->slot[S_NMASK];
     }
-    gatb_gpu_result dres;
-    if (count_dev_impl (ctx, p, repart_table, (const uint8_t*)ctx->slot[S_READS], d_off, n_reads, d_mask, &dres)) return 1;
-    // ---- device -> host ----
-    cudaEventRecord (ctx->ev[6], ctx->stream);
-    const int W = p->kmer_size < 32 ? 1 : 2;
-    gatb_gpu_result h = dres; h.on_device = 0; h.owner = 0;
-    uint64_t n = dres.n_items, na = n ? n : 1;
-    // host arrays live in one pinned staging buffer owned by the context (valid until the next count on this context
-    // or gatb_gpu_result_free): pinned memory lets the copies run at full PCIe rate
-    const size_t hist_bytes = (size_t)(p->histo_max + 1) * 8, off_bytes = (dres.n_keys + 1) * 8;
-    size_t need = off_bytes + hist_bytes + na * 8 * W + na * 4 + 256;
-    uint8_t* pin = (uint8_t*) pinned_ensure (ctx, need);
-    if (!pin) { gatb_gpu_result_free (ctx, &dres); return fail (ctx, "pinned host allocation of the result (%zu bytes) failed", need); }
-    h.kmers_lo = (uint64_t*)pin; pin += na * 8;
-    h.kmers_hi = 0; if (W == 2) { h.kmers_hi = (uint64_t*)pin; pin += na * 8; }
-    h.part_offsets = (uint64_t*)pin; pin += off_bytes;
-    h.histogram = (uint64_t*)pin; pin += hist_bytes;
-    h.counts = (int32_t*)pin;
-    CK (cudaMemcpyAsync (h.part_offsets, dres.part_offsets, (dres.n_keys + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n)
+    // the packed reads travel in chunks on the copy stream; k1 of chunk c starts as soon as chunk c has landed
+    ReadChunks rc; rc.n = (bytes > (64u << 20)) ? 8 : 1; rc.ready = ctx->cev;
+    CK (cudaMemsetAsync (d_reads + (bytes & ~15ULL), 0, (bytes & 15) + 48, ctx->stream));      // zero the padding
+    CK (cudaEventRecord (ctx->cev[39], ctx->stream));
+    CK (cudaStreamWaitEvent (ctx->copy_stream, ctx->cev[39], 0));
+    uint64_t byte_done = 0;
+    for (int c = 0; c < rc.n; c++)
     {
-        CK (cudaMemcpyAsync (h.kmers_lo, dres.kmers_lo, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (W == 2) CK (cudaMemcpyAsync (h.kmers_hi, dres.kmers_hi, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK (cudaMemcpyAsync (h.counts, dres.counts, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        rc.first[c] = n_reads * (uint64_t)c / rc.n;
+        const uint64_t last = n_reads * (uint64_t)(c + 1) / rc.n;
+        const uint64_t end_nt = read_offsets_nt ? read_offsets_nt[last] : last * (uint64_t)p->read_len;
+        uint64_t byte_end = (c == rc.n - 1) ? bytes : ((end_nt + 3) / 4 + 15) & ~15ULL;      // whole 16-byte units past the chunk's last read
+        if (byte_end > bytes) byte_end = bytes;
+        if (byte_end > byte_done) CK (cudaMemcpyAsync (d_reads + byte_done, packed_reads + byte_done, byte_end - byte_done, cudaMemcpyHostToDevice, ctx->copy_stream));
+        byte_done = byte_end > byte_done ? byte_end : byte_done;
+        CK (cudaEventRecord (ctx->cev[c], ctx->copy_stream));
     }
-    CK (cudaMemcpyAsync (h.histogram, dres.histogram, (size_t)(p->histo_max + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    rc.first[rc.n] = n_reads;
+    gatb_gpu_result h;
+    if (count_dev_impl (ctx, p, repart_table, d_reads, d_off, n_reads, d_mask, &h, &rc, true)) return 1;
     cudaEventRecord (ctx->ev[7], ctx->stream);
     CK (cudaStreamSynchronize (ctx->stream));
     float ms;
-    cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[1]); h.seconds[0] = ms * 1e-3;
-    cudaEventElapsedTime (&ms, ctx->ev[6], ctx->ev[7]); h.seconds[5] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[7]); h.seconds[7] = ms * 1e-3;
-    gatb_gpu_result_free (ctx, &dres);
     *out = h;
     return 0;
 }

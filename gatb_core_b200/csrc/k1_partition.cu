@@ -116,9 +116,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_partition (const K1Pa
     const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
     {
-        const uint64_t r = tile * K1_THREADS + tid;
+        const uint64_t ri = tile * K1_THREADS + tid;
+        const uint64_t r = P.first_read + ri;
         uint64_t roff = 0; int len = 0;
-        if (r < P.n_reads)
+        if (ri < P.n_reads)
         {
             if (P.offsets) { roff = P.offsets[r]; len = (int)(P.offsets[r+1] - roff); }
             else           { roff = r * (uint64_t)P.read_len; len = P.read_len; }

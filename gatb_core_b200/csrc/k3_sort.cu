@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
     uint64_t* s_lo = (uint64_t*)smem_raw;
     uint64_t* s_hi = (W == 2) ? s_lo + K3_SORT_CAP : 0;
     uint32_t* s_c  = (uint32_t*)(s_lo + (size_t)K3_SORT_CAP * W);
-    for (uint32_t b = blockIdx.x; b < P.n_buckets; b += gridDim.x)
+    for (uint32_t b = P.bucket_begin + blockIdx.x; b < P.bucket_end; b += gridDim.x)
     {
         const uint64_t beg = P.bucket_off[b], end = P.bucket_off[b+1];
         const uint64_t n64 = end - beg;
@@ -210,7 +210,9 @@ cudaError_t launch_k3c_sort (const LaunchCtx& L, const K3Params& P)
     const void* fn = P.W == 1 ? (const void*)k3c_sort<1> : (const void*)k3c_sort<2>;
     cudaError_t e = cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    unsigned grid = P.n_buckets < (unsigned)(L.sm_count * 32) ? P.n_buckets : (unsigned)(L.sm_count * 32);
+    const unsigned nb = P.bucket_end - P.bucket_begin;
+    if (nb == 0) return cudaSuccess;
+    unsigned grid = nb < (unsigned)(L.sm_count * 32) ? nb : (unsigned)(L.sm_count * 32);
     if (P.W == 1) k3c_sort<1><<<grid, 256, smem, L.stream>>> (P); else k3c_sort<2><<<grid, 256, smem, L.stream>>> (P);
     (*L.launches)++;
     return cudaGetLastError ();

@@ -23,7 +23,8 @@ struct K1Params
     const uint64_t* words;          // packed reads, 64-bit words
     const uint64_t* offsets;        // [n_reads+1] nucleotide offsets, or NULL with read_len
     const uint32_t* nmask;          // invalid-nucleotide bitmask or NULL
-    uint64_t n_reads;
+    uint64_t n_reads;               // reads handled by this launch: [first_read, first_read + n_reads)
+    uint64_t first_read;
     int      read_len;
     int      k, m, w, maxlen;       // m = size of the m-mers ranked; w = k-m+1; maxlen = max k-mers per record
     uint32_t mmask, mask_ma1;
@@ -74,6 +75,7 @@ struct K3Params
     uint64_t* tmp_lo; uint64_t* tmp_hi; uint32_t* tmp_cnt;     // scattered
     uint64_t* out_lo; uint64_t* out_hi; int32_t* out_cnt;      // sorted
     uint32_t n_buckets;
+    uint32_t bucket_begin, bucket_end;   // k3c sorts buckets [bucket_begin, bucket_end) (chunked so that copies overlap)
     unsigned long long* big_list;   // buckets too large for shared memory
     unsigned long long* counters;   // [0] number of big buckets
 };
