@@ -86,8 +86,8 @@ def load_library():
     L.gatb_gpu_synth_reads_dev.argtypes = [VP, U64, U64, U64, U64, I32, VP]
     L.gatb_gpu_pack_ascii.argtypes = [VP, C.c_char_p, U64, VP, VP, C.POINTER(U64)]
     L.gatb_gpu_plan.argtypes = [VP, C.POINTER(Params), U64, U64, I32, C.POINTER(Geometry)]
-    L.gatb_gpu_partition_into.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), VP, VP, U64, VP, VP, VP, VP, VP]
-    L.gatb_gpu_count_bins.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), I32, C.POINTER(VP), C.POINTER(VP), VP,
+    L.gatb_gpu_partition_into.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), VP, VP, U64, VP, VP, VP, VP]
+    L.gatb_gpu_count_bins.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), I32, C.POINTER(VP), C.POINTER(VP),
                                       C.c_uint32, VP, U64, C.POINTER(Result)]
     return L
 
@@ -215,21 +215,21 @@ class GatbGpu:
         self._check(self.L.gatb_gpu_plan(self.ctx, C.byref(params), total_kmers, n_reads, n_ranks, C.byref(g)))
         return g
 
-    def partition_into(self, params, geom, d_packed, d_offsets, n_reads, d_bins, d_cursors, d_fine_counts, d_n_mask=None):
+    def partition_into(self, params, geom, d_packed, d_offsets, n_reads, d_bins, d_cursors, d_n_mask=None):
         """k1 into caller-provided device buffers (ints).  Returns [valid, invalid, stored, dropped]."""
         st = np.zeros(4, np.uint64)
         self._check(self.L.gatb_gpu_partition_into(self.ctx, C.byref(params), C.byref(geom), _ptr(d_packed), _ptr(d_offsets),
-                                                   n_reads, _ptr(d_n_mask), _ptr(d_bins), _ptr(d_cursors), _ptr(d_fine_counts), _ptr(st)))
+                                                   n_reads, _ptr(d_n_mask), _ptr(d_bins), _ptr(d_cursors), _ptr(st)))
         return [int(x) for x in st]
 
-    def count_bins(self, params, geom, src_bins, src_cursors, d_fine_total, nb1_local, kmers_bound, repart=None):
+    def count_bins(self, params, geom, src_bins, src_cursors, nb1_local, kmers_bound, repart=None):
         """Counts nb1_local coarse bins gathered from len(src_bins) sources (device pointers).  Returns a device Result."""
         n = len(src_bins)
         a = (C.c_void_p * n)(*src_bins)
         b = (C.c_void_p * n)(*src_cursors)
         res = Result()
         rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
-        self._check(self.L.gatb_gpu_count_bins(self.ctx, C.byref(params), C.byref(geom), n, a, b, _ptr(d_fine_total), nb1_local,
+        self._check(self.L.gatb_gpu_count_bins(self.ctx, C.byref(params), C.byref(geom), n, a, b, nb1_local,
                                                _ptr(rp), kmers_bound, C.byref(res)))
         return res
 

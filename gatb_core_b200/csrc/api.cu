@@ -16,8 +16,8 @@
 static std::string g_create_error;
 
 // device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
-enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_FINECNT, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
-            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_NSLOTS };
+enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_GBUCKET, S_GCURSOR, S_NSLOTS };
 
 struct gatb_gpu_ctx
 {
@@ -230,7 +230,7 @@ static int workload_size (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uin
 static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t total_kmers, uint64_t n_reads, int n_ranks, gatb_gpu_geometry* g)
 {
     const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
-    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : 11;
+    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : k2b_default_table_log2 (W);
     if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
     if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_SOURCES) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_SOURCES);
     const uint64_t T = 1ULL << table_log2;
@@ -240,12 +240,15 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     uint64_t nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits; if (nb1 < 1) nb1 = 1;
     nb1 = (nb1 + n_ranks - 1) / n_ranks * n_ranks;                              // every rank owns nb1/n_ranks consecutive coarse bins
     if (nb1 > (1ULL << 24)) return fail (ctx, "input too large (%llu coarse bins)", (unsigned long long)nb1);
-    const int mg = pick_device_m (k, nb1 << fine_bits);
+    // m-mers ranked on the device: the register scanner (k1_scan.cuh) wants w = k-m+1 a multiple of 8 and m in [8,16];
+    // k < 15 falls back to the general kernel with the smallest m that still spreads the bins
+    const int win = k1_fast_window (k);
+    const int mg = win ? k - win + 1 : pick_device_m (k, nb1 << fine_bits);
     const int w = k - mg + 1;
     // records a rank produces for one coarse bin ~ (its k-mers * 2/(w+1)) / nb1
     double local_kmers = (double)total_kmers / n_ranks, local_reads = (double)n_reads / n_ranks;
     double est_records = local_kmers * 2.0 / (w + 1) * 1.10 + local_reads * 0.5 + 64;
-    uint64_t cap = (uint64_t)(est_records / nb1 * 1.30) + 64; cap = (cap + 7) & ~7ULL;
+    uint64_t cap = (uint64_t)(est_records / nb1 * 1.30) + 64; cap = (cap + COARSE_BLK - 1) / COARSE_BLK * COARSE_BLK;
     memset (g, 0, sizeof(*g));
     g->total_kmers = total_kmers; g->nb1 = (uint32_t)nb1; g->cap = (uint32_t)cap; g->fine_bits = fine_bits; g->table_log2 = table_log2;
     g->m_device = mg; g->w = w; g->maxlen = (W == 1) ? 28 : 60; g->words = W;                  // maxlen: Sequence2SuperKmer.hpp:147
@@ -259,7 +262,7 @@ struct ReadChunks { int n; uint64_t first[17]; cudaEvent_t* ready; };
 
 static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
                            const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
-                           void* d_bins, uint32_t* d_cursors, uint32_t* d_fine_counts, unsigned long long* h_stats,
+                           void* d_bins, uint32_t* d_cursors, unsigned long long* h_stats,
                            const ReadChunks* chunks = 0)
 {
     LaunchCtx L = lctx (ctx);
@@ -271,10 +274,11 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
     k1.words = (const uint64_t*)d_reads; k1.offsets = d_offsets; k1.nmask = d_nmask; k1.n_reads = n_reads; k1.read_len = p->read_len;
     k1.k = p->kmer_size; k1.m = g->m_device; k1.w = g->w; k1.maxlen = g->maxlen;
     k1.mmask = (g->m_device >= 16) ? 0xFFFFFFFFu : ((1u << (2 * g->m_device)) - 1); k1.mask_ma1 = 0;
-    k1.mode = K1_MODE_DEVICE; k1.nb1 = g->nb1; k1.fine_bits = g->fine_bits; k1.count_only = 0;
-    k1.bins = d_bins; k1.cap = g->cap; k1.cursors = d_cursors; k1.fine_counts = d_fine_counts; k1.stats = d_stats;
+    { const char* e = getenv ("GATB_GPU_K1_GENERAL"); k1.force_general = (e && e[0] == '1'); }
+    k1.mode = K1_MODE_DEVICE; k1.nb1 = g->nb1; k1.n_regions = g->n_ranks; k1.bins_per_region = g->bins_per_rank;
+    if (g->cap % COARSE_BLK) return fail (ctx, "geometry: cap %u is not a multiple of %d", g->cap, (int)COARSE_BLK); k1.fine_bits = g->fine_bits; k1.count_only = 0;
+    k1.bins = d_bins; k1.cap = g->cap; k1.cursors = d_cursors; k1.stats = d_stats;
     CK (cudaMemsetAsync (d_cursors, 0, (size_t)g->nb1 * 4, ctx->stream));
-    CK (cudaMemsetAsync (d_fine_counts, 0, nbins * 4, ctx->stream));
     CK (cudaMemsetAsync (d_stats, 0, 4 * 8, ctx->stream));
     cudaEventRecord (ctx->kev[0], ctx->stream);
     if (chunks && chunks->n > 1)
@@ -295,7 +299,7 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
 
 // ---- stages 2-4: fine split of nb1_local coarse bins gathered from n_src sources, count, partition id + sort --------
 static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
-                            const void* const* d_src_bins, const uint32_t* const* d_src_cursors, const uint32_t* d_fine_counts_total,
+                            const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
                             uint32_t nb1_local, const uint16_t* repart_host, uint64_t total_kmers_bound, gatb_gpu_result* out,
                             bool to_host = false)
 {
@@ -325,7 +329,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     if (ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
     K2aSrc S2; S2.n = n_src; for (int s = 0; s < n_src; s++) { S2.bins[s] = (const uint4*)d_src_bins[s]; S2.cursors[s] = d_src_cursors[s]; }
     cudaEventRecord (ctx->kev[2], ctx->stream);
-    CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], d_fine_counts_total, nb1_local, cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
+    CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
     cudaEventRecord (ctx->kev[3], ctx->stream);
     cudaEventRecord (ctx->ev[3], ctx->stream);
 
@@ -443,7 +447,21 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     CK (launch_k3a_classify (L, k3));
     CK (launch_scan_u32_to_u64 (L, k3.bucket_count, (uint64_t*)ctx->slot[S_BUCKETOFF], n_buckets, (uint64_t*)ctx->slot[S_SCAN]));
     CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
-    CK (launch_k3b_scatter (L, k3));
+    static const bool force_two_hop = getenv ("GATB_GPU_K3_TWOHOP") && getenv ("GATB_GPU_K3_TWOHOP")[0] == '1';      // test hook
+    if (force_two_hop && n_buckets > 1)
+    {   // two hops (k3_sort.cu): first into <= 2048 groups of consecutive buckets, staged in the (still unused) result arrays
+        int bits = 0; while ((1ULL << bits) < n_buckets) bits++;
+        const int shift = bits > 11 ? bits - 11 : 0;
+        const uint64_t n_groups = ((n_buckets - 1) >> shift) + 1;
+        if (ensure (ctx, S_GBUCKET, n_alloc * 4)) return 1;
+        if (ensure (ctx, S_GCURSOR, n_groups * 4)) return 1;
+        CK (cudaMemsetAsync (ctx->slot[S_GCURSOR], 0, n_groups * 4, ctx->stream));
+        CK (launch_k3b_scatter_coarse (L, k3, shift, (uint32_t*)ctx->slot[S_GCURSOR], k3.out_lo, k3.out_hi, (uint32_t*)k3.out_cnt, (uint32_t*)ctx->slot[S_GBUCKET]));
+        K3Params k3g = k3;
+        k3g.n = n_items; k3g.in_lo = k3.out_lo; k3g.in_hi = k3.out_hi; k3g.in_cnt = (const uint32_t*)k3.out_cnt; k3g.bucket_of = (uint32_t*)ctx->slot[S_GBUCKET];
+        CK (launch_k3b_scatter (L, k3g));
+    }
+    else CK (launch_k3b_scatter (L, k3));
     // host sink: the sorted arrays leave in chunks of buckets while the next chunk is being sorted
     uint8_t* pin = 0; uint64_t* h_lo = 0; uint64_t* h_hi = 0; int32_t* h_cnt32 = 0; uint64_t* h_offs = 0; uint64_t* h_hist = 0;
     const int n_chunks = (to_host && n_items > (1u << 20)) ? 8 : 1;
@@ -546,7 +564,6 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     if (plan_geometry (ctx, p, total_kmers, n_reads, 1, &g)) return 1;
     const uint64_t nbins = (uint64_t)g.nb1 << g.fine_bits;
     if (ensure (ctx, S_CURSORS, (size_t)g.nb1 * 4)) return 1;
-    if (ensure (ctx, S_FINECNT, nbins * 4)) return 1;
     uint64_t retries = 0;
     unsigned long long h_stats[4];
     for (;;)
@@ -554,18 +571,18 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         if ((uint64_t)g.cap * g.nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %u x %u bins)", g.cap, g.nb1);
         if (ensure (ctx, S_COARSE, (size_t)g.nb1 * g.cap * g.record_bytes)) return 1;
         if (partition_impl (ctx, p, &g, d_reads, d_offsets, n_reads, d_nmask, ctx->slot[S_COARSE], (uint32_t*)ctx->slot[S_CURSORS],
-                            (uint32_t*)ctx->slot[S_FINECNT], h_stats, chunks)) return 1;
+                            h_stats, chunks)) return 1;
         if (h_stats[3] == 0) break;
         // a bin overflowed: the cursors hold the true demand -> size for the largest and run again
         std::vector<uint32_t> cur (g.nb1);
         CK (cudaMemcpy (cur.data (), ctx->slot[S_CURSORS], (size_t)g.nb1 * 4, cudaMemcpyDeviceToHost));
         uint32_t mx = 0; for (uint64_t i = 0; i < g.nb1; i++) if (cur[i] > mx) mx = cur[i];
-        g.cap = (uint32_t)(((uint64_t)mx + 7) & ~7ULL);
+        g.cap = (uint32_t)(((uint64_t)mx + COARSE_BLK - 1) / COARSE_BLK * COARSE_BLK);
         if (++retries > 3) return fail (ctx, "partition kernel still overflows after %llu retries", (unsigned long long)retries);
     }
     const void* src_bins[1] = { ctx->slot[S_COARSE] };
     const uint32_t* src_cur[1] = { (const uint32_t*)ctx->slot[S_CURSORS] };
-    if (count_bins_impl (ctx, p, &g, 1, src_bins, src_cur, (const uint32_t*)ctx->slot[S_FINECNT], g.nb1, repart_host, total_kmers, out, to_host)) return 1;
+    if (count_bins_impl (ctx, p, &g, 1, src_bins, src_cur, g.nb1, repart_host, total_kmers, out, to_host)) return 1;
     out->stats[GATB_STAT_KMERS_VALID] = h_stats[0]; out->stats[GATB_STAT_KMERS_INVALID] = h_stats[1];
     out->stats[GATB_STAT_SEQUENCES] = n_reads; out->stats[GATB_STAT_NUCLEOTIDES] = total_nt; out->stats[GATB_STAT_RETRIES] = retries;
     float ms;
@@ -598,18 +615,18 @@ int gatb_gpu_plan (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t total_k
 }
 int gatb_gpu_partition_into (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
                              const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads, const uint32_t* d_n_mask,
-                             void* d_bins, uint32_t* d_cursors, uint32_t* d_fine_counts, uint64_t* stats4)
+                             void* d_bins, uint32_t* d_cursors, uint64_t* stats4)
 {
     if (!ctx) return 1;
     cudaSetDevice (ctx->device);
     if (check_params (ctx, p, (const uint16_t*)1)) return 1;
     unsigned long long h[4];
-    if (partition_impl (ctx, p, g, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, d_bins, d_cursors, d_fine_counts, h)) return 1;
+    if (partition_impl (ctx, p, g, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, d_bins, d_cursors, h)) return 1;
     for (int i = 0; i < 4; i++) stats4[i] = h[i];
     return 0;
 }
 int gatb_gpu_count_bins (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
-                         const void* const* d_src_bins, const uint32_t* const* d_src_cursors, const uint32_t* d_fine_counts_total,
+                         const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
                          uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, gatb_gpu_result* out)
 {
     if (!ctx) return 1;
@@ -617,7 +634,7 @@ int gatb_gpu_count_bins (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb
     if (!out) return fail (ctx, "out is NULL");
     if (check_params (ctx, p, repart_table)) return 1;
     cudaEventRecord (ctx->ev[1], ctx->stream);
-    if (count_bins_impl (ctx, p, g, n_src, d_src_bins, d_src_cursors, d_fine_counts_total, nb1_local, repart_table, kmers_bound, out)) return 1;
+    if (count_bins_impl (ctx, p, g, n_src, d_src_bins, d_src_cursors, nb1_local, repart_table, kmers_bound, out)) return 1;
     float ms; cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[5]); out->seconds[6] = ms * 1e-3;
     return 0;
 }
@@ -736,7 +753,7 @@ int gatb_gpu_superkmers (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint
     k1.k = k; k1.m = m; k1.w = k - m + 1; k1.maxlen = (W == 1) ? 28 : 60;
     k1.mmask = (1u << (2*m)) - 1; k1.mask_ma1 = gatb_mask_ma1 (m);
     k1.mode = K1_MODE_GATB; k1.repart = (const uint16_t*)ctx->slot[S_REPART]; k1.nb_partitions = p->nb_partitions; k1.nb_passes = p->nb_passes;
-    k1.nb1 = (uint32_t)n_keys; k1.fine_bits = 0; k1.fine_counts = 0; k1.cursors = (uint32_t*)ctx->slot[S_CURSORS]; k1.stats = d_stats;
+    k1.nb1 = (uint32_t)n_keys; k1.fine_bits = 0; k1.cursors = (uint32_t*)ctx->slot[S_CURSORS]; k1.stats = d_stats;
     // pass 1: demand per key; pass 2: fill exactly
     k1.count_only = 1; k1.cap = 0; k1.bins = 0;
     CK (cudaMemsetAsync (k1.cursors, 0, n_keys * 4, ctx->stream));

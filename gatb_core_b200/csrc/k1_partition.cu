@@ -30,12 +30,13 @@
 //                    window minimum; GATB's own partition id is recomputed exactly for each emitted k-mer in k3a.
 #include "common.cuh"
 #include "kernels.h"
+#include "k1_scan.cuh"
 
 #define K1_THREADS 128
 #define K1_QCAP    384        // events per warp queue: flush threshold 96 + 8 steps x 32 lanes + slack
 #define K1_QFLUSH  96
 
-__device__ __forceinline__ uint32_t k1_key_device (uint32_t cm) { uint32_t h = cm * 0x9E3779B1u; return h ^ (h >> 15); }
+__device__ __forceinline__ uint32_t k1_key_device (uint32_t cm) { return k1s_key (cm); }
 
 template<int W>
 __device__ __forceinline__ void k1_store_record (const K1Params& P, uint32_t key, uint32_t meta, const uint64_t* roffs,
@@ -60,7 +61,12 @@ __device__ __forceinline__ void k1_store_record (const K1Params& P, uint32_t key
     uint32_t slot = atomicAdd (&P.cursors[bin], 1u);
     if (P.count_only) return;
     if (slot >= P.cap) { dropped++; return; }
-    if (P.fine_counts) atomicAdd (&P.fine_counts[((uint64_t)bin << P.fine_bits) + fine], 1u);
+    uint64_t ridx = (uint64_t)bin * P.cap + slot;                         // GATB mode: bin-major
+    if (P.mode == K1_MODE_DEVICE)
+    {
+        const uint32_t region = bin / P.bins_per_region;
+        ridx = (uint64_t)region * P.bins_per_region * P.cap + coarse_index (bin - region * P.bins_per_region, slot, P.bins_per_region);
+    }
     stored++;
     // ---- record: nn = k+len-1 nucleotides starting at stream position roff+start ----
     const uint64_t bp = 2 * (roffs[olane] + start);
@@ -75,7 +81,7 @@ __device__ __forceinline__ void k1_store_record (const K1Params& P, uint32_t key
         if (nn <= 32) { lo &= mask2k64 (nn); hi = 0; } else { hi &= mask2k64 (nn - 32); }
         hi |= ((uint64_t)len << REC_LEN_SHIFT_W1) | ((uint64_t)fine << REC_FINE_SHIFT_W1);
         uint4 rec = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-        ((uint4*)P.bins)[(uint64_t)bin * P.cap + slot] = rec;
+        ((uint4*)P.bins)[ridx] = rec;
     }
     else
     {
@@ -92,7 +98,7 @@ __device__ __forceinline__ void k1_store_record (const K1Params& P, uint32_t key
             if (nn <= lo_nt) r[i] = 0; else if (nn < lo_nt + 32) r[i] &= mask2k64 (nn - lo_nt);
         }
         r[3] |= ((uint64_t)len << REC_LEN_SHIFT_W2) | ((uint64_t)fine << REC_FINE_SHIFT_W2);
-        uint4* dst = (uint4*)P.bins + 2 * ((uint64_t)bin * P.cap + slot);
+        uint4* dst = (uint4*)P.bins + 2 * ridx;
         dst[0] = make_uint4 ((uint32_t)r[0], (uint32_t)(r[0] >> 32), (uint32_t)r[1], (uint32_t)(r[1] >> 32));
         dst[1] = make_uint4 ((uint32_t)r[2], (uint32_t)(r[2] >> 32), (uint32_t)r[3], (uint32_t)(r[3] >> 32));
     }
@@ -238,6 +244,212 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_partition (const K1Pa
     }
 }
 
+
+// =====================================================================================================================
+//  k1_superkmer_fast<WIN,W>: the device-order partition kernel for reads without invalid nucleotides.
+//  thread <-> read; the scan itself is K1Scanner (k1_scan.cuh: registers only, ~20 instructions per nucleotide);
+//  closing lanes push 8-byte events into their warp's shared-memory queue; after every 16 positions the warp empties
+//  the queue cooperatively (lane <-> event): bin from the key, one 32-bit global atomic for the slot, the record cut
+//  out of the owner's shared-memory word ring with funnel shifts, one 16-byte store.  Per record the memory system
+//  sees exactly two scattered operations (the atomic and the store); everything else is shared memory.
+// =====================================================================================================================
+#define K1F_QCAP 640           // events per warp queue: 18 per lane per step at the very worst
+
+template<int W>
+__device__ __forceinline__ void k1f_store (const K1Params& P, uint32_t key, uint32_t meta, const uint32_t* ring_w,
+                                           unsigned long long& stored, unsigned long long& dropped)
+{
+    const int olane = meta & 31;
+    int       len   = (meta >> 5) & 63;
+    uint32_t  start = meta >> 11;
+    const uint32_t h    = mix32 (key);
+    const uint32_t bin  = __umulhi (h, P.nb1);
+    const uint32_t fine = (h * 0x9E3779B1u) >> (32 - P.fine_bits);
+    const uint32_t region = __umulhi (h, P.n_regions);      // = bin / bins_per_region (nested floors)
+    const uint64_t rbase = (uint64_t)region * P.bins_per_region * P.cap;
+    const uint32_t lbin = bin - region * P.bins_per_region;
+    const uint32_t* col = ring_w + olane;                   // the owner's column: word t at col[(t % K1S_RING) * K1_THREADS]
+    while (len > 0)
+    {
+        const int l = len < P.maxlen ? len : P.maxlen;
+        const uint32_t slot = atomicAdd (&P.cursors[bin], 1u);
+        if (slot < P.cap)
+        {
+            stored++;
+            const uint32_t w0 = start >> 4;
+            const int sh = 2 * (int)(start & 15);
+            const int nn = P.k + l - 1;
+            constexpr int NW = (W == 1) ? 5 : 9;
+            uint32_t x[NW];
+            #pragma unroll
+            for (int i = 0; i < NW; i++) x[i] = col[((w0 + i) & (K1S_RING - 1)) * K1_THREADS];
+            uint32_t r[NW - 1];
+            #pragma unroll
+            for (int i = 0; i < NW - 1; i++) r[i] = __funnelshift_r (x[i], x[i + 1], sh);
+            if (W == 1)
+            {
+                uint64_t lo = (uint64_t)r[0] | ((uint64_t)r[1] << 32), hi = (uint64_t)r[2] | ((uint64_t)r[3] << 32);
+                if (nn <= 32) { lo &= mask2k64 (nn); hi = 0; } else { hi &= mask2k64 (nn - 32); }
+                hi |= ((uint64_t)l << REC_LEN_SHIFT_W1) | ((uint64_t)fine << REC_FINE_SHIFT_W1);
+                ((uint4*)P.bins)[rbase + coarse_index (lbin, slot, P.bins_per_region)] = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+            }
+            else
+            {
+                uint64_t q[4];
+                #pragma unroll
+                for (int i = 0; i < 4; i++)
+                {
+                    q[i] = (uint64_t)r[2 * i] | ((uint64_t)r[2 * i + 1] << 32);
+                    const int lo_nt = 32 * i;
+                    if (nn <= lo_nt) q[i] = 0; else if (nn < lo_nt + 32) q[i] &= mask2k64 (nn - lo_nt);
+                }
+                q[3] |= ((uint64_t)l << REC_LEN_SHIFT_W2) | ((uint64_t)fine << REC_FINE_SHIFT_W2);
+                uint4* dst = (uint4*)P.bins + 2 * (rbase + coarse_index (lbin, slot, P.bins_per_region));
+                dst[0] = make_uint4 ((uint32_t)q[0], (uint32_t)(q[0] >> 32), (uint32_t)q[1], (uint32_t)(q[1] >> 32));
+                dst[1] = make_uint4 ((uint32_t)q[2], (uint32_t)(q[2] >> 32), (uint32_t)q[3], (uint32_t)(q[3] >> 32));
+            }
+        }
+        else dropped++;
+        start += l; len -= l;
+    }
+}
+
+template<int N> struct K1Int { static constexpr int value = N; };
+template<int N, int I, class F> __device__ __forceinline__ void k1_static_for (F& f)
+{
+    if constexpr (I < N) { f (K1Int<I> ()); k1_static_for<N, I + 1> (f); }
+}
+
+struct K1Emit
+{
+    uint32_t* q; uint32_t* tail; uint32_t lane;
+    __device__ __forceinline__ void operator() (uint32_t key, int start, int len)
+    {
+        const uint32_t e = atomicAdd (tail, 1u);
+        *(uint2*)(q + 2 * e) = make_uint2 (key, ((uint32_t)start << 11) | ((uint32_t)len << 5) | lane);
+    }
+};
+
+template<int WIN, int W>
+__global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params P)
+{
+    __shared__ __align__(16) uint32_t s_q[K1_THREADS / 32][K1F_QCAP * 2];
+    __shared__ uint32_t s_ring[K1S_RING * K1_THREADS];
+    __shared__ uint32_t s_tail[K1_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = P.k, m = P.m;
+    uint32_t* q = s_q[wid];
+    const uint32_t* ring_w = s_ring + wid * 32;
+    K1Emit emit; emit.q = q; emit.tail = &s_tail[wid]; emit.lane = (uint32_t)lane;
+    unsigned long long nvalid = 0, stored = 0, dropped = 0;
+    if (lane == 0) s_tail[wid] = 0;
+    __syncwarp ();
+
+    // empties the warp's event queue (lane <-> event)
+    auto drain = [&] ()
+    {
+        __syncwarp ();
+        const uint32_t n = *(volatile uint32_t*)&s_tail[wid];
+        for (uint32_t e0 = 0; e0 < n; e0 += 32)
+        {
+            const uint32_t e = e0 + lane;
+            if (e < n)
+            {
+                const uint2 ev = *(const uint2*)(q + 2 * e);
+                k1f_store<W> (P, ev.x, ev.y, ring_w, stored, dropped);
+            }
+        }
+        __syncwarp ();
+        if (lane == 0) s_tail[wid] = 0;
+        __syncwarp ();
+    };
+
+    const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        const uint64_t ri = tile * K1_THREADS + tid;
+        const uint64_t r = P.first_read + ri;
+        uint64_t roff = 0; int len = 0;
+        if (ri < P.n_reads)
+        {
+            if (P.offsets) { roff = P.offsets[r]; len = (int)(P.offsets[r+1] - roff); }
+            else           { roff = r * (uint64_t)P.read_len; len = P.read_len; }
+        }
+        const int nm = (len >= k) ? (len - m + 1) : 0;      // reads shorter than k are skipped (Sequence2SuperKmer.hpp:144)
+        const int nm_max = __reduce_max_sync (FULL_MASK, nm);
+        K1Scanner<WIN, K1_THREADS> sc;
+        if (nm > 0)
+        {
+            nvalid += (unsigned long long)(len - k + 1);
+            sc.begin ((const uint32_t*)P.words, roff, len, m, s_ring + tid);
+            if (sc.j >= nm) sc.finish (emit);
+        }
+        int j0 = WIN;
+        auto body = [&] (auto ph)
+        {
+            constexpr int PH = decltype (ph)::value;
+            if (j0 < nm_max)
+            {
+                if (j0 < nm)
+                {
+                    if (j0 + 16 <= nm) sc.template step16<PH, false> (emit);
+                    else               sc.template step16<PH, true>  (emit);
+                    if (j0 + 16 >= nm) sc.finish (emit);
+                }
+                j0 += 16;
+                drain ();
+            }
+        };
+        if (nm_max > 0 && nm_max <= WIN) drain ();          // reads of exactly k nucleotides: one k-mer each
+        while (j0 < nm_max) k1_static_for<K1Scanner<WIN>::PHASES, 0> (body);
+    }
+    // ---- statistics: one atomic per warp ----
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        nvalid  += __shfl_xor_sync (FULL_MASK, nvalid, o);
+        stored  += __shfl_xor_sync (FULL_MASK, stored, o);
+        dropped += __shfl_xor_sync (FULL_MASK, dropped, o);
+    }
+    if (lane == 0)
+    {
+        if (nvalid)  atomicAdd (&P.stats[0], nvalid);
+        if (stored)  atomicAdd (&P.stats[2], stored);
+        if (dropped) atomicAdd (&P.stats[3], dropped);
+    }
+}
+
+template<int WIN, int W>
+static cudaError_t k1_fast_launch_t (const LaunchCtx& L, const K1Params& P)
+{
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W>, K1_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
+    uint64_t grid = (uint64_t)L.sm_count * per_sm;                 // persistent: a multiple of the SM count
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid == 0) return cudaSuccess;
+    k1_superkmer_fast<WIN,W><<<(unsigned)grid, K1_THREADS, 0, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
+// window sizes the register scanner is compiled for: k in [WIN+7, WIN+15] with m = k-WIN+1 in [8,16]
+int k1_fast_window (int k)
+{
+    if (k < 15 || k > 63) return 0;
+    int win = ((k - 15) + 7) / 8 * 8;
+    return win < 8 ? 8 : win;
+}
+static bool k1_fast_ok (const K1Params& P)
+{
+    if (P.mode != K1_MODE_DEVICE || P.nmask || P.count_only || P.force_general) return false;
+    const int W = (P.k < 32) ? 1 : 2;
+    if (P.w != k1_fast_window (P.k) || P.m != P.k - P.w + 1 || P.m < 8 || P.m > 16) return false;
+    return (W == 1) ? (P.w == 8 || P.w == 16) : (P.w >= 24 && P.w <= 48);
+}
+
 static size_t k1_smem_bytes (int w) { return (size_t)w * K1_THREADS * 4 + 4 * (K1_QCAP * 2) * 4 + 4 * 32 * 8 + 4 * 4 + 16; }
 
 template<int W, bool HAS_N, int MODE>
@@ -262,6 +474,16 @@ static cudaError_t k1_launch_t (const LaunchCtx& L, const K1Params& P)
 cudaError_t launch_k1 (const LaunchCtx& L, const K1Params& P)
 {
     const int W = (P.k < 32) ? 1 : 2;
+    if (k1_fast_ok (P))
+        switch (P.w)
+        {
+            case 8:  return k1_fast_launch_t<8, 1>  (L, P);
+            case 16: return k1_fast_launch_t<16, 1> (L, P);
+            case 24: return k1_fast_launch_t<24, 2> (L, P);
+            case 32: return k1_fast_launch_t<32, 2> (L, P);
+            case 40: return k1_fast_launch_t<40, 2> (L, P);
+            case 48: return k1_fast_launch_t<48, 2> (L, P);
+        }
     const bool n = P.nmask != 0;
     if (P.mode == K1_MODE_GATB)
     {

@@ -1,0 +1,201 @@
+// k1_scan.cuh -- register-resident minimizer scan of one read (the per-thread part of k1_superkmer_fast).
+//
+// Replaces, for the device binning order (see k1_partition.cu, K1_MODE_DEVICE), the per-k-mer work of
+//   ModelCanonical/ModelMinimizer::next       kmer/impl/Model.hpp:857-884, 1106-1139
+//   Sequence2SuperKmer::operator()            kmer/impl/Sequence2SuperKmer.hpp:81-159
+// (paths relative to /root/reference/gatb-core/src/gatb/).
+//
+// Everything is compile-time indexed so that the whole state lives in registers:
+//   * the read is seen as a stream of NORMALISED 32-bit words (word t = stream bits [32t, 32t+32) counted from the
+//     read's first nucleotide); position j = 16t+u has its m-mer at bit 2u of (word t+1 : word t).  One funnel shift
+//     gives the stream-order m-mer x (reverse-complement value = x ^ 0b1010.., common.cuh), one funnel shift on the
+//     pair-reversed words gives the forward value; no per-nucleotide rolling state;
+//   * rank key = min(fwd, rc) * odd + odd (one IMAD): a pseudo-random minimizer order, m <= 16;
+//   * sliding minimum over WIN = k-m+1 keys by blocks of WIN (prefix minima of the current block, suffix minima of
+//     the previous one): 3 min per position, WIN registers, no data-dependent rescans;
+//   * every normalised word is also parked in a 16-deep shared-memory ring (one column per thread);
+//   * a super-k-mer ends when the window minimum changes; the scanner only hands (key, first k-mer, length) to the
+//     emitter.  Lengths are bounded by 47 (forced split), the emitter cuts them to the record capacity.
+// The code is __host__ __device__ so that tests/cpp/test_k1_scan.cu can check it on the CPU against a direct
+// restatement (every window minimum recomputed from scratch).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define K1S_HD __host__ __device__ __forceinline__
+#else
+#define K1S_HD inline
+#endif
+
+K1S_HD uint32_t k1s_fshr (uint32_t lo, uint32_t hi, int s)      // low 32 bits of (hi:lo) >> (s & 31)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r (lo, hi, s);
+#else
+    s &= 31; return s ? ((lo >> s) | (hi << (32 - s))) : lo;
+#endif
+}
+K1S_HD uint32_t k1s_fshl (uint32_t lo, uint32_t hi, int s)      // high 32 bits of (hi:lo) << (s & 31)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l (lo, hi, s);
+#else
+    s &= 31; return s ? ((hi << s) | (lo >> (32 - s))) : hi;
+#endif
+}
+K1S_HD uint32_t k1s_brev (uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __brev (x);
+#else
+    uint32_t r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r;
+#endif
+}
+K1S_HD uint32_t k1s_ldg (const uint32_t* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg (p);
+#else
+    return *p;
+#endif
+}
+#define K1S_FSHR(lo, hi, s) k1s_fshr ((lo), (hi), (s))
+#define K1S_FSHL(lo, hi, s) k1s_fshl ((lo), (hi), (s))
+#define K1S_BREV(x)         k1s_brev (x)
+#define K1S_LDG(p)          k1s_ldg (p)
+
+#define K1S_MUL 0x9E3779B1u
+#define K1S_ADD 0x7F4A7C15u
+
+// rank key of a canonical m-mer (device binning order)
+K1S_HD uint32_t k1s_key (uint32_t cm) { return cm * K1S_MUL + K1S_ADD; }
+
+K1S_HD uint32_t k1s_pair_reverse (uint32_t x)
+{
+    uint32_t r = K1S_BREV (x);
+    return ((r >> 1) & 0x55555555u) | ((r << 1) & 0xAAAAAAAAu);
+}
+
+constexpr int k1s_gcd (int a, int b) { return b ? k1s_gcd (b, a % b) : a; }
+
+// RS = stride (in words) of the optional shared-memory word ring: every normalised word is also stored at
+// ring[(word index % K1S_RING) * RS], so that whoever builds the record of a closed super-k-mer reads the nucleotides
+// from shared memory instead of going back to global memory (0 = no ring, used by the host test).
+#define K1S_RING 16
+template<int WIN, int RS = 0>
+struct K1Scanner
+{
+    static constexpr int LCM    = WIN / k1s_gcd (WIN, 16) * 16;   // positions after which (window slot, word phase) repeat
+    static constexpr int PHASES = LCM / 16;
+    static constexpr int MAXRUN = 32;                              // forced split threshold (lengths stay < 32+16)
+
+    uint32_t suf[WIN];            // keys of the current block / suffix minima of the previous one
+    uint32_t na, nb, ra, rb;      // normalised words t, t+1 and their pair-reversed images
+    uint32_t raw;                 // last raw word consumed
+    uint32_t ahead;               // raw word loaded one step early (its latency hides behind 16 positions of work)
+    const uint32_t* wp;           // next raw word
+    uint32_t* ring;               // this thread's column of the word ring (RS != 0)
+    uint32_t nw;                  // normalised words produced so far
+    uint32_t sh;                  // bit offset of the read inside its first raw word
+    uint32_t mmask, aam, fsh;     // 4^m-1, 0xAAAAAAAA & mmask, 32-2m
+    uint32_t p, cur;              // prefix minimum of the current block, key of the open super-k-mer
+    int start;                    // first k-mer of the open super-k-mer
+    int j;                        // next m-mer position
+    int nm;                       // m-mer positions of the read (len-m+1)
+
+    K1S_HD uint32_t next_word ()
+    {
+        const uint32_t r = ahead;
+        ahead = K1S_LDG (wp); wp++;
+        const uint32_t n = K1S_FSHR (raw, r, sh);
+        raw = r;
+        if (RS) { ring[(nw & (K1S_RING - 1)) * RS] = n; nw++; }
+        return n;
+    }
+    K1S_HD void advance_word () { na = nb; ra = rb; nb = next_word (); rb = k1s_pair_reverse (nb); }
+
+    template<int U> K1S_HD uint32_t key_at () const
+    {
+        const uint32_t x  = U ? K1S_FSHR (na, nb, 2 * U) : na;
+        const uint32_t rc = (x & mmask) ^ aam;
+        const uint32_t g  = U ? K1S_FSHL (rb, ra, 2 * U) : ra;
+        const uint32_t f  = g >> fsh;
+        return k1s_key (f < rc ? f : rc);
+    }
+
+    // one position: T = slot in the window block, U = nucleotide inside the normalised word; i = k-mer index j-(WIN-1)
+    template<int T, int U, bool TAIL, class Emit> K1S_HD void position (int q, Emit& emit)
+    {
+        if (TAIL && j + q >= nm) return;
+        const uint32_t key = key_at<U> ();
+        const uint32_t s = (T + 1 < WIN) ? suf[(T + 1) % WIN] : 0xFFFFFFFFu;
+        suf[T] = key;
+        p = (T == 0) ? key : (key < p ? key : p);
+        const uint32_t wmin = (T + 1 < WIN) ? (s < p ? s : p) : p;
+        if (wmin != cur)
+        {
+            const int i = j + q - (WIN - 1);
+            emit (cur, start, i - start);
+            cur = wmin; start = i;
+        }
+        if (T == WIN - 1)
+        {
+            #pragma unroll
+            for (int u = WIN - 2; u >= 1; u--) suf[u] = suf[u] < suf[u + 1] ? suf[u] : suf[u + 1];
+        }
+        if (U == 15) advance_word ();
+    }
+
+    // ---- the read starts at nucleotide 'roff' of the packed stream 'words32'; len >= k = m+WIN-1 is required -------
+    // Processes the first block (m-mer positions 0..WIN-1): afterwards the super-k-mer of k-mer 0 is open.
+    K1S_HD void begin (const uint32_t* words32, uint64_t roff, int len, int m, uint32_t* ring_column = 0)
+    {
+        ring = ring_column; nw = 0;
+        mmask = (m >= 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1);
+        aam = 0xAAAAAAAAu & mmask; fsh = 32 - 2 * m;
+        nm = len - m + 1;
+        const uint64_t b0 = 2 * roff;
+        wp = words32 + (b0 >> 5); sh = (uint32_t)(b0 & 31);
+        raw = K1S_LDG (wp); wp++;
+        ahead = K1S_LDG (wp); wp++;
+        na = next_word (); ra = k1s_pair_reverse (na);
+        nb = next_word (); rb = k1s_pair_reverse (nb);
+        first_block (Int<0> ());
+        cur = p; start = 0; j = WIN;
+        #pragma unroll
+        for (int u = WIN - 2; u >= 1; u--) suf[u] = suf[u] < suf[u + 1] ? suf[u] : suf[u + 1];
+    }
+    template<int N> struct Int {};
+    template<int T> K1S_HD void first_block (Int<T>)
+    {
+        const uint32_t key = key_at<T % 16> ();
+        suf[T] = key;
+        p = (T == 0) ? key : (key < p ? key : p);
+        if (T % 16 == 15) advance_word ();
+        first_block (Int<T + 1> ());
+    }
+    K1S_HD void first_block (Int<WIN>) {}
+
+    // ---- 16 positions starting at j (j = WIN + 16*n, PH = n % PHASES) -----------------------------------------------
+    template<int PH, bool TAIL, class Emit> K1S_HD void step16 (Emit& emit)
+    {
+        // forced split of very long runs (tandem repeats): everything but the last k-mer seen leaves, so that a change
+        // of the minimum at the next position still closes a non-empty super-k-mer
+        if (j - (WIN - 1) - start >= MAXRUN) { const int i = j - (WIN - 1) - 1; emit (cur, start, i - start); start = i; }
+        run16<PH, 0, TAIL> (emit, Int<0> ());
+        j += 16;
+    }
+    template<int PH, int Q, bool TAIL, class Emit, int QQ> K1S_HD void run16 (Emit& emit, Int<QQ>)
+    {
+        position<(WIN + 16 * PH + QQ) % WIN, (WIN + QQ) % 16, TAIL> (QQ, emit);
+        run16<PH, Q, TAIL> (emit, Int<QQ + 1> ());
+    }
+    template<int PH, int Q, bool TAIL, class Emit> K1S_HD void run16 (Emit&, Int<16>) {}
+
+    // the read is over: close the open super-k-mer
+    template<class Emit> K1S_HD void finish (Emit& emit)
+    {
+        const int nk = nm - (WIN - 1);
+        emit (cur, start, nk - start);
+    }
+};

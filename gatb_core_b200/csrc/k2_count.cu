@@ -17,6 +17,8 @@
 //      global atomics.  A bin whose distinct k-mers do not fit the table is deferred to k2c (global-memory table).
 #include "common.cuh"
 #include "kernels.h"
+#include "k2_decode.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------ mbarrier / TMA
 __device__ __forceinline__ uint32_t smem_u32 (const void* p) { return (uint32_t)__cvta_generic_to_shared (p); }
@@ -42,14 +44,26 @@ __device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.prox
 // ------------------------------------------------------------------------------------------------ k2a
 template<int W>
 __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __restrict__ dst, const uint64_t* __restrict__ coarse_off,
-                                                        const uint32_t* __restrict__ fine_counts, uint32_t cap, int fine_bits,
-                                                        uint2* __restrict__ bin_desc)
+                                                        uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc)
 {
+    const uint32_t nb = gridDim.x;                          // bins of a source region (laid out by coarse_index, kernels.h)
     __shared__ uint32_t s_off[128], s_cur[128], s_tmp[128];
     const uint32_t b = blockIdx.x;
     const int nf = 1 << fine_bits;
     const int tid = threadIdx.x;
-    if (tid < nf) { s_tmp[tid] = fine_counts[((uint64_t)b << fine_bits) + tid]; s_cur[tid] = 0; }
+    if (tid < nf) { s_tmp[tid] = 0; s_cur[tid] = 0; }
+    __syncthreads ();
+    // pass 1: records per fine bin (the second pass finds the same lines in L2)
+    for (int s = 0; s < S.n; s++)
+    {
+        const uint32_t n = min (S.cursors[s][b], cap);
+        const uint4* __restrict__ src = S.bins[s];
+        for (uint32_t i = tid; i < n; i += blockDim.x)
+        {
+            const uint32_t top = __ldg (&src[coarse_index (b, i, nb) * W + (W - 1)]).w;
+            atomicAdd (&s_tmp[top >> (32 - (W == 1 ? FINE_BITS_W1 : FINE_BITS_W2))], 1u);
+        }
+    }
     __syncthreads ();
     if (tid < 32)
     {   // exclusive scan of <=128 counters by one warp (4 per lane)
@@ -68,19 +82,20 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
     for (int s = 0; s < S.n; s++)
     {
         const uint32_t n = min (S.cursors[s][b], cap);
-        const uint4* __restrict__ src = S.bins[s] + (uint64_t)b * cap * W;
+        const uint4* __restrict__ src = S.bins[s];
         for (uint32_t i = tid; i < n; i += blockDim.x)
         {
             if (W == 1)
             {
-                uint4 rec = __ldg (&src[i]);
+                uint4 rec = __ldg (&src[coarse_index (b, i, nb)]);
                 uint32_t f = rec.w >> (32 - FINE_BITS_W1);
                 uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
                 dst[dbase + p] = rec;
             }
             else
             {
-                uint4 r0 = __ldg (&src[2*(uint64_t)i]), r1 = __ldg (&src[2*(uint64_t)i + 1]);
+                const uint64_t ci = coarse_index (b, i, nb);
+                uint4 r0 = __ldg (&src[2*ci]), r1 = __ldg (&src[2*ci + 1]);
                 uint32_t f = r1.w >> (32 - FINE_BITS_W2);
                 uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
                 dst[2*(dbase + p)] = r0; dst[2*(dbase + p) + 1] = r1;
@@ -90,11 +105,11 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
 }
 
 cudaError_t launch_k2a_split (const LaunchCtx& L, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
-                              const uint32_t* fine_counts, uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc)
+                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc)
 {
     if (nb1 == 0) return cudaSuccess;
-    if (W == 1) k2a_fine_split<1><<<nb1, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, fine_counts, cap, fine_bits, bin_desc);
-    else        k2a_fine_split<2><<<nb1, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, fine_counts, cap, fine_bits, bin_desc);
+    if (W == 1) k2a_fine_split<1><<<nb1, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, cap, fine_bits, bin_desc);
+    else        k2a_fine_split<2><<<nb1, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, cap, fine_bits, bin_desc);
     (*L.launches)++;
     return cudaGetLastError ();
 }
@@ -190,14 +205,14 @@ __device__ __forceinline__ int table_insert_w2 (unsigned long long* klo, unsigne
 // ---- consuming one table slot of the GLOBAL fallback table: histogram + statistics + emission -------------------
 struct EmitState { unsigned long long distinct, solid, emitted; };
 
-__device__ __forceinline__ void consume_entry (const K2Params& P, bool occupied, uint64_t klo, uint64_t khi, uint32_t c, EmitState& st)
+__device__ __forceinline__ void consume_entry (const K2Params& P, bool occupied, uint64_t klo, uint64_t khi, uint32_t c, EmitState& st, uint32_t* s_hist)
 {
     bool emit = false;
     if (occupied)
     {
         st.distinct++;
         uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
-        atomicAdd (&P.histogram[hb], 1ULL);
+        if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
         if (c >= P.solid_min && c <= P.solid_max) st.solid++;
         emit = (c >= P.emit_min && c <= P.emit_max);
     }
@@ -462,6 +477,564 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ k2b, k <= 31
+// Same bin pipeline as k2b_bucket_hash_count (persistent CTAs, TMA-staged bins, per-warp output blocks) with an insert
+// phase built for SIMT efficiency:
+//   * lane <-> CHUNK of four consecutive k-mers of one record.  A warp takes 32 records (lane <-> record), prefix-sums
+//     their chunk counts and walks the chunks 32 at a time; the chunk -> record map of a window is one __reduce_or_sync
+//     of "head" bits plus a popc.  The four k-mers of a chunk share one record load and one pair-reversal of their
+//     common 68-bit window (k2_decode.cuh); every shift inside the chunk is an immediate;
+//   * the whole warp stays converged through the four insert steps: one probe (LDS.64 issued for all four k-mers up
+//     front), a predicated 64-bit CAS on an empty slot, a predicated count increment.  No data-dependent loop;
+//   * first occurrences are appended to the WARP's claimed-slot list with a ballot + popc (the cursor is a warp-uniform
+//     register: no atomics); k-mers whose first slot holds another key go to the warp's retry list and are re-inserted
+//     32 at a time with the general probing loop, so the rare long probe never stalls 31 other lanes.
+// After the block barrier each warp walks its own claimed-slot list: histogram, statistics, emission, slot cleanup.
+__device__ __forceinline__ uint32_t k2_slot32 (uint32_t lo, uint32_t hi, int shift)
+{ return (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> shift; }
+
+// general open-addressing insert starting at 'slot'; returns the slot (bit 31 set when this call claimed it), or -1
+__device__ __forceinline__ int k2_probe_loop (unsigned long long* s_klo, uint32_t* s_cnt, uint32_t slot, unsigned long long key, uint32_t tmask)
+{
+    #pragma unroll 1
+    for (int probe = 0; probe < K2_MAXPROBE; probe++)
+    {
+        unsigned long long cur = s_klo[slot];
+        if (cur == EMPTY64) cur = atomicCAS (&s_klo[slot], EMPTY64, key);
+        if (cur == EMPTY64) { atomicAdd (&s_cnt[slot], 1u); return (int)(slot | 0x80000000u); }
+        if (cur == key)     { atomicAdd (&s_cnt[slot], 1u); return (int)slot; }
+        slot = (slot + 1) & tmask;
+    }
+    return -1;
+}
+
+#define K2_RETRY_CAP 160        // per warp: 31 left over + 4 steps x 32 lanes at the very worst
+
+template<int NT>
+__global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
+{
+    constexpr int CHR = 256;                               // records per staging buffer (4 KB)
+    constexpr int NWARP = NT / 32;
+    constexpr unsigned WBLOCK = 2048;                      // output slots a warp reserves at a time
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = 1 << P.table_log2;
+    const uint32_t tmask = (uint32_t)T - 1;
+    const int hshift = 32 - P.table_log2;
+    const uint32_t OCC_W = (uint32_t)((T * 3) / 4) / NWARP;                 // claimed-slot capacity per warp
+    uint4* s_recs = (uint4*)smem_raw;                                        // [2][CHR]
+    unsigned long long* s_klo = (unsigned long long*)(smem_raw + (size_t)2 * CHR * 16);
+    unsigned long long* s_retry = s_klo + T;                                 // [NWARP][K2_RETRY_CAP]
+    uint32_t* s_cnt  = (uint32_t*)(s_retry + NWARP * K2_RETRY_CAP);
+    uint32_t* s_hist = s_cnt + T;
+    uint64_t* s_bar  = (uint64_t*)(s_hist + K2_HB);                          // [2]
+    uint16_t* s_occ  = (uint16_t*)(s_bar + 2);                               // [NWARP][OCC_W]
+    __shared__ uint32_t s_bin[2], s_n[2];
+    __shared__ unsigned long long s_base[2];
+    __shared__ int s_ovf;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const int k = P.k;
+    for (int i = tid; i < T; i += NT) { s_klo[i] = EMPTY64; s_cnt[i] = 0; }
+    for (int i = tid; i < K2_HB; i += NT) s_hist[i] = 0;
+    uint16_t* occ_w = s_occ + (size_t)wid * OCC_W;
+    unsigned long long* retry_w = s_retry + wid * K2_RETRY_CAP;
+
+    auto fetch = [&] (int st)
+    {
+        uint32_t bin; uint2 d = make_uint2 (0, 0);
+        for (;;)
+        {
+            bin = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
+            if (bin >= P.nbins) break;
+            d = P.bin_desc[bin];
+            if (d.y) break;
+        }
+        s_bin[st] = bin;
+        if (bin < P.nbins)
+        {
+            const unsigned long long base = P.coarse_off[bin >> P.fine_bits] + d.x;
+            s_n[st] = d.y; s_base[st] = base;
+            const uint32_t mrec = min ((uint32_t)CHR, d.y);
+            fence_proxy_async ();
+            mbar_expect_tx (&s_bar[st], mrec * 16);
+            tma_bulk_g2s (s_recs + (size_t)st * CHR, (const uint4*)P.recs + base, mrec * 16, &s_bar[st]);
+        }
+    };
+    if (tid == 0)
+    {
+        mbar_init (&s_bar[0], 1); mbar_init (&s_bar[1], 1);
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_ovf = 0;
+        fetch (0);
+    }
+    __syncthreads ();
+    uint32_t par0 = 0, par1 = 0;
+    unsigned long long n_distinct = 0, n_solid = 0, n_emitted = 0;
+    unsigned long long out_pos = 0, out_end = 0;
+    int st = 0;
+
+    for (;;)
+    {
+        const uint32_t bin = s_bin[st];
+        if (bin >= P.nbins) break;
+        const uint32_t n = s_n[st];
+        const unsigned long long base = s_base[st];
+        if (tid == 0) fetch (st ^ 1);
+        const uint4* recs = s_recs + (size_t)st * CHR;
+        uint32_t wn = 0, rn = 0;                              // warp-uniform: claimed slots, pending retries
+        bool w_ovf = false;
+
+        // appends the slots claimed by this step (ballot order) to the warp's list
+        auto append_new = [&] (bool isnew, uint32_t slot)
+        {
+            const unsigned m = __ballot_sync (FULL_MASK, isnew);
+            if (m)
+            {
+                const uint32_t idx = wn + __popc (m & lt_mask);
+                if (isnew && idx < OCC_W) occ_w[idx] = (uint16_t)slot;
+                wn += __popc (m);
+            }
+        };
+        // re-inserts the pending retries (general probing loop), 32 at a time
+        auto drain_retries = [&] ()
+        {
+            __syncwarp ();
+            for (uint32_t e0 = 0; e0 < rn; e0 += 32)
+            {
+                const uint32_t e = e0 + lane;
+                int res = 0;
+                if (e < rn)
+                {
+                    const unsigned long long key = retry_w[e];
+                    res = k2_probe_loop (s_klo, s_cnt, k2_slot32 ((uint32_t)key, (uint32_t)(key >> 32), hshift), key, tmask);
+                    if (res == -1) w_ovf = true;
+                }
+                __syncwarp ();
+                append_new (e < rn && res != -1 && (res & 0x80000000), (uint32_t)res & 0xFFFFu);
+            }
+            rn = 0;
+            __syncwarp ();
+        };
+
+        for (uint32_t c0 = 0; c0 < n; c0 += CHR)
+        {
+            const uint32_t mrec = min ((uint32_t)CHR, n - c0);
+            if (c0)
+            {
+                __syncthreads ();
+                if (tid == 0)
+                {
+                    fence_proxy_async ();
+                    mbar_expect_tx (&s_bar[st], mrec * 16);
+                    tma_bulk_g2s ((void*)recs, (const uint4*)P.recs + (base + c0), mrec * 16, &s_bar[st]);
+                }
+            }
+            if (st == 0) { mbar_wait (&s_bar[0], par0); par0 ^= 1; } else { mbar_wait (&s_bar[1], par1); par1 ^= 1; }
+
+            for (uint32_t g0 = wid * 32; g0 < mrec; g0 += NWARP * 32)
+            {
+                const uint32_t ri = g0 + lane;
+                uint32_t nch = 0;
+                if (ri < mrec) nch = (((recs[ri].w >> (REC_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;
+                uint32_t incl = nch;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
+                const uint32_t excl = incl - nch;
+                const uint32_t total = __shfl_sync (FULL_MASK, incl, 31);
+                uint32_t r0 = 0;
+                for (uint32_t wb = 0; wb < total; wb += 32)
+                {
+                    const uint32_t h = excl - wb;
+                    const uint32_t M = __reduce_or_sync (FULL_MASK, (nch > 0 && h < 32u) ? (1u << h) : 0u);
+                    const uint32_t gk = wb + lane;
+                    const bool act = gk < total;
+                    uint32_t r = r0 + __popc (M & (0xFFFFFFFFu >> (31 - lane))) - 1;
+                    r0 += __popc (M);
+                    r &= 31u;
+                    const uint32_t ex = __shfl_sync (FULL_MASK, excl, r);
+                    const int c = act ? (int)(gk - ex) : 0;
+                    const uint4 q = recs[act ? g0 + r : g0];
+                    const int nkc = act ? (int)((q.w >> (REC_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
+                    K2Chunk C;
+                    k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (REC_LEN_SHIFT_W1 - 32)) - 1), c, k);
+                    uint32_t lo[4], hi[4], slot[4];
+                    k2_chunk_kmer<0> (C, lo[0], hi[0]); k2_chunk_kmer<1> (C, lo[1], hi[1]);
+                    k2_chunk_kmer<2> (C, lo[2], hi[2]); k2_chunk_kmer<3> (C, lo[3], hi[3]);
+                    unsigned long long cur[4];
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) { slot[i] = k2_slot32 (lo[i], hi[i], hshift); cur[i] = (i < nkc) ? s_klo[slot[i]] : 0ULL; }
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++)
+                    {
+                        const bool valid = i < nkc;
+                        const unsigned long long key = ((unsigned long long)hi[i] << 32) | lo[i];
+                        unsigned long long cv = cur[i];
+                        const bool isE = valid && cv == EMPTY64;
+                        if (isE) cv = atomicCAS (&s_klo[slot[i]], EMPTY64, key);
+                        const bool isnew = isE && cv == EMPTY64;
+                        const bool hit = valid && (isnew || cv == key);
+                        if (hit) atomicAdd (&s_cnt[slot[i]], 1u);
+                        append_new (isnew, slot[i]);
+                        const bool miss = valid && !hit;
+                        const unsigned mm = __ballot_sync (FULL_MASK, miss);
+                        if (mm)
+                        {
+                            if (miss) retry_w[rn + __popc (mm & lt_mask)] = key;
+                            rn += __popc (mm);
+                        }
+                    }
+                    if (rn >= 32) drain_retries ();
+                }
+            }
+        }
+        if (rn) drain_retries ();
+        if (w_ovf || wn > OCC_W) s_ovf = 1;
+        __syncthreads ();                                     // all inserts of the bin are done
+        const bool ovf = s_ovf != 0;
+        if (ovf)
+        {
+            if (tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin; }
+            for (int i = tid; i < T; i += NT) { s_klo[i] = EMPTY64; s_cnt[i] = 0; }
+            __syncthreads ();
+            if (tid == 0) s_ovf = 0;
+            __syncthreads ();
+            st ^= 1;
+            continue;
+        }
+        for (uint32_t q0 = 0; q0 < wn; q0 += 32)
+        {
+            const uint32_t q = q0 + lane;
+            bool emit = false; uint64_t klo = 0; uint32_t c = 0;
+            if (q < wn)
+            {
+                const uint32_t slot = occ_w[q];
+                c = s_cnt[slot]; klo = s_klo[slot];
+                s_klo[slot] = EMPTY64; s_cnt[slot] = 0;
+                n_distinct++;
+                const uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
+                if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
+                if (c >= P.solid_min && c <= P.solid_max) n_solid++;
+                emit = (c >= P.emit_min && c <= P.emit_max);
+            }
+            const unsigned ballot = __ballot_sync (FULL_MASK, emit);
+            if (ballot)
+            {
+                const unsigned ne = __popc (ballot);
+                if (out_pos + ne > out_end)
+                {
+                    for (unsigned long long hpos = out_pos + lane; hpos < out_end; hpos += 32)
+                        if (hpos < P.out_cap) P.out_lo[hpos] = EMPTY64;
+                    unsigned long long b0 = 0;
+                    if (lane == 0) b0 = atomicAdd (&P.counters[0], (unsigned long long)WBLOCK);
+                    b0 = __shfl_sync (FULL_MASK, b0, 0);
+                    out_pos = b0; out_end = b0 + WBLOCK;
+                }
+                if (emit)
+                {
+                    const unsigned long long pos = out_pos + __popc (ballot & lt_mask);
+                    n_emitted++;
+                    if (pos < P.out_cap) { P.out_lo[pos] = klo; P.out_cnt[pos] = c; }
+                }
+                out_pos += ne;
+            }
+        }
+        __syncthreads ();                                     // table clean again before the next bin's inserts
+        st ^= 1;
+    }
+    for (unsigned long long hpos = out_pos + lane; hpos < out_end; hpos += 32)
+        if (hpos < P.out_cap) P.out_lo[hpos] = EMPTY64;
+    __syncthreads ();
+    for (int i = tid; i < K2_HB; i += NT) { uint32_t v = s_hist[i]; if (v) atomicAdd (&P.histogram[i], (unsigned long long)v); }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        n_distinct += __shfl_xor_sync (FULL_MASK, n_distinct, o); n_solid += __shfl_xor_sync (FULL_MASK, n_solid, o);
+        n_emitted += __shfl_xor_sync (FULL_MASK, n_emitted, o);
+    }
+    if (lane == 0)
+    {
+        if (n_distinct) atomicAdd (&P.counters[1], n_distinct);
+        if (n_solid)    atomicAdd (&P.counters[2], n_solid);
+        if (n_emitted)  atomicAdd (&P.counters[6], n_emitted);
+    }
+}
+static size_t k2b_w1_smem_bytes (int table_log2, int nt)
+{
+    const size_t T = (size_t)1 << table_log2, nwarp = nt / 32;
+    size_t occ_w = ((T * 3) / 4) / nwarp;
+    return 2 * 256 * 16 + T * 8 + nwarp * K2_RETRY_CAP * 8 + T * 4 + K2_HB * 4 + 16 + nwarp * occ_w * 2 + 16;
+}
+template<int NT>
+static cudaError_t k2b_w1_launch (const LaunchCtx& L, const K2Params& P)
+{
+    const size_t smem = k2b_w1_smem_bytes (P.table_log2, NT);
+    cudaError_t e = cudaFuncSetAttribute (k2b_count_w1<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k2b_count_w1<NT>, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)L.sm_count * per_sm;
+    if (grid > P.nbins) grid = P.nbins;
+    k2b_count_w1<NT><<<(unsigned)grid, NT, smem, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
+// ------------------------------------------------------------------------------------------------ k2b, k <= 31, warp per bin
+// One WARP owns a fine bin from its first record to its last emitted k-mer: private shared-memory table (T slots),
+// private claimed-slot and retry lists, no block barrier and no work counter (warp g takes bins g, g+G, g+2G, ...).
+// The records of a bin go straight from global memory into registers (lane <-> record, one coalesced 16-byte load per
+// lane; the chunk -> record gather inside the warp is four shuffles), and the descriptor and first records of the NEXT
+// bin are requested before the current bin is processed, so their latency hides behind the inserts.
+// Insert and scan phases are those of k2b_count_w1 (chunks of four k-mers, converged probe/claim/count steps).
+template<int NT>
+__global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
+{
+    constexpr int NWARP = NT / 32;
+    constexpr unsigned WBLOCK = 2048;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = 1 << P.table_log2;
+    const uint32_t tmask = (uint32_t)T - 1;
+    const int hshift = 32 - P.table_log2;
+    const uint32_t OCC_W = (uint32_t)(T * 3) / 4;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const int k = P.k;
+    // per warp: keys T*8 | retry K2_RETRY_CAP*8 | counts T*4 | claimed OCC_W*2 ; per CTA: histogram
+    const size_t per_warp = (size_t)T * 8 + K2_RETRY_CAP * 8 + (size_t)T * 4 + (((size_t)OCC_W * 2 + 15) & ~(size_t)15);
+    unsigned char* wbase = smem_raw + per_warp * wid;
+    unsigned long long* s_klo = (unsigned long long*)wbase;
+    unsigned long long* retry_w = s_klo + T;
+    uint32_t* s_cnt = (uint32_t*)(retry_w + K2_RETRY_CAP);
+    uint16_t* occ_w = (uint16_t*)(s_cnt + T);
+    uint32_t* s_hist = (uint32_t*)(smem_raw + per_warp * NWARP);
+
+    for (int i = lane; i < T; i += 32) { s_klo[i] = EMPTY64; s_cnt[i] = 0; }
+    for (int i = tid; i < K2_HB; i += NT) s_hist[i] = 0;
+    __syncthreads ();
+
+    unsigned long long n_distinct = 0, n_solid = 0, n_emitted = 0;
+    unsigned long long out_pos = 0, out_end = 0;
+    const uint32_t G = gridDim.x * NWARP;
+    const uint4 zero4 = make_uint4 (0, 0, 0, 0);
+
+    // software pipeline over this warp's bins: (bin0, d0, base0, rec0) is current; d1/co1 of the next bin are in flight
+    uint32_t bin0 = blockIdx.x * NWARP + wid;
+    uint2 d0 = bin0 < P.nbins ? P.bin_desc[bin0] : make_uint2 (0, 0);
+    unsigned long long base0 = bin0 < P.nbins ? P.coarse_off[bin0 >> P.fine_bits] + d0.x : 0;
+    uint4 rec0 = ((uint32_t)lane < d0.y) ? __ldg ((const uint4*)P.recs + base0 + lane) : zero4;
+    uint32_t bin1 = bin0 + G;
+    uint2 d1 = bin1 < P.nbins ? P.bin_desc[bin1] : make_uint2 (0, 0);
+    unsigned long long co1 = bin1 < P.nbins ? P.coarse_off[bin1 >> P.fine_bits] : 0;
+
+    while (bin0 < P.nbins)
+    {
+        // ---- requests for the following bins ----
+        const unsigned long long base1 = co1 + d1.x;
+        const uint4 rec1 = ((uint32_t)lane < d1.y) ? __ldg ((const uint4*)P.recs + base1 + lane) : zero4;
+        const uint32_t bin2 = bin1 + G;
+        const uint2 d2 = bin2 < P.nbins ? P.bin_desc[bin2] : make_uint2 (0, 0);
+        const unsigned long long co2 = bin2 < P.nbins ? P.coarse_off[bin2 >> P.fine_bits] : 0;
+
+        const uint32_t n = d0.y;
+        if (n)
+        {
+            uint32_t wn = 0, rn = 0;                              // warp-uniform: claimed slots, pending retries
+            bool w_ovf = false;
+            auto append_new = [&] (bool isnew, uint32_t slot)
+            {
+                const unsigned m = __ballot_sync (FULL_MASK, isnew);
+                if (m)
+                {
+                    const uint32_t idx = wn + __popc (m & lt_mask);
+                    if (isnew && idx < OCC_W) occ_w[idx] = (uint16_t)slot;
+                    wn += __popc (m);
+                }
+            };
+            auto drain_retries = [&] ()
+            {
+                __syncwarp ();
+                for (uint32_t e0 = 0; e0 < rn; e0 += 32)
+                {
+                    const uint32_t e = e0 + lane;
+                    int res = 0;
+                    if (e < rn)
+                    {
+                        const unsigned long long key = retry_w[e];
+                        res = k2_probe_loop (s_klo, s_cnt, k2_slot32 ((uint32_t)key, (uint32_t)(key >> 32), hshift), key, tmask);
+                        if (res == -1) w_ovf = true;
+                    }
+                    __syncwarp ();
+                    append_new (e < rn && res != -1 && (res & 0x80000000), (uint32_t)res & 0xFFFFu);
+                }
+                rn = 0;
+                __syncwarp ();
+            };
+
+            for (uint32_t g0 = 0; g0 < n; g0 += 32)
+            {
+                uint4 rec = rec0;
+                if (g0) rec = (g0 + lane < n) ? __ldg ((const uint4*)P.recs + base0 + g0 + lane) : zero4;
+                const uint32_t nch = (((rec.w >> (REC_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;      // 0 for the zero record
+                uint32_t incl = nch;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
+                const uint32_t excl = incl - nch;
+                const uint32_t total = __shfl_sync (FULL_MASK, incl, 31);
+                uint32_t r0 = 0;
+                for (uint32_t wb = 0; wb < total; wb += 32)
+                {
+                    const uint32_t h = excl - wb;
+                    const uint32_t M = __reduce_or_sync (FULL_MASK, (nch > 0 && h < 32u) ? (1u << h) : 0u);
+                    const uint32_t gk = wb + lane;
+                    const bool act = gk < total;
+                    uint32_t r = r0 + __popc (M & (0xFFFFFFFFu >> (31 - lane))) - 1;
+                    r0 += __popc (M);
+                    r &= 31u;
+                    const uint32_t ex = __shfl_sync (FULL_MASK, excl, r);
+                    uint4 q;
+                    q.x = __shfl_sync (FULL_MASK, rec.x, r); q.y = __shfl_sync (FULL_MASK, rec.y, r);
+                    q.z = __shfl_sync (FULL_MASK, rec.z, r); q.w = __shfl_sync (FULL_MASK, rec.w, r);
+                    const int c = act ? (int)(gk - ex) : 0;
+                    const int nkc = act ? (int)((q.w >> (REC_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
+                    K2Chunk C;
+                    k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (REC_LEN_SHIFT_W1 - 32)) - 1), c, k);
+                    uint32_t lo[4], hi[4], slot[4];
+                    k2_chunk_kmer<0> (C, lo[0], hi[0]); k2_chunk_kmer<1> (C, lo[1], hi[1]);
+                    k2_chunk_kmer<2> (C, lo[2], hi[2]); k2_chunk_kmer<3> (C, lo[3], hi[3]);
+                    unsigned long long cur[4];
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) { slot[i] = k2_slot32 (lo[i], hi[i], hshift); cur[i] = (i < nkc) ? s_klo[slot[i]] : 0ULL; }
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++)
+                    {
+                        const bool valid = i < nkc;
+                        const unsigned long long key = ((unsigned long long)hi[i] << 32) | lo[i];
+                        unsigned long long cv = cur[i];
+                        const bool isE = valid && cv == EMPTY64;
+                        if (isE) cv = atomicCAS (&s_klo[slot[i]], EMPTY64, key);
+                        const bool isnew = isE && cv == EMPTY64;
+                        const bool hit = valid && (isnew || cv == key);
+                        if (hit) atomicAdd (&s_cnt[slot[i]], 1u);
+                        append_new (isnew, slot[i]);
+                        const bool miss = valid && !hit;
+                        const unsigned mm = __ballot_sync (FULL_MASK, miss);
+                        if (mm)
+                        {
+                            if (miss) retry_w[rn + __popc (mm & lt_mask)] = key;
+                            rn += __popc (mm);
+                        }
+                    }
+                    if (rn >= 32) drain_retries ();
+                }
+            }
+            if (rn) drain_retries ();
+            __syncwarp ();
+            if (__any_sync (FULL_MASK, w_ovf) || wn > OCC_W)
+            {   // the bin goes to the global-memory fallback (k2c): wipe the warp's table
+                if (lane == 0) { const uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin0; }
+                for (int i = lane; i < T; i += 32) { s_klo[i] = EMPTY64; s_cnt[i] = 0; }
+                __syncwarp ();
+            }
+            else
+            {
+                for (uint32_t q0 = 0; q0 < wn; q0 += 32)
+                {
+                    const uint32_t q = q0 + lane;
+                    bool emit = false; uint64_t klo = 0; uint32_t c = 0;
+                    if (q < wn)
+                    {
+                        const uint32_t slot = occ_w[q];
+                        c = s_cnt[slot]; klo = s_klo[slot];
+                        s_klo[slot] = EMPTY64; s_cnt[slot] = 0;
+                        n_distinct++;
+                        const uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
+                        if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
+                        if (c >= P.solid_min && c <= P.solid_max) n_solid++;
+                        emit = (c >= P.emit_min && c <= P.emit_max);
+                    }
+                    const unsigned ballot = __ballot_sync (FULL_MASK, emit);
+                    if (ballot)
+                    {
+                        const unsigned ne = __popc (ballot);
+                        if (out_pos + ne > out_end)
+                        {
+                            for (unsigned long long hpos = out_pos + lane; hpos < out_end; hpos += 32)
+                                if (hpos < P.out_cap) P.out_lo[hpos] = EMPTY64;
+                            unsigned long long b0 = 0;
+                            if (lane == 0) b0 = atomicAdd (&P.counters[0], (unsigned long long)WBLOCK);
+                            b0 = __shfl_sync (FULL_MASK, b0, 0);
+                            out_pos = b0; out_end = b0 + WBLOCK;
+                        }
+                        if (emit)
+                        {
+                            const unsigned long long pos = out_pos + __popc (ballot & lt_mask);
+                            n_emitted++;
+                            if (pos < P.out_cap) { P.out_lo[pos] = klo; P.out_cnt[pos] = c; }
+                        }
+                        out_pos += ne;
+                    }
+                }
+                __syncwarp ();
+            }
+        }
+        bin0 = bin1; d0 = d1; base0 = base1; rec0 = rec1;
+        bin1 = bin2; d1 = d2; co1 = co2;
+    }
+    for (unsigned long long hpos = out_pos + lane; hpos < out_end; hpos += 32)
+        if (hpos < P.out_cap) P.out_lo[hpos] = EMPTY64;
+    __syncthreads ();
+    for (int i = tid; i < K2_HB; i += NT) { uint32_t v = s_hist[i]; if (v) atomicAdd (&P.histogram[i], (unsigned long long)v); }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        n_distinct += __shfl_xor_sync (FULL_MASK, n_distinct, o); n_solid += __shfl_xor_sync (FULL_MASK, n_solid, o);
+        n_emitted += __shfl_xor_sync (FULL_MASK, n_emitted, o);
+    }
+    if (lane == 0)
+    {
+        if (n_distinct) atomicAdd (&P.counters[1], n_distinct);
+        if (n_solid)    atomicAdd (&P.counters[2], n_solid);
+        if (n_emitted)  atomicAdd (&P.counters[6], n_emitted);
+    }
+}
+static size_t k2b_warp_smem_bytes (int table_log2, int nt)
+{
+    const size_t T = (size_t)1 << table_log2, occ = (T * 3) / 4;
+    const size_t per_warp = T * 8 + K2_RETRY_CAP * 8 + T * 4 + ((occ * 2 + 15) & ~(size_t)15);
+    return per_warp * (nt / 32) + K2_HB * 4;
+}
+template<int NT>
+static cudaError_t k2b_warp_launch (const LaunchCtx& L, const K2Params& P)
+{
+    const size_t smem = k2b_warp_smem_bytes (P.table_log2, NT);
+    cudaError_t e = cudaFuncSetAttribute (k2b_warp_bins<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k2b_warp_bins<NT>, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)L.sm_count * per_sm;
+    const uint64_t need = (P.nbins + NT / 32 - 1) / (NT / 32);
+    if (grid > need) grid = need;
+    k2b_warp_bins<NT><<<(unsigned)grid, NT, smem, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
+// which counting kernel serves k <= 31 (GATB_GPU_K2B): 1 = warp per bin (default), 128 / 256 = CTA per bin with the chunked
+// insert, 0 = CTA per bin, one k-mer per lane.  The table size the planner picks follows from it.
+int k2b_variant ()
+{
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv ("GATB_GPU_K2B"); variant = e ? atoi (e) : 1; }
+    return variant;
+}
+int k2b_default_table_log2 (int W) { return (W == 1 && k2b_variant () == 1) ? 9 : 11; }
+
 static size_t k2b_smem_bytes (int W, int table_log2)
 {
     size_t T = (size_t)1 << table_log2, occ = (T * 3) / 4; occ += occ & 1;
@@ -473,6 +1046,10 @@ cudaError_t launch_k2b_count (const LaunchCtx& L, const K2Params& P)
 {
     if (P.nbins == 0) return cudaSuccess;
     size_t smem = k2b_smem_bytes (P.W, P.table_log2);
+    const int variant = k2b_variant ();
+    if (P.W == 1 && variant == 1) return k2b_warp_launch<128> (L, P);
+    if (P.W == 1 && variant == 128) return k2b_w1_launch<128> (L, P);
+    if (P.W == 1 && variant == 256) return k2b_w1_launch<256> (L, P);
     const void* fn = (P.W == 1) ? (const void*)k2b_bucket_hash_count<1> : (const void*)k2b_bucket_hash_count<2>;
     cudaError_t e = cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -551,6 +1128,9 @@ template<int W>
 __global__ void __launch_bounds__(256) k2c_scan (const K2Params P)
 {
     const uint64_t T = 1ULL << P.g_log2;
+    __shared__ uint32_t s_hist[K2_HB];                     // abundances below K2_HB: one global atomic per CTA and value at the end
+    for (int i = threadIdx.x; i < K2_HB; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads ();
     EmitState st; st.distinct = 0; st.solid = 0; st.emitted = 0;
     // every thread of a warp runs the same number of iterations (consume_entry uses warp collectives)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -564,8 +1144,10 @@ __global__ void __launch_bounds__(256) k2c_scan (const K2Params P)
             klo = P.g_lo[i]; khi = (W == 2) ? P.g_hi[i] : 0; c = P.g_cnt[i];
             occ = (W == 1) ? (klo != EMPTY64) : (khi != EMPTY64);
         }
-        consume_entry (P, occ, klo, khi, c, st);
+        consume_entry (P, occ, klo, khi, c, st, s_hist);
     }
+    __syncthreads ();
+    for (int i = threadIdx.x; i < K2_HB; i += blockDim.x) { const uint32_t v = s_hist[i]; if (v) atomicAdd (&P.histogram[i], (unsigned long long)v); }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { st.distinct += __shfl_xor_sync (FULL_MASK, st.distinct, o); st.solid += __shfl_xor_sync (FULL_MASK, st.solid, o); st.emitted += __shfl_xor_sync (FULL_MASK, st.emitted, o); }
     if ((threadIdx.x & 31) == 0) { if (st.distinct) atomicAdd (&P.counters[1], st.distinct); if (st.solid) atomicAdd (&P.counters[2], st.solid); if (st.emitted) atomicAdd (&P.counters[6], st.emitted); }

@@ -1,0 +1,53 @@
+// k2_decode.cuh -- rebuilding the canonical k-mers of a super-k-mer record, four at a time (k <= 31, 16-byte records).
+//
+// Replaces the per-k-mer rolling of the reference's partition readers
+//   ReadSuperKCommand::execute / PartitionsByHashCommand decode   kmer/impl/PartitionsCommand.cpp:944-1128, 420-501
+// (paths relative to /root/reference/gatb-core/src/gatb/).
+//
+// A record holds the nucleotides of the super-k-mer in stream order (nucleotide n in bits [2n, 2n+2), kernels.h).
+// Chunk c = k-mers 4c .. 4c+3.  Their union is the window X = record bits [8c, 8c+2k+6) (at most 68 bits):
+//   stream bits of k-mer i     x_i  = (X >> 2i) & mask(2k)              reverse-complement VALUE = x_i ^ 0b1010..
+//   forward VALUE              f_i  = pair_reverse(x_i) aligned right   = (Z >> (6-2i)) & mask(2k)
+// where Z = pair_reverse of the whole window, computed once per chunk (3 BREV).  All shifts inside the chunk are
+// compile-time constants; canonical = min(forward, reverse complement) as kmer/impl/Model.hpp:857-884.
+// __host__ __device__ so that tests/cpp/test_k2_decode.cpp checks it on the CPU nucleotide by nucleotide.
+#pragma once
+#include "k1_scan.cuh"      // k1s_fshr / k1s_pair_reverse / K1S_HD
+
+struct K2Chunk
+{
+    uint32_t x0, x1, x2;        // window X (stream order)
+    uint32_t z0, z1, z2;        // pair-reversed window, right aligned
+    uint32_t lmask, hmask;      // masks of the low / high word of a 2k-bit value
+};
+
+// r0..r3 = the record's 32-bit words (r3 already stripped of the length / fine-bin fields); c = chunk index
+K1S_HD void k2_chunk_begin (K2Chunk& C, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, int c, int k)
+{
+    const int s = 8 * c;                             // 0..48
+    const bool hiw = s >= 32;
+    const uint32_t a0 = hiw ? r1 : r0, a1 = hiw ? r2 : r1, a2 = hiw ? r3 : r2, a3 = hiw ? 0u : r3;
+    const int sh = s & 31;
+    C.x0 = k1s_fshr (a0, a1, sh); C.x1 = k1s_fshr (a1, a2, sh); C.x2 = k1s_fshr (a2, a3, sh);
+    C.lmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1);
+    C.hmask = (k > 16) ? ((1u << (2 * k - 32)) - 1) : 0u;
+    // Y = pair reversal of the 96-bit window (y2 most significant) ; Z = Y >> (96 - (2k+6))
+    const uint32_t y2 = k1s_pair_reverse (C.x0), y1 = k1s_pair_reverse (C.x1), y0 = k1s_pair_reverse (C.x2);
+    const int t = 90 - 2 * k;                        // 28..86, even
+    if (t < 32)      { C.z0 = k1s_fshr (y0, y1, t); C.z1 = k1s_fshr (y1, y2, t); C.z2 = y2 >> t; }
+    else if (t < 64) { C.z0 = k1s_fshr (y1, y2, t - 32); C.z1 = y2 >> (t - 32); C.z2 = 0; }
+    else             { C.z0 = y2 >> (t - 64); C.z1 = 0; C.z2 = 0; }
+}
+
+// canonical value of k-mer I (0..3) of the chunk
+template<int I> K1S_HD void k2_chunk_kmer (const K2Chunk& C, uint32_t& lo, uint32_t& hi)
+{
+    const uint32_t xl = I ? k1s_fshr (C.x0, C.x1, 2 * I) : C.x0;
+    const uint32_t xh = I ? k1s_fshr (C.x1, C.x2, 2 * I) : C.x1;
+    const uint32_t rl = (xl & C.lmask) ^ (0xAAAAAAAAu & C.lmask);
+    const uint32_t rh = (xh & C.hmask) ^ (0xAAAAAAAAu & C.hmask);
+    const uint32_t fl = ((I < 3) ? k1s_fshr (C.z0, C.z1, 6 - 2 * I) : C.z0) & C.lmask;
+    const uint32_t fh = ((I < 3) ? k1s_fshr (C.z1, C.z2, 6 - 2 * I) : C.z1) & C.hmask;
+    const bool f_lt = (fh < rh) || (fh == rh && fl < rl);
+    lo = f_lt ? fl : rl; hi = f_lt ? fh : rh;
+}

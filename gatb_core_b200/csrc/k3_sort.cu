@@ -51,52 +51,135 @@ __device__ __forceinline__ uint32_t gatb_minimizer_w2 (u128 v, int k, int m, uin
     return best;
 }
 
+// Both passes are chains of dependent memory operations (load -> atomic -> store) on random addresses: every thread
+// keeps K3_ILP independent items in flight so that the latencies overlap.
+#define K3_ILP 4
 __global__ void __launch_bounds__(256) k3a_classify (const K3Params P)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    uint32_t key = 0, topbits = 0;
+    const uint64_t base = (uint64_t)blockIdx.x * (256 * K3_ILP) + threadIdx.x;
     const int k = P.k, t = P.t_bits;
-    // holes left by k2b's block-wise output reservation carry an all-ones key: skip them
-    if ((P.W == 1 ? P.in_lo[i] : P.in_hi[i]) == 0xFFFFFFFFFFFFFFFFULL) { P.bucket_of[i] = 0xFFFFFFFFu; return; }
-    if (P.W == 1)
+    uint64_t lo[K3_ILP], hi[K3_ILP];
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
     {
-        uint64_t v = P.in_lo[i];
-        if (P.n_keys > 1)
-        {
-            uint32_t mini = gatb_minimizer_w1 (v, k, P.m, P.mmask, P.mask_ma1);
-            key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
-        }
-        if (t) topbits = (uint32_t)(v >> (2*k - t));
+        const uint64_t i = base + 256 * j;
+        lo[j] = i < P.n ? P.in_lo[i] : 0xFFFFFFFFFFFFFFFFULL;
+        hi[j] = (P.W == 2) ? (i < P.n ? P.in_hi[i] : 0xFFFFFFFFFFFFFFFFULL) : 0;
     }
-    else
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
     {
-        u128 v; v.lo = P.in_lo[i]; v.hi = P.in_hi[i];
-        if (P.n_keys > 1)
+        const uint64_t i = base + 256 * j;
+        if (i >= P.n) continue;
+        // holes left by k2b's block-wise output reservation carry an all-ones key: skip them
+        if ((P.W == 1 ? lo[j] : hi[j]) == 0xFFFFFFFFFFFFFFFFULL) { P.bucket_of[i] = 0xFFFFFFFFu; continue; }
+        uint32_t key = 0, topbits = 0;
+        if (P.W == 1)
         {
-            uint32_t mini = gatb_minimizer_w2 (v, k, P.m, P.mmask, P.mask_ma1);
-            key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
+            const uint64_t v = lo[j];
+            if (P.n_keys > 1)
+            {
+                const uint32_t mini = gatb_minimizer_w1 (v, k, P.m, P.mmask, P.mask_ma1);
+                key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
+            }
+            if (t) topbits = (uint32_t)(v >> (2*k - t));
         }
-        if (t) { int s = 2*k - t; topbits = (uint32_t)(s >= 64 ? (v.hi >> (s - 64)) : ((v.lo >> s) | (v.hi << (64 - s)))); }
+        else
+        {
+            u128 v; v.lo = lo[j]; v.hi = hi[j];
+            if (P.n_keys > 1)
+            {
+                const uint32_t mini = gatb_minimizer_w2 (v, k, P.m, P.mmask, P.mask_ma1);
+                key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
+            }
+            if (t) { const int s = 2*k - t; topbits = (uint32_t)(s >= 64 ? (v.hi >> (s - 64)) : ((v.lo >> s) | (v.hi << (64 - s)))); }
+        }
+        const uint32_t b = (key << t) | topbits;
+        P.bucket_of[i] = b;
+        atomicAdd (&P.bucket_count[b], 1u);
     }
-    uint32_t b = (key << t) | topbits;
-    P.bucket_of[i] = b;
-    atomicAdd (&P.bucket_count[b], 1u);
+}
+
+// Scatter into bucket order.  With ~10^6 buckets the write tails (one 32-byte sector per bucket and array) no longer fit
+// the L2 next to the streaming input, and every 8/4-byte store becomes a DRAM read-modify-write.  So large inputs go in
+// TWO hops: k3b_scatter_coarse groups the items (with their bucket id) by the top bits of the bucket id -- 2^c groups,
+// whose tails stay in L2 -- and k3b_scatter then runs over that grouped copy, where consecutive items touch only the
+// 2^(bits-c) buckets of one group.  Offsets of both hops come from the same prefix sums: group g starts at
+// bucket_off[g << shift].
+__global__ void __launch_bounds__(256) k3b_scatter_coarse (const K3Params P, int shift, uint32_t* __restrict__ group_cursor,
+                                                            uint64_t* __restrict__ g_lo, uint64_t* __restrict__ g_hi,
+                                                            uint32_t* __restrict__ g_cnt, uint32_t* __restrict__ g_bucket)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * (256 * K3_ILP) + threadIdx.x;
+    uint32_t b[K3_ILP]; uint64_t lo[K3_ILP], hi[K3_ILP], pos[K3_ILP]; uint32_t c[K3_ILP];
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++) { const uint64_t i = base + 256 * j; b[j] = i < P.n ? P.bucket_of[i] : 0xFFFFFFFFu; }
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+    {
+        const uint64_t i = base + 256 * j;
+        if (b[j] != 0xFFFFFFFFu)
+        {
+            const uint32_t g = b[j] >> shift;
+            pos[j] = P.bucket_off[(uint64_t)g << shift] + atomicAdd (&group_cursor[g], 1u);
+            lo[j] = P.in_lo[i]; c[j] = P.in_cnt[i];
+            if (P.W == 2) hi[j] = P.in_hi[i];
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+        if (b[j] != 0xFFFFFFFFu)
+        {
+            g_lo[pos[j]] = lo[j];
+            if (P.W == 2) g_hi[pos[j]] = hi[j];
+            g_cnt[pos[j]] = c[j];
+            g_bucket[pos[j]] = b[j];
+        }
 }
 
 __global__ void __launch_bounds__(256) k3b_scatter (const K3Params P)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    const uint32_t b = P.bucket_of[i];
-    if (b == 0xFFFFFFFFu) return;
-    const uint64_t pos = P.bucket_off[b] + atomicAdd (&P.bucket_count[b], 1u);     // bucket_count was re-zeroed: it is the cursor now
-    P.tmp_lo[pos] = P.in_lo[i];
-    if (P.W == 2) P.tmp_hi[pos] = P.in_hi[i];
-    P.tmp_cnt[pos] = P.in_cnt[i];
+    const uint64_t base = (uint64_t)blockIdx.x * (256 * K3_ILP) + threadIdx.x;
+    uint32_t b[K3_ILP]; uint64_t lo[K3_ILP], hi[K3_ILP], pos[K3_ILP]; uint32_t c[K3_ILP];
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++) { const uint64_t i = base + 256 * j; b[j] = i < P.n ? P.bucket_of[i] : 0xFFFFFFFFu; }
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+    {
+        const uint64_t i = base + 256 * j;
+        if (b[j] != 0xFFFFFFFFu)
+        {
+            pos[j] = P.bucket_off[b[j]] + atomicAdd (&P.bucket_count[b[j]], 1u);     // bucket_count was re-zeroed: it is the cursor now
+            lo[j] = P.in_lo[i]; c[j] = P.in_cnt[i];
+            if (P.W == 2) hi[j] = P.in_hi[i];
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+        if (b[j] != 0xFFFFFFFFu)
+        {
+            P.tmp_lo[pos[j]] = lo[j];
+            if (P.W == 2) P.tmp_hi[pos[j]] = hi[j];
+            P.tmp_cnt[pos[j]] = c[j];
+        }
 }
 
-// ---- bitonic sort of (key128, count) in shared memory ----------------------------------------------------------
+// ---- per-bucket sort in shared memory ------------------------------------------------------------------------------
+// The k-mers of a bucket share their top t_bits; below them the values are close to uniform.  So the bucket is sorted by
+// DISTRIBUTION: the next B bits (2^B >= n) pick a sub-bucket (shared-memory histogram, in-place scan, scatter with the
+// scanned counters as cursors), and inside a sub-bucket (about one k-mer on average) every k-mer finds its rank by
+// comparing itself with its few neighbours -- k-mers are distinct, so ranks are unique.  O(n) work, two block barriers.
+// A bucket with a crowded sub-bucket (skewed values) takes the bitonic network instead.
+#define K3_SUB_MAX 48
+template<int W>
+__device__ __forceinline__ uint32_t k3_sub_bucket (uint64_t lo, uint64_t hi, int shift, uint32_t mask)
+{
+    // bits [shift, shift+B) of the (hi:lo) value
+    if (W == 1) return (uint32_t)(lo >> shift) & mask;
+    if (shift >= 64) return (uint32_t)(hi >> (shift - 64)) & mask;
+    return (uint32_t)((shift ? ((lo >> shift) | (hi << (64 - shift))) : lo)) & mask;
+}
+
 template<int W>
 __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
 {
@@ -104,6 +187,10 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
     uint64_t* s_lo = (uint64_t*)smem_raw;
     uint64_t* s_hi = (W == 2) ? s_lo + K3_SORT_CAP : 0;
     uint32_t* s_c  = (uint32_t*)(s_lo + (size_t)K3_SORT_CAP * W);
+    uint32_t* s_off = s_c + K3_SORT_CAP;                      // [K3_SORT_CAP] sub-bucket counters -> end offsets
+    __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_max;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (uint32_t b = P.bucket_begin + blockIdx.x; b < P.bucket_end; b += gridDim.x)
     {
         const uint64_t beg = P.bucket_off[b], end = P.bucket_off[b+1];
@@ -111,11 +198,77 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
         if (n64 == 0) continue;
         if (n64 > K3_SORT_CAP)
         {
-            if (threadIdx.x == 0) { unsigned long long idx = atomicAdd (&P.counters[0], 1ULL); P.big_list[idx] = b; }
+            if (tid == 0) { unsigned long long idx = atomicAdd (&P.counters[0], 1ULL); P.big_list[idx] = b; }
             continue;
         }
         const int n = (int)n64;
-        int np = 1; while (np < n) np <<= 1;
+        int np = 1, B = 0; while (np < n) { np <<= 1; B++; }
+        // value bits below the bucket's own t_bits: 2k - t_bits of them; the sub-bucket takes the top B of those
+        const int free_bits = 2 * P.k - P.t_bits;
+        bool ranked = false;
+        if (n == 1)
+        {
+            if (tid == 0) { P.out_lo[beg] = P.tmp_lo[beg]; if (W == 2) P.out_hi[beg] = P.tmp_hi[beg]; P.out_cnt[beg] = (int32_t)P.tmp_cnt[beg]; }
+            continue;
+        }
+        if (free_bits >= B)
+        {
+            const int shift = free_bits - B; const uint32_t mask = (uint32_t)np - 1;
+            for (int i = tid; i < np; i += 256) s_off[i] = 0;
+            if (tid == 0) s_max = 0;
+            __syncthreads ();
+            for (int i = tid; i < n; i += 256)
+                atomicAdd (&s_off[k3_sub_bucket<W> (P.tmp_lo[beg + i], W == 2 ? P.tmp_hi[beg + i] : 0, shift, mask)], 1u);
+            __syncthreads ();
+            // in-place exclusive scan of np counters: every thread owns np/256 consecutive ones (np >= 256) or one (np < 256)
+            {
+                const int per = np >= 256 ? np / 256 : 1;
+                const int i0 = tid * per;
+                uint32_t sum = 0, mx = 0;
+                if (i0 < np) for (int u = 0; u < per; u++) { const uint32_t v = s_off[i0 + u]; sum += v; mx = v > mx ? v : mx; }
+                uint32_t incl = sum;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const uint32_t y = __shfl_xor_sync (FULL_MASK, mx, o); mx = y > mx ? y : mx; }
+                if (lane == 31) s_wsum[wid] = incl;
+                if (lane == 0 && mx) atomicMax (&s_max, mx);
+                __syncthreads ();
+                uint32_t run = incl - sum;
+                for (int u = 0; u < wid; u++) run += s_wsum[u];
+                if (i0 < np) for (int u = 0; u < per; u++) { const uint32_t v = s_off[i0 + u]; s_off[i0 + u] = run; run += v; }
+                __syncthreads ();
+            }
+            if (s_max <= K3_SUB_MAX)
+            {
+                ranked = true;
+                // scatter by sub-bucket (arrival order inside); s_off[sb] ends up as the END of sub-bucket sb
+                for (int i = tid; i < n; i += 256)
+                {
+                    const uint64_t lo = P.tmp_lo[beg + i], hi = (W == 2) ? P.tmp_hi[beg + i] : 0;
+                    const uint32_t pos = atomicAdd (&s_off[k3_sub_bucket<W> (lo, hi, shift, mask)], 1u);
+                    s_lo[pos] = lo; if (W == 2) s_hi[pos] = hi; s_c[pos] = P.tmp_cnt[beg + i];
+                }
+                __syncthreads ();
+                for (int i = tid; i < n; i += 256)
+                {
+                    const uint64_t lo = s_lo[i], hi = (W == 2) ? s_hi[i] : 0;
+                    const uint32_t sb = k3_sub_bucket<W> (lo, hi, shift, mask);
+                    const uint32_t e = s_off[sb], st0 = sb ? s_off[sb - 1] : 0;
+                    uint32_t rank = 0;
+                    for (uint32_t j = st0; j < e; j++)
+                    {
+                        const uint64_t ol = s_lo[j];
+                        if (W == 1) rank += (ol < lo);
+                        else { const uint64_t oh = s_hi[j]; rank += (oh < hi || (oh == hi && ol < lo)); }
+                    }
+                    const uint64_t dst = beg + st0 + rank;
+                    P.out_lo[dst] = lo; if (W == 2) P.out_hi[dst] = hi; P.out_cnt[dst] = (int32_t)s_c[i];
+                }
+                __syncthreads ();
+            }
+        }
+        if (ranked) continue;
         for (int i = threadIdx.x; i < np; i += blockDim.x)
         {
             if (i < n) { s_lo[i] = P.tmp_lo[beg + i]; if (W == 2) s_hi[i] = P.tmp_hi[beg + i]; s_c[i] = P.tmp_cnt[beg + i]; }
@@ -192,21 +345,29 @@ __global__ void __launch_bounds__(1024) k3d_sort_big (const K3Params P, uint32_t
 cudaError_t launch_k3a_classify (const LaunchCtx& L, const K3Params& P)
 {
     if (P.n == 0) return cudaSuccess;
-    k3a_classify<<<(unsigned)((P.n + 255) / 256), 256, 0, L.stream>>> (P);
+    k3a_classify<<<(unsigned)((P.n + 256 * K3_ILP - 1) / (256 * K3_ILP)), 256, 0, L.stream>>> (P);
     (*L.launches)++;
     return cudaGetLastError ();
 }
 cudaError_t launch_k3b_scatter (const LaunchCtx& L, const K3Params& P)
 {
     if (P.n == 0) return cudaSuccess;
-    k3b_scatter<<<(unsigned)((P.n + 255) / 256), 256, 0, L.stream>>> (P);
+    k3b_scatter<<<(unsigned)((P.n + 256 * K3_ILP - 1) / (256 * K3_ILP)), 256, 0, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+cudaError_t launch_k3b_scatter_coarse (const LaunchCtx& L, const K3Params& P, int shift, uint32_t* group_cursor,
+                                       uint64_t* g_lo, uint64_t* g_hi, uint32_t* g_cnt, uint32_t* g_bucket)
+{
+    if (P.n == 0) return cudaSuccess;
+    k3b_scatter_coarse<<<(unsigned)((P.n + 256 * K3_ILP - 1) / (256 * K3_ILP)), 256, 0, L.stream>>> (P, shift, group_cursor, g_lo, g_hi, g_cnt, g_bucket);
     (*L.launches)++;
     return cudaGetLastError ();
 }
 cudaError_t launch_k3c_sort (const LaunchCtx& L, const K3Params& P)
 {
     if (P.n == 0) return cudaSuccess;
-    size_t smem = (size_t)K3_SORT_CAP * (8 * P.W + 4);
+    size_t smem = (size_t)K3_SORT_CAP * (8 * P.W + 4 + 4);
     const void* fn = P.W == 1 ? (const void*)k3c_sort<1> : (const void*)k3c_sort<2>;
     cudaError_t e = cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

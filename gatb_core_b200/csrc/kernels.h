@@ -15,6 +15,19 @@
 enum { REC_LEN_SHIFT_W1 = 52, REC_FINE_SHIFT_W1 = 57, FINE_BITS_W1 = 7,
        REC_LEN_SHIFT_W2 = 52, REC_FINE_SHIFT_W2 = 58, FINE_BITS_W2 = 6 };
 
+// ----------------------------------------------------------------------------------------------------------------
+// Layout of a region of coarse bins (device mode): ROUNDS of COARSE_BLK records.  Record 'slot' of bin 'b' of a region
+// of 'nb' bins lives at ((slot / BLK) * nb + b) * BLK + slot % BLK: block r of every bin sits in round r.  All bins
+// fill at about the same rate (hashed minimizers), so at any time the partition kernel writes into a few neighbouring
+// rounds -- a window of tens of MB instead of one open line in every 100 KB of a 25 GB buffer.  Measured on B200: the
+// scattered record stores cost 4.0 ms per 3*10^8 records in the bin-major layout and 0.9 ms inside a small window
+// (address translation, not bandwidth).  Readers take a bin's blocks at stride nb*BLK records; CTAs working on
+// neighbouring bins share the pages.  cap is a multiple of COARSE_BLK.
+// ----------------------------------------------------------------------------------------------------------------
+enum { COARSE_BLK = 16 };
+__host__ __device__ __forceinline__ uint64_t coarse_index (uint32_t b, uint32_t slot, uint32_t nb)
+{ return ((uint64_t)(slot / COARSE_BLK) * nb + b) * COARSE_BLK + (slot % COARSE_BLK); }
+
 enum { K1_MODE_DEVICE = 0,   // hashed-order signature, device bins (the counting path)
        K1_MODE_GATB   = 1 }; // GATB minimizer (lexicographic + AA rule), bins = pass*nb_partitions + repart[minimizer]
 
@@ -32,13 +45,15 @@ struct K1Params
     const uint16_t* repart;         // GATB mode
     int      nb_partitions, nb_passes;
     uint32_t nb1;                   // number of (coarse) bins
+    uint32_t n_regions, bins_per_region;   // device mode: nb1 = n_regions * bins_per_region; region r (one per owner rank) is a
+                                    // contiguous block of bins_per_region*cap records laid out by coarse_index()
     uint32_t cap;                   // records per bin
     int      fine_bits;
     void*    bins;                  // nb1*cap records
     uint32_t* cursors;              // [nb1] demand per bin (may exceed cap)
-    uint32_t* fine_counts;          // [nb1<<fine_bits] stored records per fine bin, or NULL
     unsigned long long* stats;      // [0] valid k-mers [1] invalid k-mers [2] records stored [3] records dropped (overflow)
     int      count_only;            // 1: only count demand (cursors), store nothing
+    int      force_general;         // 1: never take the register-scanner kernel (testing / reads with invalid nucleotides)
 };
 
 struct K2Params
@@ -84,17 +99,22 @@ struct LaunchCtx { cudaStream_t stream; int sm_count; uint64_t* launches; };
 
 // k1_partition.cu
 cudaError_t launch_k1 (const LaunchCtx&, const K1Params&);
+int         k1_fast_window (int k);      // window (k-m+1) the register-scanner kernel is compiled for, 0 = none
 // k2_count.cu
 struct K2aSrc { const uint4* bins[8]; const uint32_t* cursors[8]; int n; };     // the same coarse bins gathered from n sources
 cudaError_t launch_k2a_split (const LaunchCtx&, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
-                              const uint32_t* fine_counts, uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc);
+                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc);
 cudaError_t launch_k2b_count (const LaunchCtx&, const K2Params&);
+int         k2b_variant ();
+int         k2b_default_table_log2 (int W);
 cudaError_t launch_k2c_measure (const LaunchCtx&, const K2Params&, uint32_t n_ovf);
 cudaError_t launch_k2c_insert (const LaunchCtx&, const K2Params&, uint32_t n_ovf);
 cudaError_t launch_k2c_scan (const LaunchCtx&, const K2Params&);
 // k3_sort.cu
 cudaError_t launch_k3a_classify (const LaunchCtx&, const K3Params&);
 cudaError_t launch_k3b_scatter (const LaunchCtx&, const K3Params&);
+cudaError_t launch_k3b_scatter_coarse (const LaunchCtx&, const K3Params&, int shift, uint32_t* group_cursor,
+                                       uint64_t* g_lo, uint64_t* g_hi, uint32_t* g_cnt, uint32_t* g_bucket);
 cudaError_t launch_k3c_sort (const LaunchCtx&, const K3Params&);
 cudaError_t launch_k3d_sort_big (const LaunchCtx&, const K3Params&, uint32_t n_big);
 cudaError_t launch_scan_u32_to_u64 (const LaunchCtx&, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch);

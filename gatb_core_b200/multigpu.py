@@ -22,27 +22,24 @@ def owner_of_bin(b, bins_per_rank):
     return b // bins_per_rank
 
 
-def exchange_bins(bins, cursors, fine_counts, world):
+def exchange_bins(bins, cursors, world):
     """All-to-all of the partition buffers.
 
     bins        uint8  [nb1 * cap * record_bytes]   (nb1 = world * bins_per_rank; bin regions contiguous per owner)
     cursors     int32  [nb1]
-    fine_counts int32  [nb1 << fine_bits]
-    Returns (recv_bins [world, bpr*cap*rb], recv_cursors [world, bpr], recv_fine [world, bpr << fine_bits]):
-    row s = what source rank s produced for the bins THIS rank owns.
+    Returns (recv_bins [world, bpr*cap*rb], recv_cursors [world, bpr]):
+    row s = what source rank s produced for the bins THIS rank owns.  (The fine split counts its own bins from the
+    records, so nothing but the records and their cursors has to travel.)
     """
     recv_bins = torch.empty_like(bins)
     recv_cur = torch.empty_like(cursors)
-    recv_fine = torch.empty_like(fine_counts)
     if world == 1:
         recv_bins.copy_(bins)
         recv_cur.copy_(cursors)
-        recv_fine.copy_(fine_counts)
     else:
         dist.all_to_all_single(recv_bins, bins)
         dist.all_to_all_single(recv_cur, cursors)
-        dist.all_to_all_single(recv_fine, fine_counts)
-    return recv_bins.view(world, -1), recv_cur.view(world, -1), recv_fine.view(world, -1)
+    return recv_bins.view(world, -1), recv_cur.view(world, -1)
 
 
 def merge_sorted_runs(runs):
@@ -66,22 +63,20 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
         nb1, cap, rb, fb = geom.nb1, geom.cap, geom.record_bytes, geom.fine_bits
         bins = torch.empty(nb1 * cap * rb, dtype=torch.uint8, device=dev)
         cursors = torch.zeros(nb1, dtype=torch.int32, device=dev)
-        fine = torch.zeros(nb1 << fb, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
         t0 = time.time()
-        st = gpu.partition_into(params, geom, d_reads, d_offsets, n_reads_local, bins.data_ptr(), cursors.data_ptr(), fine.data_ptr())
+        st = gpu.partition_into(params, geom, d_reads, d_offsets, n_reads_local, bins.data_ptr(), cursors.data_ptr())
         t["partition"] = time.time() - t0
         flag = torch.tensor([st[3], int(cursors.max().item())], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         if int(flag[0].item()) == 0:
             break
-        geom.cap = (int(flag[1].item()) + 7) & ~7          # a bin overflowed somewhere: every rank re-runs with the global demand
-        del bins, cursors, fine
+        geom.cap = (int(flag[1].item()) + 15) & ~15         # a bin overflowed somewhere: every rank re-runs with the global demand
+        del bins, cursors
     t0 = time.time()
-    recv_bins, recv_cur, recv_fine = exchange_bins(bins, cursors, fine, world)
-    fine_total = recv_fine.sum(0, dtype=torch.int32).contiguous()
-    del bins, cursors, fine
+    recv_bins, recv_cur = exchange_bins(bins, cursors, world)
+    del bins, cursors
     torch.cuda.synchronize()
     t["exchange"] = time.time() - t0
     bpr = geom.bins_per_rank
@@ -95,7 +90,7 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
     # k-mers in the bins this rank owns: estimate with 25 % head-room, never above the hard bound
     kmers_bound = int(min(gathered * geom.maxlen, gathered * avg_len * 1.25 + 65536))
     t0 = time.time()
-    res = gpu.count_bins(params, geom, src_bins, src_cur, fine_total.data_ptr(), bpr, kmers_bound, repart=repart)
+    res = gpu.count_bins(params, geom, src_bins, src_cur, bpr, kmers_bound, repart=repart)
     t["count"] = time.time() - t0
     t["count_kernels"] = [float(x) for x in res.kernel_seconds][:5]
     t["overflow_kmers"] = int(res.stats[11])

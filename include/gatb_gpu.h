@@ -129,15 +129,15 @@ typedef struct gatb_gpu_geometry
     uint32_t n_ranks, bins_per_rank, record_bytes, pad;
 } gatb_gpu_geometry;
 int gatb_gpu_plan (gatb_gpu_ctx*, const gatb_gpu_params*, uint64_t total_kmers, uint64_t n_reads, int n_ranks, gatb_gpu_geometry* out);
-/* k1 into caller buffers: d_bins [nb1*cap records], d_cursors [nb1] (demand; > cap means overflow), d_fine_counts
- * [nb1 << fine_bits]; stats4 (host): valid k-mers, invalid k-mers, records stored, records dropped. */
+/* k1 into caller buffers: d_bins [nb1*cap records], d_cursors [nb1] (demand; > cap means overflow);
+ * stats4 (host): valid k-mers, invalid k-mers, records stored, records dropped. */
 int gatb_gpu_partition_into (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_geometry*,
                              const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads, const uint32_t* d_n_mask,
-                             void* d_bins, uint32_t* d_cursors, uint32_t* d_fine_counts, uint64_t* stats4);
+                             void* d_bins, uint32_t* d_cursors, uint64_t* stats4);
 /* counts nb1_local coarse bins gathered from n_src sources: d_src_bins[s] = [nb1_local*cap records], d_src_cursors[s] =
- * [nb1_local]; d_fine_counts_total = [nb1_local << fine_bits] summed over the sources; kmers_bound >= k-mers in these bins. */
+ * [nb1_local]; kmers_bound >= k-mers in these bins (the fine split counts its own bins, nothing else is exchanged). */
 int gatb_gpu_count_bins (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_geometry*, int n_src,
-                         const void* const* d_src_bins, const uint32_t* const* d_src_cursors, const uint32_t* d_fine_counts_total,
+                         const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
                          uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, gatb_gpu_result* out);
 
 /* ---- GATB-exact super-k-mer partitioning (rows A3-A6): per key, the record stream [u8 nbK][packed bytes]... that

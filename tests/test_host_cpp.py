@@ -27,3 +27,22 @@ def test_host_api_gpu():
     build()
     out = subprocess.run([BIN, "gpu"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def _run_device_logic_test(name):
+    """The register scanner (k1_scan.cuh) and the chunked record decoder (k2_decode.cuh) are __host__ __device__:
+    the same source the kernels use is compiled with g++ and checked against nucleotide-by-nucleotide restatements."""
+    src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", name)
+    inc = os.path.join(ROOT, "gatb_core_b200", "csrc")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unknown-pragmas", "-I" + inc, src, "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_k1_scanner_cpu():
+    _run_device_logic_test("test_k1_scan")
+
+
+def test_k2_decoder_cpu():
+    _run_device_logic_test("test_k2_decode")

@@ -32,9 +32,8 @@ def worker(rank, world, port, q):
             for i in range(cap):
                 bins[b, i, 0], bins[b, i, 1], bins[b, i, 2] = rank, b, i
         cursors = torch.tensor([(b + rank) % (cap + 1) for b in range(nb1)], dtype=torch.int32)
-        fine = torch.arange(nb1 << fb, dtype=torch.int32) * (rank + 1)
-        rbins, rcur, rfine = multigpu.exchange_bins(bins.view(-1), cursors, fine, world)
-        ok = rbins.shape == (world, bpr * cap * rb) and rcur.shape == (world, bpr) and rfine.shape == (world, bpr << fb)
+        rbins, rcur = multigpu.exchange_bins(bins.view(-1), cursors, world)
+        ok = rbins.shape == (world, bpr * cap * rb) and rcur.shape == (world, bpr)
         for s in range(world):
             piece = rbins[s].view(bpr, cap, rb)
             for lb in range(bpr):
@@ -42,8 +41,6 @@ def worker(rank, world, port, q):
                 assert multigpu.owner_of_bin(gb, bpr) == rank
                 ok &= bool((piece[lb, :, 0] == s).all() and (piece[lb, :, 1] == gb).all())
                 ok &= int(rcur[s, lb]) == (gb + s) % (cap + 1)
-            want_fine = torch.arange(nb1 << fb, dtype=torch.int32).view(world, -1)[rank] * (s + 1)
-            ok &= bool((rfine[s] == want_fine).all())
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -66,9 +63,8 @@ def test_exchange_bins_world2_gloo():
 def test_exchange_bins_world1_is_identity():
     bins = torch.arange(4 * 3 * 16, dtype=torch.uint8)
     cur = torch.tensor([1, 2, 3, 0], dtype=torch.int32)
-    fine = torch.arange(16, dtype=torch.int32)
-    a, b, c = multigpu.exchange_bins(bins, cur, fine, 1)
-    assert (a.view(-1) == bins).all() and (b.view(-1) == cur).all() and (c.view(-1) == fine).all()
+    a, b = multigpu.exchange_bins(bins, cur, 1)
+    assert (a.view(-1) == bins).all() and (b.view(-1) == cur).all()
 
 
 def test_merge_sorted_runs():
