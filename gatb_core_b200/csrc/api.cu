@@ -17,7 +17,7 @@ static std::string g_create_error;
 
 // device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
 enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
-            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_GBUCKET, S_GCURSOR, S_NSLOTS };
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_NSLOTS };
 
 struct gatb_gpu_ctx
 {
@@ -418,7 +418,6 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     void* d_offs = ctx->slot[S_RESMISC]; void* d_hist = (void*)((uint64_t*)ctx->slot[S_RESMISC] + (n_keys + 1));
     dr->offs = d_offs; dr->histo = d_hist;
 
-    if (ensure (ctx, S_BUCKETOF, (n_range + 1) * 4)) return 1;
     if (ensure (ctx, S_BUCKETCNT, n_buckets * 4)) return 1;
     if (ensure (ctx, S_BUCKETOFF, (n_buckets + 1) * 8)) return 1;
     if (ensure (ctx, S_SCAN, scan_scratch_elems (n_buckets) * 8)) return 1;
@@ -429,39 +428,57 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         if (ensure (ctx, S_REPART, rbytes)) return 1;
         CK (cudaMemcpyAsync (ctx->slot[S_REPART], repart_host, rbytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    // the fine buffer is dead after k2b/k2c: it holds the bucket-ordered copy
-    if (ctx->slot_cap[S_FINE] < n_alloc * item_bytes) { if (ensure (ctx, S_FINE, n_alloc * item_bytes)) return 1; }
+    // the fine buffer is dead after k2b/k2c: it holds the bucket-ordered copy (pool blocks, or the exact layout)
     K3Params k3; memset (&k3, 0, sizeof(k3));
     k3.k = k; k3.m = p->minimizer_size; k3.W = W;
     k3.mmask = (1u << (2 * p->minimizer_size)) - 1; k3.mask_ma1 = gatb_mask_ma1 (p->minimizer_size);
     k3.repart = (const uint16_t*)ctx->slot[S_REPART]; k3.nb_partitions = p->nb_partitions; k3.nb_passes = p->nb_passes; k3.n_keys = (uint32_t)n_keys;
     k3.t_bits = t_bits; k3.n = n_range;
     k3.in_lo = u_lo; k3.in_hi = u_hi; k3.in_cnt = u_cnt;
-    k3.bucket_of = (uint32_t*)ctx->slot[S_BUCKETOF]; k3.bucket_count = (uint32_t*)ctx->slot[S_BUCKETCNT];
+    k3.bucket_count = (uint32_t*)ctx->slot[S_BUCKETCNT];
     k3.bucket_off = (const uint64_t*)ctx->slot[S_BUCKETOFF];
-    k3.tmp_lo = (uint64_t*)ctx->slot[S_FINE]; k3.tmp_hi = (W == 2) ? k3.tmp_lo + n_alloc : 0; k3.tmp_cnt = (uint32_t*)(k3.tmp_lo + n_alloc * W);
     k3.out_lo = (uint64_t*)dr->lo; k3.out_hi = (uint64_t*)dr->hi; k3.out_cnt = (int32_t*)dr->cnt;
     k3.n_buckets = (uint32_t)n_buckets; k3.big_list = (unsigned long long*)ctx->slot[S_BIGLIST]; k3.counters = d_cnt + 8;
-    CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
     cudaEventRecord (ctx->kev[6], ctx->stream);
-    CK (launch_k3a_classify (L, k3));
-    CK (launch_scan_u32_to_u64 (L, k3.bucket_count, (uint64_t*)ctx->slot[S_BUCKETOFF], n_buckets, (uint64_t*)ctx->slot[S_SCAN]));
-    CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
-    static const bool force_two_hop = getenv ("GATB_GPU_K3_TWOHOP") && getenv ("GATB_GPU_K3_TWOHOP")[0] == '1';      // test hook
-    if (force_two_hop && n_buckets > 1)
-    {   // two hops (k3_sort.cu): first into <= 2048 groups of consecutive buckets, staged in the (still unused) result arrays
-        int bits = 0; while ((1ULL << bits) < n_buckets) bits++;
-        const int shift = bits > 11 ? bits - 11 : 0;
-        const uint64_t n_groups = ((n_buckets - 1) >> shift) + 1;
-        if (ensure (ctx, S_GBUCKET, n_alloc * 4)) return 1;
-        if (ensure (ctx, S_GCURSOR, n_groups * 4)) return 1;
-        CK (cudaMemsetAsync (ctx->slot[S_GCURSOR], 0, n_groups * 4, ctx->stream));
-        CK (launch_k3b_scatter_coarse (L, k3, shift, (uint32_t*)ctx->slot[S_GCURSOR], k3.out_lo, k3.out_hi, (uint32_t*)k3.out_cnt, (uint32_t*)ctx->slot[S_GBUCKET]));
-        K3Params k3g = k3;
-        k3g.n = n_items; k3g.in_lo = k3.out_lo; k3g.in_hi = k3.out_hi; k3g.in_cnt = (const uint32_t*)k3.out_cnt; k3g.bucket_of = (uint32_t*)ctx->slot[S_GBUCKET];
-        CK (launch_k3b_scatter (L, k3g));
+    // ---- bucket scatter: pooled single pass (k3s) unless a bucket outgrows the block directory, then the exact two-pass path ----
+    static const bool no_pool = getenv ("GATB_GPU_K3_POOL") && getenv ("GATB_GPU_K3_POOL")[0] == '0';                 // test hook
+    bool pooled = false;
+    if (!no_pool && n_items)
+    {
+        static const int dir_rounds_env = getenv ("GATB_GPU_K3_DIR_ROUNDS") ? atoi (getenv ("GATB_GPU_K3_DIR_ROUNDS")) : 0;         // test hook: small directory -> fallback
+        const uint32_t dir_rounds = dir_rounds_env > 0 ? (uint32_t)dir_rounds_env : k3_sort_cap () / K3_BLK;
+        const uint64_t pool_blocks = n_items / K3_BLK + n_buckets + 1;
+        if (pool_blocks < (1ULL << 32))
+        {
+            if (ensure (ctx, S_FINE, pool_blocks * K3_BLK * 16 * W)) return 1;
+            if (ensure (ctx, S_DIR, (size_t)dir_rounds * n_buckets * 4)) return 1;
+            CK (cudaMemsetAsync (ctx->slot[S_DIR], 0xFF, (size_t)dir_rounds * n_buckets * 4, ctx->stream));
+            CK (cudaMemsetAsync (d_cnt + 8, 0, 4 * 8, ctx->stream));
+            CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
+            k3.pool = (uint4*)ctx->slot[S_FINE]; k3.pool_blocks = (uint32_t)pool_blocks; k3.pool_ptr = (uint32_t*)(d_cnt + 10);
+            k3.dir = (uint32_t*)ctx->slot[S_DIR]; k3.dir_rounds = dir_rounds; k3.ovf_flag = (uint32_t*)(d_cnt + 11);
+            CK (launch_k3s_pool_scatter (L, k3));
+            CK (launch_scan_u32_to_u64 (L, k3.bucket_count, (uint64_t*)ctx->slot[S_BUCKETOFF], n_buckets, (uint64_t*)ctx->slot[S_SCAN]));
+            uint32_t flag = 0;
+            CK (cudaMemcpyAsync (&flag, k3.ovf_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+            pooled = (flag == 0);
+            if (!pooled) { k3.pool = 0; k3.dir = 0; }
+        }
     }
-    else CK (launch_k3b_scatter (L, k3));
+    if (!pooled)
+    {
+        if (ctx->slot_cap[S_FINE] < n_alloc * item_bytes) { if (ensure (ctx, S_FINE, n_alloc * item_bytes)) return 1; }
+        k3.tmp_lo = (uint64_t*)ctx->slot[S_FINE]; k3.tmp_hi = (W == 2) ? k3.tmp_lo + n_alloc : 0; k3.tmp_cnt = (uint32_t*)(k3.tmp_lo + n_alloc * W);
+        if (ensure (ctx, S_BUCKETOF, (n_range + 1) * 4)) return 1;
+        k3.bucket_of = (uint32_t*)ctx->slot[S_BUCKETOF];
+        CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
+        CK (launch_k3a_classify (L, k3));
+        CK (launch_scan_u32_to_u64 (L, k3.bucket_count, (uint64_t*)ctx->slot[S_BUCKETOFF], n_buckets, (uint64_t*)ctx->slot[S_SCAN]));
+        CK (cudaMemsetAsync (k3.bucket_count, 0, n_buckets * 4, ctx->stream));
+        CK (cudaMemsetAsync (d_cnt + 8, 0, 8, ctx->stream));
+        CK (launch_k3b_scatter (L, k3));
+    }
     // host sink: the sorted arrays leave in chunks of buckets while the next chunk is being sorted
     uint8_t* pin = 0; uint64_t* h_lo = 0; uint64_t* h_hi = 0; int32_t* h_cnt32 = 0; uint64_t* h_offs = 0; uint64_t* h_hist = 0;
     const int n_chunks = (to_host && n_items > (1u << 20)) ? 8 : 1;

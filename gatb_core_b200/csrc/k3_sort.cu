@@ -18,6 +18,7 @@
 #include "kernels.h"
 
 #define K3_SORT_CAP 4096
+#define K3_ILP 4          // independent items a thread of the classify / scatter passes keeps in flight
 
 // minimizer (GATB lexicographic order with the AA rule) of one canonical k-mer value
 __device__ __forceinline__ uint32_t gatb_minimizer_w1 (uint64_t v, int k, int m, uint32_t mmask, uint32_t mask_ma1)
@@ -51,13 +52,107 @@ __device__ __forceinline__ uint32_t gatb_minimizer_w2 (u128 v, int k, int m, uin
     return best;
 }
 
+// bucket = (partition key << t_bits) | top t_bits of the k-mer value
+__device__ __forceinline__ uint32_t k3_bucket_of (const K3Params& P, uint64_t lo, uint64_t hi)
+{
+    const int k = P.k, t = P.t_bits;
+    uint32_t key = 0, topbits = 0;
+    if (P.W == 1)
+    {
+        if (P.n_keys > 1)
+        {
+            const uint32_t mini = gatb_minimizer_w1 (lo, k, P.m, P.mmask, P.mask_ma1);
+            key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
+        }
+        if (t) topbits = (uint32_t)(lo >> (2*k - t));
+    }
+    else
+    {
+        u128 v; v.lo = lo; v.hi = hi;
+        if (P.n_keys > 1)
+        {
+            const uint32_t mini = gatb_minimizer_w2 (v, k, P.m, P.mmask, P.mask_ma1);
+            key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
+        }
+        if (t) { const int s = 2*k - t; topbits = (uint32_t)(s >= 64 ? (v.hi >> (s - 64)) : ((v.lo >> s) | (v.hi << (64 - s)))); }
+    }
+    return (key << t) | topbits;
+}
+
+// ---- k3s: classify + scatter in ONE pass over the emitted k-mers ------------------------------------------------------
+// Scattering 6*10^8 items into 10^6 buckets with exact offsets keeps one open line per bucket and array, spread over
+// the whole multi-GB copy: every store is an address-translation miss (measured: the same scatter folded into a
+// 256 MB window costs a quarter).  Here a bucket is a chain of K3_BLK-item blocks taken from ONE bump allocator, so
+// all open blocks are the most recently allocated ones -- a window of n_buckets * 512 B whatever the skew between
+// buckets -- and an item is one 16-byte (k <= 31) store instead of an 8- and a 4-byte one.  No counting pass is needed
+// first: the item's slot comes from its bucket's cursor, the lane that opens a block (slot % K3_BLK == 0) takes it from
+// the allocator and publishes it in dir[block number][bucket]; the others read it there (they can only have been
+// given their slot after the opener got its own, so the entry is on its way).
+// A bucket that outgrows dir_rounds * K3_BLK items raises ovf_flag: the caller then falls back to the exact two-pass
+// path (k3a + k3b), which has no such limit.
+__global__ void __launch_bounds__(256) k3s_pool_scatter (const K3Params P)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * (256 * K3_ILP) + threadIdx.x;
+    uint64_t lo[K3_ILP], hi[K3_ILP]; uint32_t c[K3_ILP], b[K3_ILP], slot[K3_ILP], blk[K3_ILP];
+    bool ok[K3_ILP];
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+    {
+        const uint64_t i = base + 256 * j;
+        lo[j] = i < P.n ? P.in_lo[i] : 0xFFFFFFFFFFFFFFFFULL;
+        hi[j] = (P.W == 2) ? (i < P.n ? P.in_hi[i] : 0xFFFFFFFFFFFFFFFFULL) : 0;
+        c[j] = i < P.n ? P.in_cnt[i] : 0;
+    }
+    const uint32_t cap = P.dir_rounds * K3_BLK;
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+    {
+        // holes left by k2b's block-wise output reservation carry an all-ones key: skip them
+        ok[j] = (P.W == 1 ? lo[j] : hi[j]) != 0xFFFFFFFFFFFFFFFFULL;
+        if (ok[j])
+        {
+            b[j] = k3_bucket_of (P, lo[j], hi[j]);
+            slot[j] = atomicAdd (&P.bucket_count[b[j]], 1u);
+            if (slot[j] >= cap) { ok[j] = false; atomicOr (P.ovf_flag, 1u); }
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+        if (ok[j] && (slot[j] % K3_BLK) == 0)
+        {
+            blk[j] = atomicAdd (P.pool_ptr, 1u);
+            if (blk[j] >= P.pool_blocks) { ok[j] = false; atomicOr (P.ovf_flag, 2u); blk[j] = 0; }
+            *(volatile uint32_t*)&P.dir[(uint64_t)(slot[j] / K3_BLK) * P.n_buckets + b[j]] = blk[j];
+        }
+    __syncwarp ();
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+        if (ok[j] && (slot[j] % K3_BLK) != 0)
+        {
+            const volatile uint32_t* e = (const volatile uint32_t*)&P.dir[(uint64_t)(slot[j] / K3_BLK) * P.n_buckets + b[j]];
+            uint32_t v;
+            while ((v = *e) == 0xFFFFFFFFu) __nanosleep (20);
+            blk[j] = v;
+        }
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+        if (ok[j])
+        {
+            const uint64_t at = (uint64_t)blk[j] * K3_BLK + (slot[j] % K3_BLK);
+            if (P.W == 1) P.pool[at] = make_uint4 ((uint32_t)lo[j], (uint32_t)(lo[j] >> 32), c[j], 0u);
+            else
+            {
+                P.pool[2 * at]     = make_uint4 ((uint32_t)lo[j], (uint32_t)(lo[j] >> 32), (uint32_t)hi[j], (uint32_t)(hi[j] >> 32));
+                P.pool[2 * at + 1] = make_uint4 (c[j], 0u, 0u, 0u);
+            }
+        }
+}
+
 // Both passes are chains of dependent memory operations (load -> atomic -> store) on random addresses: every thread
 // keeps K3_ILP independent items in flight so that the latencies overlap.
-#define K3_ILP 4
 __global__ void __launch_bounds__(256) k3a_classify (const K3Params P)
 {
     const uint64_t base = (uint64_t)blockIdx.x * (256 * K3_ILP) + threadIdx.x;
-    const int k = P.k, t = P.t_bits;
     uint64_t lo[K3_ILP], hi[K3_ILP];
     #pragma unroll
     for (int j = 0; j < K3_ILP; j++)
@@ -73,70 +168,13 @@ __global__ void __launch_bounds__(256) k3a_classify (const K3Params P)
         if (i >= P.n) continue;
         // holes left by k2b's block-wise output reservation carry an all-ones key: skip them
         if ((P.W == 1 ? lo[j] : hi[j]) == 0xFFFFFFFFFFFFFFFFULL) { P.bucket_of[i] = 0xFFFFFFFFu; continue; }
-        uint32_t key = 0, topbits = 0;
-        if (P.W == 1)
-        {
-            const uint64_t v = lo[j];
-            if (P.n_keys > 1)
-            {
-                const uint32_t mini = gatb_minimizer_w1 (v, k, P.m, P.mmask, P.mask_ma1);
-                key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
-            }
-            if (t) topbits = (uint32_t)(v >> (2*k - t));
-        }
-        else
-        {
-            u128 v; v.lo = lo[j]; v.hi = hi[j];
-            if (P.n_keys > 1)
-            {
-                const uint32_t mini = gatb_minimizer_w2 (v, k, P.m, P.mmask, P.mask_ma1);
-                key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
-            }
-            if (t) { const int s = 2*k - t; topbits = (uint32_t)(s >= 64 ? (v.hi >> (s - 64)) : ((v.lo >> s) | (v.hi << (64 - s)))); }
-        }
-        const uint32_t b = (key << t) | topbits;
+        const uint32_t b = k3_bucket_of (P, lo[j], hi[j]);
         P.bucket_of[i] = b;
         atomicAdd (&P.bucket_count[b], 1u);
     }
 }
 
-// Scatter into bucket order.  With ~10^6 buckets the write tails (one 32-byte sector per bucket and array) no longer fit
-// the L2 next to the streaming input, and every 8/4-byte store becomes a DRAM read-modify-write.  So large inputs go in
-// TWO hops: k3b_scatter_coarse groups the items (with their bucket id) by the top bits of the bucket id -- 2^c groups,
-// whose tails stay in L2 -- and k3b_scatter then runs over that grouped copy, where consecutive items touch only the
-// 2^(bits-c) buckets of one group.  Offsets of both hops come from the same prefix sums: group g starts at
-// bucket_off[g << shift].
-__global__ void __launch_bounds__(256) k3b_scatter_coarse (const K3Params P, int shift, uint32_t* __restrict__ group_cursor,
-                                                            uint64_t* __restrict__ g_lo, uint64_t* __restrict__ g_hi,
-                                                            uint32_t* __restrict__ g_cnt, uint32_t* __restrict__ g_bucket)
-{
-    const uint64_t base = (uint64_t)blockIdx.x * (256 * K3_ILP) + threadIdx.x;
-    uint32_t b[K3_ILP]; uint64_t lo[K3_ILP], hi[K3_ILP], pos[K3_ILP]; uint32_t c[K3_ILP];
-    #pragma unroll
-    for (int j = 0; j < K3_ILP; j++) { const uint64_t i = base + 256 * j; b[j] = i < P.n ? P.bucket_of[i] : 0xFFFFFFFFu; }
-    #pragma unroll
-    for (int j = 0; j < K3_ILP; j++)
-    {
-        const uint64_t i = base + 256 * j;
-        if (b[j] != 0xFFFFFFFFu)
-        {
-            const uint32_t g = b[j] >> shift;
-            pos[j] = P.bucket_off[(uint64_t)g << shift] + atomicAdd (&group_cursor[g], 1u);
-            lo[j] = P.in_lo[i]; c[j] = P.in_cnt[i];
-            if (P.W == 2) hi[j] = P.in_hi[i];
-        }
-    }
-    #pragma unroll
-    for (int j = 0; j < K3_ILP; j++)
-        if (b[j] != 0xFFFFFFFFu)
-        {
-            g_lo[pos[j]] = lo[j];
-            if (P.W == 2) g_hi[pos[j]] = hi[j];
-            g_cnt[pos[j]] = c[j];
-            g_bucket[pos[j]] = b[j];
-        }
-}
-
+// exact two-pass scatter (after k3a + scan): the fallback of the pooled single-pass scatter above
 __global__ void __launch_bounds__(256) k3b_scatter (const K3Params P)
 {
     const uint64_t base = (uint64_t)blockIdx.x * (256 * K3_ILP) + threadIdx.x;
@@ -191,6 +229,17 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_max;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // item i of bucket b: from the pooled blocks (k3s) or from the exact bucket-ordered copy (k3b)
+    auto fetch = [&] (uint32_t b, uint64_t beg, int i, uint64_t& lo, uint64_t& hi, uint32_t& c)
+    {
+        if (P.pool)
+        {
+            const uint64_t at = (uint64_t)P.dir[(uint64_t)(i / K3_BLK) * P.n_buckets + b] * K3_BLK + (i % K3_BLK);
+            if (W == 1) { const uint4 q = P.pool[at]; lo = (uint64_t)q.x | ((uint64_t)q.y << 32); hi = 0; c = q.z; }
+            else { const uint4 q = P.pool[2 * at]; lo = (uint64_t)q.x | ((uint64_t)q.y << 32); hi = (uint64_t)q.z | ((uint64_t)q.w << 32); c = P.pool[2 * at + 1].x; }
+        }
+        else { lo = P.tmp_lo[beg + i]; hi = (W == 2) ? P.tmp_hi[beg + i] : 0; c = P.tmp_cnt[beg + i]; }
+    };
     for (uint32_t b = P.bucket_begin + blockIdx.x; b < P.bucket_end; b += gridDim.x)
     {
         const uint64_t beg = P.bucket_off[b], end = P.bucket_off[b+1];
@@ -208,7 +257,7 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
         bool ranked = false;
         if (n == 1)
         {
-            if (tid == 0) { P.out_lo[beg] = P.tmp_lo[beg]; if (W == 2) P.out_hi[beg] = P.tmp_hi[beg]; P.out_cnt[beg] = (int32_t)P.tmp_cnt[beg]; }
+            if (tid == 0) { uint64_t lo, hi; uint32_t c; fetch (b, beg, 0, lo, hi, c); P.out_lo[beg] = lo; if (W == 2) P.out_hi[beg] = hi; P.out_cnt[beg] = (int32_t)c; }
             continue;
         }
         if (free_bits >= B)
@@ -218,7 +267,10 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
             if (tid == 0) s_max = 0;
             __syncthreads ();
             for (int i = tid; i < n; i += 256)
-                atomicAdd (&s_off[k3_sub_bucket<W> (P.tmp_lo[beg + i], W == 2 ? P.tmp_hi[beg + i] : 0, shift, mask)], 1u);
+            {
+                uint64_t lo, hi; uint32_t c; fetch (b, beg, i, lo, hi, c);
+                atomicAdd (&s_off[k3_sub_bucket<W> (lo, hi, shift, mask)], 1u);
+            }
             __syncthreads ();
             // in-place exclusive scan of np counters: every thread owns np/256 consecutive ones (np >= 256) or one (np < 256)
             {
@@ -245,9 +297,9 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
                 // scatter by sub-bucket (arrival order inside); s_off[sb] ends up as the END of sub-bucket sb
                 for (int i = tid; i < n; i += 256)
                 {
-                    const uint64_t lo = P.tmp_lo[beg + i], hi = (W == 2) ? P.tmp_hi[beg + i] : 0;
+                    uint64_t lo, hi; uint32_t c; fetch (b, beg, i, lo, hi, c);
                     const uint32_t pos = atomicAdd (&s_off[k3_sub_bucket<W> (lo, hi, shift, mask)], 1u);
-                    s_lo[pos] = lo; if (W == 2) s_hi[pos] = hi; s_c[pos] = P.tmp_cnt[beg + i];
+                    s_lo[pos] = lo; if (W == 2) s_hi[pos] = hi; s_c[pos] = c;
                 }
                 __syncthreads ();
                 for (int i = tid; i < n; i += 256)
@@ -271,7 +323,7 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
         if (ranked) continue;
         for (int i = threadIdx.x; i < np; i += blockDim.x)
         {
-            if (i < n) { s_lo[i] = P.tmp_lo[beg + i]; if (W == 2) s_hi[i] = P.tmp_hi[beg + i]; s_c[i] = P.tmp_cnt[beg + i]; }
+            if (i < n) { uint64_t lo, hi; uint32_t c; fetch (b, beg, i, lo, hi, c); s_lo[i] = lo; if (W == 2) s_hi[i] = hi; s_c[i] = c; }
             else       { s_lo[i] = ~0ULL; if (W == 2) s_hi[i] = ~0ULL; s_c[i] = 0; }
         }
         __syncthreads ();
@@ -356,14 +408,14 @@ cudaError_t launch_k3b_scatter (const LaunchCtx& L, const K3Params& P)
     (*L.launches)++;
     return cudaGetLastError ();
 }
-cudaError_t launch_k3b_scatter_coarse (const LaunchCtx& L, const K3Params& P, int shift, uint32_t* group_cursor,
-                                       uint64_t* g_lo, uint64_t* g_hi, uint32_t* g_cnt, uint32_t* g_bucket)
+cudaError_t launch_k3s_pool_scatter (const LaunchCtx& L, const K3Params& P)
 {
     if (P.n == 0) return cudaSuccess;
-    k3b_scatter_coarse<<<(unsigned)((P.n + 256 * K3_ILP - 1) / (256 * K3_ILP)), 256, 0, L.stream>>> (P, shift, group_cursor, g_lo, g_hi, g_cnt, g_bucket);
+    k3s_pool_scatter<<<(unsigned)((P.n + 256 * K3_ILP - 1) / (256 * K3_ILP)), 256, 0, L.stream>>> (P);
     (*L.launches)++;
     return cudaGetLastError ();
 }
+uint32_t k3_sort_cap () { return K3_SORT_CAP; }
 cudaError_t launch_k3c_sort (const LaunchCtx& L, const K3Params& P)
 {
     if (P.n == 0) return cudaSuccess;

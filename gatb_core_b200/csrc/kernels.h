@@ -93,7 +93,11 @@ struct K3Params
     uint32_t bucket_begin, bucket_end;   // k3c sorts buckets [bucket_begin, bucket_end) (chunked so that copies overlap)
     unsigned long long* big_list;   // buckets too large for shared memory
     unsigned long long* counters;   // [0] number of big buckets
+    // pooled scatter (k3s): bucket b keeps its items in blocks of K3_BLK items taken from one bump allocator; block j of
+    // bucket b is pool block dir[j * n_buckets + b].  NULL pool = the exact two-pass layout (tmp_*) is used instead.
+    uint4*    pool; uint32_t pool_blocks; uint32_t* pool_ptr; uint32_t* dir; uint32_t dir_rounds; uint32_t* ovf_flag;
 };
+enum { K3_BLK = 32 };
 
 struct LaunchCtx { cudaStream_t stream; int sm_count; uint64_t* launches; };
 
@@ -113,6 +117,10 @@ cudaError_t launch_k2c_scan (const LaunchCtx&, const K2Params&);
 // k3_sort.cu
 cudaError_t launch_k3a_classify (const LaunchCtx&, const K3Params&);
 cudaError_t launch_k3b_scatter (const LaunchCtx&, const K3Params&);
+cudaError_t launch_k3s_pool_scatter (const LaunchCtx&, const K3Params&);
+uint32_t    k3_sort_cap ();
+cudaError_t launch_k3s_pool_scatter (const LaunchCtx&, const K3Params&);
+uint32_t    k3_sort_cap ();
 cudaError_t launch_k3b_scatter_coarse (const LaunchCtx&, const K3Params&, int shift, uint32_t* group_cursor,
                                        uint64_t* g_lo, uint64_t* g_hi, uint32_t* g_cnt, uint32_t* g_bucket);
 cudaError_t launch_k3c_sort (const LaunchCtx&, const K3Params&);
