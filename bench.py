@@ -40,6 +40,17 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, reads):
+    """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/r01_traffic.json: {kernel: {reads: bytes}}); None when no capture of this size exists."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(p))
+        return float(t[kernel][str(reads)]), "ncu --set full capture, profiles/r01_traffic.json"
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -232,19 +243,21 @@ def run_ours(args):
     bytes_k1 = n * L / 4.0 + s_alg                                   # read 2-bit input once, write records once
     bytes_k2 = s_alg + distinct * 12.0                               # read records once, write each distinct (kmer,count) once
     peak, peak_src = measured_peak()
-    kernels = {"k1_superkmer_partition": (bytes_k1, ksec[0]), "k2b_bucket_hash_count": (bytes_k2, ksec[2])}
+    kernels = {"k1_superkmer_fast": (bytes_k1, ksec[0]), "k2b_warp_bins": (bytes_k2, ksec[2])}
     dom = max(kernels, key=lambda name: kernels[name][1])
     dom_bytes, dom_sec = kernels[dom]
     achieved = dom_bytes / dom_sec / 1e9
+    traffic, traffic_src = ncu_traffic(dom, n)
     pair_bytes = n * L / 4.0 + 2 * s_alg + distinct * 12.0
     pair_sec = ksec[0] + ksec[1] + ksec[2]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_sec * 1e3,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_sec * 1e3,
                 "pair": {"what": "partition + fine split + hash count vs A = N_nt/4 + 2S + D(W+4) (SURVEY.md 8d)",
                          "algorithmic_bytes": pair_bytes, "ms": pair_sec * 1e3, "achieved": pair_bytes / pair_sec / 1e9,
                          "frac": pair_bytes / pair_sec / 1e9 / peak, "frac_of_8TBps": pair_bytes / pair_sec / 1e9 / 8000.0},
                 "kernel_ms": {"k1_superkmer_partition": ksec[0] * 1e3, "k2a_fine_split": ksec[1] * 1e3,
-                              "k2b_bucket_hash_count": ksec[2] * 1e3, "k3_partition_id_sort": ksec[3] * 1e3}}
+                              "k2b_bucket_hash_count": ksec[2] * 1e3, "k3_partition_id_sort": ksec[3] * 1e3,
+                              "k2c_overflow_bins": ksec[4] * 1e3}}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1) ----
     cpu = None

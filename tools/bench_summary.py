@@ -8,6 +8,6 @@ for f in sys.argv[1:]:
         km = d['roofline']['kernel_ms']
         print('%-28s ms/step %7.1f  value %.3g  e2e %7.1f | k1 %6.1f k2a %6.1f k2b %6.1f k3 %6.1f | ovf %d retries %d bins %d pair %.4f' % (
             f.split('/')[-1], d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], km['k1_superkmer_partition'], km['k2a_fine_split'],
-            km['k2b_bucket_hash_count'], km['k3_partition_id_sort'], d['overflow_bins'], d['retries'], d['bins'], d['roofline']['pair']['frac']))
+            km['k2b_bucket_hash_count'], km["k3_partition_id_sort"], d["overflow_bins"], d['retries'], d['bins'], d['roofline']['pair']['frac']))
     except Exception as e:
         print(f, 'ERR', e)
