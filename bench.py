@@ -154,7 +154,7 @@ def run_reference(args):
             "config": {"workload": "k=31, m=10, abundance-min=2, synthetic 150bp reads (bounded sample: %d reads per step)" % n},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -176,6 +176,7 @@ def run_ours(args):
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29533")
             dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
+        args.emit = emit
         return multigpu.bench(args, rank, world, local)
 
     gpu = gatb_core_b200.GatbGpu(local)
@@ -289,11 +290,34 @@ def run_ours(args):
             "e2e": {"value": distinct / e2e_step, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_step * 1e3},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     gpu.close()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1, the
+    reference prints progress notes), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -23,7 +23,7 @@ EXPORTS = ["gatb_gpu_create", "gatb_gpu_destroy", "gatb_gpu_last_error", "gatb_g
            "gatb_gpu_free_host", "gatb_gpu_bloom_params", "gatb_gpu_bloom_layout", "gatb_gpu_bloom", "gatb_gpu_bloom_dev",
            "gatb_gpu_histogram_cutoff", "gatb_gpu_malloc", "gatb_gpu_free", "gatb_gpu_memcpy_h2d", "gatb_gpu_memcpy_d2h",
            "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii", "gatb_gpu_plan",
-           "gatb_gpu_partition_into", "gatb_gpu_count_bins"]
+           "gatb_gpu_partition_into", "gatb_gpu_partition_range_into", "gatb_gpu_count_bins"]
 
 
 class GatbGpuError(RuntimeError):
@@ -87,6 +87,7 @@ def load_library():
     L.gatb_gpu_pack_ascii.argtypes = [VP, C.c_char_p, U64, VP, VP, C.POINTER(U64)]
     L.gatb_gpu_plan.argtypes = [VP, C.POINTER(Params), U64, U64, I32, C.POINTER(Geometry)]
     L.gatb_gpu_partition_into.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), VP, VP, U64, VP, VP, VP, VP]
+    L.gatb_gpu_partition_range_into.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), VP, VP, U64, U64, VP, VP, VP, VP]
     L.gatb_gpu_count_bins.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), I32, C.POINTER(VP), C.POINTER(VP),
                                       C.c_uint32, VP, U64, C.POINTER(Result)]
     return L
@@ -215,11 +216,12 @@ class GatbGpu:
         self._check(self.L.gatb_gpu_plan(self.ctx, C.byref(params), total_kmers, n_reads, n_ranks, C.byref(g)))
         return g
 
-    def partition_into(self, params, geom, d_packed, d_offsets, n_reads, d_bins, d_cursors, d_n_mask=None):
-        """k1 into caller-provided device buffers (ints).  Returns [valid, invalid, stored, dropped]."""
+    def partition_into(self, params, geom, d_packed, d_offsets, n_reads, d_bins, d_cursors, d_n_mask=None, first_read=0):
+        """k1 over the reads [first_read, first_read + n_reads) into caller-provided device buffers (ints).
+        Returns [valid, invalid, stored, dropped]."""
         st = np.zeros(4, np.uint64)
-        self._check(self.L.gatb_gpu_partition_into(self.ctx, C.byref(params), C.byref(geom), _ptr(d_packed), _ptr(d_offsets),
-                                                   n_reads, _ptr(d_n_mask), _ptr(d_bins), _ptr(d_cursors), _ptr(st)))
+        self._check(self.L.gatb_gpu_partition_range_into(self.ctx, C.byref(params), C.byref(geom), _ptr(d_packed), _ptr(d_offsets),
+                                                         first_read, n_reads, _ptr(d_n_mask), _ptr(d_bins), _ptr(d_cursors), _ptr(st)))
         return [int(x) for x in st]
 
     def count_bins(self, params, geom, src_bins, src_cursors, nb1_local, kmers_bound, repart=None):

@@ -17,7 +17,7 @@ static std::string g_create_error;
 
 // device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
 enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
-            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_NSLOTS };
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_OVFLIST2, S_NSLOTS };
 
 struct gatb_gpu_ctx
 {
@@ -232,10 +232,12 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
     const int table_log2 = p->table_log2 > 0 ? p->table_log2 : k2b_default_table_log2 (W);
     if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
-    if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_SOURCES) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_SOURCES);
+    if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
     const uint64_t T = 1ULL << table_log2;
     const uint64_t occ_per_bin = (T * 55) / 100;
-    const int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
+    // k <= 31: one more fine-bin bit per doubling of the ranks, so that nb1 (the coarse bins every rank scatters into) stays put
+    int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
+    if (W == 1) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
     uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
     uint64_t nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits; if (nb1 < 1) nb1 = 1;
     nb1 = (nb1 + n_ranks - 1) / n_ranks * n_ranks;                              // every rank owns nb1/n_ranks consecutive coarse bins
@@ -248,10 +250,12 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     // records a rank produces for one coarse bin ~ (its k-mers * 2/(w+1)) / nb1
     double local_kmers = (double)total_kmers / n_ranks, local_reads = (double)n_reads / n_ranks;
     double est_records = local_kmers * 2.0 / (w + 1) * 1.10 + local_reads * 0.5 + 64;
-    uint64_t cap = (uint64_t)(est_records / nb1 * 1.30) + 64; cap = (cap + COARSE_BLK - 1) / COARSE_BLK * COARSE_BLK;
+    // several ranks: a (rank, bin) piece is small and the minimizer space of a multi-Gb input is crowded, so the relative
+    // spread of the pieces is larger; the exchange only moves the used rounds, so head-room costs memory, not time
+    uint64_t cap = (uint64_t)(est_records / nb1 * (n_ranks > 1 ? 1.60 : 1.30)) + (n_ranks > 1 ? 96 : 64); cap = (cap + COARSE_BLK - 1) / COARSE_BLK * COARSE_BLK;
     memset (g, 0, sizeof(*g));
     g->total_kmers = total_kmers; g->nb1 = (uint32_t)nb1; g->cap = (uint32_t)cap; g->fine_bits = fine_bits; g->table_log2 = table_log2;
-    g->m_device = mg; g->w = w; g->maxlen = (W == 1) ? 28 : 60; g->words = W;                  // maxlen: Sequence2SuperKmer.hpp:147
+    g->m_device = mg; g->w = w; g->maxlen = (W == 1) ? DEV_MAXLEN_W1 : 60; g->words = W;                  // maxlen: Sequence2SuperKmer.hpp:147
     g->n_ranks = n_ranks; g->bins_per_rank = (uint32_t)(nb1 / n_ranks); g->record_bytes = 16 * W;
     return 0;
 }
@@ -263,7 +267,7 @@ struct ReadChunks { int n; uint64_t first[17]; cudaEvent_t* ready; };
 static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
                            const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
                            void* d_bins, uint32_t* d_cursors, unsigned long long* h_stats,
-                           const ReadChunks* chunks = 0)
+                           const ReadChunks* chunks = 0, uint64_t first_read = 0)
 {
     LaunchCtx L = lctx (ctx);
     if (ensure (ctx, S_STATS, 64 * 8)) return 1;
@@ -290,7 +294,7 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
             if (k1.n_reads) CK (launch_k1 (L, k1));
         }
     }
-    else if (n_reads) CK (launch_k1 (L, k1));
+    else if (n_reads) { k1.first_read = first_read; CK (launch_k1 (L, k1)); }
     cudaEventRecord (ctx->kev[1], ctx->stream);
     CK (cudaMemcpyAsync (h_stats, d_stats, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK (cudaStreamSynchronize (ctx->stream));
@@ -349,9 +353,10 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
     if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
     if (ensure (ctx, S_OVFLIST, nbins * 4)) return 1;
+    if (ensure (ctx, S_OVFLIST2, nbins * 4)) return 1;
     unsigned long long* d_cnt = (unsigned long long*)ctx->slot[S_COUNTERS];
-    unsigned long long h_cnt[8];
-    uint64_t n_ovf = 0;
+    unsigned long long h_cnt[16];
+    uint64_t n_ovf = 0, n_ovf_first = 0;
     uint64_t* u_lo = 0; uint64_t* u_hi = 0; uint32_t* u_cnt = 0;
     K2Params k2;
     for (int attempt = 0; ; attempt++)
@@ -368,16 +373,40 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
         k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
         k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
-        k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST];
+        k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST]; k2.ovf_counter = 4;
         cudaEventRecord (ctx->kev[4], ctx->stream);
         CK (launch_k2b_count (L, k2));
         cudaEventRecord (ctx->kev[5], ctx->stream);
         CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK (cudaStreamSynchronize (ctx->stream));
         n_ovf = h_cnt[4];
+        n_ovf_first = n_ovf;
+        if (n_ovf) cudaEventRecord (ctx->kev[8], ctx->stream);
+        static const bool no_tier2 = getenv ("GATB_GPU_K2B_TIER2") && getenv ("GATB_GPU_K2B_TIER2")[0] == '0';       // test hook: straight to the global table
+        if (n_ovf && W == 1 && k2b_variant () == 1 && !no_tier2)
+        {   // ---- further tiers: the bins a warp's 2^table_log2-slot table could not hold are counted by CTAs with 2048,
+            //      then 8192 slots (k2b_count_w1 over a bin list); what still overflows goes to the global table ----
+            const int tier_log2[2] = { 11, 13 }, tier_counter[2] = { 7, 12 };
+            int cur_list = S_OVFLIST;
+            for (int t = 0; t < 2 && n_ovf; t++)
+            {
+                if (tier_log2[t] <= table_log2) continue;
+                const int other = (cur_list == S_OVFLIST) ? S_OVFLIST2 : S_OVFLIST;
+                K2Params k2t = k2;
+                k2t.bin_list = (const uint32_t*)ctx->slot[cur_list]; k2t.n_list = (uint32_t)n_ovf;
+                k2t.ovf_list = (uint32_t*)ctx->slot[other]; k2t.ovf_counter = tier_counter[t]; k2t.table_log2 = tier_log2[t];
+                CK (cudaMemsetAsync (d_cnt + 3, 0, 8, ctx->stream));                 // work counter
+                CK (launch_k2b_count_list (L, k2t));
+                CK (cudaMemcpyAsync (h_cnt, d_cnt, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK (cudaStreamSynchronize (ctx->stream));
+                n_ovf = h_cnt[tier_counter[t]];
+                cur_list = other;
+            }
+            k2.ovf_list = (uint32_t*)ctx->slot[cur_list];                            // what is left goes to the global table
+            if (!n_ovf) cudaEventRecord (ctx->kev[9], ctx->stream);
+        }
         if (n_ovf)
         {   // ---- k2c: bins that did not fit the shared-memory table share one global table ----
-            cudaEventRecord (ctx->kev[8], ctx->stream);
             CK (launch_k2c_measure (L, k2, (uint32_t)n_ovf));
             CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK (cudaStreamSynchronize (ctx->stream));
@@ -558,14 +587,14 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         out->part_offsets = h_offs; out->kmers_lo = h_lo; out->kmers_hi = h_hi; out->counts = h_cnt32; out->histogram = h_hist;
     }
     out->stats[GATB_STAT_DISTINCT] = h_cnt[1]; out->stats[GATB_STAT_SOLID] = h_cnt[2];
-    out->stats[GATB_STAT_RECORDS] = n_records; out->stats[GATB_STAT_BINS] = nbins; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf;
+    out->stats[GATB_STAT_RECORDS] = n_records; out->stats[GATB_STAT_BINS] = nbins; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf_first; out->stats[12] = n_ovf;
     out->stats[GATB_STAT_RECORD_BYTES] = n_records * rec_bytes;
     float ms;
     cudaEventElapsedTime (&ms, ctx->ev[2], ctx->ev[3]); out->seconds[2] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[3], ctx->ev[4]); out->seconds[3] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[4], ctx->ev[5]); out->seconds[4] = ms * 1e-3;
     for (int i = 1; i < 4; i++) { cudaEventElapsedTime (&ms, ctx->kev[2*i], ctx->kev[2*i+1]); out->kernel_seconds[i] = ms * 1e-3; }
-    if (n_ovf) { cudaEventElapsedTime (&ms, ctx->kev[8], ctx->kev[9]); out->kernel_seconds[4] = ms * 1e-3; out->stats[11] = h_cnt[5]; }
+    if (n_ovf_first) { cudaEventElapsedTime (&ms, ctx->kev[8], ctx->kev[9]); out->kernel_seconds[4] = ms * 1e-3; out->stats[11] = h_cnt[5]; }
     return 0;
 }
 
@@ -630,18 +659,22 @@ int gatb_gpu_plan (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t total_k
     if (check_params (ctx, p, (const uint16_t*)1)) return 1;
     return plan_geometry (ctx, p, total_kmers, n_reads, n_ranks, g);
 }
-int gatb_gpu_partition_into (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
-                             const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads, const uint32_t* d_n_mask,
-                             void* d_bins, uint32_t* d_cursors, uint64_t* stats4)
+int gatb_gpu_partition_range_into (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
+                                   const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t first_read, uint64_t n_reads,
+                                   const uint32_t* d_n_mask, void* d_bins, uint32_t* d_cursors, uint64_t* stats4)
 {
     if (!ctx) return 1;
     cudaSetDevice (ctx->device);
     if (check_params (ctx, p, (const uint16_t*)1)) return 1;
     unsigned long long h[4];
-    if (partition_impl (ctx, p, g, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, d_bins, d_cursors, h)) return 1;
+    if (partition_impl (ctx, p, g, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, d_bins, d_cursors, h, 0, first_read)) return 1;
     for (int i = 0; i < 4; i++) stats4[i] = h[i];
     return 0;
 }
+int gatb_gpu_partition_into (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
+                             const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads, const uint32_t* d_n_mask,
+                             void* d_bins, uint32_t* d_cursors, uint64_t* stats4)
+{ return gatb_gpu_partition_range_into (ctx, p, g, d_packed_reads, d_read_offsets_nt, 0, n_reads, d_n_mask, d_bins, d_cursors, stats4); }
 int gatb_gpu_count_bins (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
                          const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
                          uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, gatb_gpu_result* out)

@@ -79,7 +79,8 @@ __device__ __forceinline__ void k1_store_record (const K1Params& P, uint32_t key
         uint64_t lo = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
         uint64_t hi = sh ? ((w1 >> sh) | (w2 << (64 - sh))) : w1;
         if (nn <= 32) { lo &= mask2k64 (nn); hi = 0; } else { hi &= mask2k64 (nn - 32); }
-        hi |= ((uint64_t)len << REC_LEN_SHIFT_W1) | ((uint64_t)fine << REC_FINE_SHIFT_W1);
+        if (P.mode == K1_MODE_DEVICE) hi |= ((uint64_t)len << DEV_LEN_SHIFT_W1) | ((uint64_t)fine << DEV_FINE_SHIFT_W1);
+        else                          hi |= ((uint64_t)len << REC_LEN_SHIFT_W1) | ((uint64_t)fine << REC_FINE_SHIFT_W1);
         uint4 rec = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
         ((uint4*)P.bins)[ridx] = rec;
     }
@@ -290,7 +291,7 @@ __device__ __forceinline__ void k1f_store (const K1Params& P, uint32_t key, uint
             {
                 uint64_t lo = (uint64_t)r[0] | ((uint64_t)r[1] << 32), hi = (uint64_t)r[2] | ((uint64_t)r[3] << 32);
                 if (nn <= 32) { lo &= mask2k64 (nn); hi = 0; } else { hi &= mask2k64 (nn - 32); }
-                hi |= ((uint64_t)l << REC_LEN_SHIFT_W1) | ((uint64_t)fine << REC_FINE_SHIFT_W1);
+                hi |= ((uint64_t)l << DEV_LEN_SHIFT_W1) | ((uint64_t)fine << DEV_FINE_SHIFT_W1);
                 ((uint4*)P.bins)[rbase + coarse_index (lbin, slot, P.bins_per_region)] = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
             }
             else

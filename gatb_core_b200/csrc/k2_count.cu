@@ -47,59 +47,71 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
                                                         uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc)
 {
     const uint32_t nb = gridDim.x;                          // bins of a source region (laid out by coarse_index, kernels.h)
-    __shared__ uint32_t s_off[128], s_cur[128], s_tmp[128];
+    __shared__ uint32_t s_off[1024], s_cur[1024], s_tmp[1024];         // 1 << fine_bits <= 1024 fine bins per coarse bin
+    __shared__ uint32_t s_first[17];                        // record range of every source inside the gathered bin
     const uint32_t b = blockIdx.x;
     const int nf = 1 << fine_bits;
     const int tid = threadIdx.x;
-    if (tid < nf) { s_tmp[tid] = 0; s_cur[tid] = 0; }
-    __syncthreads ();
-    // pass 1: records per fine bin (the second pass finds the same lines in L2)
-    for (int s = 0; s < S.n; s++)
+    for (int i = tid; i < nf; i += blockDim.x) { s_tmp[i] = 0; s_cur[i] = 0; }
+    if (tid == 0)
     {
-        const uint32_t n = min (S.cursors[s][b], cap);
-        const uint4* __restrict__ src = S.bins[s];
-        for (uint32_t i = tid; i < n; i += blockDim.x)
-        {
-            const uint32_t top = __ldg (&src[coarse_index (b, i, nb) * W + (W - 1)]).w;
-            atomicAdd (&s_tmp[top >> (32 - (W == 1 ? FINE_BITS_W1 : FINE_BITS_W2))], 1u);
-        }
+        uint32_t run = 0;
+        for (int s = 0; s < S.n; s++) { s_first[s] = run; run += min (S.cursors[s][b], cap); }
+        for (int s = S.n; s <= 16; s++) s_first[s] = run;
+    }
+    __syncthreads ();
+    const uint32_t n_all = s_first[16];
+    // record g of the gathered bin: the pieces of all sources laid end to end, so that the threads stay busy however
+    // small a single piece is (16 sources of a few hundred records each on 8 GPUs)
+    auto locate = [&] (uint32_t g, const uint4*& src, uint64_t& ci)
+    {
+        int s = 0;
+        #pragma unroll
+        for (int u = 8; u > 0; u >>= 1) if (s + u < 16 && g >= s_first[s + u]) s += u;
+        src = S.bins[s];
+        ci = coarse_index (b, g - s_first[s], nb);
+    };
+    // pass 1: records per fine bin (the second pass finds the same lines in L2)
+    for (uint32_t g = tid; g < n_all; g += blockDim.x)
+    {
+        const uint4* src; uint64_t ci; locate (g, src, ci);
+        const uint32_t top = __ldg (&src[ci * W + (W - 1)]).w;
+        atomicAdd (&s_tmp[W == 1 ? (top >> (DEV_FINE_SHIFT_W1 - 32)) : (top >> (32 - FINE_BITS_W2))], 1u);
     }
     __syncthreads ();
     if (tid < 32)
-    {   // exclusive scan of <=128 counters by one warp (4 per lane)
-        uint32_t v[4], sum = 0;
-        #pragma unroll
-        for (int i=0; i<4; i++) { int idx = tid*4 + i; v[i] = idx < nf ? s_tmp[idx] : 0; sum += v[i]; }
+    {   // exclusive scan of the nf counters by one warp (nf/32 consecutive ones per lane, at least one)
+        const int per = nf > 32 ? nf / 32 : 1;
+        uint32_t sum = 0;
+        for (int i = 0; i < per; i++) { const int idx = tid * per + i; if (idx < nf) sum += s_tmp[idx]; }
         uint32_t incl = sum;
         #pragma unroll
         for (int o=1; o<32; o<<=1) { uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (tid >= o) incl += y; }
         uint32_t run = incl - sum;
-        #pragma unroll
-        for (int i=0; i<4; i++) { int idx = tid*4 + i; if (idx < nf) { s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v[i]); } run += v[i]; }
+        for (int i = 0; i < per; i++)
+        {
+            const int idx = tid * per + i;
+            if (idx < nf) { const uint32_t v = s_tmp[idx]; s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v); run += v; }
+        }
     }
     __syncthreads ();
     const uint64_t dbase = coarse_off[b];
-    for (int s = 0; s < S.n; s++)
+    for (uint32_t g = tid; g < n_all; g += blockDim.x)
     {
-        const uint32_t n = min (S.cursors[s][b], cap);
-        const uint4* __restrict__ src = S.bins[s];
-        for (uint32_t i = tid; i < n; i += blockDim.x)
+        const uint4* src; uint64_t ci; locate (g, src, ci);
+        if (W == 1)
         {
-            if (W == 1)
-            {
-                uint4 rec = __ldg (&src[coarse_index (b, i, nb)]);
-                uint32_t f = rec.w >> (32 - FINE_BITS_W1);
-                uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
-                dst[dbase + p] = rec;
-            }
-            else
-            {
-                const uint64_t ci = coarse_index (b, i, nb);
-                uint4 r0 = __ldg (&src[2*ci]), r1 = __ldg (&src[2*ci + 1]);
-                uint32_t f = r1.w >> (32 - FINE_BITS_W2);
-                uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
-                dst[2*(dbase + p)] = r0; dst[2*(dbase + p) + 1] = r1;
-            }
+            uint4 rec = __ldg (&src[ci]);
+            uint32_t f = rec.w >> (DEV_FINE_SHIFT_W1 - 32);
+            uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+            dst[dbase + p] = rec;
+        }
+        else
+        {
+            uint4 r0 = __ldg (&src[2*ci]), r1 = __ldg (&src[2*ci + 1]);
+            uint32_t f = r1.w >> (32 - FINE_BITS_W2);
+            uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+            dst[2*(dbase + p)] = r0; dst[2*(dbase + p) + 1] = r1;
         }
     }
 }
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
                 if (lane < GRP && ri < mrec)
                 {
                     const uint32_t top = recs[(size_t)ri * W + (W - 1)].w;
-                    len = (W == 1) ? (int)((top >> (REC_LEN_SHIFT_W1 - 32)) & 31) : (int)((top >> (REC_LEN_SHIFT_W2 - 32)) & 63);
+                    len = (W == 1) ? (int)((top >> (DEV_LEN_SHIFT_W1 - 32)) & 31) : (int)((top >> (REC_LEN_SHIFT_W2 - 32)) & 63);
                 }
                 uint32_t incl = (uint32_t)len;
                 #pragma unroll
@@ -361,7 +373,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
                         {
                             const uint4 q = recs[rr];
                             const uint64_t lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
-                            const uint64_t hi = ((uint64_t)q.z | ((uint64_t)q.w << 32)) & ((1ULL << REC_LEN_SHIFT_W1) - 1);
+                            const uint64_t hi = ((uint64_t)q.z | ((uint64_t)q.w << 32)) & ((1ULL << DEV_LEN_SHIFT_W1) - 1);
                             const uint64_t key = rec_kmer_w1 (lo, hi, j, k);
                             uint32_t slot = smem_slot64 (key, P.table_log2);
                             int probe = 0;
@@ -546,8 +558,9 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
         uint32_t bin; uint2 d = make_uint2 (0, 0);
         for (;;)
         {
-            bin = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
-            if (bin >= P.nbins) break;
+            const uint32_t idx = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
+            if (P.bin_list) { if (idx >= P.n_list) { bin = P.nbins; break; } bin = P.bin_list[idx]; }
+            else            { bin = idx; if (bin >= P.nbins) break; }
             d = P.bin_desc[bin];
             if (d.y) break;
         }
@@ -637,7 +650,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
             {
                 const uint32_t ri = g0 + lane;
                 uint32_t nch = 0;
-                if (ri < mrec) nch = (((recs[ri].w >> (REC_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;
+                if (ri < mrec) nch = (((recs[ri].w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;
                 uint32_t incl = nch;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
@@ -656,9 +669,9 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
                     const uint32_t ex = __shfl_sync (FULL_MASK, excl, r);
                     const int c = act ? (int)(gk - ex) : 0;
                     const uint4 q = recs[act ? g0 + r : g0];
-                    const int nkc = act ? (int)((q.w >> (REC_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
+                    const int nkc = act ? (int)((q.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
                     K2Chunk C;
-                    k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (REC_LEN_SHIFT_W1 - 32)) - 1), c, k);
+                    k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (DEV_LEN_SHIFT_W1 - 32)) - 1), c, k);
                     uint32_t lo[4], hi[4], slot[4];
                     k2_chunk_kmer<0> (C, lo[0], hi[0]); k2_chunk_kmer<1> (C, lo[1], hi[1]);
                     k2_chunk_kmer<2> (C, lo[2], hi[2]); k2_chunk_kmer<3> (C, lo[3], hi[3]);
@@ -695,7 +708,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
         const bool ovf = s_ovf != 0;
         if (ovf)
         {
-            if (tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin; }
+            if (tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[P.ovf_counter], 1ULL); P.ovf_list[idx] = bin; }
             for (int i = tid; i < T; i += NT) { s_klo[i] = EMPTY64; s_cnt[i] = 0; }
             __syncthreads ();
             if (tid == 0) s_ovf = 0;
@@ -878,7 +891,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
             {
                 uint4 rec = rec0;
                 if (g0) rec = (g0 + lane < n) ? __ldg ((const uint4*)P.recs + base0 + g0 + lane) : zero4;
-                const uint32_t nch = (((rec.w >> (REC_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;      // 0 for the zero record
+                const uint32_t nch = (((rec.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;      // 0 for the zero record
                 uint32_t incl = nch;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
@@ -899,9 +912,9 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                     q.x = __shfl_sync (FULL_MASK, rec.x, r); q.y = __shfl_sync (FULL_MASK, rec.y, r);
                     q.z = __shfl_sync (FULL_MASK, rec.z, r); q.w = __shfl_sync (FULL_MASK, rec.w, r);
                     const int c = act ? (int)(gk - ex) : 0;
-                    const int nkc = act ? (int)((q.w >> (REC_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
+                    const int nkc = act ? (int)((q.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
                     K2Chunk C;
-                    k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (REC_LEN_SHIFT_W1 - 32)) - 1), c, k);
+                    k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (DEV_LEN_SHIFT_W1 - 32)) - 1), c, k);
                     uint32_t lo[4], hi[4], slot[4];
                     k2_chunk_kmer<0> (C, lo[0], hi[0]); k2_chunk_kmer<1> (C, lo[1], hi[1]);
                     k2_chunk_kmer<2> (C, lo[2], hi[2]); k2_chunk_kmer<3> (C, lo[3], hi[3]);
@@ -929,7 +942,9 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                         }
                     }
                     if (rn >= 32) drain_retries ();
+                    if (wn > OCC_W) break;                      // the bin cannot fit any more: it goes to the next tier as a whole
                 }
+                if (wn > OCC_W) break;
             }
             if (rn) drain_retries ();
             __syncwarp ();
@@ -1025,6 +1040,24 @@ static cudaError_t k2b_warp_launch (const LaunchCtx& L, const K2Params& P)
     return cudaGetLastError ();
 }
 
+// second tier: the bins the warp kernel could not hold, counted by CTAs with the table size of P.table_log2
+cudaError_t launch_k2b_count_list (const LaunchCtx& L, const K2Params& P)
+{
+    if (P.n_list == 0) return cudaSuccess;
+    const size_t smem = k2b_w1_smem_bytes (P.table_log2, 256);
+    cudaError_t e = cudaFuncSetAttribute (k2b_count_w1<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k2b_count_w1<256>, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)L.sm_count * per_sm;
+    if (grid > P.n_list) grid = P.n_list;
+    k2b_count_w1<256><<<(unsigned)grid, 256, smem, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
 // which counting kernel serves k <= 31 (GATB_GPU_K2B): 1 = warp per bin (default), 128 / 256 = CTA per bin with the chunked
 // insert, 0 = CTA per bin, one k-mer per lane.  The table size the planner picks follows from it.
 int k2b_variant ()
@@ -1082,7 +1115,7 @@ __global__ void __launch_bounds__(256) k2c_measure (const K2Params P, uint32_t n
         {
             uint4 last = __ldg (&base[(uint64_t)i * W + (W - 1)]);
             uint64_t hi = (uint64_t)last.z | ((uint64_t)last.w << 32);
-            sum += (W == 1) ? ((hi >> REC_LEN_SHIFT_W1) & 31) : ((hi >> REC_LEN_SHIFT_W2) & 63);
+            sum += (W == 1) ? ((hi >> DEV_LEN_SHIFT_W1) & 31) : ((hi >> REC_LEN_SHIFT_W2) & 63);
         }
     }
     #pragma unroll
@@ -1105,8 +1138,8 @@ __global__ void __launch_bounds__(256) k2c_insert (const K2Params P, uint32_t n_
             {
                 uint4 r = __ldg (&base[i]);
                 uint64_t lo = (uint64_t)r.x | ((uint64_t)r.y << 32), hi = (uint64_t)r.z | ((uint64_t)r.w << 32);
-                const int len = (int)((hi >> REC_LEN_SHIFT_W1) & 31);
-                hi &= (1ULL << REC_LEN_SHIFT_W1) - 1;
+                const int len = (int)((hi >> DEV_LEN_SHIFT_W1) & 31);
+                hi &= (1ULL << DEV_LEN_SHIFT_W1) - 1;
                 for (int j = 0; j < len; j++)
                     table_insert_w1 ((unsigned long long*)P.g_lo, P.g_cnt, P.g_log2, rec_kmer_w1 (lo, hi, j, k), 1 << 30);
             }

@@ -14,6 +14,11 @@
 // ----------------------------------------------------------------------------------------------------------------
 enum { REC_LEN_SHIFT_W1 = 52, REC_FINE_SHIFT_W1 = 57, FINE_BITS_W1 = 7,
        REC_LEN_SHIFT_W2 = 52, REC_FINE_SHIFT_W2 = 58, FINE_BITS_W2 = 6 };
+// Device-mode records of k <= 31 trade nucleotides for fine-bin bits: at most DEV_MAXLEN_W1 = 24 k-mers (54 nucleotides,
+// bits [0,108)), nbK in bits [108,113), fine-bin id in bits [113,128) (up to 15 bits; the planner uses 7 on one GPU and
+// one more per doubling of the ranks, so that the number of COARSE bins a partition kernel scatters into stays put).
+// The shifts below are relative to the upper 64-bit half, like the ones above.
+enum { DEV_LEN_SHIFT_W1 = 44, DEV_FINE_SHIFT_W1 = 49, DEV_MAXLEN_W1 = 24, DEV_FINE_BITS_MAX_W1 = 10 };
 
 // ----------------------------------------------------------------------------------------------------------------
 // Layout of a region of coarse bins (device mode): ROUNDS of COARSE_BLK records.  Record 'slot' of bin 'b' of a region
@@ -70,8 +75,10 @@ struct K2Params
     int      histo_max;
     unsigned long long* histogram;  // [histo_max+1]
     uint64_t* out_lo; uint64_t* out_hi; uint32_t* out_cnt; unsigned long long out_cap;
-    unsigned long long* counters;   // [0] output cursor (incl. holes) [1] distinct [2] solid [3] work counter [4] overflow bins [5] k-mers in overflow bins [6] emitted
+    unsigned long long* counters;   // [0] output cursor (incl. holes) [1] distinct [2] solid [3] work counter [4] overflow bins [5] k-mers in overflow bins [6] emitted [7] overflow bins of the second tier
     uint32_t* ovf_list;             // [nbins] ids of bins whose table overflowed
+    const uint32_t* bin_list; uint32_t n_list;   // second-tier run (k2b_count_w1 only): count these bins instead of [0, nbins)
+    int      ovf_counter;           // index into counters[] of the overflow count this launch appends to (4, or 7 for the second tier)
     // global-memory fallback table
     uint64_t* g_lo; uint64_t* g_hi; uint32_t* g_cnt; int g_log2;
 };
@@ -105,10 +112,11 @@ struct LaunchCtx { cudaStream_t stream; int sm_count; uint64_t* launches; };
 cudaError_t launch_k1 (const LaunchCtx&, const K1Params&);
 int         k1_fast_window (int k);      // window (k-m+1) the register-scanner kernel is compiled for, 0 = none
 // k2_count.cu
-struct K2aSrc { const uint4* bins[8]; const uint32_t* cursors[8]; int n; };     // the same coarse bins gathered from n sources
+struct K2aSrc { const uint4* bins[16]; const uint32_t* cursors[16]; int n; };     // the same coarse bins gathered from n sources
 cudaError_t launch_k2a_split (const LaunchCtx&, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
                               uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc);
 cudaError_t launch_k2b_count (const LaunchCtx&, const K2Params&);
+cudaError_t launch_k2b_count_list (const LaunchCtx&, const K2Params&);     // CTA-per-bin kernel over P.bin_list (k <= 31)
 int         k2b_variant ();
 int         k2b_default_table_log2 (int W);
 cudaError_t launch_k2c_measure (const LaunchCtx&, const K2Params&, uint32_t n_ovf);

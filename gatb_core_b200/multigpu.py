@@ -22,24 +22,46 @@ def owner_of_bin(b, bins_per_rank):
     return b // bins_per_rank
 
 
-def exchange_bins(bins, cursors, world):
+def exchange_bins(bins, cursors, world, rank=0, used_bytes=None, wait=True):
     """All-to-all of the partition buffers.
 
-    bins        uint8  [nb1 * cap * record_bytes]   (nb1 = world * bins_per_rank; bin regions contiguous per owner)
+    bins        uint8  [nb1 * cap * record_bytes]   (nb1 = world * bins_per_rank; one contiguous region per owner rank)
     cursors     int32  [nb1]
-    Returns (recv_bins [world, bpr*cap*rb], recv_cursors [world, bpr]):
-    row s = what source rank s produced for the bins THIS rank owns.  (The fine split counts its own bins from the
-    records, so nothing but the records and their cursors has to travel.)
+    used_bytes  optional list [world]: how much of region r is in use (a region is filled round by round from its
+                start, kernels.h coarse_index, so everything past the last used round is slack that need not travel)
+    Returns (pieces, recv_cursors [world, bpr]): pieces[s] is a uint8 tensor holding what source rank s produced for the
+    bins THIS rank owns (its used prefix at least); pieces[rank] is a view of this rank's own region -- no copy.
+    With wait=False the transfers are only started: a third value, the list of requests to wait for, is returned.
+    (The fine split counts its own bins from the records, so nothing but the records and their cursors has to travel.)
     """
-    recv_bins = torch.empty_like(bins)
+    region = bins.numel() // world
     recv_cur = torch.empty_like(cursors)
     if world == 1:
-        recv_bins.copy_(bins)
         recv_cur.copy_(cursors)
-    else:
-        dist.all_to_all_single(recv_bins, bins)
-        dist.all_to_all_single(recv_cur, cursors)
-    return recv_bins.view(world, -1), recv_cur.view(world, -1)
+        return ([bins.view(world, -1)[0]], recv_cur.view(world, -1)) if wait else ([bins.view(world, -1)[0]], recv_cur.view(world, -1), [])
+    dist.all_to_all_single(recv_cur, cursors)
+    send = torch.tensor([region] * world if used_bytes is None else [int(x) for x in used_bytes], dtype=torch.int64, device=bins.device)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)                       # how much every source is going to send me
+    recv = [int(x) for x in recv.tolist()]
+    send = [int(x) for x in send.tolist()]
+    views = bins.view(world, -1)
+    pieces, ops = [None] * world, []
+    for s in range(world):
+        if s == rank:
+            pieces[s] = views[rank]
+            continue
+        pieces[s] = torch.empty(max(recv[s], 16), dtype=torch.uint8, device=bins.device)
+        if recv[s]:
+            ops.append(dist.P2POp(dist.irecv, pieces[s][:recv[s]], s))
+        if send[s]:
+            ops.append(dist.P2POp(dist.isend, views[s][:send[s]], s))
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    if wait:
+        for req in reqs:
+            req.wait()
+        return pieces, recv_cur.view(world, -1)
+    return pieces, recv_cur.view(world, -1), reqs
 
 
 def merge_sorted_runs(runs):
@@ -53,35 +75,72 @@ def merge_sorted_runs(runs):
     return lo[order], hi[order], cn[order]
 
 
+N_PIECES = 2      # a rank partitions its reads in this many pieces: piece i travels while piece i+1 is being partitioned
+
+
 def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total_kmers_global, rank, world, repart=None,
                       d_offsets=None, timers=None):
-    """One distributed counting pass.  Returns (device Result of this rank's bins, stats dict with GLOBAL sums)."""
+    """One distributed counting pass.  Returns (device Result of this rank's bins, stats dict with GLOBAL sums).
+
+    partition piece 0 -> [send piece 0 || partition piece 1] -> send piece 1 -> count: every (source rank, piece) is one
+    source of the owner's fine split (gatb_gpu_count_bins, at most 16 sources)."""
     dev = torch.device("cuda", gpu.device)
     geom = gpu.plan(params, total_kmers_global, n_reads_global, world)
-    t = {}
-    while True:
-        nb1, cap, rb, fb = geom.nb1, geom.cap, geom.record_bytes, geom.fine_bits
-        bins = torch.empty(nb1 * cap * rb, dtype=torch.uint8, device=dev)
-        cursors = torch.zeros(nb1, dtype=torch.int32, device=dev)
-        torch.cuda.synchronize()
-        t0 = time.time()
-        st = gpu.partition_into(params, geom, d_reads, d_offsets, n_reads_local, bins.data_ptr(), cursors.data_ptr())
-        t["partition"] = time.time() - t0
-        flag = torch.tensor([st[3], int(cursors.max().item())], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag[0].item()) == 0:
-            break
-        geom.cap = (int(flag[1].item()) + 15) & ~15         # a bin overflowed somewhere: every rank re-runs with the global demand
-        del bins, cursors
+    npc = N_PIECES if (world > 1 and world * N_PIECES <= 16 and n_reads_local >= 1024) else 1
+    t = {"partition": 0.0, "exchange_wait": 0.0}
+    nb1, rb, bpr = geom.nb1, geom.record_bytes, geom.bins_per_rank
+    if npc > 1:                                          # a piece holds 1/npc of the records of a bin: shrink the capacity with it
+        geom.cap = (int(geom.cap / npc * 1.15) + 64 + 15) & ~15
+    firsts = [(n_reads_local * i // npc) & ~31 for i in range(npc)] + [n_reads_local]      # multiples of 32 reads
+    st_sum = [0, 0, 0, 0]
+    all_pieces, all_cur, keep, used_total = [], [], [], 0
+    pending = None
+    t_begin = time.time()
+    for i in range(npc):
+        n_i = firsts[i + 1] - firsts[i]
+        while True:
+            cap = geom.cap
+            bins = torch.empty(nb1 * cap * rb, dtype=torch.uint8, device=dev)
+            cursors = torch.zeros(nb1, dtype=torch.int32, device=dev)
+            torch.cuda.current_stream().synchronize()    # torch's fills run on torch's stream, the library on its own
+            t0 = time.time()
+            st = gpu.partition_into(params, geom, d_reads, d_offsets, n_i, bins.data_ptr(), cursors.data_ptr(), first_read=firsts[i])
+            t["partition"] += time.time() - t0
+            flag = torch.tensor([st[3], int(cursors.max().item())], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag[0].item()) == 0:
+                break
+            geom.cap = (int(flag[1].item()) + 15) & ~15     # a bin overflowed somewhere: every rank re-runs this piece with the global demand
+            del bins, cursors
+        for k in range(4):
+            st_sum[k] += st[k]
+        if pending is not None:                          # the previous piece has had the whole partition of this one to travel
+            t0 = time.time()
+            for req in pending:
+                req.wait()
+            t["exchange_wait"] += time.time() - t0
+        # region r is filled round by round (16 records per bin and round): only the rounds in use travel
+        rounds = (cursors.view(world, bpr).max(dim=1).values.clamp(max=cap).to(torch.int64) + 15) // 16
+        used = (rounds * (bpr * 16 * rb)).tolist()
+        pieces, recv_cur, pending = exchange_bins(bins, cursors, world, rank, used, wait=False)
+        used_total += int(sum(used) - used[rank])
+        keep.append((bins, cursors, geom.cap))
+        all_pieces.append(pieces)
+        all_cur.append(recv_cur)
     t0 = time.time()
-    recv_bins, recv_cur = exchange_bins(bins, cursors, world)
-    del bins, cursors
+    for req in pending:
+        req.wait()
     torch.cuda.synchronize()
-    t["exchange"] = time.time() - t0
-    bpr = geom.bins_per_rank
-    src_bins = [recv_bins[s].data_ptr() for s in range(world)]
-    src_cur = [recv_cur[s].data_ptr() for s in range(world)]
+    t["exchange_wait"] += time.time() - t0
+    t["exchange"] = t["exchange_wait"]
+    t["partition_and_exchange"] = time.time() - t_begin
+    t["exchanged_bytes"] = used_total
+    geom.cap = max(c for (_, _, c) in keep)              # the fine split only clamps cursors with it: the largest piece capacity serves all
+    st = st_sum
+    src_bins = [all_pieces[i][s].data_ptr() for i in range(npc) for s in range(world)]
+    src_cur = [all_cur[i][s].data_ptr() for i in range(npc) for s in range(world)]
+    recv_cur = torch.cat([c.reshape(-1) for c in all_cur])
     gathered = int(recv_cur.clamp(max=geom.cap).sum().item())
     tot = torch.tensor([st[0], st[2]], dtype=torch.int64, device=dev)
     if world > 1:
@@ -96,13 +155,14 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
     t["overflow_kmers"] = int(res.stats[11])
     t["count_stages"] = [float(x) for x in res.seconds][:7]
     t["overflow_bins"] = int(res.stats[8])
+    t["owned_records"], t["owned_distinct"] = int(res.stats[4]), int(res.stats[2])
     t["bins"] = int(res.stats[7])
     sums = torch.tensor([st[0], st[1], int(res.stats[2]), int(res.stats[3]), st[2], int(res.n_items)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(sums)
     stats = dict(zip(["kmers_nb_valid", "kmers_nb_invalid", "kmers_nb_distinct", "kmers_nb_solid", "records", "items"],
                      [int(x) for x in sums.tolist()]))
-    stats["exchanged_bytes_per_rank"] = int(geom.nb1 * geom.cap * geom.record_bytes * (world - 1) // world)
+    stats["exchanged_bytes_per_rank"] = t["exchanged_bytes"]
     if timers is not None:
         timers.update(t)
     return res, stats
@@ -139,7 +199,7 @@ def result_to_pinned(gpu, res, params):
 def bench(args, rank, world, local):
     """bench.py --gpus N (N>1): weak scaling, args.reads reads per GPU out of one genome sized for all of them."""
     import gatb_core_b200
-    from bench import K, M, L, ABUNDANCE_MIN, COVERAGE, SEED, METRIC, UNIT, ClockSampler
+    from bench import K, M, L, ABUNDANCE_MIN, COVERAGE, SEED, METRIC, UNIT, ClockSampler, measured_peak
     gpu = gatb_core_b200.GatbGpu(local)
     dev = torch.device("cuda", local)
     n = args.reads
@@ -147,6 +207,7 @@ def bench(args, rank, world, local):
     genome = n_global * L // COVERAGE
     nbytes = (n * L + 3) // 4
     reads = torch.zeros(nbytes + 64, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()          # the zero fill runs on torch's stream, the library works on its own: order them
     gpu.synth_reads_dev(SEED, genome, rank * n, n, L, reads.data_ptr())
     gpu.synchronize()
     params = gpu.make_params(K, M, abundance_min=ABUNDANCE_MIN, read_len=L)
@@ -205,6 +266,16 @@ def bench(args, rank, world, local):
     e2e_step = sum(e2e) / len(e2e)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
+        # roofline of the dominant kernel on rank 0 (same accounting as the single-GPU line)
+        occ_owned = stats["kmers_nb_valid"] / world
+        s_alg = timers["owned_records"] * (1 + (K - 1) / 4.0 + 0.375) + occ_owned / 4.0
+        kern = {"k1_superkmer_fast": (n * L / 4.0 + stats["records"] / world * (1 + (K - 1) / 4.0 + 0.375) + occ_owned / 4.0, timers["partition"]),
+                "k2b_warp_bins": (s_alg + timers["owned_distinct"] * 12.0, timers["count_kernels"][2])}
+        dom = max(kern, key=lambda name: kern[name][1])
+        peak, peak_src = measured_peak()
+        roofline = {"bound": "hbm", "kernel": dom, "rank": 0, "achieved": kern[dom][0] / kern[dom][1] / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom][0] / kern[dom][1] / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kern[dom][0], "ms_per_launch": kern[dom][1] * 1e3}
         line = {"metric": METRIC, "value": stats["kmers_nb_distinct"] / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic",
@@ -216,7 +287,7 @@ def bench(args, rank, world, local):
                 "stage_seconds_rank0_last_step": timers, "exchanged_bytes_per_rank": stats["exchanged_bytes_per_rank"],
                 "e2e": {"value": stats["kmers_nb_distinct"] / e2e_step, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
                         "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": e2e_step * 1e3},
-                "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line))
+                "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline, "cpu_baseline": None}
+        args.emit(line)
     gpu.close()
     dist.destroy_process_group()

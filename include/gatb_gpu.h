@@ -58,7 +58,7 @@ typedef struct gatb_gpu_params
     int32_t  reserved[5];
 } gatb_gpu_params;
 
-enum { GATB_GPU_NSTATS = 16, GATB_GPU_MAX_SOURCES = 8 };
+enum { GATB_GPU_NSTATS = 16, GATB_GPU_MAX_RANKS = 8, GATB_GPU_MAX_SOURCES = 16 };   /* sources = ranks x pieces per rank */
 /* indices into gatb_gpu_result.stats */
 enum {
     GATB_STAT_KMERS_VALID = 0,   /* kmers_nb_valid   (SortingCountAlgorithm.cpp:737)   */
@@ -69,7 +69,9 @@ enum {
     GATB_STAT_SEQUENCES = 5,
     GATB_STAT_NUCLEOTIDES = 6,
     GATB_STAT_BINS = 7,          /* device bins used                                    */
-    GATB_STAT_OVERFLOW_BINS = 8, /* bins counted through the global-memory fallback     */
+    GATB_STAT_OVERFLOW_BINS = 8, /* bins the first-tier (per-warp) table could not hold; stats[12] = those that also
+                                    overflowed the second-tier (per-CTA, 8192 slots) table and went to the global table,
+                                    stats[11] = k-mer occurrences in the latter */
     GATB_STAT_RETRIES = 9,       /* partition-kernel re-runs after a bucket overflow    */
     GATB_STAT_RECORD_BYTES = 10  /* bytes of super-k-mer records (S of SURVEY.md 8d)    */
 };
@@ -133,6 +135,12 @@ int gatb_gpu_plan (gatb_gpu_ctx*, const gatb_gpu_params*, uint64_t total_kmers, 
  * stats4 (host): valid k-mers, invalid k-mers, records stored, records dropped. */
 int gatb_gpu_partition_into (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_geometry*,
                              const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads, const uint32_t* d_n_mask,
+                             void* d_bins, uint32_t* d_cursors, uint64_t* stats4);
+/* the same for the reads [first_read, first_read + n_reads) of the batch only: a rank that partitions its reads in
+ * several pieces (each into its own buffers) can send piece i while piece i+1 is being partitioned; the owner hands all
+ * pieces of all ranks to gatb_gpu_count_bins as separate sources (n_src <= GATB_GPU_MAX_SOURCES). */
+int gatb_gpu_partition_range_into (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_geometry*,
+                             const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t first_read, uint64_t n_reads, const uint32_t* d_n_mask,
                              void* d_bins, uint32_t* d_cursors, uint64_t* stats4);
 /* counts nb1_local coarse bins gathered from n_src sources: d_src_bins[s] = [nb1_local*cap records], d_src_cursors[s] =
  * [nb1_local]; kmers_bound >= k-mers in these bins (the fine split counts its own bins, nothing else is exchanged). */

@@ -32,14 +32,20 @@ def worker(rank, world, port, q):
             for i in range(cap):
                 bins[b, i, 0], bins[b, i, 1], bins[b, i, 2] = rank, b, i
         cursors = torch.tensor([(b + rank) % (cap + 1) for b in range(nb1)], dtype=torch.int32)
-        rbins, rcur = multigpu.exchange_bins(bins.view(-1), cursors, world)
-        ok = rbins.shape == (world, bpr * cap * rb) and rcur.shape == (world, bpr)
+        # rank r only uses (and sends) the first `used[r]` bytes of each region: a whole number of bins here
+        used = [(1 + (rank + r) % bpr) * cap * rb for r in range(world)]
+        pieces, rcur = multigpu.exchange_bins(bins.view(-1), cursors, world, rank, used)
+        ok = len(pieces) == world and rcur.shape == (world, bpr)
         for s in range(world):
-            piece = rbins[s].view(bpr, cap, rb)
+            nbin = bpr if s == rank else 1 + (s + rank) % bpr                   # own region: a view of everything
+            ok &= pieces[s].numel() >= nbin * cap * rb
+            piece = torch.zeros(bpr, cap, rb, dtype=torch.uint8)
+            piece.view(-1)[:nbin * cap * rb] = pieces[s][:nbin * cap * rb]
             for lb in range(bpr):
                 gb = rank * bpr + lb                                  # global id of the bin this rank owns
                 assert multigpu.owner_of_bin(gb, bpr) == rank
-                ok &= bool((piece[lb, :, 0] == s).all() and (piece[lb, :, 1] == gb).all())
+                if lb < nbin:
+                    ok &= bool((piece[lb, :, 0] == s).all() and (piece[lb, :, 1] == gb).all())
                 ok &= int(rcur[s, lb]) == (gb + s) % (cap + 1)
         q.put((rank, bool(ok)))
     finally:
@@ -64,7 +70,7 @@ def test_exchange_bins_world1_is_identity():
     bins = torch.arange(4 * 3 * 16, dtype=torch.uint8)
     cur = torch.tensor([1, 2, 3, 0], dtype=torch.int32)
     a, b = multigpu.exchange_bins(bins, cur, 1)
-    assert (a.view(-1) == bins).all() and (b.view(-1) == cur).all()
+    assert len(a) == 1 and (a[0].view(-1) == bins).all() and (b.view(-1) == cur).all()
 
 
 def test_merge_sorted_runs():

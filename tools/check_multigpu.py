@@ -27,6 +27,7 @@ def main():
         params = gpu.make_params(k, m, nb_partitions=nparts, abundance_min=2, read_len=L)
         nbytes = (n * L + 3) // 4
         reads = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()      # torch's zero fill vs the library's own stream
         gpu.synth_reads_dev(7, genome, rank * n, n, L, reads.data_ptr())
         gpu.synchronize()
         res, stats = multigpu.count_distributed(gpu, params, reads.data_ptr(), n, n_global, n_global * (L - k + 1), rank, world, repart=repart)
@@ -36,6 +37,7 @@ def main():
         dist.all_gather_object(gathered, {"parts": mine["parts"], "hist": mine["histogram"]})
         if rank == 0:
             allr = torch.zeros((n_global * L + 3) // 4 + 64, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
             assert (n * L) % 4 == 0
             gpu.synth_reads_dev(7, genome, 0, n_global, L, allr.data_ptr())
             gpu.synchronize()
