@@ -48,7 +48,7 @@ class Geometry(C.Structure):
     _fields_ = [("total_kmers", C.c_uint64), ("nb1", C.c_uint32), ("cap", C.c_uint32), ("fine_bits", C.c_int32),
                 ("table_log2", C.c_int32), ("m_device", C.c_int32), ("w", C.c_int32), ("maxlen", C.c_int32),
                 ("words", C.c_int32), ("n_ranks", C.c_uint32), ("bins_per_rank", C.c_uint32), ("record_bytes", C.c_uint32),
-                ("pad", C.c_uint32)]
+                ("coarse_blk", C.c_uint32)]
 
 
 def load_library():

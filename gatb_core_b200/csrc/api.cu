@@ -256,7 +256,7 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     memset (g, 0, sizeof(*g));
     g->total_kmers = total_kmers; g->nb1 = (uint32_t)nb1; g->cap = (uint32_t)cap; g->fine_bits = fine_bits; g->table_log2 = table_log2;
     g->m_device = mg; g->w = w; g->maxlen = (W == 1) ? DEV_MAXLEN_W1 : 60; g->words = W;                  // maxlen: Sequence2SuperKmer.hpp:147
-    g->n_ranks = n_ranks; g->bins_per_rank = (uint32_t)(nb1 / n_ranks); g->record_bytes = 16 * W;
+    g->n_ranks = n_ranks; g->bins_per_rank = (uint32_t)(nb1 / n_ranks); g->record_bytes = 16 * W; g->coarse_blk = COARSE_BLK;
     return 0;
 }
 

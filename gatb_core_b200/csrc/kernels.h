@@ -21,7 +21,7 @@ enum { REC_LEN_SHIFT_W1 = 52, REC_FINE_SHIFT_W1 = 57, FINE_BITS_W1 = 7,
 enum { DEV_LEN_SHIFT_W1 = 44, DEV_FINE_SHIFT_W1 = 49, DEV_MAXLEN_W1 = 24, DEV_FINE_BITS_MAX_W1 = 10 };
 
 // ----------------------------------------------------------------------------------------------------------------
-// Layout of a region of coarse bins (device mode): ROUNDS of COARSE_BLK records.  Record 'slot' of bin 'b' of a region
+// Layout of a region of coarse bins (device mode): ROUNDS of COARSE_BLK (= 64) records.  Record 'slot' of bin 'b' of a region
 // of 'nb' bins lives at ((slot / BLK) * nb + b) * BLK + slot % BLK: block r of every bin sits in round r.  All bins
 // fill at about the same rate (hashed minimizers), so at any time the partition kernel writes into a few neighbouring
 // rounds -- a window of tens of MB instead of one open line in every 100 KB of a 25 GB buffer.  Measured on B200: the
@@ -29,7 +29,7 @@ enum { DEV_LEN_SHIFT_W1 = 44, DEV_FINE_SHIFT_W1 = 49, DEV_MAXLEN_W1 = 24, DEV_FI
 // (address translation, not bandwidth).  Readers take a bin's blocks at stride nb*BLK records; CTAs working on
 // neighbouring bins share the pages.  cap is a multiple of COARSE_BLK.
 // ----------------------------------------------------------------------------------------------------------------
-enum { COARSE_BLK = 16 };
+enum { COARSE_BLK = 64 };          // 1 KB blocks (k <= 31): the readers' address translations amortise over 64 records
 __host__ __device__ __forceinline__ uint64_t coarse_index (uint32_t b, uint32_t slot, uint32_t nb)
 { return ((uint64_t)(slot / COARSE_BLK) * nb + b) * COARSE_BLK + (slot % COARSE_BLK); }
 

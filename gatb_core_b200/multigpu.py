@@ -88,9 +88,9 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
     geom = gpu.plan(params, total_kmers_global, n_reads_global, world)
     npc = N_PIECES if (world > 1 and world * N_PIECES <= 16 and n_reads_local >= 1024) else 1
     t = {"partition": 0.0, "exchange_wait": 0.0}
-    nb1, rb, bpr = geom.nb1, geom.record_bytes, geom.bins_per_rank
+    nb1, rb, bpr, blk = geom.nb1, geom.record_bytes, geom.bins_per_rank, geom.coarse_blk
     if npc > 1:                                          # a piece holds 1/npc of the records of a bin: shrink the capacity with it
-        geom.cap = (int(geom.cap / npc * 1.15) + 64 + 15) & ~15
+        geom.cap = (int(geom.cap / npc * 1.15) + 64 + blk - 1) // blk * blk
     firsts = [(n_reads_local * i // npc) & ~31 for i in range(npc)] + [n_reads_local]      # multiples of 32 reads
     st_sum = [0, 0, 0, 0]
     all_pieces, all_cur, keep, used_total = [], [], [], 0
@@ -111,7 +111,7 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
                 dist.all_reduce(flag, op=dist.ReduceOp.MAX)
             if int(flag[0].item()) == 0:
                 break
-            geom.cap = (int(flag[1].item()) + 15) & ~15     # a bin overflowed somewhere: every rank re-runs this piece with the global demand
+            geom.cap = (int(flag[1].item()) + blk - 1) // blk * blk     # a bin overflowed somewhere: every rank re-runs this piece with the global demand
             del bins, cursors
         for k in range(4):
             st_sum[k] += st[k]
@@ -120,9 +120,9 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
             for req in pending:
                 req.wait()
             t["exchange_wait"] += time.time() - t0
-        # region r is filled round by round (16 records per bin and round): only the rounds in use travel
-        rounds = (cursors.view(world, bpr).max(dim=1).values.clamp(max=cap).to(torch.int64) + 15) // 16
-        used = (rounds * (bpr * 16 * rb)).tolist()
+        # region r is filled round by round (blk records per bin and round): only the rounds in use travel
+        rounds = (cursors.view(world, bpr).max(dim=1).values.clamp(max=cap).to(torch.int64) + blk - 1) // blk
+        used = (rounds * (bpr * blk * rb)).tolist()
         pieces, recv_cur, pending = exchange_bins(bins, cursors, world, rank, used, wait=False)
         used_total += int(sum(used) - used[rank])
         keep.append((bins, cursors, geom.cap))

@@ -128,7 +128,10 @@ typedef struct gatb_gpu_geometry
     int32_t  fine_bits;         /* fine bins per coarse bin = 1 << fine_bits                                             */
     int32_t  table_log2;
     int32_t  m_device, w, maxlen, words;
-    uint32_t n_ranks, bins_per_rank, record_bytes, pad;
+    uint32_t n_ranks, bins_per_rank, record_bytes;
+    uint32_t coarse_blk;        /* records per block of the round-interleaved region layout; cap is a multiple of it, and a region
+                                   that holds at most c records per bin only uses its first ceil(c/coarse_blk) rounds:
+                                   ceil(c/coarse_blk) * bins_per_rank * coarse_blk * record_bytes bytes                          */
 } gatb_gpu_geometry;
 int gatb_gpu_plan (gatb_gpu_ctx*, const gatb_gpu_params*, uint64_t total_kmers, uint64_t n_reads, int n_ranks, gatb_gpu_geometry* out);
 /* k1 into caller buffers: d_bins [nb1*cap records], d_cursors [nb1] (demand; > cap means overflow);
