@@ -40,6 +40,28 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def check_invariants(res, occurrences):
+    """Size-independent properties of a full-size result (host arrays of gatb_gpu_count; one partition key, abundance
+    range [ABUNDANCE_MIN, inf)): the oracle cannot run at 10^8 reads, these can.
+      * the histogram counts every distinct k-mer once:           sum(hist) == kmers_nb_distinct
+      * every k-mer occurrence is in exactly one count:           sum_{c < min} c*hist[c] + sum(solid counts) == occurrences
+      * the solid k-mers are the tail of the histogram:           sum(hist[min:]) == n_items == kmers_nb_solid
+      * strictly ascending k-mers (order of ICountProcessor::process), all below 4^k, all counts in range"""
+    import ctypes as C
+    n_items = int(res.n_items)
+    hist = np.ctypeslib.as_array(C.cast(res.histogram, C.POINTER(C.c_uint64)), shape=(10001,))
+    lo = np.ctypeslib.as_array(C.cast(res.kmers_lo, C.POINTER(C.c_uint64)), shape=(max(n_items, 1),))[:n_items]
+    cnt = np.ctypeslib.as_array(C.cast(res.counts, C.POINTER(C.c_int32)), shape=(max(n_items, 1),))[:n_items]
+    low = sum(int(c) * int(hist[c]) for c in range(ABUNDANCE_MIN))
+    out = {"sum_hist_eq_distinct": int(hist.sum()) == int(res.stats[2]),
+           "occurrences_accounted": low + int(cnt.sum(dtype=np.int64)) == occurrences,
+           "solid_is_histogram_tail": int(hist[ABUNDANCE_MIN:].sum()) == n_items == int(res.stats[3]),
+           "strictly_ascending": bool(n_items < 2 or (lo[1:] > lo[:-1]).all()),
+           "values_in_range": bool(n_items == 0 or (int(lo.max()) < 4 ** K and int(cnt.min()) >= ABUNDANCE_MIN))}
+    out["all"] = all(out.values())
+    return out
+
+
 def ncu_traffic(kernel, reads):
     """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` capture of this workload
     (profiles/r01_traffic.json: {kernel: {reads: bytes}}); None when no capture of this size exists."""
@@ -234,6 +256,8 @@ def run_ours(args):
         if i >= 2:
             e2e_times.append(max(wall, float(res.seconds[7])))
         d2h_bytes = int(res.n_items) * 12 + (10001 + 2) * 8
+        if i == 1 + args.steps:
+            invariants = check_invariants(res, n * (L - K + 1))          # outside every timed region
         gpu.result_free(res)
     clocks = sampler.stop()
     e2e_step = sum(e2e_times) / len(e2e_times)
@@ -289,7 +313,8 @@ def run_ours(args):
             "overflow_bins": info["overflow_bins"], "retries": info["retries"],
             "e2e": {"value": distinct / e2e_step, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_step * 1e3},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "invariants": invariants}
     emit(line)
     gpu.close()
 
