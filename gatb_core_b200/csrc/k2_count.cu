@@ -853,7 +853,13 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
         const unsigned long long co2 = bin2 < P.nbins ? P.coarse_off[bin2 >> P.fine_bits] : 0;
 
         const uint32_t n = d0.y;
-        if (n)
+        // a bin with this many records (five times the planned load) practically never fits the warp's table: hand it to the
+        // next tier untouched instead of filling the table first (any bin may go there, this only saves the wasted attempt)
+        if (n > (uint32_t)T / 3)
+        {
+            if (lane == 0) { const uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin0; }
+        }
+        else if (n)
         {
             uint32_t wn = 0, rn = 0;                              // warp-uniform: claimed slots, pending retries
             bool w_ovf = false;

@@ -265,6 +265,25 @@ def bench(args, rank, world, local):
             e2e.append(float(el2.item()))
     e2e_step = sum(e2e) / len(e2e)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- size-independent invariants of the full-size result (the host arrays of the last end-to-end step; outside every
+    #      timed region): the oracle cannot run at this size, these properties can be checked ----
+    local, err = [0, 0, 0, 0, 1], 0
+    try:
+        hist = np.asarray(host["histogram"], dtype=np.int64)
+        ni = int(host["n_items"])
+        cnt, lo = host["counts"][:ni], host["kmers_lo"][:ni]
+        asc = ni < 2 or bool((lo[1:] > lo[:-1]).all())       # k <= 31: one 64-bit word per k-mer
+        local = [int(hist.sum()), sum(c * int(hist[c]) for c in range(ABUNDANCE_MIN)) + int(cnt.sum(dtype=np.int64)),
+                 int(hist[ABUNDANCE_MIN:].sum()), ni, 0 if asc else 1]
+    except Exception:                                        # never let the checker take the measurement down
+        err = 1
+    loc = torch.tensor(local + [err], dtype=torch.int64, device=dev)
+    dist.all_reduce(loc)                                     # every rank gets here, whatever happened above
+    loc = [int(x) for x in loc.tolist()]
+    invariants = {"sum_hist_eq_distinct": loc[0] == stats["kmers_nb_distinct"], "occurrences_accounted": loc[1] == stats["kmers_nb_valid"],
+                  "solid_is_histogram_tail": loc[2] == loc[3] == stats["kmers_nb_solid"], "strictly_ascending_per_rank": loc[4] == 0,
+                  "checker_errors": loc[5]}
+    invariants["all"] = all(v is True for k, v in invariants.items() if k != "checker_errors") and loc[5] == 0
     if rank == 0:
         # roofline of the dominant kernel on rank 0 (same accounting as the single-GPU line)
         occ_owned = stats["kmers_nb_valid"] / world
@@ -287,7 +306,8 @@ def bench(args, rank, world, local):
                 "stage_seconds_rank0_last_step": timers, "exchanged_bytes_per_rank": stats["exchanged_bytes_per_rank"],
                 "e2e": {"value": stats["kmers_nb_distinct"] / e2e_step, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
                         "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": e2e_step * 1e3},
-                "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline, "cpu_baseline": None}
+                "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline, "cpu_baseline": None,
+                "invariants": invariants}
         args.emit(line)
     gpu.close()
     dist.destroy_process_group()
