@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_partition (const K1Pa
 
 
 // =====================================================================================================================
-//  k1_superkmer_fast<WIN,W>: the device-order partition kernel for reads without invalid nucleotides.
+//  k1_superkmer_fast<WIN,W,HAS_N>: the device-order partition kernel (HAS_N: the reads may hold invalid nucleotides).
 //  thread <-> read; the scan itself is K1Scanner (k1_scan.cuh: registers only, ~20 instructions per nucleotide);
 //  closing lanes push 8-byte events into their warp's shared-memory queue; after every 16 positions the warp empties
 //  the queue cooperatively (lane <-> event): bin from the key, one 32-bit global atomic for the slot, the record cut
@@ -331,7 +331,7 @@ struct K1Emit
     }
 };
 
-template<int WIN, int W>
+template<int WIN, int W, bool HAS_N>
 __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params P)
 {
     __shared__ __align__(16) uint32_t s_q[K1_THREADS / 32][K1F_QCAP * 2];
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
     uint32_t* q = s_q[wid];
     const uint32_t* ring_w = s_ring + wid * 32;
     K1Emit emit; emit.q = q; emit.tail = &s_tail[wid]; emit.lane = (uint32_t)lane;
-    unsigned long long nvalid = 0, stored = 0, dropped = 0;
+    unsigned long long nvalid = 0, ninvalid = 0, stored = 0, dropped = 0;
     if (lane == 0) s_tail[wid] = 0;
     __syncwarp ();
 
@@ -378,11 +378,11 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
         }
         const int nm = (len >= k) ? (len - m + 1) : 0;      // reads shorter than k are skipped (Sequence2SuperKmer.hpp:144)
         const int nm_max = __reduce_max_sync (FULL_MASK, nm);
-        K1Scanner<WIN, K1_THREADS> sc;
+        K1Scanner<WIN, K1_THREADS, HAS_N> sc;
         if (nm > 0)
         {
             nvalid += (unsigned long long)(len - k + 1);
-            sc.begin ((const uint32_t*)P.words, roff, len, m, s_ring + tid);
+            sc.begin ((const uint32_t*)P.words, roff, len, m, s_ring + tid, P.nmask);
             if (sc.j >= nm) sc.finish (emit);
         }
         int j0 = WIN;
@@ -403,38 +403,44 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
         };
         if (nm_max > 0 && nm_max <= WIN) drain ();          // reads of exactly k nucleotides: one k-mer each
         while (j0 < nm_max) k1_static_for<K1Scanner<WIN>::PHASES, 0> (body);
+        if (HAS_N && nm > 0) { nvalid -= sc.ninv; ninvalid += sc.ninv; }
     }
     // ---- statistics: one atomic per warp ----
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
-        nvalid  += __shfl_xor_sync (FULL_MASK, nvalid, o);
-        stored  += __shfl_xor_sync (FULL_MASK, stored, o);
-        dropped += __shfl_xor_sync (FULL_MASK, dropped, o);
+        nvalid   += __shfl_xor_sync (FULL_MASK, nvalid, o);
+        ninvalid += __shfl_xor_sync (FULL_MASK, ninvalid, o);
+        stored   += __shfl_xor_sync (FULL_MASK, stored, o);
+        dropped  += __shfl_xor_sync (FULL_MASK, dropped, o);
     }
     if (lane == 0)
     {
-        if (nvalid)  atomicAdd (&P.stats[0], nvalid);
-        if (stored)  atomicAdd (&P.stats[2], stored);
-        if (dropped) atomicAdd (&P.stats[3], dropped);
+        if (nvalid)   atomicAdd (&P.stats[0], nvalid);
+        if (ninvalid) atomicAdd (&P.stats[1], ninvalid);
+        if (stored)   atomicAdd (&P.stats[2], stored);
+        if (dropped)  atomicAdd (&P.stats[3], dropped);
     }
 }
 
-template<int WIN, int W>
-static cudaError_t k1_fast_launch_t (const LaunchCtx& L, const K1Params& P)
+template<int WIN, int W, bool HAS_N>
+static cudaError_t k1_fast_launch_n (const LaunchCtx& L, const K1Params& P)
 {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W>, K1_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W,HAS_N>, K1_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
     uint64_t grid = (uint64_t)L.sm_count * per_sm;                 // persistent: a multiple of the SM count
     if (grid > n_tiles) grid = n_tiles;
     if (grid == 0) return cudaSuccess;
-    k1_superkmer_fast<WIN,W><<<(unsigned)grid, K1_THREADS, 0, L.stream>>> (P);
+    k1_superkmer_fast<WIN,W,HAS_N><<<(unsigned)grid, K1_THREADS, 0, L.stream>>> (P);
     (*L.launches)++;
     return cudaGetLastError ();
 }
+template<int WIN, int W>
+static cudaError_t k1_fast_launch_t (const LaunchCtx& L, const K1Params& P)
+{ return P.nmask ? k1_fast_launch_n<WIN, W, true> (L, P) : k1_fast_launch_n<WIN, W, false> (L, P); }
 
 // window sizes the register scanner is compiled for: k in [WIN+7, WIN+15] with m = k-WIN+1 in [8,16]
 int k1_fast_window (int k)
@@ -445,7 +451,7 @@ int k1_fast_window (int k)
 }
 static bool k1_fast_ok (const K1Params& P)
 {
-    if (P.mode != K1_MODE_DEVICE || P.nmask || P.count_only || P.force_general) return false;
+    if (P.mode != K1_MODE_DEVICE || P.count_only || P.force_general) return false;
     const int W = (P.k < 32) ? 1 : 2;
     if (P.w != k1_fast_window (P.k) || P.m != P.k - P.w + 1 || P.m < 8 || P.m > 16) return false;
     return (W == 1) ? (P.w == 8 || P.w == 16) : (P.w >= 24 && P.w <= 48);

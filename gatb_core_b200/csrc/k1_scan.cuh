@@ -82,7 +82,11 @@ constexpr int k1s_gcd (int a, int b) { return b ? k1s_gcd (b, a % b) : a; }
 // ring[(word index % K1S_RING) * RS], so that whoever builds the record of a closed super-k-mer reads the nucleotides
 // from shared memory instead of going back to global memory (0 = no ring, used by the host test).
 #define K1S_RING 16
-template<int WIN, int RS = 0>
+// HAS_N: the read may hold invalid nucleotides (1 bit per nucleotide in 'nmask', include/gatb_gpu.h): a k-mer that
+// overlaps one is invalid, it is dropped and it ends the open super-k-mer (Sequence2SuperKmer.hpp:95-108).  The scanner
+// keeps the number of nucleotides since the last invalid one; the keys are computed as usual (an invalid nucleotide is
+// encoded like G), only the k-mers are masked.
+template<int WIN, int RS = 0, bool HAS_N = false>
 struct K1Scanner
 {
     static constexpr int LCM    = WIN / k1s_gcd (WIN, 16) * 16;   // positions after which (window slot, word phase) repeat
@@ -102,6 +106,22 @@ struct K1Scanner
     int start;                    // first k-mer of the open super-k-mer
     int j;                        // next m-mer position
     int nm;                       // m-mer positions of the read (len-m+1)
+    // HAS_N only
+    const uint32_t* nmask; uint64_t roff_nt;
+    uint32_t bb;                  // invalid bits of the nucleotides [16t, 16t+32) of the read, t = current word
+    int bg;                       // next 16-nucleotide group to fetch
+    int since_bad, kk, m1;        // nucleotides since the last invalid one; k; m-1
+    bool open;                    // a super-k-mer is open
+    uint32_t ninv;                // invalid k-mers met
+
+    K1S_HD uint32_t bad_group (int g) const
+    {
+        const uint64_t a = roff_nt + 16 * (uint64_t)g;
+        const uint32_t w0 = K1S_LDG (nmask + (a >> 5)), w1 = K1S_LDG (nmask + (a >> 5) + 1);
+        return K1S_FSHR (w0, w1, (int)(a & 31)) & 0xFFFFu;
+    }
+    // the nucleotide entering the window at word position u is nucleotide 16t+u+m-1 of the read
+    K1S_HD void note_nucleotide (int u) { since_bad = ((bb >> (u + m1)) & 1u) ? 0 : since_bad + 1; }
 
     K1S_HD uint32_t next_word ()
     {
@@ -112,7 +132,11 @@ struct K1Scanner
         if (RS) { ring[(nw & (K1S_RING - 1)) * RS] = n; nw++; }
         return n;
     }
-    K1S_HD void advance_word () { na = nb; ra = rb; nb = next_word (); rb = k1s_pair_reverse (nb); }
+    K1S_HD void advance_word ()
+    {
+        na = nb; ra = rb; nb = next_word (); rb = k1s_pair_reverse (nb);
+        if (HAS_N) { bb = (bb >> 16) | (bad_group (bg) << 16); bg++; }
+    }
 
     template<int U> K1S_HD uint32_t key_at () const
     {
@@ -132,7 +156,25 @@ struct K1Scanner
         suf[T] = key;
         p = (T == 0) ? key : (key < p ? key : p);
         const uint32_t wmin = (T + 1 < WIN) ? (s < p ? s : p) : p;
-        if (wmin != cur)
+        if (HAS_N)
+        {
+            note_nucleotide (U);
+            const int i = j + q - (WIN - 1);
+            if (since_bad >= kk)
+            {
+                if (!open || wmin != cur)
+                {
+                    if (open) emit (cur, start, i - start);
+                    cur = wmin; start = i; open = true;
+                }
+            }
+            else
+            {
+                ninv++;
+                if (open) { emit (cur, start, i - start); open = false; }
+            }
+        }
+        else if (wmin != cur)
         {
             const int i = j + q - (WIN - 1);
             emit (cur, start, i - start);
@@ -148,9 +190,17 @@ struct K1Scanner
 
     // ---- the read starts at nucleotide 'roff' of the packed stream 'words32'; len >= k = m+WIN-1 is required -------
     // Processes the first block (m-mer positions 0..WIN-1): afterwards the super-k-mer of k-mer 0 is open.
-    K1S_HD void begin (const uint32_t* words32, uint64_t roff, int len, int m, uint32_t* ring_column = 0)
+    K1S_HD void begin (const uint32_t* words32, uint64_t roff, int len, int m, uint32_t* ring_column = 0, const uint32_t* n_mask = 0)
     {
         ring = ring_column; nw = 0;
+        if (HAS_N)
+        {
+            nmask = n_mask; roff_nt = roff; kk = m + WIN - 1; m1 = m - 1; ninv = 0; open = false;
+            bb = bad_group (0) | (bad_group (1) << 16); bg = 2;
+            const uint32_t lowbits = bb & ((1u << m1) - 1);             // the m-1 nucleotides before the first entering one
+            int msb = -1; for (int b = 0; b < 16; b++) if (lowbits & (1u << b)) msb = b;
+            since_bad = m1 - 1 - msb;
+        }
         mmask = (m >= 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1);
         aam = 0xAAAAAAAAu & mmask; fsh = 32 - 2 * m;
         nm = len - m + 1;
@@ -162,6 +212,7 @@ struct K1Scanner
         nb = next_word (); rb = k1s_pair_reverse (nb);
         first_block (Int<0> ());
         cur = p; start = 0; j = WIN;
+        if (HAS_N) { open = since_bad >= kk; if (!open) ninv++; }
         #pragma unroll
         for (int u = WIN - 2; u >= 1; u--) suf[u] = suf[u] < suf[u + 1] ? suf[u] : suf[u + 1];
     }
@@ -171,6 +222,7 @@ struct K1Scanner
         const uint32_t key = key_at<T % 16> ();
         suf[T] = key;
         p = (T == 0) ? key : (key < p ? key : p);
+        if (HAS_N) note_nucleotide (T % 16);
         if (T % 16 == 15) advance_word ();
         first_block (Int<T + 1> ());
     }
@@ -181,7 +233,7 @@ struct K1Scanner
     {
         // forced split of very long runs (tandem repeats): everything but the last k-mer seen leaves, so that a change
         // of the minimum at the next position still closes a non-empty super-k-mer
-        if (j - (WIN - 1) - start >= MAXRUN) { const int i = j - (WIN - 1) - 1; emit (cur, start, i - start); start = i; }
+        if ((!HAS_N || open) && j - (WIN - 1) - start >= MAXRUN) { const int i = j - (WIN - 1) - 1; emit (cur, start, i - start); start = i; }
         run16<PH, 0, TAIL> (emit, Int<0> ());
         j += 16;
     }
@@ -196,6 +248,6 @@ struct K1Scanner
     template<class Emit> K1S_HD void finish (Emit& emit)
     {
         const int nk = nm - (WIN - 1);
-        emit (cur, start, nk - start);
+        if (!HAS_N || open) emit (cur, start, nk - start);
     }
 };
