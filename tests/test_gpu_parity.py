@@ -134,6 +134,36 @@ def test_reference_golden_vectors_dsk(gpu, oracle):
     assert sum(lo.tolist()) % 2 ** 64 == G.DSK2_CHECKSUM
 
 
+# every window size the register scanner is compiled for (k-m+1 = 8, 16, ..., 48), their edges, and the k values that fall
+# back to the general partition kernel (k < 15); ragged reads, some with invalid nucleotides, several partitions
+@pytest.mark.parametrize("k", [5, 14, 15, 16, 22, 23, 24, 27, 32, 33, 39, 40, 47, 48, 55, 56, 62, 63])
+def test_dsk_every_kmer_size_class(gpu, oracle, k):
+    seqs, m, nparts, repart = kmer_class_case(k)
+    packed, offs, mask = pack_seqs(oracle, seqs)
+    want = oracle.dsk(seqs, k, m, repart, nparts, abundance_min=2)
+    got = gpu.count(packed, offs, len(seqs), gpu.make_params(k, m, nb_partitions=nparts, abundance_min=2), repart=repart, n_mask=mask)
+    check_parts(got, want["solid"], nparts, 1 if k < 32 else 2)
+    assert (got["histogram"] == want["histogram"]).all()
+    assert got["stats"]["kmers_nb_valid"] == int(want["stats"][0]) and got["stats"]["kmers_nb_invalid"] == int(want["stats"][1])
+    assert got["stats"]["kmers_nb_distinct"] == int(want["stats"][2])
+
+
+def kmer_class_case(k):
+    rng = np.random.default_rng(1000 + k)
+    m = min(8, k - 1)
+    nparts = 3
+    base = rand_seq(rng, 3000)                                         # reads drawn from one short genome: real multiplicities
+    seqs = []
+    for i in range(260):
+        a = int(rng.integers(0, 2600)); n = int(rng.integers(1, 400))
+        sq = bytearray(base[a:a + n])
+        if i % 3 == 0 and len(sq) > 3:
+            sq[int(rng.integers(0, len(sq)))] = ord("N")
+        seqs.append(bytes(sq))
+    repart = (np.arange(4 ** m) * 2654435761 % nparts).astype(np.uint16)
+    return seqs, m, nparts, repart
+
+
 def test_edge_cases(gpu, oracle):
     rng = np.random.default_rng(5)
     k, m = 31, 10
