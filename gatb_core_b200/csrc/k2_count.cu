@@ -1046,6 +1046,275 @@ static cudaError_t k2b_warp_launch (const LaunchCtx& L, const K2Params& P)
     return cudaGetLastError ();
 }
 
+// ------------------------------------------------------------------------------------------------ k2b, 32 <= k <= 63, warp per bin
+// The warp-per-bin scheme of k2b_warp_bins for 128-bit k-mers (Kmer<64>, 32-byte records): private table (low and high
+// halves of the keys in two arrays), records staged per 32 in the warp's shared memory (a chunk reads the six words it
+// needs at its own word offset), chunks of four k-mers decoded by k2_chunk2_* (k2_decode.cuh).
+// Claiming a 128-bit key: the high half is taken with a 64-bit CAS from EMPTY to LOCK, the winner publishes the low
+// half and then the real high half.  The table is private to the warp and the warp stays converged through a step, so
+// after the __syncwarp that follows the publication nobody can still see LOCK: no spinning in the converged path.
+// Collisions go to the warp's retry list and are re-inserted 32 at a time with table_insert_w2 (general probing).
+#define K2W2_RETRY_CAP 96       // 31 left over + 2 steps x 32 lanes between two drain checks
+template<int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) k2b_warp_bins_w2 (const K2Params P)
+{
+    constexpr int NWARP = NT / 32;
+    constexpr unsigned WBLOCK = 2048;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = 1 << P.table_log2;
+    const int hshift = 32 - P.table_log2;
+    const uint32_t OCC_W = (uint32_t)(T * 3) / 4;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const int k = P.k;
+    // per warp: staging 32 x 32 B | keys lo T*8 | keys hi T*8 | retry lo/hi CAP*16 | counts T*4 | claimed OCC_W*2 (16-aligned)
+    const size_t per_warp = 1024 + (size_t)T * 16 + K2W2_RETRY_CAP * 16 + (size_t)T * 4 + (((size_t)OCC_W * 2 + 15) & ~(size_t)15);
+    unsigned char* wbase = smem_raw + per_warp * wid;
+    uint4* stage = (uint4*)wbase;
+    const uint32_t* stage32 = (const uint32_t*)wbase;
+    unsigned long long* s_klo = (unsigned long long*)(wbase + 1024);
+    unsigned long long* s_khi = s_klo + T;
+    unsigned long long* retry_lo = s_khi + T;
+    unsigned long long* retry_hi = retry_lo + K2W2_RETRY_CAP;
+    uint32_t* s_cnt = (uint32_t*)(retry_hi + K2W2_RETRY_CAP);
+    uint16_t* occ_w = (uint16_t*)(s_cnt + T);
+    uint32_t* s_hist = (uint32_t*)(smem_raw + per_warp * NWARP);
+
+    for (int i = lane; i < T; i += 32) { s_khi[i] = EMPTY64; s_klo[i] = 0; s_cnt[i] = 0; }
+    for (int i = tid; i < K2_HB; i += NT) s_hist[i] = 0;
+    __syncthreads ();
+
+    uint32_t n_distinct = 0, n_solid = 0, n_emitted = 0;           // per lane; flushed as 64-bit sums at the end
+    unsigned long long out_pos = 0, out_end = 0;
+    const uint32_t G = gridDim.x * NWARP;
+    const uint4 zero4 = make_uint4 (0, 0, 0, 0);
+    const uint4* recs = (const uint4*)P.recs;
+
+    // software pipeline over this warp's bins: (bin0, d0, base0, ra0, rb0) is current; d1/co1 of the next bin are in flight
+    uint32_t bin0 = blockIdx.x * NWARP + wid;
+    uint2 d0 = bin0 < P.nbins ? P.bin_desc[bin0] : make_uint2 (0, 0);
+    unsigned long long base0 = bin0 < P.nbins ? P.coarse_off[bin0 >> P.fine_bits] + d0.x : 0;
+    uint4 ra0 = ((uint32_t)lane < d0.y) ? __ldg (recs + 2 * (base0 + lane)) : zero4;
+    uint4 rb0 = ((uint32_t)lane < d0.y) ? __ldg (recs + 2 * (base0 + lane) + 1) : zero4;
+    uint32_t bin1 = bin0 + G;
+    uint2 d1 = bin1 < P.nbins ? P.bin_desc[bin1] : make_uint2 (0, 0);
+    unsigned long long co1 = bin1 < P.nbins ? P.coarse_off[bin1 >> P.fine_bits] : 0;
+
+    while (bin0 < P.nbins)
+    {
+        const unsigned long long base1 = co1 + d1.x;
+        const uint4 ra1 = ((uint32_t)lane < d1.y) ? __ldg (recs + 2 * (base1 + lane)) : zero4;
+        const uint4 rb1 = ((uint32_t)lane < d1.y) ? __ldg (recs + 2 * (base1 + lane) + 1) : zero4;
+        const uint32_t bin2 = bin1 + G;
+        const uint2 d2 = bin2 < P.nbins ? P.bin_desc[bin2] : make_uint2 (0, 0);
+        const unsigned long long co2 = bin2 < P.nbins ? P.coarse_off[bin2 >> P.fine_bits] : 0;
+
+        const uint32_t n = d0.y;
+        if (n)
+        {
+            uint32_t wn = 0, rn = 0;                              // warp-uniform: claimed slots, pending retries
+            bool w_ovf = false;
+            auto append_new = [&] (bool isnew, uint32_t slot)
+            {
+                const unsigned m = __ballot_sync (FULL_MASK, isnew);
+                if (m)
+                {
+                    const uint32_t idx = wn + __popc (m & lt_mask);
+                    if (isnew && idx < OCC_W) occ_w[idx] = (uint16_t)slot;
+                    wn += __popc (m);
+                }
+            };
+            auto drain_retries = [&] ()
+            {
+                __syncwarp ();
+                for (uint32_t e0 = 0; e0 < rn; e0 += 32)
+                {
+                    const uint32_t e = e0 + lane;
+                    int res = 0;
+                    if (e < rn)
+                    {
+                        u128 key; key.lo = retry_lo[e]; key.hi = retry_hi[e];
+                        const uint32_t slot = ((uint32_t)key.lo * 0x9E3779B1u + (uint32_t)(key.lo >> 32) * 0x85EBCA77u +
+                                               (uint32_t)key.hi * 0xC2B2AE3Du + (uint32_t)(key.hi >> 32) * 0x27D4EB2Fu) >> hshift;
+                        res = table_insert_w2<false> (s_klo, s_khi, s_cnt, P.table_log2, slot, key, K2_MAXPROBE);
+                        if (res < 0) w_ovf = true;
+                    }
+                    __syncwarp ();
+                    append_new (e < rn && res >= 0 && (res & 0x40000000), (uint32_t)res & 0xFFFFu);
+                }
+                rn = 0;
+                __syncwarp ();
+            };
+
+            for (uint32_t g0 = 0; g0 < n; g0 += 32)
+            {
+                uint4 ra = ra0, rb = rb0;
+                if (g0)
+                {
+                    ra = (g0 + lane < n) ? __ldg (recs + 2 * (base0 + g0 + lane)) : zero4;
+                    rb = (g0 + lane < n) ? __ldg (recs + 2 * (base0 + g0 + lane) + 1) : zero4;
+                }
+                __syncwarp ();                                      // the previous group (or bin) is fully consumed
+                const uint32_t len_own = (rb.w >> (REC_LEN_SHIFT_W2 - 32)) & 63u;
+                rb.w &= (1u << (REC_LEN_SHIFT_W2 - 32)) - 1;        // nucleotides only in the staged copy
+                stage[2 * lane] = ra; stage[2 * lane + 1] = rb;
+                const uint32_t nch = (len_own + 3u) >> 2;           // 0 for the zero record
+                uint32_t incl = nch;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
+                const uint32_t excl = incl - nch;
+                const uint32_t total = __shfl_sync (FULL_MASK, incl, 31);
+                const uint32_t own = (excl << 8) | len_own;          // first chunk id and k-mer count of the lane's record
+                __syncwarp ();
+                uint32_t r0 = 0;
+                for (uint32_t wb = 0; wb < total; wb += 32)
+                {
+                    const uint32_t h = excl - wb;
+                    const uint32_t M = __reduce_or_sync (FULL_MASK, (nch > 0 && h < 32u) ? (1u << h) : 0u);
+                    const uint32_t gk = wb + lane;
+                    const bool act = gk < total;
+                    uint32_t r = r0 + __popc (M & (0xFFFFFFFFu >> (31 - lane))) - 1;
+                    r0 += __popc (M);
+                    r &= 31u;
+                    const uint32_t ow = __shfl_sync (FULL_MASK, own, r);
+                    const int c = act ? (int)(gk - (ow >> 8)) : 0;
+                    const int nkc = act ? (int)(ow & 0xFFu) - 4 * c : 0;      // k-mers of this chunk
+                    K2Chunk2 C;
+                    k2_chunk2_begin (C, stage32 + 8 * r, c, k);
+                    uint32_t v[4][4], slot[4];
+                    k2_chunk2_kmer<0> (C, v[0]); k2_chunk2_kmer<1> (C, v[1]); k2_chunk2_kmer<2> (C, v[2]); k2_chunk2_kmer<3> (C, v[3]);
+                    unsigned long long cur[4];
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++)
+                    {
+                        slot[i] = (v[i][0] * 0x9E3779B1u + v[i][1] * 0x85EBCA77u + v[i][2] * 0xC2B2AE3Du + v[i][3] * 0x27D4EB2Fu) >> hshift;
+                        cur[i] = (i < nkc) ? s_khi[slot[i]] : 0ULL;
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++)
+                    {
+                        const bool valid = i < nkc;
+                        const unsigned long long klo = ((unsigned long long)v[i][1] << 32) | v[i][0];
+                        const unsigned long long khi = ((unsigned long long)v[i][3] << 32) | v[i][2];
+                        unsigned long long ch = cur[i];
+                        const bool isE = valid && ch == EMPTY64;
+                        if (isE) ch = atomicCAS (&s_khi[slot[i]], EMPTY64, LOCK64);
+                        const bool isnew = isE && ch == EMPTY64;
+                        if (isnew) { s_klo[slot[i]] = klo; s_khi[slot[i]] = khi; }            // publish: low half, then the real high half
+                        __syncwarp ();
+                        bool hit = isnew;
+                        if (valid && !isnew) hit = (s_khi[slot[i]] == khi) && (s_klo[slot[i]] == klo);
+                        if (hit) atomicAdd (&s_cnt[slot[i]], 1u);
+                        append_new (isnew, slot[i]);
+                        const bool miss = valid && !hit;
+                        const unsigned mm = __ballot_sync (FULL_MASK, miss);
+                        if (mm)
+                        {
+                            const uint32_t at = rn + __popc (mm & lt_mask);
+                            if (miss) { retry_lo[at] = klo; retry_hi[at] = khi; }
+                            rn += __popc (mm);
+                        }
+                        if ((i & 1) && rn >= 32) drain_retries ();
+                    }
+                    if (wn > OCC_W) break;                          // the bin cannot fit any more: it goes to the fallback as a whole
+                }
+                if (wn > OCC_W) break;
+            }
+            if (rn) drain_retries ();
+            __syncwarp ();
+            if (__any_sync (FULL_MASK, w_ovf) || wn > OCC_W)
+            {   // the bin goes to the global-memory fallback (k2c): wipe the warp's table
+                if (lane == 0) { const uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin0; }
+                for (int i = lane; i < T; i += 32) { s_khi[i] = EMPTY64; s_klo[i] = 0; s_cnt[i] = 0; }
+                __syncwarp ();
+            }
+            else
+            {
+                for (uint32_t q0 = 0; q0 < wn; q0 += 32)
+                {
+                    const uint32_t q = q0 + lane;
+                    bool emit = false; uint64_t klo = 0, khi = 0; uint32_t c = 0;
+                    if (q < wn)
+                    {
+                        const uint32_t slot = occ_w[q];
+                        c = s_cnt[slot]; klo = s_klo[slot]; khi = s_khi[slot];
+                        s_khi[slot] = EMPTY64; s_klo[slot] = 0; s_cnt[slot] = 0;
+                        n_distinct++;
+                        const uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
+                        if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
+                        if (c >= P.solid_min && c <= P.solid_max) n_solid++;
+                        emit = (c >= P.emit_min && c <= P.emit_max);
+                    }
+                    const unsigned ballot = __ballot_sync (FULL_MASK, emit);
+                    if (ballot)
+                    {
+                        const unsigned ne = __popc (ballot);
+                        if (out_pos + ne > out_end)
+                        {
+                            for (unsigned long long hpos = out_pos + lane; hpos < out_end; hpos += 32)
+                                if (hpos < P.out_cap) P.out_hi[hpos] = EMPTY64;
+                            unsigned long long b0 = 0;
+                            if (lane == 0) b0 = atomicAdd (&P.counters[0], (unsigned long long)WBLOCK);
+                            b0 = __shfl_sync (FULL_MASK, b0, 0);
+                            out_pos = b0; out_end = b0 + WBLOCK;
+                        }
+                        if (emit)
+                        {
+                            const unsigned long long pos = out_pos + __popc (ballot & lt_mask);
+                            n_emitted++;
+                            if (pos < P.out_cap) { P.out_lo[pos] = klo; P.out_hi[pos] = khi; P.out_cnt[pos] = c; }
+                        }
+                        out_pos += ne;
+                    }
+                }
+                __syncwarp ();
+            }
+        }
+        bin0 = bin1; d0 = d1; base0 = base1; ra0 = ra1; rb0 = rb1;
+        bin1 = bin2; d1 = d2; co1 = co2;
+    }
+    for (unsigned long long hpos = out_pos + lane; hpos < out_end; hpos += 32)
+        if (hpos < P.out_cap) P.out_hi[hpos] = EMPTY64;
+    __syncthreads ();
+    for (int i = tid; i < K2_HB; i += NT) { uint32_t v = s_hist[i]; if (v) atomicAdd (&P.histogram[i], (unsigned long long)v); }
+    unsigned long long t_distinct = n_distinct, t_solid = n_solid, t_emitted = n_emitted;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        t_distinct += __shfl_xor_sync (FULL_MASK, t_distinct, o); t_solid += __shfl_xor_sync (FULL_MASK, t_solid, o);
+        t_emitted += __shfl_xor_sync (FULL_MASK, t_emitted, o);
+    }
+    if (lane == 0)
+    {
+        if (t_distinct) atomicAdd (&P.counters[1], t_distinct);
+        if (t_solid)    atomicAdd (&P.counters[2], t_solid);
+        if (t_emitted)  atomicAdd (&P.counters[6], t_emitted);
+    }
+}
+static size_t k2b_warp_w2_smem_bytes (int table_log2, int nt)
+{
+    const size_t T = (size_t)1 << table_log2, occ = (T * 3) / 4;
+    const size_t per_warp = 1024 + T * 16 + K2W2_RETRY_CAP * 16 + T * 4 + ((occ * 2 + 15) & ~(size_t)15);
+    return per_warp * (nt / 32) + K2_HB * 4;
+}
+template<int NT>
+static cudaError_t k2b_warp_w2_launch (const LaunchCtx& L, const K2Params& P)
+{
+    const size_t smem = k2b_warp_w2_smem_bytes (P.table_log2, NT);
+    cudaError_t e = cudaFuncSetAttribute (k2b_warp_bins_w2<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k2b_warp_bins_w2<NT>, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)L.sm_count * per_sm;
+    const uint64_t need = (P.nbins + NT / 32 - 1) / (NT / 32);
+    if (grid > need) grid = need;
+    k2b_warp_bins_w2<NT><<<(unsigned)grid, NT, smem, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
 // second tier: the bins the warp kernel could not hold, counted by CTAs with the table size of P.table_log2
 cudaError_t launch_k2b_count_list (const LaunchCtx& L, const K2Params& P)
 {
@@ -1072,7 +1341,16 @@ int k2b_variant ()
     if (variant < 0) { const char* e = getenv ("GATB_GPU_K2B"); variant = e ? atoi (e) : 1; }
     return variant;
 }
-int k2b_default_table_log2 (int W) { return (W == 1 && k2b_variant () == 1) ? 9 : 11; }
+// 32 <= k <= 63: the warp-per-bin kernel (k2b_warp_bins_w2) passes the whole GPU parity suite, but its 512-slot tables are too
+// small for the long super-k-mers of k = 63 (2*10^7 reads x 250 bp: half of the k-mers sit in overflowing bins and the global
+// fallback table would need 2^32 slots), and it has no overflow tiers yet.  It stays opt-in (GATB_GPU_K2B_W2=1) until it has them.
+static bool k2b_w2_warp ()
+{
+    static int on = -1;
+    if (on < 0) { const char* e = getenv ("GATB_GPU_K2B_W2"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
+int k2b_default_table_log2 (int W) { return (k2b_variant () == 1 && (W == 1 || k2b_w2_warp ())) ? 9 : 11; }
 
 static size_t k2b_smem_bytes (int W, int table_log2)
 {
@@ -1087,6 +1365,7 @@ cudaError_t launch_k2b_count (const LaunchCtx& L, const K2Params& P)
     size_t smem = k2b_smem_bytes (P.W, P.table_log2);
     const int variant = k2b_variant ();
     if (P.W == 1 && variant == 1) return k2b_warp_launch<128> (L, P);
+    if (P.W == 2 && variant == 1 && k2b_w2_warp ()) return k2b_warp_w2_launch<128> (L, P);
     if (P.W == 1 && variant == 128) return k2b_w1_launch<128> (L, P);
     if (P.W == 1 && variant == 256) return k2b_w1_launch<256> (L, P);
     const void* fn = (P.W == 1) ? (const void*)k2b_bucket_hash_count<1> : (const void*)k2b_bucket_hash_count<2>;

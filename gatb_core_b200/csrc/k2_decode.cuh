@@ -51,3 +51,63 @@ template<int I> K1S_HD void k2_chunk_kmer (const K2Chunk& C, uint32_t& lo, uint3
     const bool f_lt = (fh < rh) || (fh == rh && fl < rl);
     lo = f_lt ? fl : rl; hi = f_lt ? fh : rh;
 }
+
+// ---- 32 <= k <= 63 (32-byte records, 128-bit values as four 32-bit words, word 0 least significant) ----------------------
+// Same scheme: chunk c = k-mers 4c .. 4c+3, window X = record bits [8c, 8c+2k+6) (at most 132 bits, five words), one pair
+// reversal of the window per chunk, every shift inside the chunk an immediate.
+struct K2Chunk2
+{
+    uint32_t x[5];              // window X (stream order)
+    uint32_t z[5];              // pair-reversed window, right aligned
+    uint32_t m[4];              // masks of the four words of a 2k-bit value
+};
+
+// rw = the record's eight 32-bit words (rw[7] already stripped of the length / fine-bin fields); c = chunk index (0..14)
+K1S_HD void k2_chunk2_begin (K2Chunk2& C, const uint32_t* rw, int c, int k)
+{
+    const int s = 8 * c, wi = s >> 5, sh = s & 31;          // wi in 0..3
+    uint32_t a[6];
+    #pragma unroll
+    for (int i = 0; i < 6; i++) a[i] = (wi + i < 8) ? rw[wi + i] : 0u;
+    #pragma unroll
+    for (int i = 0; i < 5; i++) C.x[i] = k1s_fshr (a[i], a[i + 1], sh);
+    #pragma unroll
+    for (int w = 0; w < 4; w++)
+    {
+        const int bits = 2 * k - 32 * w;                    // bits of the value that fall into word w
+        C.m[w] = bits >= 32 ? 0xFFFFFFFFu : (bits <= 0 ? 0u : ((1u << bits) - 1));
+    }
+    // Y = pair reversal of the 160-bit window (y[4] most significant = reversal of x[0]); Z = Y >> (160 - (2k+6))
+    uint32_t y[8];
+    #pragma unroll
+    for (int i = 0; i < 5; i++) y[4 - i] = k1s_pair_reverse (C.x[i]);
+    y[5] = y[6] = y[7] = 0;
+    const int t = 154 - 2 * k;                              // 28..90, even
+    const int wo = t >> 5, ts = t & 31;                     // wo in 0..2
+    #pragma unroll
+    for (int i = 0; i < 5; i++)
+    {
+        const uint32_t lo = wo == 0 ? y[i] : wo == 1 ? y[i + 1] : y[i + 2];
+        const uint32_t hi = wo == 0 ? y[i + 1] : wo == 1 ? y[i + 2] : y[i + 3];
+        C.z[i] = k1s_fshr (lo, hi, ts);
+    }
+}
+
+// canonical value of k-mer I (0..3) of the chunk: v[0] least significant word
+template<int I> K1S_HD void k2_chunk2_kmer (const K2Chunk2& C, uint32_t v[4])
+{
+    uint32_t f[4], r[4];
+    #pragma unroll
+    for (int w = 0; w < 4; w++)
+    {
+        const uint32_t xs = I ? k1s_fshr (C.x[w], C.x[w + 1], 2 * I) : C.x[w];
+        r[w] = (xs & C.m[w]) ^ (0xAAAAAAAAu & C.m[w]);
+        f[w] = ((I < 3) ? k1s_fshr (C.z[w], C.z[w + 1], 6 - 2 * I) : C.z[w]) & C.m[w];
+    }
+    bool f_lt = false, decided = false;
+    #pragma unroll
+    for (int w = 3; w >= 0; w--)
+        if (!decided && f[w] != r[w]) { f_lt = f[w] < r[w]; decided = true; }
+    #pragma unroll
+    for (int w = 0; w < 4; w++) v[w] = f_lt ? f[w] : r[w];
+}
