@@ -1,6 +1,8 @@
 // kernels.h -- parameter blocks and host-side launchers of the sm_100a kernels (definitions in k*.cu).
 #pragma once
+#ifndef KERNELS_H_NO_CUDA_RUNTIME      // tests/cpp/test_layout.cpp compiles the layout helpers with plain g++
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -46,3 +46,7 @@ def test_k1_scanner_cpu():
 
 def test_k2_decoder_cpu():
     _run_device_logic_test("test_k2_decode")
+
+
+def test_coarse_layout_cpu():
+    _run_device_logic_test("test_layout")
