@@ -1,4 +1,4 @@
-// k1_partition.cu -- k1_superkmer_partition: reads -> super-k-mer records scattered into HBM bins.
+// k1_partition.cu -- k1_superkmer_fast / k1_superkmer_partition: reads -> super-k-mer records scattered into HBM bins.
 //
 // Replaces (paths relative to /root/reference/gatb-core/src/gatb/):
 //   ModelAbstract::iterate + ModelMinimizer::next         kmer/impl/Model.hpp:725-765, 1106-1139
@@ -6,28 +6,25 @@
 //   FillPartitions<span,true>::processSuperkmer           kmer/impl/SortingCountAlgorithm.cpp:1081-1151
 //   SuperKmer::save (+ CacheSuperKmerBinFiles)            kmer/impl/Model.hpp:1386-1471, tools/storage/impl/Storage.cpp:567-580
 //
-// Work shape (integer only, no tensor cores):
-//   * one thread <-> one read; the thread streams its 2-bit nucleotides through a 64-bit shift register refilled by
-//     8-byte loads (a warp's 32 reads are contiguous in the packed stream, so the loads of a warp hit the same few
-//     128-byte lines -- L1 serves them; DRAM sees each line once);
-//   * per nucleotide: rolling forward and reverse-complement m-mer (2 x 32 bit), canonical m-mer, rank key, and a
-//     sliding-window minimum over w = k-m+1 keys done WITHOUT data-dependent rescans: the stream of keys is cut in
-//     blocks of w, window min = min(suffix-min of the previous block, prefix-min of the current block); the per-thread
-//     ring of w keys lives in shared memory laid out [slot][thread] (bank-conflict free);
-//   * a super-k-mer closes when the window minimum changes, at an invalid k-mer, at maxlen k-mers, or at the end of
-//     the read -- the closing lane only pushes an 8-byte event into its warp's shared-memory queue;
-//   * every 8 nucleotides the warp drains the queue COOPERATIVELY (lane <-> event): builds the fixed-size record from
-//     the packed stream with funnel shifts, picks the bin, reserves a slot with one 32-bit global atomic and writes the
-//     record with one 16-byte store.  This keeps the divergent part (record construction) at full lane occupancy.
+// Two kernels (integer only, no tensor cores), both thread <-> read with a per-warp shared-memory event queue that the
+// warp empties cooperatively (lane <-> closed super-k-mer: bin, one 32-bit global atomic for the slot, record built with
+// funnel shifts, one 16-byte store), so that the divergent part runs at full lane occupancy:
+//   * k1_superkmer_fast<WIN,W,HAS_N> -- the counting path (K1_MODE_DEVICE, k >= 15): the scan is K1Scanner (k1_scan.cuh),
+//     compile-time indexed so that it lives in registers; records are cut out of a shared-memory ring of the words the
+//     scanner has already seen.  Second half of this file.
+//   * k1_superkmer_partition<W,HAS_N,MODE> -- the general kernel (GATB order, k < 15): 64-bit nucleotide shift register,
+//     rolling forward / reverse-complement m-mers, sliding-window minimum over w = k-m+1 keys WITHOUT data-dependent
+//     rescans (blocks of w keys: suffix minima of the previous block, prefix minima of the current one; the ring of w
+//     keys per thread lives in shared memory laid out [slot][thread]); records are rebuilt from the packed stream.
 //
-// Two rank functions share the kernel:
+// Two rank functions:
 //   K1_MODE_GATB   : key = GATB's mmer_lut value (min(mmer, revcomp) or 4^m-1 when an "AA" sits anywhere but at the
 //                    prefix; Model.hpp:1040-1064, 1220-1251) under integer '<' -- bit-exact super-k-mers and partitions
 //                    p = repart[minimizer] (PartiInfo.hpp:323), pass = minimizer % nb_passes.
-//   K1_MODE_DEVICE : key = multiplicative hash of the canonical m-mer (m up to 16) -- a *random* minimizer order, whose
+//   K1_MODE_DEVICE : key = canonical m-mer * odd + odd (m up to 16, k1s_key) -- a *random* minimizer order, whose
 //                    buckets are balanced enough for one bin's distinct k-mers to fit a shared-memory hash table in k2b.
 //                    Any order works for counting because every occurrence of a canonical k-mer has the same
-//                    window minimum; GATB's own partition id is recomputed exactly for each emitted k-mer in k3a.
+//                    window minimum; GATB's own partition id is recomputed exactly for each emitted k-mer in k3.
 #include "common.cuh"
 #include "kernels.h"
 #include "k1_scan.cuh"

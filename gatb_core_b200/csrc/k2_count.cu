@@ -1,4 +1,4 @@
-// k2_count.cu -- k2a_fine_split + k2b_bucket_hash_count (+ global-memory fallback k2c_*).
+// k2_count.cu -- fine split (k2a) and per-bin counting (k2b tiers, global-memory fallback k2c).
 //
 // Replaces (paths relative to /root/reference/gatb-core/src/gatb/):
 //   ReadSuperKCommand::execute / hash-mode decode    kmer/impl/PartitionsCommand.cpp:944-1128, 420-501
@@ -7,14 +7,19 @@
 //   CountProcessorHistogram::process                 kmer/impl/CountProcessorHistogram.hpp:173 (Histogram::inc, Histogram.hpp:92)
 //   CountProcessorSoliditySum::check                 kmer/impl/CountProcessorSolidity.hpp:186
 //
-// k2a: one CTA per coarse bin; reads its records once (coalesced 16-byte loads) and scatters them to their fine bin,
-//      whose exact extent comes from the per-fine-bin counters k1 maintained (no histogram pass).
-// k2b: persistent CTAs pull fine bins from an atomic work counter; the bin's records are staged into shared memory
-//      with TMA bulk copies (cp.async.bulk + mbarrier), every k-mer of every record is rebuilt with bit tricks
-//      (common.cuh) and inserted into an open-addressed shared-memory table: 64-bit atomicCAS claims the key slot,
-//      a 32-bit shared atomicAdd counts.  The table scan then feeds the abundance histogram (shared-memory bins,
-//      flushed once per CTA) and appends the k-mers inside [emit_min, emit_max] to the output with warp-aggregated
-//      global atomics.  A bin whose distinct k-mers do not fit the table is deferred to k2c (global-memory table).
+// k2a_fine_split      one CTA per coarse bin (gathered from up to 16 source pieces, walked as one record range): pass 1
+//                     counts the records per fine bin in shared memory, pass 2 scatters them (16-byte loads / stores).
+// k2b_warp_bins       k <= 31, the default: one WARP owns a fine bin (private 512-slot table, no block barrier); lane <->
+//                     chunk of four k-mers (k2_decode.cuh), converged probe / 64-bit CAS claim / count steps.
+// k2b_count_w1        k <= 31, CTA per bin with TMA-staged records (cp.async.bulk + mbarrier) and the same chunked
+//                     insert: the second and third TIER for bins that overflow a warp's table (2048, then 8192 slots,
+//                     bins taken from a list), and a test variant of the first tier (GATB_GPU_K2B=128|256).
+// k2b_bucket_hash_count<W>  CTA per bin, one k-mer per lane: the path of 32 <= k <= 63 (128-bit keys claimed through a LOCK
+//                     value in the high half), test variant for k <= 31 (GATB_GPU_K2B=0).
+// k2b_warp_bins_w2    warp per bin for 32 <= k <= 63 (opt-in, see k2b_default_table_log2).
+// k2c_*               what overflows every tier shares one global-memory table.
+// All of them feed the abundance histogram (shared-memory bins, flushed once per CTA), the solidity statistics, and
+// append the k-mers inside [emit_min, emit_max] to per-warp blocks of the output.
 #include "common.cuh"
 #include "kernels.h"
 #include "k2_decode.cuh"

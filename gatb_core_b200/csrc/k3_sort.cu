@@ -7,12 +7,16 @@
 //                                                     kmer/impl/PartitionsCommand.cpp:1599-1805, 544
 //   CountProcessorDump::process (append to dsk/solid/<pass*nb_partitions+part>)   kmer/impl/CountProcessorDump.hpp:148
 //
-// k3a  one thread per emitted k-mer: GATB minimizer by rolling the forward/reverse m-mer along the k-mer (no table:
-//      lut value = min(mmer, revcomp) with the "AA" rule applied arithmetically), key = pass*nb_partitions + repart[min];
-//      bucket = key << t | (top t bits of the k-mer value); per-bucket population by global atomics.
-// scan exclusive prefix sum over buckets (u32 -> u64), tile scan + block-sum scan + add.
-// k3b  scatter into bucket order (atomic cursor per bucket).
-// k3c  one CTA per bucket: bitonic sort by k-mer value in shared memory, write to the final position.
+// bucket of an emitted k-mer = key << t | (top t bits of the k-mer value), key = pass*nb_partitions + repart[minimizer] with
+// the GATB minimizer found by rolling the forward/reverse m-mer along the k-mer (no table: lut value = min(mmer, revcomp)
+// with the "AA" rule applied arithmetically).
+// k3s  classify + scatter in ONE pass: a bucket is a chain of 32-item blocks from one bump allocator (block directory),
+//      an item is one 16-byte store; four items in flight per thread.  The default.
+// scan exclusive prefix sum over the bucket populations (u32 -> u64), tile scan + block-sum scan + add: output offsets.
+// k3c  one CTA per bucket: distribution sort by k-mer value in shared memory (sub-bucket histogram, scan, scatter, rank among
+//      the few neighbours), bitonic network for skewed buckets; writes to the final position.
+// k3a / k3b  exact two-pass classify and scatter (atomic cursor per bucket): the fallback when a bucket outgrows the block
+//      directory of k3s.
 // k3d  buckets larger than the shared-memory budget: bitonic sort in global memory by one CTA (rare; skewed value ranges).
 #include "common.cuh"
 #include "kernels.h"
