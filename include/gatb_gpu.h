@@ -54,7 +54,8 @@ typedef struct gatb_gpu_params
     int32_t  minimizer_type;     /* _minimizerType   0 = lexicographic (supported); 1 = frequency (not yet)     */
     int32_t  emit_all;           /* 1: return EVERY distinct k-mer (for custom ICountProcessor chains); 0: solid only */
     int32_t  read_len;           /* >0: all reads have this length and read_offsets_nt may be NULL               */
-    int32_t  table_log2;         /* 0 = default (11); log2 slots of the per-bin shared-memory table, 5..13 */
+    int32_t  table_log2;         /* 0 = default (9 for kmer_size < 32: one warp per bin; 11 otherwise); log2 slots of the
+                                    first-tier per-bin shared-memory table, 5..13                                  */
     int32_t  reserved[5];
 } gatb_gpu_params;
 
@@ -88,8 +89,8 @@ typedef struct gatb_gpu_result
     uint64_t  stats[GATB_GPU_NSTATS];
     double    seconds[8];        /* stream time per stage (CUDA events): 0 h2d, 1 partition, 2 split, 3 count, 4 sort, 5 d2h,
                                     6 device total, 7 end to end */
-    double    kernel_seconds[8]; /* kernel-only durations: 0 k1_superkmer_partition, 1 k2a_fine_split, 2 k2b_bucket_hash_count,
-                                    3 k3 (classify + scan + scatter + sort) */
+    double    kernel_seconds[8]; /* kernel-only durations: 0 partition (k1), 1 fine split (k2a), 2 first-tier count (k2b),
+                                    3 k3 (classify + scatter + scan + sort), 4 overflow tiers + global fallback   */
     int32_t   on_device;         /* 1: the arrays above are DEVICE pointers (gatb_gpu_count_dev), 0: host            */
     int32_t   pad;
     void*     owner;             /* internal */
@@ -118,7 +119,8 @@ void gatb_gpu_result_free (gatb_gpu_ctx*, gatb_gpu_result*);
 /* ---- the same path in stages, for multi-GPU runs (one process per GPU) -------------------------------------------
  * The device binning: every rank partitions ITS reads into nb1 coarse bins with the SAME geometry;
  * coarse bin b is owned by rank b / bins_per_rank; the caller moves each bin region to its owner (one all-to-all of
- * [bins_per_rank][cap] records + cursors + fine counters) and the owner counts the bins it gathered from all sources.
+ * [bins_per_rank][cap] records + cursors, or only the used rounds of it) and the owner counts the bins it gathered
+ * from all sources.
  * Replaces the reference's only exchange medium, the SuperKmerBinFiles temp files (tools/storage/impl/Storage.cpp:310-347). */
 typedef struct gatb_gpu_geometry
 {
