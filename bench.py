@@ -208,7 +208,8 @@ def run_ours(args):
     d_reads = gpu.malloc(nbytes + 64)
     gpu.synth_reads_dev(SEED, genome, 0, n, L, d_reads)
     gpu.synchronize()
-    params = gpu.make_params(K, M, abundance_min=ABUNDANCE_MIN, read_len=L)
+    params = gpu.make_params(K, M, abundance_min=ABUNDANCE_MIN, read_len=L, path_flags=args.path_flags, bin_load_pct=args.bin_load_pct,
+                             table_log2=args.table_log2)
     stream = torch.cuda.ExternalStream(gpu.stream, device=torch.device("cuda", local))
 
     def step():
@@ -352,6 +353,9 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=1_000_000, help="reads per step of the reference arm")
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path-flags", type=int, default=0, help="gatb_gpu_params.path_flags (experiments; 0 = the product path)")
+    ap.add_argument("--bin-load-pct", type=int, default=0, help="gatb_gpu_params.bin_load_pct (experiments; 0 = default)")
+    ap.add_argument("--table-log2", type=int, default=0, help="gatb_gpu_params.table_log2 (experiments; 0 = default)")
     ap.add_argument("--staged", action="store_true", help="N=1 through the staged multi-GPU code path (debugging aid)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

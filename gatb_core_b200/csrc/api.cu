@@ -230,11 +230,12 @@ static int workload_size (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uin
 static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t total_kmers, uint64_t n_reads, int n_ranks, gatb_gpu_geometry* g)
 {
     const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
-    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : k2b_default_table_log2 (W);
+    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : k2b_default_table_log2 (W, p->path_flags);
     if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
     if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
     const uint64_t T = 1ULL << table_log2;
-    const uint64_t occ_per_bin = (T * 55) / 100;
+    if (p->bin_load_pct < 0 || p->bin_load_pct > 400) return fail (ctx, "bin_load_pct must be in [0,400]");
+    const uint64_t occ_per_bin = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : 55)) / 100 + 1;
     // k <= 31: one more fine-bin bit per doubling of the ranks, so that nb1 (the coarse bins every rank scatters into) stays put
     int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
     if (W == 1) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
@@ -260,6 +261,24 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     return 0;
 }
 
+// caller-supplied geometry (staged entry points): everything the kernels index with is checked against the parameters
+static int check_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g)
+{
+    if (!g) return fail (ctx, "geometry is NULL");
+    const int W = (p->kmer_size < 32) ? 1 : 2;
+    if (g->words != W || g->record_bytes != 16u * W) return fail (ctx, "geometry: %d-word records do not match kmer_size %d", g->words, p->kmer_size);
+    if (g->n_ranks < 1 || g->n_ranks > GATB_GPU_MAX_RANKS || g->bins_per_rank < 1 || (uint64_t)g->n_ranks * g->bins_per_rank != g->nb1)
+        return fail (ctx, "geometry: nb1 %u != n_ranks %u x bins_per_rank %u", g->nb1, g->n_ranks, g->bins_per_rank);
+    const int fmax = (W == 1) ? DEV_FINE_BITS_MAX_W1 : FINE_BITS_W2, fmin = (W == 1) ? 0 : FINE_BITS_W2;
+    if (g->fine_bits < fmin || g->fine_bits > fmax) return fail (ctx, "geometry: fine_bits %d out of range", g->fine_bits);
+    if (g->table_log2 < 5 || g->table_log2 > 13) return fail (ctx, "geometry: table_log2 %d out of range", g->table_log2);
+    if (g->cap == 0 || g->cap % COARSE_BLK || g->coarse_blk != COARSE_BLK) return fail (ctx, "geometry: cap %u is not a multiple of %d", g->cap, (int)COARSE_BLK);
+    if (g->m_device < 1 || g->m_device > 16 || g->m_device >= p->kmer_size || g->w != p->kmer_size - g->m_device + 1)
+        return fail (ctx, "geometry: device minimizer %d / window %d do not match kmer_size %d", g->m_device, g->w, p->kmer_size);
+    if (g->maxlen < 1 || g->maxlen > ((W == 1) ? DEV_MAXLEN_W1 : 60)) return fail (ctx, "geometry: maxlen %d out of range", g->maxlen);
+    return 0;
+}
+
 // ---- stage 1: k1 into caller-provided buffers (no retry here).  h_stats: valid, invalid, stored, dropped ------------
 // chunks of reads whose host->device copy is still in flight on the copy stream: k1 of chunk c waits for ready[c]
 struct ReadChunks { int n; uint64_t first[17]; cudaEvent_t* ready; };
@@ -278,7 +297,8 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
     k1.words = (const uint64_t*)d_reads; k1.offsets = d_offsets; k1.nmask = d_nmask; k1.n_reads = n_reads; k1.read_len = p->read_len;
     k1.k = p->kmer_size; k1.m = g->m_device; k1.w = g->w; k1.maxlen = g->maxlen;
     k1.mmask = (g->m_device >= 16) ? 0xFFFFFFFFu : ((1u << (2 * g->m_device)) - 1); k1.mask_ma1 = 0;
-    { const char* e = getenv ("GATB_GPU_K1_GENERAL"); k1.force_general = (e && e[0] == '1'); }
+    k1.force_general = (p->path_flags & GATB_PATH_K1_GENERAL) ? 1 : 0;
+    k1.oriented = k1_oriented (p->kmer_size, g->m_device, g->w, p->path_flags) ? 1 : 0;
     k1.mode = K1_MODE_DEVICE; k1.nb1 = g->nb1; k1.n_regions = g->n_ranks; k1.bins_per_region = g->bins_per_rank;
     if (g->cap % COARSE_BLK) return fail (ctx, "geometry: cap %u is not a multiple of %d", g->cap, (int)COARSE_BLK); k1.fine_bits = g->fine_bits; k1.count_only = 0;
     k1.bins = d_bins; k1.cap = g->cap; k1.cursors = d_cursors; k1.stats = d_stats;
@@ -370,6 +390,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         memset (&k2, 0, sizeof(k2));
         k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins;
         k2.coarse_off = (const uint64_t*)ctx->slot[S_COARSEOFF]; k2.fine_bits = fine_bits; k2.table_log2 = table_log2;
+        k2.path_flags = p->path_flags; k2.oriented = k1_oriented (k, g->m_device, g->w, p->path_flags) ? 1 : 0;
         k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
         k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
         k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
@@ -382,8 +403,8 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         n_ovf = h_cnt[4];
         n_ovf_first = n_ovf;
         if (n_ovf) cudaEventRecord (ctx->kev[8], ctx->stream);
-        static const bool no_tier2 = getenv ("GATB_GPU_K2B_TIER2") && getenv ("GATB_GPU_K2B_TIER2")[0] == '0';       // test hook: straight to the global table
-        if (n_ovf && W == 1 && k2b_variant () == 1 && !no_tier2)
+        const bool no_tier2 = (p->path_flags & GATB_PATH_NO_TIER2) != 0;                      // test selector: straight to the global table
+        if (n_ovf && W == 1 && k2b_variant (p->path_flags) == 1 && !no_tier2)
         {   // ---- further tiers: the bins a warp's 2^table_log2-slot table could not hold are counted by CTAs with 2048,
             //      then 8192 slots (k2b_count_w1 over a bin list); what still overflows goes to the global table ----
             const int tier_log2[2] = { 11, 13 }, tier_counter[2] = { 7, 12 };
@@ -470,12 +491,11 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     k3.n_buckets = (uint32_t)n_buckets; k3.big_list = (unsigned long long*)ctx->slot[S_BIGLIST]; k3.counters = d_cnt + 8;
     cudaEventRecord (ctx->kev[6], ctx->stream);
     // ---- bucket scatter: pooled single pass (k3s) unless a bucket outgrows the block directory, then the exact two-pass path ----
-    static const bool no_pool = getenv ("GATB_GPU_K3_POOL") && getenv ("GATB_GPU_K3_POOL")[0] == '0';                 // test hook
+    const bool no_pool = (p->path_flags & GATB_PATH_K3_NO_POOL) != 0;                          // test selector
     bool pooled = false;
     if (!no_pool && n_items)
     {
-        static const int dir_rounds_env = getenv ("GATB_GPU_K3_DIR_ROUNDS") ? atoi (getenv ("GATB_GPU_K3_DIR_ROUNDS")) : 0;         // test hook: small directory -> fallback
-        const uint32_t dir_rounds = dir_rounds_env > 0 ? (uint32_t)dir_rounds_env : k3_sort_cap () / K3_BLK;
+        const uint32_t dir_rounds = p->k3_dir_rounds > 0 ? (uint32_t)p->k3_dir_rounds : k3_sort_cap () / K3_BLK;   // a tiny directory forces the fallback
         const uint64_t pool_blocks = n_items / K3_BLK + n_buckets + 1;
         if (pool_blocks < (1ULL << 32))
         {
@@ -606,6 +626,11 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     uint64_t total_kmers = 0, total_nt = 0, max_len = 0;
     if (workload_size (ctx, p, d_offsets, n_reads, &total_kmers, &total_nt, &max_len)) return 1;
     if (max_len >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported by the partition kernel yet (longest: %llu)", (unsigned long long)max_len);
+    gatb_gpu_params p_long;
+    if (max_len >= (1ULL << 20) && !(p->path_flags & GATB_PATH_K1_GENERAL))
+    {   // the oriented register scanner keeps 20 bits of k-mer index per event: longer reads take the general kernel
+        p_long = *p; p_long.path_flags |= GATB_PATH_K1_GENERAL; p = &p_long;
+    }
     gatb_gpu_geometry g;
     if (plan_geometry (ctx, p, total_kmers, n_reads, 1, &g)) return 1;
     const uint64_t nbins = (uint64_t)g.nb1 << g.fine_bits;
@@ -666,6 +691,14 @@ int gatb_gpu_partition_range_into (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, 
     if (!ctx) return 1;
     cudaSetDevice (ctx->device);
     if (check_params (ctx, p, (const uint16_t*)1)) return 1;
+    if (check_geometry (ctx, p, g)) return 1;
+    {   // the limits of the partition kernels are enforced here too (the event word keeps 21, oriented 20, bits of k-mer index)
+        uint64_t tk = 0, tn = 0, max_len = 0;
+        if (workload_size (ctx, p, d_read_offsets_nt ? d_read_offsets_nt + first_read : 0, n_reads, &tk, &tn, &max_len)) return 1;
+        if (max_len >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported by the partition kernel yet (longest: %llu)", (unsigned long long)max_len);
+        if (max_len >= (1ULL << 20) && !(p->path_flags & GATB_PATH_K1_GENERAL))
+            return fail (ctx, "reads of 2^20 nucleotides and more need path_flags |= GATB_PATH_K1_GENERAL on every rank (plan, partition and count)");
+    }
     unsigned long long h[4];
     if (partition_impl (ctx, p, g, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, d_bins, d_cursors, h, 0, first_read)) return 1;
     for (int i = 0; i < 4; i++) stats4[i] = h[i];
@@ -683,6 +716,8 @@ int gatb_gpu_count_bins (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb
     cudaSetDevice (ctx->device);
     if (!out) return fail (ctx, "out is NULL");
     if (check_params (ctx, p, repart_table)) return 1;
+    if (check_geometry (ctx, p, g)) return 1;
+    if (nb1_local > g->nb1) return fail (ctx, "nb1_local %u exceeds the geometry's %u coarse bins", nb1_local, g->nb1);
     cudaEventRecord (ctx->ev[1], ctx->stream);
     if (count_bins_impl (ctx, p, g, n_src, d_src_bins, d_src_cursors, nb1_local, repart_table, kmers_bound, out)) return 1;
     float ms; cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[5]); out->seconds[6] = ms * 1e-3;

@@ -253,61 +253,103 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_partition (const K1Pa
 // =====================================================================================================================
 #define K1F_QCAP 640           // events per warp queue: 18 per lane per step at the very worst
 
-template<int W>
+// ORI (k <= 31 only): 'key' is the strand-tagged window minimum t of k1_scan.cuh (bin from its rank t >> 1, class R when t is
+// odd: the record holds the reverse complement of the span), meta = start << 12 | ambiguous << 11 | len << 5 | lane.  A
+// super-k-mer flagged ambiguous is taken apart: every k-mer is classified exactly (k1s_classify_kmer) and leaves as a
+// record of its own, ambiguous k-mers in their canonical orientation min(K, revcomp K) like kmer/impl/Model.hpp:857-884.
+struct K1fBin { uint32_t bin, fine, lbin; uint64_t rbase; };
+
+// one record: l k-mers from k-mer 'st' of the owner's read on; cls 0 = as read, 1 = reverse-complemented
+template<int W, bool ORI>
+__device__ __forceinline__ void k1f_put (const K1Params& P, const K1fBin& B, const uint32_t* col, uint32_t st, int l, int cls,
+                                         unsigned long long& stored, unsigned long long& dropped)
+{
+    const uint32_t slot = atomicAdd (&P.cursors[B.bin], 1u);
+    if (slot >= P.cap) { dropped++; return; }
+    stored++;
+    const uint32_t w0 = st >> 4;
+    const int sh = 2 * (int)(st & 15);
+    const int nn = P.k + l - 1;
+    constexpr int NW = (W == 1) ? 5 : 9;
+    uint32_t x[NW];
+    #pragma unroll
+    for (int i = 0; i < NW; i++) x[i] = col[((w0 + i) & (K1S_RING - 1)) * K1_THREADS];
+    uint32_t r[NW - 1];
+    #pragma unroll
+    for (int i = 0; i < NW - 1; i++) r[i] = __funnelshift_r (x[i], x[i + 1], sh);
+    if (W == 1)
+    {
+        uint64_t lo = (uint64_t)r[0] | ((uint64_t)r[1] << 32), hi = (uint64_t)r[2] | ((uint64_t)r[3] << 32);
+        if (nn <= 32) { lo &= mask2k64 (nn); hi = 0; } else { hi &= mask2k64 (nn - 32); }
+        if (ORI && cls) k1s_revcomp_span (lo, hi, nn);
+        hi |= ((uint64_t)l << DEV_LEN_SHIFT_W1) | ((uint64_t)B.fine << DEV_FINE_SHIFT_W1);
+        ((uint4*)P.bins)[B.rbase + coarse_index (B.lbin, slot, P.bins_per_region)] = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    }
+    else
+    {
+        uint64_t q[4];
+        #pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            q[i] = (uint64_t)r[2 * i] | ((uint64_t)r[2 * i + 1] << 32);
+            const int lo_nt = 32 * i;
+            if (nn <= lo_nt) q[i] = 0; else if (nn < lo_nt + 32) q[i] &= mask2k64 (nn - lo_nt);
+        }
+        q[3] |= ((uint64_t)l << REC_LEN_SHIFT_W2) | ((uint64_t)B.fine << REC_FINE_SHIFT_W2);
+        uint4* dst = (uint4*)P.bins + 2 * (B.rbase + coarse_index (B.lbin, slot, P.bins_per_region));
+        dst[0] = make_uint4 ((uint32_t)q[0], (uint32_t)(q[0] >> 32), (uint32_t)q[1], (uint32_t)(q[1] >> 32));
+        dst[1] = make_uint4 ((uint32_t)q[2], (uint32_t)(q[2] >> 32), (uint32_t)q[3], (uint32_t)(q[3] >> 32));
+    }
+}
+
+// A super-k-mer flagged ambiguous (rare: hairpins, palindromic minimizers) is taken apart: every k-mer is classified
+// exactly (k1s_classify_kmer) and leaves as a record of its own, ambiguous k-mers in their canonical orientation
+// min(K, revcomp K) like kmer/impl/Model.hpp:857-884.  Kept out of line so that it costs the scan no registers.
+template<int WIN>
+__device__ __noinline__ void k1f_store_ambiguous (const K1Params& P, const K1fBin& B, const uint32_t* col, uint32_t start, int len,
+                                                  unsigned long long& stored, unsigned long long& dropped)
+{
+    auto word = [&] (int t) { return col[(t & (K1S_RING - 1)) * K1_THREADS]; };
+    for (int i = 0; i < len; i++)
+    {
+        const uint32_t st = start + i;
+        int cls = k1s_classify_kmer (word, (int)st, WIN, P.m);
+        if (cls == 2)
+        {   // canonical orientation of this one k-mer: the strand with the smaller VALUE
+            const uint32_t w0 = st >> 4; const int sh = 2 * (int)(st & 15);
+            const uint32_t a0 = word (w0), a1 = word (w0 + 1), a2 = word (w0 + 2);
+            const uint64_t xs = ((uint64_t)__funnelshift_r (a0, a1, sh) | ((uint64_t)__funnelshift_r (a1, a2, sh) << 32)) & mask2k64 (P.k);
+            const uint64_t rcv = xs ^ (0xAAAAAAAAAAAAAAAAULL & mask2k64 (P.k));
+            const uint64_t fwv = pair_reverse64 (xs) >> (64 - 2 * P.k);
+            cls = (rcv < fwv) ? 1 : 0;
+        }
+        k1f_put<1, true> (P, B, col, st, 1, cls, stored, dropped);
+    }
+}
+
+// ORI (k <= 31 only): 'key' is the strand-tagged window minimum t of k1_scan.cuh (bin from its rank t >> 1, class R when t is
+// odd: the record holds the reverse complement of the span), meta = start << 12 | ambiguous << 11 | len << 5 | lane.
+template<int W, bool ORI, int WIN>
 __device__ __forceinline__ void k1f_store (const K1Params& P, uint32_t key, uint32_t meta, const uint32_t* ring_w,
                                            unsigned long long& stored, unsigned long long& dropped)
 {
     const int olane = meta & 31;
     int       len   = (meta >> 5) & 63;
-    uint32_t  start = meta >> 11;
-    const uint32_t h    = mix32 (key);
-    const uint32_t bin  = __umulhi (h, P.nb1);
-    const uint32_t fine = (h * 0x9E3779B1u) >> (32 - P.fine_bits);
+    uint32_t  start = ORI ? (meta >> 12) : (meta >> 11);
+    const uint32_t h    = mix32 (ORI ? (key >> 1) : key);
+    K1fBin B;
+    B.bin  = __umulhi (h, P.nb1);
+    B.fine = (h * 0x9E3779B1u) >> (32 - P.fine_bits);
     const uint32_t region = __umulhi (h, P.n_regions);      // = bin / bins_per_region (nested floors)
-    const uint64_t rbase = (uint64_t)region * P.bins_per_region * P.cap;
-    const uint32_t lbin = bin - region * P.bins_per_region;
+    B.rbase = (uint64_t)region * P.bins_per_region * P.cap;
+    B.lbin = B.bin - region * P.bins_per_region;
     const uint32_t* col = ring_w + olane;                   // the owner's column: word t at col[(t % K1S_RING) * K1_THREADS]
+    if constexpr (ORI)
+        if ((meta >> 11) & 1u) { k1f_store_ambiguous<WIN> (P, B, col, start, len, stored, dropped); return; }
     while (len > 0)
     {
         const int l = len < P.maxlen ? len : P.maxlen;
-        const uint32_t slot = atomicAdd (&P.cursors[bin], 1u);
-        if (slot < P.cap)
-        {
-            stored++;
-            const uint32_t w0 = start >> 4;
-            const int sh = 2 * (int)(start & 15);
-            const int nn = P.k + l - 1;
-            constexpr int NW = (W == 1) ? 5 : 9;
-            uint32_t x[NW];
-            #pragma unroll
-            for (int i = 0; i < NW; i++) x[i] = col[((w0 + i) & (K1S_RING - 1)) * K1_THREADS];
-            uint32_t r[NW - 1];
-            #pragma unroll
-            for (int i = 0; i < NW - 1; i++) r[i] = __funnelshift_r (x[i], x[i + 1], sh);
-            if (W == 1)
-            {
-                uint64_t lo = (uint64_t)r[0] | ((uint64_t)r[1] << 32), hi = (uint64_t)r[2] | ((uint64_t)r[3] << 32);
-                if (nn <= 32) { lo &= mask2k64 (nn); hi = 0; } else { hi &= mask2k64 (nn - 32); }
-                hi |= ((uint64_t)l << DEV_LEN_SHIFT_W1) | ((uint64_t)fine << DEV_FINE_SHIFT_W1);
-                ((uint4*)P.bins)[rbase + coarse_index (lbin, slot, P.bins_per_region)] = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-            }
-            else
-            {
-                uint64_t q[4];
-                #pragma unroll
-                for (int i = 0; i < 4; i++)
-                {
-                    q[i] = (uint64_t)r[2 * i] | ((uint64_t)r[2 * i + 1] << 32);
-                    const int lo_nt = 32 * i;
-                    if (nn <= lo_nt) q[i] = 0; else if (nn < lo_nt + 32) q[i] &= mask2k64 (nn - lo_nt);
-                }
-                q[3] |= ((uint64_t)l << REC_LEN_SHIFT_W2) | ((uint64_t)fine << REC_FINE_SHIFT_W2);
-                uint4* dst = (uint4*)P.bins + 2 * (rbase + coarse_index (lbin, slot, P.bins_per_region));
-                dst[0] = make_uint4 ((uint32_t)q[0], (uint32_t)(q[0] >> 32), (uint32_t)q[1], (uint32_t)(q[1] >> 32));
-                dst[1] = make_uint4 ((uint32_t)q[2], (uint32_t)(q[2] >> 32), (uint32_t)q[3], (uint32_t)(q[3] >> 32));
-            }
-        }
-        else dropped++;
+        k1f_put<W, ORI> (P, B, col, start, l, ORI ? (int)(key & 1u) : 0, stored, dropped);
         start += l; len -= l;
     }
 }
@@ -326,9 +368,14 @@ struct K1Emit
         const uint32_t e = atomicAdd (tail, 1u);
         *(uint2*)(q + 2 * e) = make_uint2 (key, ((uint32_t)start << 11) | ((uint32_t)len << 5) | lane);
     }
+    __device__ __forceinline__ void operator() (uint32_t key, int start, int len, bool amb)      // oriented scan
+    {
+        const uint32_t e = atomicAdd (tail, 1u);
+        *(uint2*)(q + 2 * e) = make_uint2 (key, ((uint32_t)start << 12) | ((uint32_t)amb << 11) | ((uint32_t)len << 5) | lane);
+    }
 };
 
-template<int WIN, int W, bool HAS_N>
+template<int WIN, int W, bool HAS_N, bool ORI>
 __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params P)
 {
     __shared__ __align__(16) uint32_t s_q[K1_THREADS / 32][K1F_QCAP * 2];
@@ -354,7 +401,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
             if (e < n)
             {
                 const uint2 ev = *(const uint2*)(q + 2 * e);
-                k1f_store<W> (P, ev.x, ev.y, ring_w, stored, dropped);
+                k1f_store<W, ORI, WIN> (P, ev.x, ev.y, ring_w, stored, dropped);
             }
         }
         __syncwarp ();
@@ -375,7 +422,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
         }
         const int nm = (len >= k) ? (len - m + 1) : 0;      // reads shorter than k are skipped (Sequence2SuperKmer.hpp:144)
         const int nm_max = __reduce_max_sync (FULL_MASK, nm);
-        K1Scanner<WIN, K1_THREADS, HAS_N> sc;
+        K1Scanner<WIN, K1_THREADS, HAS_N, ORI> sc;
         if (nm > 0)
         {
             nvalid += (unsigned long long)(len - k + 1);
@@ -420,24 +467,28 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
     }
 }
 
-template<int WIN, int W, bool HAS_N>
+template<int WIN, int W, bool HAS_N, bool ORI>
 static cudaError_t k1_fast_launch_n (const LaunchCtx& L, const K1Params& P)
 {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W,HAS_N>, K1_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W,HAS_N,ORI>, K1_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
     uint64_t grid = (uint64_t)L.sm_count * per_sm;                 // persistent: a multiple of the SM count
     if (grid > n_tiles) grid = n_tiles;
     if (grid == 0) return cudaSuccess;
-    k1_superkmer_fast<WIN,W,HAS_N><<<(unsigned)grid, K1_THREADS, 0, L.stream>>> (P);
+    k1_superkmer_fast<WIN,W,HAS_N,ORI><<<(unsigned)grid, K1_THREADS, 0, L.stream>>> (P);
     (*L.launches)++;
     return cudaGetLastError ();
 }
 template<int WIN, int W>
 static cudaError_t k1_fast_launch_t (const LaunchCtx& L, const K1Params& P)
-{ return P.nmask ? k1_fast_launch_n<WIN, W, true> (L, P) : k1_fast_launch_n<WIN, W, false> (L, P); }
+{
+    if constexpr (W == 1)
+        if (P.oriented) return P.nmask ? k1_fast_launch_n<WIN, W, true, true> (L, P) : k1_fast_launch_n<WIN, W, false, true> (L, P);
+    return P.nmask ? k1_fast_launch_n<WIN, W, true, false> (L, P) : k1_fast_launch_n<WIN, W, false, false> (L, P);
+}
 
 // window sizes the register scanner is compiled for: k in [WIN+7, WIN+15] with m = k-WIN+1 in [8,16]
 int k1_fast_window (int k)
@@ -446,13 +497,20 @@ int k1_fast_window (int k)
     int win = ((k - 15) + 7) / 8 * 8;
     return win < 8 ? 8 : win;
 }
+static bool k1_fast_geometry_ok (int k, int m, int w)
+{
+    const int W = (k < 32) ? 1 : 2;
+    if (w != k1_fast_window (k) || m != k - w + 1 || m < 8 || m > 16) return false;
+    return (W == 1) ? (w == 8 || w == 16) : (w >= 24 && w <= 48);
+}
 static bool k1_fast_ok (const K1Params& P)
 {
     if (P.mode != K1_MODE_DEVICE || P.count_only || P.force_general) return false;
-    const int W = (P.k < 32) ? 1 : 2;
-    if (P.w != k1_fast_window (P.k) || P.m != P.k - P.w + 1 || P.m < 8 || P.m > 16) return false;
-    return (W == 1) ? (P.w == 8 || P.w == 16) : (P.w >= 24 && P.w <= 48);
+    return k1_fast_geometry_ok (P.k, P.m, P.w);
 }
+// oriented records: the register scanner for k <= 31 unless a test asks for the canonical variant (path_flags of gatb_gpu.h)
+bool k1_oriented (int k, int m, int w, int path_flags)
+{ return k < 32 && !(path_flags & 1) && !(path_flags & 64) && k1_fast_geometry_ok (k, m, w); }
 
 static size_t k1_smem_bytes (int w) { return (size_t)w * K1_THREADS * 4 + 4 * (K1_QCAP * 2) * 4 + 4 * 32 * 8 + 4 * 4 + 16; }
 

@@ -70,6 +70,26 @@ K1S_HD uint32_t k1s_ldg (const uint32_t* p)
 // rank key of a canonical m-mer (device binning order)
 K1S_HD uint32_t k1s_key (uint32_t cm) { return cm * K1S_MUL + K1S_ADD; }
 
+// ---- ORIENTED scan (ORI = true): strand-tagged rank keys -----------------------------------------------------------
+// The forward m-mer f of a position gets an EVEN key, its reverse complement rc an ODD one, with the same 31-bit rank
+// function in the upper bits:  hF = 2*(f*MUL + C) , hR = 2*(rc*MUL + C) + 1  (mod 2^32).
+// For a k-mer K let A = min hF, B = min hR over its window; for revcomp(K) the two swap roles (B-1, A+1).  Rule:
+//   t = min(A, B);  t even and B != A+1 : K is taken as read            (class F)
+//                   t odd               : revcomp(K) is taken            (class R; then B>>1 < A>>1 strictly)
+//                   B == A+1            : the minimal rank occurs on both strands (or in a palindrome): AMBIGUOUS,
+//                                         the k-mer is stored as min(K, revcomp K) like GATB's canonical form.
+// The representative is a function of the k-mer alone and the same for K and revcomp(K) whatever the rank function
+// (tools/prototypes/oriented_keys.cpp checks the rule; tests/cpp/test_k1_scan.cpp checks this implementation), and
+// t >> 1 (the rank of the minimizer) is the same for both strands: it selects the bin.  All k-mers of a super-k-mer
+// (constant t) therefore share one orientation relative to the read: the whole record is stored in that orientation
+// and the counting kernel uses plain slices of the record as table keys -- no reverse complement, no min() per k-mer
+// occurrence.
+#define K1S_MUL2 ((K1S_MUL << 1) & 0xFFFFFFFFu)
+#define K1S_ADDF (K1S_ADD & ~1u)
+#define K1S_ADDR (K1S_ADD | 1u)
+K1S_HD uint32_t k1s_key_fwd (uint32_t f)  { return f  * K1S_MUL2 + K1S_ADDF; }
+K1S_HD uint32_t k1s_key_rc  (uint32_t rc) { return rc * K1S_MUL2 + K1S_ADDR; }
+
 K1S_HD uint32_t k1s_pair_reverse (uint32_t x)
 {
     uint32_t r = K1S_BREV (x);
@@ -86,14 +106,17 @@ constexpr int k1s_gcd (int a, int b) { return b ? k1s_gcd (b, a % b) : a; }
 // overlaps one is invalid, it is dropped and it ends the open super-k-mer (Sequence2SuperKmer.hpp:95-108).  The scanner
 // keeps the number of nucleotides since the last invalid one; the keys are computed as usual (an invalid nucleotide is
 // encoded like G), only the k-mers are masked.
-template<int WIN, int RS = 0, bool HAS_N = false>
+// ORI: oriented scan (see above); emit gets a fourth argument: true when some k-mer of the super-k-mer is ambiguous.
+template<int WIN, int RS = 0, bool HAS_N = false, bool ORI = false>
 struct K1Scanner
 {
     static constexpr int LCM    = WIN / k1s_gcd (WIN, 16) * 16;   // positions after which (window slot, word phase) repeat
     static constexpr int PHASES = LCM / 16;
     static constexpr int MAXRUN = 32;                              // forced split threshold (lengths stay < 32+16)
 
-    uint32_t suf[WIN];            // keys of the current block / suffix minima of the previous one
+    uint32_t suf[WIN];            // keys of the current block / suffix minima of the previous one (ORI: forward-strand keys)
+    uint32_t sur[ORI ? WIN : 1];  // ORI: the same for the reverse-complement keys
+    uint32_t pr, amb;             // ORI: prefix minimum of the reverse keys; min over the open super-k-mer of A ^ B (1 = ambiguous)
     uint32_t na, nb, ra, rb;      // normalised words t, t+1 and their pair-reversed images
     uint32_t raw;                 // last raw word consumed
     uint32_t ahead;               // raw word loaded one step early (its latency hides behind 16 positions of work)
@@ -147,15 +170,43 @@ struct K1Scanner
         return k1s_key (f < rc ? f : rc);
     }
 
+    template<int U> K1S_HD void keys_at (uint32_t& hf, uint32_t& hr) const
+    {
+        const uint32_t x  = U ? K1S_FSHR (na, nb, 2 * U) : na;
+        const uint32_t rc = (x & mmask) ^ aam;
+        const uint32_t g  = U ? K1S_FSHL (rb, ra, 2 * U) : ra;
+        hf = k1s_key_fwd (g >> fsh); hr = k1s_key_rc (rc);
+    }
+    K1S_HD static uint32_t min2 (uint32_t a, uint32_t b) { return a < b ? a : b; }
+    template<class Emit> K1S_HD void do_emit (Emit& emit, uint32_t key, int s, int l)
+    {
+        if constexpr (ORI) emit (key, s, l, amb == 1u); else emit (key, s, l);
+    }
+
     // one position: T = slot in the window block, U = nucleotide inside the normalised word; i = k-mer index j-(WIN-1)
     template<int T, int U, bool TAIL, class Emit> K1S_HD void position (int q, Emit& emit)
     {
         if (TAIL && j + q >= nm) return;
-        const uint32_t key = key_at<U> ();
-        const uint32_t s = (T + 1 < WIN) ? suf[(T + 1) % WIN] : 0xFFFFFFFFu;
-        suf[T] = key;
-        p = (T == 0) ? key : (key < p ? key : p);
-        const uint32_t wmin = (T + 1 < WIN) ? (s < p ? s : p) : p;
+        uint32_t wmin, x = 0;
+        if constexpr (ORI)
+        {
+            uint32_t hf, hr; keys_at<U> (hf, hr);
+            const uint32_t sf = (T + 1 < WIN) ? suf[(T + 1) % WIN] : 0xFFFFFFFFu;
+            const uint32_t sr = (T + 1 < WIN) ? sur[(T + 1) % WIN] : 0xFFFFFFFFu;
+            suf[T] = hf; sur[T] = hr;
+            p  = (T == 0) ? hf : min2 (hf, p);
+            pr = (T == 0) ? hr : min2 (hr, pr);
+            const uint32_t wf = (T + 1 < WIN) ? min2 (sf, p) : p, wr = (T + 1 < WIN) ? min2 (sr, pr) : pr;
+            wmin = min2 (wf, wr); x = wf ^ wr;
+        }
+        else
+        {
+            const uint32_t key = key_at<U> ();
+            const uint32_t s = (T + 1 < WIN) ? suf[(T + 1) % WIN] : 0xFFFFFFFFu;
+            suf[T] = key;
+            p = (T == 0) ? key : (key < p ? key : p);
+            wmin = (T + 1 < WIN) ? (s < p ? s : p) : p;
+        }
         if (HAS_N)
         {
             note_nucleotide (U);
@@ -164,26 +215,33 @@ struct K1Scanner
             {
                 if (!open || wmin != cur)
                 {
-                    if (open) emit (cur, start, i - start);
-                    cur = wmin; start = i; open = true;
+                    if (open) do_emit (emit, cur, start, i - start);
+                    cur = wmin; start = i; open = true; amb = x;
                 }
+                else if (ORI) amb = min2 (amb, x);
             }
             else
             {
                 ninv++;
-                if (open) { emit (cur, start, i - start); open = false; }
+                if (open) { do_emit (emit, cur, start, i - start); open = false; }
             }
         }
         else if (wmin != cur)
         {
             const int i = j + q - (WIN - 1);
-            emit (cur, start, i - start);
-            cur = wmin; start = i;
+            do_emit (emit, cur, start, i - start);
+            cur = wmin; start = i; amb = x;
         }
+        else if (ORI) amb = min2 (amb, x);
         if (T == WIN - 1)
         {
             #pragma unroll
             for (int u = WIN - 2; u >= 1; u--) suf[u] = suf[u] < suf[u + 1] ? suf[u] : suf[u + 1];
+            if constexpr (ORI)
+            {
+                #pragma unroll
+                for (int u = WIN - 2; u >= 1; u--) sur[u] = sur[u] < sur[u + 1] ? sur[u] : sur[u + 1];
+            }
         }
         if (U == 15) advance_word ();
     }
@@ -211,17 +269,32 @@ struct K1Scanner
         na = next_word (); ra = k1s_pair_reverse (na);
         nb = next_word (); rb = k1s_pair_reverse (nb);
         first_block (Int<0> ());
-        cur = p; start = 0; j = WIN;
+        cur = p; start = 0; j = WIN; amb = 0xFFFFFFFFu; pr = ORI ? pr : 0u;
+        if constexpr (ORI) { cur = min2 (p, pr); amb = p ^ pr; }
         if (HAS_N) { open = since_bad >= kk; if (!open) ninv++; }
         #pragma unroll
         for (int u = WIN - 2; u >= 1; u--) suf[u] = suf[u] < suf[u + 1] ? suf[u] : suf[u + 1];
+        if constexpr (ORI)
+        {
+            #pragma unroll
+            for (int u = WIN - 2; u >= 1; u--) sur[u] = sur[u] < sur[u + 1] ? sur[u] : sur[u + 1];
+        }
     }
     template<int N> struct Int {};
     template<int T> K1S_HD void first_block (Int<T>)
     {
-        const uint32_t key = key_at<T % 16> ();
-        suf[T] = key;
-        p = (T == 0) ? key : (key < p ? key : p);
+        if constexpr (ORI)
+        {
+            uint32_t hf, hr; keys_at<T % 16> (hf, hr);
+            suf[T] = hf; sur[T] = hr;
+            p = (T == 0) ? hf : min2 (hf, p); pr = (T == 0) ? hr : min2 (hr, pr);
+        }
+        else
+        {
+            const uint32_t key = key_at<T % 16> ();
+            suf[T] = key;
+            p = (T == 0) ? key : (key < p ? key : p);
+        }
         if (HAS_N) note_nucleotide (T % 16);
         if (T % 16 == 15) advance_word ();
         first_block (Int<T + 1> ());
@@ -233,7 +306,7 @@ struct K1Scanner
     {
         // forced split of very long runs (tandem repeats): everything but the last k-mer seen leaves, so that a change
         // of the minimum at the next position still closes a non-empty super-k-mer
-        if ((!HAS_N || open) && j - (WIN - 1) - start >= MAXRUN) { const int i = j - (WIN - 1) - 1; emit (cur, start, i - start); start = i; }
+        if ((!HAS_N || open) && j - (WIN - 1) - start >= MAXRUN) { const int i = j - (WIN - 1) - 1; do_emit (emit, cur, start, i - start); start = i; }
         run16<PH, 0, TAIL> (emit, Int<0> ());
         j += 16;
     }
@@ -248,6 +321,41 @@ struct K1Scanner
     template<class Emit> K1S_HD void finish (Emit& emit)
     {
         const int nk = nm - (WIN - 1);
-        if (!HAS_N || open) emit (cur, start, nk - start);
+        if (!HAS_N || open) do_emit (emit, cur, start, nk - start);
     }
 };
+
+// ---- exact class of ONE k-mer under the orientation rule (slow path of the emitter: super-k-mers flagged ambiguous) ---
+// word(t) returns the normalised 32-bit word t of the read (stream bits [32t, 32t+32)); i = index of the k-mer.
+// Returns 0 = class F (stored as read), 1 = class R (stored reverse-complemented), 2 = ambiguous.
+template<class WordAt> K1S_HD int k1s_classify_kmer (WordAt word, int i, int win, int m)
+{
+    const uint32_t mmask = (m >= 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1);
+    const uint32_t aam = 0xAAAAAAAAu & mmask;
+    uint32_t A = 0xFFFFFFFFu, B = 0xFFFFFFFFu;
+    for (int j = i; j < i + win; j++)
+    {
+        const uint32_t x  = K1S_FSHR (word (j >> 4), word ((j >> 4) + 1), 2 * (j & 15)) & mmask;
+        const uint32_t hf = k1s_key_fwd (k1s_pair_reverse (x) >> (32 - 2 * m)), hr = k1s_key_rc (x ^ aam);
+        A = hf < A ? hf : A; B = hr < B ? hr : B;
+    }
+    return ((A ^ B) == 1u) ? 2 : (A < B ? 0 : 1);
+}
+
+// ---- stream bits of a span of nn <= 64 nucleotides, reverse-complemented (still in stream order) ---------------------
+// s = the span's 2nn stream bits (lo, hi), masked.  revcomp in stream order = pair-reversal of the whole span with
+// every nucleotide complemented (XOR 0b10).
+K1S_HD void k1s_revcomp_span (uint64_t& lo, uint64_t& hi, int nn)
+{
+    const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32), w2 = (uint32_t)hi, w3 = (uint32_t)(hi >> 32);
+    const uint64_t ylo = ((uint64_t)k1s_pair_reverse (w2) << 32) | k1s_pair_reverse (w3);      // pair-reversed 128-bit value
+    const uint64_t yhi = ((uint64_t)k1s_pair_reverse (w0) << 32) | k1s_pair_reverse (w1);
+    const int s = 128 - 2 * nn;                                                                  // 0..126, even
+    uint64_t rl, rh;
+    if (s == 0)      { rl = ylo; rh = yhi; }
+    else if (s < 64) { rl = (ylo >> s) | (yhi << (64 - s)); rh = yhi >> s; }
+    else if (s == 64){ rl = yhi; rh = 0; }
+    else             { rl = yhi >> (s - 64); rh = 0; }
+    const uint64_t ml = nn >= 32 ? ~0ULL : ((1ULL << (2 * nn)) - 1), mh = nn <= 32 ? 0ULL : (nn >= 64 ? ~0ULL : ((1ULL << (2 * nn - 64)) - 1));
+    lo = rl ^ (0xAAAAAAAAAAAAAAAAULL & ml); hi = rh ^ (0xAAAAAAAAAAAAAAAAULL & mh);
+}

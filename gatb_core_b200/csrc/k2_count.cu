@@ -512,15 +512,15 @@ __device__ __forceinline__ uint32_t k2_slot32 (uint32_t lo, uint32_t hi, int shi
 { return (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> shift; }
 
 // general open-addressing insert starting at 'slot'; returns the slot (bit 31 set when this call claimed it), or -1
-__device__ __forceinline__ int k2_probe_loop (unsigned long long* s_klo, uint32_t* s_cnt, uint32_t slot, unsigned long long key, uint32_t tmask)
+__device__ __forceinline__ int k2_probe_loop (unsigned long long* s_klo, uint32_t* s_cnt, uint32_t slot, unsigned long long key, uint32_t tmask, uint32_t add = 1u)
 {
     #pragma unroll 1
     for (int probe = 0; probe < K2_MAXPROBE; probe++)
     {
         unsigned long long cur = s_klo[slot];
         if (cur == EMPTY64) cur = atomicCAS (&s_klo[slot], EMPTY64, key);
-        if (cur == EMPTY64) { atomicAdd (&s_cnt[slot], 1u); return (int)(slot | 0x80000000u); }
-        if (cur == key)     { atomicAdd (&s_cnt[slot], 1u); return (int)slot; }
+        if (cur == EMPTY64) { atomicAdd (&s_cnt[slot], add); return (int)(slot | 0x80000000u); }
+        if (cur == key)     { atomicAdd (&s_cnt[slot], add); return (int)slot; }
         slot = (slot + 1) & tmask;
     }
     return -1;
@@ -808,7 +808,11 @@ static cudaError_t k2b_w1_launch (const LaunchCtx& L, const K2Params& P)
 // lane; the chunk -> record gather inside the warp is four shuffles), and the descriptor and first records of the NEXT
 // bin are requested before the current bin is processed, so their latency hides behind the inserts.
 // Insert and scan phases are those of k2b_count_w1 (chunks of four k-mers, converged probe/claim/count steps).
-template<int NT>
+// ORI: the records are oriented (k1_scan.cuh): keys are plain slices of the record, identical records of a batch are
+// collapsed first (lane <-> record, four MATCH.ANY: reads covering the same locus without an error in the span produce
+// the same record whatever their strand) and inserted once with their multiplicity; the canonical VALUE is rebuilt
+// only for the k-mers that are emitted.
+template<int NT, bool ORI>
 __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
 {
     constexpr int NWARP = NT / 32;
@@ -821,13 +825,14 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1;
     const int k = P.k;
-    // per warp: keys T*8 | retry K2_RETRY_CAP*8 | counts T*4 | claimed OCC_W*2 ; per CTA: histogram
-    const size_t per_warp = (size_t)T * 8 + K2_RETRY_CAP * 8 + (size_t)T * 4 + (((size_t)OCC_W * 2 + 15) & ~(size_t)15);
+    // per warp: keys T*8 | retry K2_RETRY_CAP*8 | counts T*4 | claimed OCC_W*2 | retry multiplicities ; per CTA: histogram
+    const size_t per_warp = (size_t)T * 8 + K2_RETRY_CAP * 8 + (size_t)T * 4 + (((size_t)OCC_W * 2 + 15) & ~(size_t)15) + K2_RETRY_CAP;
     unsigned char* wbase = smem_raw + per_warp * wid;
     unsigned long long* s_klo = (unsigned long long*)wbase;
     unsigned long long* retry_w = s_klo + T;
     uint32_t* s_cnt = (uint32_t*)(retry_w + K2_RETRY_CAP);
     uint16_t* occ_w = (uint16_t*)(s_cnt + T);
+    uint8_t* retry_m = (uint8_t*)wbase + per_warp - K2_RETRY_CAP;
     uint32_t* s_hist = (uint32_t*)(smem_raw + per_warp * NWARP);
 
     for (int i = lane; i < T; i += 32) { s_klo[i] = EMPTY64; s_cnt[i] = 0; }
@@ -888,7 +893,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                     if (e < rn)
                     {
                         const unsigned long long key = retry_w[e];
-                        res = k2_probe_loop (s_klo, s_cnt, k2_slot32 ((uint32_t)key, (uint32_t)(key >> 32), hshift), key, tmask);
+                        res = k2_probe_loop (s_klo, s_cnt, k2_slot32 ((uint32_t)key, (uint32_t)(key >> 32), hshift), key, tmask, ORI ? (uint32_t)retry_m[e] : 1u);
                         if (res == -1) w_ovf = true;
                     }
                     __syncwarp ();
@@ -902,7 +907,14 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
             {
                 uint4 rec = rec0;
                 if (g0) rec = (g0 + lane < n) ? __ldg ((const uint4*)P.recs + base0 + g0 + lane) : zero4;
-                const uint32_t nch = (((rec.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;      // 0 for the zero record
+                uint32_t nch = (((rec.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;            // 0 for the zero record
+                if (ORI)
+                {   // identical records -> the lowest lane keeps the record with the multiplicity in place of the fine-bin id
+                    const unsigned same = __match_any_sync (FULL_MASK, rec.x) & __match_any_sync (FULL_MASK, rec.y)
+                                        & __match_any_sync (FULL_MASK, rec.z) & __match_any_sync (FULL_MASK, rec.w);
+                    if ((same & lt_mask) != 0) nch = 0;
+                    rec.w = (rec.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | ((uint32_t)__popc (same) << (DEV_FINE_SHIFT_W1 - 32));
+                }
                 uint32_t incl = nch;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
@@ -925,10 +937,20 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                     const int c = act ? (int)(gk - ex) : 0;
                     const int nkc = act ? (int)((q.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
                     K2Chunk C;
-                    k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (DEV_LEN_SHIFT_W1 - 32)) - 1), c, k);
                     uint32_t lo[4], hi[4], slot[4];
-                    k2_chunk_kmer<0> (C, lo[0], hi[0]); k2_chunk_kmer<1> (C, lo[1], hi[1]);
-                    k2_chunk_kmer<2> (C, lo[2], hi[2]); k2_chunk_kmer<3> (C, lo[3], hi[3]);
+                    const uint32_t mult = ORI ? (q.w >> (DEV_FINE_SHIFT_W1 - 32)) : 1u;
+                    if (ORI)
+                    {
+                        k2_chunk_begin_raw (C, q.x, q.y, q.z, q.w & ((1u << (DEV_LEN_SHIFT_W1 - 32)) - 1), c, k);
+                        k2_chunk_kmer_raw<0> (C, lo[0], hi[0]); k2_chunk_kmer_raw<1> (C, lo[1], hi[1]);
+                        k2_chunk_kmer_raw<2> (C, lo[2], hi[2]); k2_chunk_kmer_raw<3> (C, lo[3], hi[3]);
+                    }
+                    else
+                    {
+                        k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (DEV_LEN_SHIFT_W1 - 32)) - 1), c, k);
+                        k2_chunk_kmer<0> (C, lo[0], hi[0]); k2_chunk_kmer<1> (C, lo[1], hi[1]);
+                        k2_chunk_kmer<2> (C, lo[2], hi[2]); k2_chunk_kmer<3> (C, lo[3], hi[3]);
+                    }
                     unsigned long long cur[4];
                     #pragma unroll
                     for (int i = 0; i < 4; i++) { slot[i] = k2_slot32 (lo[i], hi[i], hshift); cur[i] = (i < nkc) ? s_klo[slot[i]] : 0ULL; }
@@ -942,13 +964,13 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                         if (isE) cv = atomicCAS (&s_klo[slot[i]], EMPTY64, key);
                         const bool isnew = isE && cv == EMPTY64;
                         const bool hit = valid && (isnew || cv == key);
-                        if (hit) atomicAdd (&s_cnt[slot[i]], 1u);
+                        if (hit) atomicAdd (&s_cnt[slot[i]], mult);
                         append_new (isnew, slot[i]);
                         const bool miss = valid && !hit;
                         const unsigned mm = __ballot_sync (FULL_MASK, miss);
                         if (mm)
                         {
-                            if (miss) retry_w[rn + __popc (mm & lt_mask)] = key;
+                            if (miss) { retry_w[rn + __popc (mm & lt_mask)] = key; if (ORI) retry_m[rn + __popc (mm & lt_mask)] = (uint8_t)mult; }
                             rn += __popc (mm);
                         }
                     }
@@ -999,7 +1021,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                         {
                             const unsigned long long pos = out_pos + __popc (ballot & lt_mask);
                             n_emitted++;
-                            if (pos < P.out_cap) { P.out_lo[pos] = klo; P.out_cnt[pos] = c; }
+                            if (pos < P.out_cap) { P.out_lo[pos] = ORI ? k2_raw_to_canonical (klo, k) : klo; P.out_cnt[pos] = c; }
                         }
                         out_pos += ne;
                     }
@@ -1030,23 +1052,23 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
 static size_t k2b_warp_smem_bytes (int table_log2, int nt)
 {
     const size_t T = (size_t)1 << table_log2, occ = (T * 3) / 4;
-    const size_t per_warp = T * 8 + K2_RETRY_CAP * 8 + T * 4 + ((occ * 2 + 15) & ~(size_t)15);
+    const size_t per_warp = T * 8 + K2_RETRY_CAP * 8 + T * 4 + ((occ * 2 + 15) & ~(size_t)15) + K2_RETRY_CAP;
     return per_warp * (nt / 32) + K2_HB * 4;
 }
-template<int NT>
+template<int NT, bool ORI>
 static cudaError_t k2b_warp_launch (const LaunchCtx& L, const K2Params& P)
 {
     const size_t smem = k2b_warp_smem_bytes (P.table_log2, NT);
-    cudaError_t e = cudaFuncSetAttribute (k2b_warp_bins<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute (k2b_warp_bins<NT, ORI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k2b_warp_bins<NT>, NT, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k2b_warp_bins<NT, ORI>, NT, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)L.sm_count * per_sm;
     const uint64_t need = (P.nbins + NT / 32 - 1) / (NT / 32);
     if (grid > need) grid = need;
-    k2b_warp_bins<NT><<<(unsigned)grid, NT, smem, L.stream>>> (P);
+    k2b_warp_bins<NT, ORI><<<(unsigned)grid, NT, smem, L.stream>>> (P);
     (*L.launches)++;
     return cudaGetLastError ();
 }
@@ -1338,24 +1360,17 @@ cudaError_t launch_k2b_count_list (const LaunchCtx& L, const K2Params& P)
     return cudaGetLastError ();
 }
 
-// which counting kernel serves k <= 31 (GATB_GPU_K2B): 1 = warp per bin (default), 128 / 256 = CTA per bin with the chunked
-// insert, 0 = CTA per bin, one k-mer per lane.  The table size the planner picks follows from it.
-int k2b_variant ()
+// which counting kernel serves k <= 31 (gatb_gpu_params.path_flags & GATB_PATH_K2B_MASK): 1 = warp per bin (default),
+// 128 / 256 = CTA per bin with the chunked insert, 0 = CTA per bin, one k-mer per lane.  The table size the planner picks follows.
+int k2b_variant (int path_flags)
 {
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv ("GATB_GPU_K2B"); variant = e ? atoi (e) : 1; }
-    return variant;
+    switch (path_flags & 6) { case 2: return 128; case 4: return 256; case 6: return 0; }
+    return 1;
 }
 // 32 <= k <= 63: the warp-per-bin kernel (k2b_warp_bins_w2) passes the whole GPU parity suite, but its 512-slot tables are too
-// small for the long super-k-mers of k = 63 (2*10^7 reads x 250 bp: half of the k-mers sit in overflowing bins and the global
-// fallback table would need 2^32 slots), and it has no overflow tiers yet.  It stays opt-in (GATB_GPU_K2B_W2=1) until it has them.
-static bool k2b_w2_warp ()
-{
-    static int on = -1;
-    if (on < 0) { const char* e = getenv ("GATB_GPU_K2B_W2"); on = (e && e[0] == '1') ? 1 : 0; }
-    return on == 1;
-}
-int k2b_default_table_log2 (int W) { return (k2b_variant () == 1 && (W == 1 || k2b_w2_warp ())) ? 9 : 11; }
+// small for the long super-k-mers of k = 63 and it has no overflow tiers yet: opt-in (GATB_PATH_K2B_W2_WARP).
+static bool k2b_w2_warp (int path_flags) { return (path_flags & 8) != 0; }
+int k2b_default_table_log2 (int W, int path_flags) { return (k2b_variant (path_flags) == 1 && (W == 1 || k2b_w2_warp (path_flags))) ? 9 : 11; }
 
 static size_t k2b_smem_bytes (int W, int table_log2)
 {
@@ -1368,9 +1383,9 @@ cudaError_t launch_k2b_count (const LaunchCtx& L, const K2Params& P)
 {
     if (P.nbins == 0) return cudaSuccess;
     size_t smem = k2b_smem_bytes (P.W, P.table_log2);
-    const int variant = k2b_variant ();
-    if (P.W == 1 && variant == 1) return k2b_warp_launch<128> (L, P);
-    if (P.W == 2 && variant == 1 && k2b_w2_warp ()) return k2b_warp_w2_launch<128> (L, P);
+    const int variant = k2b_variant (P.path_flags);
+    if (P.W == 1 && variant == 1) return P.oriented ? k2b_warp_launch<128, true> (L, P) : k2b_warp_launch<128, false> (L, P);
+    if (P.W == 2 && variant == 1 && k2b_w2_warp (P.path_flags)) return k2b_warp_w2_launch<128> (L, P);
     if (P.W == 1 && variant == 128) return k2b_w1_launch<128> (L, P);
     if (P.W == 1 && variant == 256) return k2b_w1_launch<256> (L, P);
     const void* fn = (P.W == 1) ? (const void*)k2b_bucket_hash_count<1> : (const void*)k2b_bucket_hash_count<2>;

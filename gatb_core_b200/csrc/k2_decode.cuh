@@ -52,6 +52,34 @@ template<int I> K1S_HD void k2_chunk_kmer (const K2Chunk& C, uint32_t& lo, uint3
     lo = f_lt ? fl : rl; hi = f_lt ? fh : rh;
 }
 
+// ---- oriented records (k1_scan.cuh, ORI): the table key of a k-mer is the plain slice of the record -------------------
+// Every k-mer of an oriented record is already in its representative orientation, so its 2k stream bits identify it:
+// no reversal, no min().  GATB's canonical VALUE is rebuilt only for the distinct k-mers that are emitted (k2_raw_to_canonical).
+K1S_HD void k2_chunk_begin_raw (K2Chunk& C, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, int c, int k)
+{
+    const int s = 8 * c;                             // 0..48
+    const bool hiw = s >= 32;
+    const uint32_t a0 = hiw ? r1 : r0, a1 = hiw ? r2 : r1, a2 = hiw ? r3 : r2, a3 = hiw ? 0u : r3;
+    const int sh = s & 31;
+    C.x0 = k1s_fshr (a0, a1, sh); C.x1 = k1s_fshr (a1, a2, sh); C.x2 = k1s_fshr (a2, a3, sh);
+    C.lmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1);
+    C.hmask = (k > 16) ? ((1u << (2 * k - 32)) - 1) : 0u;
+    C.z0 = C.z1 = C.z2 = 0;
+}
+template<int I> K1S_HD void k2_chunk_kmer_raw (const K2Chunk& C, uint32_t& lo, uint32_t& hi)
+{
+    lo = (I ? k1s_fshr (C.x0, C.x1, 2 * I) : C.x0) & C.lmask;
+    hi = (I ? k1s_fshr (C.x1, C.x2, 2 * I) : C.x1) & C.hmask;
+}
+// stream bits of a k-mer (k <= 31) -> canonical value min(forward, reverse complement), kmer/impl/Model.hpp:857-884
+K1S_HD uint64_t k2_raw_to_canonical (uint64_t x, int k)
+{
+    const uint64_t mask = (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    const uint64_t rc = x ^ (0xAAAAAAAAAAAAAAAAULL & mask);
+    const uint64_t fwd = (((uint64_t)k1s_pair_reverse ((uint32_t)x) << 32) | k1s_pair_reverse ((uint32_t)(x >> 32))) >> (64 - 2 * k);
+    return fwd < rc ? fwd : rc;
+}
+
 // ---- 32 <= k <= 63 (32-byte records, 128-bit values as four 32-bit words, word 0 least significant) ----------------------
 // Same scheme: chunk c = k-mers 4c .. 4c+3, window X = record bits [8c, 8c+2k+6) (at most 132 bits, five words), one pair
 // reversal of the window per chunk, every shift inside the chunk an immediate.

@@ -60,7 +60,8 @@ struct K1Params
     uint32_t* cursors;              // [nb1] demand per bin (may exceed cap)
     unsigned long long* stats;      // [0] valid k-mers [1] invalid k-mers [2] records stored [3] records dropped (overflow)
     int      count_only;            // 1: only count demand (cursors), store nothing
-    int      force_general;         // 1: never take the register-scanner kernel (testing / reads with invalid nucleotides)
+    int      force_general;         // 1: never take the register-scanner kernel (GATB_PATH_K1_GENERAL, reads of 2^20 nucleotides and more)
+    int      oriented;              // 1: records oriented by the strand of their minimizer (k1_scan.cuh); see k1_oriented()
 };
 
 struct K2Params
@@ -72,6 +73,8 @@ struct K2Params
     const uint64_t* coarse_off;     // [nb1+1] first record of each coarse bin in the fine-split copy
     int fine_bits;
     int      table_log2;            // log2 slots of the shared-memory table
+    int      path_flags;            // gatb_gpu_params.path_flags
+    int      oriented;              // the records are oriented: keys are plain slices of the records (k2b_warp_bins<NT,true>)
     uint32_t emit_min, emit_max;    // emit k-mers with emit_min <= count <= emit_max
     uint32_t solid_min, solid_max;  // solidity range (stats only)
     int      histo_max;
@@ -113,14 +116,15 @@ struct LaunchCtx { cudaStream_t stream; int sm_count; uint64_t* launches; };
 // k1_partition.cu
 cudaError_t launch_k1 (const LaunchCtx&, const K1Params&);
 int         k1_fast_window (int k);      // window (k-m+1) the register-scanner kernel is compiled for, 0 = none
+bool        k1_oriented (int k, int m, int w, int path_flags);   // does launch_k1 write oriented records for these parameters?
 // k2_count.cu
 struct K2aSrc { const uint4* bins[16]; const uint32_t* cursors[16]; int n; };     // the same coarse bins gathered from n sources
 cudaError_t launch_k2a_split (const LaunchCtx&, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
                               uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc);
 cudaError_t launch_k2b_count (const LaunchCtx&, const K2Params&);
 cudaError_t launch_k2b_count_list (const LaunchCtx&, const K2Params&);     // CTA-per-bin kernel over P.bin_list (k <= 31)
-int         k2b_variant ();
-int         k2b_default_table_log2 (int W);
+int         k2b_variant (int path_flags);            // 1 warp per bin, 128 / 256 CTA per bin (chunked insert), 0 one k-mer per lane
+int         k2b_default_table_log2 (int W, int path_flags);
 cudaError_t launch_k2c_measure (const LaunchCtx&, const K2Params&, uint32_t n_ovf);
 cudaError_t launch_k2c_insert (const LaunchCtx&, const K2Params&, uint32_t n_ovf);
 cudaError_t launch_k2c_scan (const LaunchCtx&, const K2Params&);

@@ -56,8 +56,25 @@ typedef struct gatb_gpu_params
     int32_t  read_len;           /* >0: all reads have this length and read_offsets_nt may be NULL               */
     int32_t  table_log2;         /* 0 = default (9 for kmer_size < 32: one warp per bin; 11 otherwise); log2 slots of the
                                     first-tier per-bin shared-memory table, 5..13                                  */
-    int32_t  reserved[5];
+    int32_t  path_flags;         /* 0 = the product path.  Selectors of the alternate code paths (GATB_PATH_*), so that one
+                                    process can run the parity suite through every kernel variant                    */
+    int32_t  k3_dir_rounds;      /* 0 = default; >0: rounds of the block directory of the bucket scatter (a tiny one forces the
+                                    exact two-pass fallback)                                                         */
+    int32_t  bin_load_pct;       /* 0 = default; planned k-mer occurrences per fine bin in % of the first-tier table slots */
+    int32_t  reserved[2];
 } gatb_gpu_params;
+/* gatb_gpu_params.path_flags */
+enum {
+    GATB_PATH_K1_GENERAL   = 1,      /* general partition kernel instead of the register scanner (records not oriented)   */
+    GATB_PATH_K2B_MASK     = 6,      /* k <= 31 counting kernel: 0 warp per bin (default), 2 CTA per bin 128 threads,      */
+    GATB_PATH_K2B_CTA128   = 2,      /*   4 CTA per bin 256 threads, 6 CTA per bin one k-mer per lane                      */
+    GATB_PATH_K2B_CTA256   = 4,
+    GATB_PATH_K2B_LANE     = 6,
+    GATB_PATH_K2B_W2_WARP  = 8,      /* 32 <= k <= 63: warp-per-bin kernel instead of CTA per bin                          */
+    GATB_PATH_NO_TIER2     = 16,     /* overflowing bins go straight to the global-memory table                            */
+    GATB_PATH_K3_NO_POOL   = 32,     /* exact two-pass bucket scatter instead of the pooled single pass                    */
+    GATB_PATH_CANONICAL    = 64      /* register scanner without orientation: k2b rebuilds min(forward, revcomp) per k-mer  */
+};
 
 enum { GATB_GPU_NSTATS = 16, GATB_GPU_MAX_RANKS = 8, GATB_GPU_MAX_SOURCES = 16 };   /* sources = ranks x pieces per rank */
 /* indices into gatb_gpu_result.stats */

@@ -120,6 +120,80 @@ def test_small_tables_force_the_global_fallback(gpu, oracle, table_log2):
     assert (got["histogram"] == fx.z["histogram"]).all()
 
 
+# every alternate code path behind gatb_gpu_params.path_flags (one process, no environment variables): general partition
+# kernel, CTA-per-bin counting kernels, one k-mer per lane, no second tier, exact two-pass bucket scatter, a directory too
+# small for the pooled scatter, the register scanner without orientation, and other bin loads
+def path_variants():
+    import gatb_core_b200 as g
+    return [("general_k1", dict(path_flags=g.PATH_K1_GENERAL)), ("cta128", dict(path_flags=g.PATH_K2B_CTA128)),
+            ("cta256", dict(path_flags=g.PATH_K2B_CTA256)), ("lane", dict(path_flags=g.PATH_K2B_LANE)),
+            ("no_tier2_small_table", dict(path_flags=g.PATH_NO_TIER2, table_log2=6)), ("k3_no_pool", dict(path_flags=g.PATH_K3_NO_POOL)),
+            ("k3_tiny_directory", dict(k3_dir_rounds=1)), ("canonical_records", dict(path_flags=g.PATH_CANONICAL)),
+            ("canonical_cta128", dict(path_flags=g.PATH_CANONICAL | g.PATH_K2B_CTA128)),
+            ("dense_bins", dict(bin_load_pct=150)), ("sparse_bins", dict(bin_load_pct=10)), ("tier_tables", dict(table_log2=6))]
+
+
+@pytest.mark.parametrize("variant", [v[0] for v in path_variants()])
+@pytest.mark.parametrize("name", ["dsk_k31_parts", "dsk_k21_cfg1"])
+def test_alternate_code_paths(gpu, oracle, name, variant):
+    fx = fixtures.Fixture(name, oracle)
+    packed, offs, mask = pack_seqs(oracle, fx.seqs)
+    kw = dict(path_variants())[variant]
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, nb_passes=fx.nb_passes, abundance_min=fx.abundance_min, **kw)
+    got = gpu.count(packed, offs, len(fx.seqs), params, repart=fx.repart, n_mask=mask)
+    nkeys = fx.nb_partitions * fx.nb_passes
+    check_parts(got, {key: fx.solid(key) for key in range(nkeys)}, nkeys, fx.words)
+    assert (got["histogram"] == fx.z["histogram"]).all()
+
+
+def test_k63_warp_per_bin_kernel(gpu, oracle):
+    import gatb_core_b200 as g
+    fx = fixtures.Fixture("dsk_k63_w16", oracle)
+    packed, offs, mask = pack_seqs(oracle, fx.seqs)
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, nb_passes=fx.nb_passes, abundance_min=fx.abundance_min,
+                             path_flags=g.PATH_K2B_W2_WARP)
+    got = gpu.count(packed, offs, len(fx.seqs), params, repart=fx.repart, n_mask=mask)
+    nkeys = fx.nb_partitions * fx.nb_passes
+    check_parts(got, {key: fx.solid(key) for key in range(nkeys)}, nkeys, 2)
+    assert (got["histogram"] == fx.z["histogram"]).all()
+
+
+def revcomp_ascii(s):
+    return s[::-1].translate(bytes.maketrans(b"ACGT", b"TGCA"))
+
+
+@pytest.mark.parametrize("k,m", [(31, 10), (23, 8), (27, 9), (15, 7)])
+def test_oriented_records_on_both_strands_hairpins_and_palindromes(gpu, oracle, k, m):
+    # the oriented partition (k1_scan.cuh) must give every k-mer ONE representative whatever the strand it is read from:
+    # reads from both strands of a genome rich in hairpins (a minimizer and its reverse complement inside one k-mer),
+    # palindromic m-mers, tandem repeats and homopolymers; ambiguous k-mers take the exact slow path
+    rng = np.random.default_rng(k * 100 + m)
+    g = bytearray(rand_seq(rng, 6000))
+    for i in range(100, 5800, 97):
+        kind = (i // 97) % 4
+        if kind == 0:
+            g[i:i + 24] = revcomp_ascii(bytes(g[i - 24:i]))                  # hairpin
+        elif kind == 1:
+            h = bytes(g[i:i + 8]); g[i + 8:i + 16] = revcomp_ascii(h)        # palindromic 16-mer
+        elif kind == 2:
+            g[i:i + 40] = bytes(g[i - 5:i]) * 8                              # tandem repeat
+        else:
+            g[i:i + 40] = b"AT" * 20 if (i // 97) % 8 == 3 else b"A" * 40
+    g = bytes(g)
+    seqs = []
+    for i in range(1500):
+        a = int(rng.integers(0, len(g) - 200)); n = int(rng.integers(k, 200))
+        sq = g[a:a + n]
+        seqs.append(revcomp_ascii(sq) if i % 2 else sq)
+    packed, offs, mask = pack_seqs(oracle, seqs)
+    want = oracle.dsk(seqs, k, m, np.zeros(4 ** m, np.uint16), 1, abundance_min=1)
+    for kw in (dict(), dict(table_log2=6), dict(bin_load_pct=200)):
+        got = gpu.count(packed, offs, len(seqs), gpu.make_params(k, m, abundance_min=1, **kw), n_mask=mask)
+        check_parts(got, want["solid"], 1, 1)
+        assert (got["histogram"] == want["histogram"]).all()
+        assert got["stats"]["kmers_nb_distinct"] == int(want["stats"][2])
+
+
 def test_reference_golden_vectors_dsk(gpu, oracle):
     # TestDSK.cpp:147-241 (solid counts) and :244-341 (exact set + checksum)
     for seqs, k, nks, expected in G.DSK1_CASES:
