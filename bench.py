@@ -209,12 +209,12 @@ def run_ours(args):
     gpu.synth_reads_dev(SEED, genome, 0, n, L, d_reads)
     gpu.synchronize()
     params = gpu.make_params(K, M, abundance_min=ABUNDANCE_MIN, read_len=L, path_flags=args.path_flags, bin_load_pct=args.bin_load_pct,
-                             table_log2=args.table_log2)
+                             table_log2=args.table_log2, fine_bits=args.fine_bits)
     stream = torch.cuda.ExternalStream(gpu.stream, device=torch.device("cuda", local))
 
     def step():
         res = gpu.count_dev(d_reads, None, n, params)
-        info = {"distinct": int(res.stats[2]), "solid": int(res.stats[3]), "valid": int(res.stats[0]), "records": int(res.stats[4]),
+        info = {"distinct": int(res.stats[2]), "solid": int(res.stats[3]), "valid": int(res.stats[0]), "records": int(res.stats[4]), "unique_records": int(res.stats[13]),
                 "items": int(res.n_items), "kernel_seconds": [float(x) for x in res.kernel_seconds], "bins": int(res.stats[7]),
                 "overflow_bins": int(res.stats[8]), "retries": int(res.stats[9])}
         gpu.result_free(res)
@@ -355,6 +355,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path-flags", type=int, default=0, help="gatb_gpu_params.path_flags (experiments; 0 = the product path)")
     ap.add_argument("--bin-load-pct", type=int, default=0, help="gatb_gpu_params.bin_load_pct (experiments; 0 = default)")
+    ap.add_argument("--fine-bits", type=int, default=0, help="gatb_gpu_params.fine_bits (experiments; 0 = default)")
     ap.add_argument("--table-log2", type=int, default=0, help="gatb_gpu_params.table_log2 (experiments; 0 = default)")
     ap.add_argument("--staged", action="store_true", help="N=1 through the staged multi-GPU code path (debugging aid)")
     args = ap.parse_args()

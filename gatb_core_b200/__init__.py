@@ -23,7 +23,8 @@ EXPORTS = ["gatb_gpu_create", "gatb_gpu_destroy", "gatb_gpu_last_error", "gatb_g
            "gatb_gpu_free_host", "gatb_gpu_bloom_params", "gatb_gpu_bloom_layout", "gatb_gpu_bloom", "gatb_gpu_bloom_dev",
            "gatb_gpu_histogram_cutoff", "gatb_gpu_malloc", "gatb_gpu_free", "gatb_gpu_memcpy_h2d", "gatb_gpu_memcpy_d2h",
            "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii", "gatb_gpu_plan",
-           "gatb_gpu_partition_into", "gatb_gpu_partition_range_into", "gatb_gpu_count_bins"]
+           "gatb_gpu_partition_into", "gatb_gpu_partition_range_into", "gatb_gpu_count_bins", "gatb_gpu_reads_begin",
+           "gatb_gpu_reads_push_ascii", "gatb_gpu_reads_count"]
 
 
 class GatbGpuError(RuntimeError):
@@ -35,12 +36,12 @@ class Params(C.Structure):
                 ("nb_passes", C.c_int32), ("abundance_min", C.c_int32), ("abundance_max", C.c_int32),
                 ("histo_max", C.c_int32), ("minimizer_type", C.c_int32), ("emit_all", C.c_int32),
                 ("read_len", C.c_int32), ("table_log2", C.c_int32), ("path_flags", C.c_int32),
-                ("k3_dir_rounds", C.c_int32), ("bin_load_pct", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("k3_dir_rounds", C.c_int32), ("bin_load_pct", C.c_int32), ("fine_bits", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 # gatb_gpu_params.path_flags (include/gatb_gpu.h): selectors of the alternate code paths, 0 = the product path
 PATH_K1_GENERAL, PATH_K2B_CTA128, PATH_K2B_CTA256, PATH_K2B_LANE = 1, 2, 4, 6
-PATH_K2B_W2_WARP, PATH_NO_TIER2, PATH_K3_NO_POOL, PATH_CANONICAL = 8, 16, 32, 64
+PATH_K2B_W2_WARP, PATH_NO_TIER2, PATH_K3_NO_POOL, PATH_CANONICAL, PATH_NO_DEDUP, PATH_FUSED = 8, 16, 32, 64, 128, 256
 
 
 class Result(C.Structure):
@@ -76,6 +77,9 @@ def load_library():
     for f in ("gatb_gpu_count", "gatb_gpu_count_dev"):
         getattr(L, f).argtypes = [VP, C.POINTER(Params), VP, VP, VP, VP, U64, VP, C.POINTER(Result)]
     L.gatb_gpu_result_free.argtypes = [VP, C.POINTER(Result)]
+    L.gatb_gpu_reads_begin.argtypes = [VP, U64]
+    L.gatb_gpu_reads_push_ascii.argtypes = [VP, C.c_char_p, VP, U64]
+    L.gatb_gpu_reads_count.argtypes = [VP, C.POINTER(Params), VP, VP, C.POINTER(Result)]
     L.gatb_gpu_superkmers.argtypes = [VP, C.POINTER(Params), VP, VP, VP, U64, VP, C.POINTER(VP), VP, VP]
     L.gatb_gpu_free_host.argtypes = [VP]
     L.gatb_gpu_bloom_params.argtypes = [I32, U64, C.POINTER(U64), C.POINTER(C.c_int32)]
@@ -147,9 +151,9 @@ class GatbGpu:
     # ---- DSK ---------------------------------------------------------------------------------------------------
     @staticmethod
     def make_params(k, m, nb_partitions=1, nb_passes=1, abundance_min=2, abundance_max=2**31 - 1, histo_max=10000,
-                    emit_all=False, read_len=0, table_log2=0, path_flags=0, k3_dir_rounds=0, bin_load_pct=0):
+                    emit_all=False, read_len=0, table_log2=0, path_flags=0, k3_dir_rounds=0, bin_load_pct=0, fine_bits=0):
         p = Params()
-        p.path_flags, p.k3_dir_rounds, p.bin_load_pct = path_flags, k3_dir_rounds, bin_load_pct
+        p.path_flags, p.k3_dir_rounds, p.bin_load_pct, p.fine_bits = path_flags, k3_dir_rounds, bin_load_pct, fine_bits
         p.kmer_size, p.minimizer_size, p.nb_partitions, p.nb_passes = k, m, nb_partitions, nb_passes
         p.abundance_min, p.abundance_max, p.histo_max, p.minimizer_type = abundance_min, abundance_max, histo_max, 0
         p.emit_all, p.read_len, p.table_log2 = int(emit_all), read_len, table_log2
@@ -161,6 +165,23 @@ class GatbGpu:
         rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
         self._check(self.L.gatb_gpu_count(self.ctx, C.byref(params), _ptr(rp), None, _ptr(packed), _ptr(offsets), n_reads,
                                           _ptr(n_mask), C.byref(res)))
+        try:
+            return self._unpack_host(res, params)
+        finally:
+            self.L.gatb_gpu_result_free(self.ctx, C.byref(res))
+
+    def count_pushed(self, batches, params, repart=None):
+        """Streaming input: `batches` is an iterable of lists of ASCII sequences (bytes); each batch is pushed with
+        gatb_gpu_reads_push_ascii and packed on the device; one count at the end (host arrays out, like count())."""
+        self._check(self.L.gatb_gpu_reads_begin(self.ctx, 0))
+        for seqs in batches:
+            blob = b"".join(seqs)
+            offs = np.zeros(len(seqs) + 1, np.uint64)
+            offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+            self._check(self.L.gatb_gpu_reads_push_ascii(self.ctx, blob, _ptr(offs), len(seqs)))
+        res = Result()
+        rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
+        self._check(self.L.gatb_gpu_reads_count(self.ctx, C.byref(params), _ptr(rp), None, C.byref(res)))
         try:
             return self._unpack_host(res, params)
         finally:

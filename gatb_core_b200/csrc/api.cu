@@ -28,6 +28,8 @@ struct gatb_gpu_ctx
     cudaStream_t copy_stream; cudaEvent_t cev[40];
     void* pinned; size_t pinned_cap;
     const uint16_t* repart_host_cached; uint64_t repart_bytes_cached;
+    // streaming input (gatb_gpu_reads_*): reads pushed so far live in S_READS / S_OFFSETS / S_NMASK
+    uint64_t push_nt, push_seqs, push_invalid;
 };
 
 static int fail (gatb_gpu_ctx* c, const char* fmt, ...)
@@ -76,6 +78,7 @@ gatb_gpu_ctx* gatb_gpu_create (int device)
     if ((e = cudaSetDevice (device)) != cudaSuccess) { fail (0, "cudaSetDevice(%d): %s", device, cudaGetErrorString (e)); return 0; }
     gatb_gpu_ctx* ctx = new gatb_gpu_ctx ();
     ctx->device = device; ctx->launches = 0; ctx->pinned = 0; ctx->pinned_cap = 0; ctx->repart_host_cached = 0; ctx->repart_bytes_cached = 0;
+    ctx->push_nt = ctx->push_seqs = ctx->push_invalid = 0;
     memset (ctx->slot, 0, sizeof(ctx->slot)); memset (ctx->slot_cap, 0, sizeof(ctx->slot_cap));
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties (&prop, device)) != cudaSuccess) { fail (0, "cudaGetDeviceProperties: %s", cudaGetErrorString (e)); delete ctx; return 0; }
@@ -195,13 +198,23 @@ __global__ void k_count_kmers (const uint64_t* offsets, uint64_t n_reads, int k,
 
 // tot[b] = sum over sources of min(cursor_s[b], cap)
 struct CursorList { const uint32_t* cur[GATB_GPU_MAX_SOURCES]; int n; };
-__global__ void k_sum_cursors (CursorList C, uint32_t nb1, uint32_t cap, uint32_t* tot)
+// fine bins of the listed coarse bins: out[i << fine_bits | f] = list[i] << fine_bits | f
+__global__ void k_expand_bins (const uint32_t* list, uint32_t n, int fine_bits, uint32_t* out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ((uint64_t)n << fine_bits)) out[i] = (list[i >> fine_bits] << fine_bits) | (uint32_t)(i & ((1u << fine_bits) - 1));
+}
+__global__ void k_sum_cursors (CursorList C, uint32_t nb1, uint32_t cap, uint32_t* tot, uint32_t* max_tot)
 {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb1) return;
     uint32_t t = 0;
-    for (int s = 0; s < C.n; s++) t += min (C.cur[s][b], cap);
-    tot[b] = t;
+    if (b < nb1)
+    {
+        for (int s = 0; s < C.n; s++) t += min (C.cur[s][b], cap);
+        tot[b] = t;
+    }
+    t = __reduce_max_sync (FULL_MASK, t);
+    if ((threadIdx.x & 31) == 0 && t) atomicMax (max_tot, t);
 }
 
 static int workload_size (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint64_t* d_offsets, uint64_t n_reads,
@@ -226,21 +239,44 @@ static int workload_size (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uin
     return 0;
 }
 
+// k <= 31 can count straight out of the coarse bins (k2_fused.cu, opt-in) instead of the fine-split pipeline
+static bool path_fused (const gatb_gpu_params* p)
+{ return p->kmer_size < 32 && (p->path_flags & GATB_PATH_FUSED) && !(p->path_flags & GATB_PATH_K2B_MASK); }
+
 // ---- geometry of the device binning: must be identical on every rank of a multi-GPU run ----------------------------
 static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t total_kmers, uint64_t n_reads, int n_ranks, gatb_gpu_geometry* g)
 {
     const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
-    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : k2b_default_table_log2 (W, p->path_flags);
+    const bool fused = path_fused (p);
+    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : (fused ? 13 : k2b_default_table_log2 (W, p->path_flags));
     if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
     if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
     const uint64_t T = 1ULL << table_log2;
     if (p->bin_load_pct < 0 || p->bin_load_pct > 400) return fail (ctx, "bin_load_pct must be in [0,400]");
-    const uint64_t occ_per_bin = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : 55)) / 100 + 1;
-    // k <= 31: one more fine-bin bit per doubling of the ranks, so that nb1 (the coarse bins every rank scatters into) stays put
     int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
-    if (W == 1) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
-    uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
-    uint64_t nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits; if (nb1 < 1) nb1 = 1;
+    if (fused) fine_bits = 5;
+    if (W == 1 && p->fine_bits > 0)
+    {
+        if (p->fine_bits > DEV_FINE_BITS_MAX_W1) return fail (ctx, "fine_bits must be in [1,%d]", (int)DEV_FINE_BITS_MAX_W1);
+        fine_bits = p->fine_bits;
+    }
+    uint64_t nb1;
+    if (fused)
+    {   // one CTA-wide table per COARSE bin (k2_fused.cu): planned k-mer occurrences per bin = 160 % of the slots, which is a
+        // half-full table when three occurrences in ten are new k-mers (30x coverage); sparser data overflows into the
+        // fine-split pipeline, whose fine bins (1/32 of a coarse bin) fit the tier tables
+        const uint64_t occ_per_coarse = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : 160)) / 100 + 1;
+        nb1 = (total_kmers + occ_per_coarse - 1) / occ_per_coarse;
+    }
+    else
+    {
+        const uint64_t occ_per_bin = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : 55)) / 100 + 1;
+        // k <= 31: one more fine-bin bit per doubling of the ranks, so that nb1 (the coarse bins every rank scatters into) stays put
+        if (W == 1) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
+        uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
+        nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits;
+    }
+    if (nb1 < 1) nb1 = 1;
     nb1 = (nb1 + n_ranks - 1) / n_ranks * n_ranks;                              // every rank owns nb1/n_ranks consecutive coarse bins
     if (nb1 > (1ULL << 24)) return fail (ctx, "input too large (%llu coarse bins)", (unsigned long long)nb1);
     // m-mers ranked on the device: the register scanner (k1_scan.cuh) wants w = k-m+1 a multiple of 8 and m in [8,16];
@@ -253,7 +289,11 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     double est_records = local_kmers * 2.0 / (w + 1) * 1.10 + local_reads * 0.5 + 64;
     // several ranks: a (rank, bin) piece is small and the minimizer space of a multi-Gb input is crowded, so the relative
     // spread of the pieces is larger; the exchange only moves the used rounds, so head-room costs memory, not time
-    uint64_t cap = (uint64_t)(est_records / nb1 * (n_ranks > 1 ? 1.60 : 1.30)) + (n_ranks > 1 ? 96 : 64); cap = (cap + COARSE_BLK - 1) / COARSE_BLK * COARSE_BLK;
+    // head-room: the records of one locus (~21 at 30x coverage, spread over the ranks) arrive together, so the load of a bin
+    // of r records has a standard deviation near sqrt ((21/n_ranks + 1) r); 7.5 sigma covers millions of bins.  The
+    // exchange only moves the used rounds, so head-room costs memory, not time; an overflow costs a second partition run.
+    const double per_bin = est_records / nb1;
+    uint64_t cap = (uint64_t)(per_bin + 7.5 * sqrt ((21.0 / n_ranks + 1.0) * per_bin) + per_bin * 0.10) + 64; cap = (cap + COARSE_BLK - 1) / COARSE_BLK * COARSE_BLK;
     memset (g, 0, sizeof(*g));
     g->total_kmers = total_kmers; g->nb1 = (uint32_t)nb1; g->cap = (uint32_t)cap; g->fine_bits = fine_bits; g->table_log2 = table_log2;
     g->m_device = mg; g->w = w; g->maxlen = (W == 1) ? DEV_MAXLEN_W1 : 60; g->words = W;                  // maxlen: Sequence2SuperKmer.hpp:147
@@ -342,26 +382,58 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     if (ensure (ctx, S_SCAN, scan_scratch_elems (nb1_local > (n_keys << 24) ? nb1_local : (n_keys << 24)) * 8)) return 1;
     if (ensure (ctx, S_BINDESC, nbins * 8)) return 1;
     CursorList CL; CL.n = n_src; for (int s = 0; s < n_src; s++) CL.cur[s] = d_src_cursors[s];
-    k_sum_cursors<<<(nb1_local + 255) / 256, 256, 0, ctx->stream>>> (CL, nb1_local, cap, (uint32_t*)ctx->slot[S_TOTCUR]); ctx->launches++;
+    if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
+    uint32_t* d_maxbin = (uint32_t*)((unsigned long long*)ctx->slot[S_COUNTERS] + 15);
+    CK (cudaMemsetAsync (d_maxbin, 0, 8, ctx->stream));
+    k_sum_cursors<<<(nb1_local + 255) / 256, 256, 0, ctx->stream>>> (CL, nb1_local, cap, (uint32_t*)ctx->slot[S_TOTCUR], d_maxbin); ctx->launches++;
     CK (launch_scan_u32_to_u64 (L, (const uint32_t*)ctx->slot[S_TOTCUR], (uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, (uint64_t*)ctx->slot[S_SCAN]));
-    uint64_t n_records = 0;
+    uint64_t n_records = 0; uint32_t max_bin = 0;
     CK (cudaMemcpyAsync (&n_records, (const uint64_t*)ctx->slot[S_COARSEOFF] + nb1_local, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaMemcpyAsync (&max_bin, d_maxbin, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK (cudaStreamSynchronize (ctx->stream));
     cudaEventRecord (ctx->ev[2], ctx->stream);
 
-    // ---- k2a: fine split ----
-    if (ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
+    // ---- k2a: fine split (not on the fused path: k <= 31 counts straight out of the coarse bins) ----
+    const bool fused = path_fused (p);
+    const int dedup = (p->path_flags & GATB_PATH_NO_DEDUP) ? 0 : 1;
+    if (!fused && ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
     K2aSrc S2; S2.n = n_src; for (int s = 0; s < n_src; s++) { S2.bins[s] = (const uint4*)d_src_bins[s]; S2.cursors[s] = d_src_cursors[s]; }
     cudaEventRecord (ctx->kev[2], ctx->stream);
-    CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
-    cudaEventRecord (ctx->kev[3], ctx->stream);
+    uint64_t n_unique_records = n_records;
+    if (fused) cudaEventRecord (ctx->kev[3], ctx->stream);
+    else if (W == 1 && dedup && n_records)
+    {   // ---- k <= 31: the bin is staged in shared memory once, identical records collapse, multiplicities travel with the records ----
+        if (ensure (ctx, S_OVFLIST, (nbins > nb1_local ? nbins : nb1_local) * 4)) return 1;
+        unsigned long long* d_k2a = (unsigned long long*)ctx->slot[S_COUNTERS] + 12;
+        CK (cudaMemsetAsync (d_k2a, 0, 2 * 8, ctx->stream));
+        const uint32_t rmax = k2a_dedup_rmax (max_bin, fine_bits);
+        CK (launch_k2a_dedup_split (L, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
+                                    (uint2*)ctx->slot[S_BINDESC], rmax, (uint32_t*)ctx->slot[S_OVFLIST], d_k2a));
+        unsigned long long h_k2a[2] = { 0, 0 };
+        if (max_bin > rmax)
+        {   // bins too large for shared memory: the plain two-pass split (multiplicity 1)
+            CK (cudaMemcpyAsync (h_k2a, d_k2a, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+            CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
+                                  (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)h_k2a[0]));
+        }
+        CK (cudaMemcpyAsync (h_k2a, d_k2a, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaEventRecord (ctx->kev[3], ctx->stream);
+        CK (cudaStreamSynchronize (ctx->stream));
+        n_unique_records = h_k2a[1];                 // (bins of the two-pass kernel are not in this figure)
+    }
+    else
+    {
+        CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
+        cudaEventRecord (ctx->kev[3], ctx->stream);
+    }
     cudaEventRecord (ctx->ev[3], ctx->stream);
 
     // ---- k2b: count.  When the single source is the context's own coarse buffer it is dead now and becomes the output. ----
     const uint32_t amin = p->abundance_min < 1 ? 1 : (uint32_t)p->abundance_min;
     const uint32_t amax = p->abundance_max < 0 ? 0x7fffffffu : (uint32_t)p->abundance_max;
     const uint32_t emin = p->emit_all ? 1u : amin, emax = p->emit_all ? 0xffffffffu : amax;
-    const int S_OUT = (n_src == 1 && d_src_bins[0] == ctx->slot[S_COARSE]) ? S_COARSE : S_UNSORTED;
+    const int S_OUT = (!fused && n_src == 1 && d_src_bins[0] == ctx->slot[S_COARSE]) ? S_COARSE : S_UNSORTED;   // (the fused kernel reads the coarse bins while it emits)
     uint64_t out_bound = total_kmers_bound / emin + 1;                         // a k-mer emitted needs >= emin occurrences
     const size_t item_bytes = 8 * W + 4;
     const uint64_t block_slack = (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;  // every warp of k2b reserves output in blocks of 2048 slots
@@ -371,8 +443,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     if (out_cap < ctx->slot_cap[S_OUT] / item_bytes) out_cap = ctx->slot_cap[S_OUT] / item_bytes;   // never shrink: no re-allocation per call
 
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
-    if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
-    if (ensure (ctx, S_OVFLIST, nbins * 4)) return 1;
+    if (ensure (ctx, S_OVFLIST, (nbins > nb1_local ? nbins : nb1_local) * 4)) return 1;
     if (ensure (ctx, S_OVFLIST2, nbins * 4)) return 1;
     unsigned long long* d_cnt = (unsigned long long*)ctx->slot[S_COUNTERS];
     unsigned long long h_cnt[16];
@@ -396,22 +467,35 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
         k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST]; k2.ovf_counter = 4;
         cudaEventRecord (ctx->kev[4], ctx->stream);
-        CK (launch_k2b_count (L, k2));
+        if (fused) CK (launch_k2f_count (L, k2, S2, nb1_local, cap, nb1_local, dedup));
+        else       CK (launch_k2b_count (L, k2));
         cudaEventRecord (ctx->kev[5], ctx->stream);
         CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK (cudaStreamSynchronize (ctx->stream));
         n_ovf = h_cnt[4];
         n_ovf_first = n_ovf;
         if (n_ovf) cudaEventRecord (ctx->kev[8], ctx->stream);
+        int cur_list = S_OVFLIST;
+        if (fused && n_ovf)
+        {   // ---- coarse bins whose distinct k-mers outgrew the CTA's table: fine split of just those bins (multiplicity 1), then
+            //      their fine bins (1 << fine_bits each) go through the tier kernels below ----
+            if (ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
+            CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
+                                  (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)n_ovf));
+            k_expand_bins<<<(unsigned)(((n_ovf << fine_bits) + 255) / 256), 256, 0, ctx->stream>>> ((const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)n_ovf, fine_bits,
+                                                                                                      (uint32_t*)ctx->slot[S_OVFLIST2]); ctx->launches++;
+            k2.recs = ctx->slot[S_FINE];
+            n_ovf <<= fine_bits; cur_list = S_OVFLIST2;
+            k2.ovf_list = (uint32_t*)ctx->slot[cur_list];
+        }
         const bool no_tier2 = (p->path_flags & GATB_PATH_NO_TIER2) != 0;                      // test selector: straight to the global table
-        if (n_ovf && W == 1 && k2b_variant (p->path_flags) == 1 && !no_tier2)
+        if (n_ovf && W == 1 && (fused || k2b_variant (p->path_flags) == 1) && !no_tier2)
         {   // ---- further tiers: the bins a warp's 2^table_log2-slot table could not hold are counted by CTAs with 2048,
             //      then 8192 slots (k2b_count_w1 over a bin list); what still overflows goes to the global table ----
             const int tier_log2[2] = { 11, 13 }, tier_counter[2] = { 7, 12 };
-            int cur_list = S_OVFLIST;
             for (int t = 0; t < 2 && n_ovf; t++)
             {
-                if (tier_log2[t] <= table_log2) continue;
+                if (!fused && tier_log2[t] <= table_log2) continue;
                 const int other = (cur_list == S_OVFLIST) ? S_OVFLIST2 : S_OVFLIST;
                 K2Params k2t = k2;
                 k2t.bin_list = (const uint32_t*)ctx->slot[cur_list]; k2t.n_list = (uint32_t)n_ovf;
@@ -608,7 +692,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     }
     out->stats[GATB_STAT_DISTINCT] = h_cnt[1]; out->stats[GATB_STAT_SOLID] = h_cnt[2];
     out->stats[GATB_STAT_RECORDS] = n_records; out->stats[GATB_STAT_BINS] = nbins; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf_first; out->stats[12] = n_ovf;
-    out->stats[GATB_STAT_RECORD_BYTES] = n_records * rec_bytes;
+    out->stats[GATB_STAT_RECORD_BYTES] = n_records * rec_bytes; out->stats[GATB_STAT_UNIQUE_RECORDS] = n_unique_records;
     float ms;
     cudaEventElapsedTime (&ms, ctx->ev[2], ctx->ev[3]); out->seconds[2] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->ev[3], ctx->ev[4]); out->seconds[3] = ms * 1e-3;
@@ -787,6 +871,90 @@ int gatb_gpu_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t*
     CK (cudaStreamSynchronize (ctx->stream));
     float ms;
     cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[7]); h.seconds[7] = ms * 1e-3;
+    *out = h;
+    return 0;
+}
+
+// =====================================================================================================================
+//  streaming input
+// =====================================================================================================================
+// grows a slot to 'bytes' keeping its first 'used' bytes; everything beyond 'used' is zero afterwards
+static int grow_keep (gatb_gpu_ctx* ctx, int s, size_t bytes, size_t used)
+{
+    if (ctx->slot_cap[s] >= bytes) return 0;
+    size_t want = ctx->slot_cap[s] * 2; if (want < bytes) want = bytes; want = (want + 255) & ~(size_t)255;
+    void* fresh = 0;
+    cudaError_t e = cudaMalloc (&fresh, want);
+    if (e != cudaSuccess) { want = (bytes + 255) & ~(size_t)255; e = cudaMalloc (&fresh, want); }
+    if (e != cudaSuccess) return fail (ctx, "cudaMalloc of %zu bytes (slot %d) failed: %s", want, s, cudaGetErrorString (e));
+    if (used) CK (cudaMemcpyAsync (fresh, ctx->slot[s], used, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK (cudaMemsetAsync ((uint8_t*)fresh + used, 0, want - used, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    if (ctx->slot[s]) cudaFree (ctx->slot[s]);
+    ctx->slot[s] = fresh; ctx->slot_cap[s] = want;
+    return 0;
+}
+
+int gatb_gpu_reads_begin (gatb_gpu_ctx* ctx, uint64_t expected_nt)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    ctx->push_nt = ctx->push_seqs = ctx->push_invalid = 0;
+    if (grow_keep (ctx, S_READS, expected_nt / 4 + 256, 0)) return 1;
+    if (grow_keep (ctx, S_NMASK, expected_nt / 8 + 256, 0)) return 1;
+    if (grow_keep (ctx, S_OFFSETS, 4096, 0)) return 1;
+    // appended batches OR their edge words in: the buffers start from zero
+    CK (cudaMemsetAsync (ctx->slot[S_READS], 0, ctx->slot_cap[S_READS], ctx->stream));
+    CK (cudaMemsetAsync (ctx->slot[S_NMASK], 0, ctx->slot_cap[S_NMASK], ctx->stream));
+    CK (cudaMemsetAsync (ctx->slot[S_OFFSETS], 0, 8, ctx->stream));
+    return 0;
+}
+
+int gatb_gpu_reads_push_ascii (gatb_gpu_ctx* ctx, const char* ascii, const uint64_t* seq_offsets, uint64_t n_seqs)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (n_seqs == 0) return 0;
+    if (!ascii || !seq_offsets) return fail (ctx, "reads_push_ascii: NULL buffer");
+    const uint64_t n = seq_offsets[n_seqs] - seq_offsets[0];
+    for (uint64_t i = 0; i < n_seqs; i++) if (seq_offsets[i+1] < seq_offsets[i]) return fail (ctx, "reads_push_ascii: offsets must not decrease");
+    const uint64_t base = ctx->push_nt, total = base + n;
+    if (grow_keep (ctx, S_READS, total / 4 + 256, base / 4 + 8)) return 1;
+    if (grow_keep (ctx, S_NMASK, total / 8 + 256, base / 8 + 8)) return 1;
+    if (grow_keep (ctx, S_OFFSETS, (ctx->push_seqs + n_seqs + 1) * 8 + 64, (ctx->push_seqs + 1) * 8)) return 1;
+    if (ensure (ctx, S_MISC, n + (n_seqs + 1) * 8 + 64)) return 1;
+    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
+    uint64_t* d_in_off = (uint64_t*)ctx->slot[S_MISC];
+    char* d_ascii = (char*)ctx->slot[S_MISC] + (n_seqs + 1) * 8;
+    unsigned long long* d_bad = (unsigned long long*)ctx->slot[S_STATS] + 40;
+    CK (cudaMemcpyAsync (d_in_off, seq_offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) CK (cudaMemcpyAsync (d_ascii, ascii + seq_offsets[0], n, cudaMemcpyHostToDevice, ctx->stream));
+    CK (cudaMemsetAsync (d_bad, 0, 8, ctx->stream));
+    CK (launch_pack_ascii_at (lctx (ctx), d_ascii, n, base, (uint32_t*)ctx->slot[S_READS], (uint32_t*)ctx->slot[S_NMASK], d_bad));
+    CK (launch_rebase_offsets (lctx (ctx), d_in_off, n_seqs + 1, base, (uint64_t*)ctx->slot[S_OFFSETS] + ctx->push_seqs));
+    unsigned long long bad = 0;
+    CK (cudaMemcpyAsync (&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));                    // the caller may reuse its buffers on return
+    ctx->push_invalid += bad; ctx->push_nt = total; ctx->push_seqs += n_seqs;
+    return 0;
+}
+
+int gatb_gpu_reads_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_table, const uint32_t* freq_order, gatb_gpu_result* out)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (!out) return fail (ctx, "out is NULL");
+    if (check_params (ctx, p, repart_table)) return 1;
+    (void)freq_order;
+    if (ctx->push_seqs == 0) { if (gatb_gpu_reads_begin (ctx, 0)) return 1; }
+    gatb_gpu_params pp = *p; pp.read_len = 0;                    // pushed reads always come with offsets
+    cudaEventRecord (ctx->ev[0], ctx->stream);
+    gatb_gpu_result h;
+    if (count_dev_impl (ctx, &pp, repart_table, (const uint8_t*)ctx->slot[S_READS], (const uint64_t*)ctx->slot[S_OFFSETS], ctx->push_seqs,
+                        ctx->push_invalid ? (const uint32_t*)ctx->slot[S_NMASK] : 0, &h, 0, true)) return 1;
+    cudaEventRecord (ctx->ev[7], ctx->stream);
+    CK (cudaStreamSynchronize (ctx->stream));
+    float ms; cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[7]); h.seconds[7] = ms * 1e-3;
     *out = h;
     return 0;
 }

@@ -23,38 +23,20 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "k2_decode.cuh"
+#include "k2_common.cuh"
 #include <stdlib.h>
 
-// ------------------------------------------------------------------------------------------------ mbarrier / TMA
-__device__ __forceinline__ uint32_t smem_u32 (const void* p) { return (uint32_t)__cvta_generic_to_shared (p); }
-__device__ __forceinline__ void mbar_init (uint64_t* bar, uint32_t count)
-{ asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, uint32_t bytes)
-{ asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void mbar_wait (uint64_t* bar, uint32_t parity)
-{
-    asm volatile (
-        "{\n .reg .pred p;\n WAIT_%=:\n"
-        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" :: "r"(smem_u32 (bar)), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> shared (1D), completion on the mbarrier; bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void tma_bulk_g2s (void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                  :: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // ------------------------------------------------------------------------------------------------ k2a
+// After the fine split the fine-bin id of a 16-byte record is implied by its position: the field carries the MULTIPLICITY of
+// the record instead (1 here; k2a_dedup_split collapses identical records).  Every k <= 31 counting kernel adds it.
 template<int W>
 __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __restrict__ dst, const uint64_t* __restrict__ coarse_off,
-                                                        uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc)
+                                                        uint32_t nb, uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc, const uint32_t* __restrict__ bin_list)
 {
-    const uint32_t nb = gridDim.x;                          // bins of a source region (laid out by coarse_index, kernels.h)
+    // nb = bins of a source region (laid out by coarse_index, kernels.h)
     __shared__ uint32_t s_off[1024], s_cur[1024], s_tmp[1024];         // 1 << fine_bits <= 1024 fine bins per coarse bin
     __shared__ uint32_t s_first[17];                        // record range of every source inside the gathered bin
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = bin_list ? bin_list[blockIdx.x] : blockIdx.x;
     const int nf = 1 << fine_bits;
     const int tid = threadIdx.x;
     for (int i = tid; i < nf; i += blockDim.x) { s_tmp[i] = 0; s_cur[i] = 0; }
@@ -109,6 +91,7 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
             uint4 rec = __ldg (&src[ci]);
             uint32_t f = rec.w >> (DEV_FINE_SHIFT_W1 - 32);
             uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+            rec.w = (rec.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | (1u << (DEV_FINE_SHIFT_W1 - 32));
             dst[dbase + p] = rec;
         }
         else
@@ -121,12 +104,162 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k2a with deduplication
+// k <= 31.  One CTA stages a whole gathered coarse bin in shared memory (read ONCE from HBM), collapses identical records
+// (oriented records of the reads that cover one locus without an error in the span are bit-identical, whatever the
+// strand: about half of all records), and writes every distinct record once, in fine-bin order, with its multiplicity
+// in place of the fine-bin id.  The counting kernels then insert a record's k-mers once, adding the multiplicity.
+//   dedup table: TS slots of {record index : 16, count : 16}; a slot is claimed with a 32-bit CAS, duplicates add 1 << 16.
+// Shared memory: records rmax * 16 | table ts * 4 | fine-bin counters 3 * nf * 4.  Bins with more than rmax records are
+// listed for the plain two-pass kernel above.
+template<int NT>
+__global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __restrict__ dst, const uint64_t* __restrict__ coarse_off,
+                                                       uint32_t nb, uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc,
+                                                       uint32_t rmax, uint32_t ts, uint32_t* __restrict__ big_list, unsigned long long* __restrict__ counters)
+{
+    extern __shared__ __align__(16) unsigned char k2a_smem[];
+    uint4*    recs  = (uint4*)k2a_smem;
+    uint32_t* tbl   = (uint32_t*)(recs + rmax);
+    const int nf = 1 << fine_bits;
+    uint32_t* s_off = tbl + ts;
+    uint32_t* s_cur = s_off + nf;
+    uint32_t* s_tmp = s_cur + nf;
+    __shared__ uint32_t s_first[17];
+    const int tid = threadIdx.x;
+    const uint32_t tmask = ts - 1;
+    unsigned long long n_unique = 0;
+    for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x)
+    {
+        __syncthreads ();
+        for (uint32_t i = tid; i < ts; i += NT) tbl[i] = 0xFFFFFFFFu;
+        for (int i = tid; i < nf; i += NT) { s_tmp[i] = 0; s_cur[i] = 0; }
+        if (tid == 0)
+        {
+            uint32_t run = 0;
+            for (int s = 0; s < S.n; s++) { s_first[s] = run; run += min (S.cursors[s][b], cap); }
+            for (int s = S.n; s <= 16; s++) s_first[s] = run;
+        }
+        __syncthreads ();
+        const uint32_t n_all = s_first[16];
+        if (n_all > rmax)
+        {   // rare: handed to the two-pass kernel
+            if (tid == 0) { const uint32_t idx = (uint32_t) atomicAdd (&counters[0], 1ULL); big_list[idx] = b; }
+            continue;
+        }
+        // ---- stage the bin: four independent 16-byte loads in flight per thread ----
+        auto src_of = [&] (uint32_t g) -> const uint4*
+        {
+            int s = 0;
+            #pragma unroll
+            for (int u = 8; u > 0; u >>= 1) if (s + u < 16 && g >= s_first[s + u]) s += u;
+            return S.bins[s] + coarse_index (b, g - s_first[s], nb);
+        };
+        for (uint32_t g0 = tid; g0 < n_all; g0 += 4 * NT)
+        {
+            uint4 r[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) { const uint32_t g = g0 + u * NT; if (g < n_all) r[u] = __ldg (src_of (g)); }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) { const uint32_t g = g0 + u * NT; if (g < n_all) recs[g] = r[u]; }
+        }
+        __syncthreads ();
+        // ---- collapse identical records ----
+        for (uint32_t g = tid; g < n_all; g += NT)
+        {
+            const uint4 r = recs[g];
+            uint32_t h = (r.x * 0x9E3779B1u) ^ (r.y * 0x85EBCA77u) ^ (r.z * 0xC2B2AE3Du) ^ (r.w * 0x27D4EB2Fu);
+            h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+            h &= tmask;
+            for (;;)
+            {
+                uint32_t e = *(volatile uint32_t*)&tbl[h];
+                if (e == 0xFFFFFFFFu) { e = atomicCAS (&tbl[h], 0xFFFFFFFFu, g | (1u << 16)); if (e == 0xFFFFFFFFu) break; }
+                const uint4 o = recs[e & 0xFFFFu];
+                if (o.x == r.x && o.y == r.y && o.z == r.z && o.w == r.w) { atomicAdd (&tbl[h], 1u << 16); break; }
+                h = (h + 1) & tmask;
+            }
+        }
+        __syncthreads ();
+        // ---- distinct records per fine bin ----
+        for (uint32_t i = tid; i < ts; i += NT)
+        {
+            const uint32_t e = tbl[i];
+            if (e != 0xFFFFFFFFu) atomicAdd (&s_tmp[recs[e & 0xFFFFu].w >> (DEV_FINE_SHIFT_W1 - 32)], 1u);
+        }
+        __syncthreads ();
+        if (tid < 32)
+        {
+            const int per = nf > 32 ? nf / 32 : 1;
+            uint32_t sum = 0;
+            for (int i = 0; i < per; i++) { const int idx = tid * per + i; if (idx < nf) sum += s_tmp[idx]; }
+            uint32_t incl = sum;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (tid >= o) incl += y; }
+            uint32_t run = incl - sum;
+            for (int i = 0; i < per; i++)
+            {
+                const int idx = tid * per + i;
+                if (idx < nf) { const uint32_t v = s_tmp[idx]; s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v); run += v; }
+            }
+            if (tid == 31) n_unique += run;
+        }
+        __syncthreads ();
+        // ---- write them in fine-bin order, multiplicity in place of the fine-bin id ----
+        const uint64_t dbase = coarse_off[b];
+        for (uint32_t i = tid; i < ts; i += NT)
+        {
+            const uint32_t e = tbl[i];
+            if (e == 0xFFFFFFFFu) continue;
+            uint4 r = recs[e & 0xFFFFu];
+            const uint32_t f = r.w >> (DEV_FINE_SHIFT_W1 - 32);
+            const uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+            r.w = (r.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | ((e >> 16) << (DEV_FINE_SHIFT_W1 - 32));
+            dst[dbase + p] = r;
+        }
+    }
+    if (tid == 31 && n_unique) atomicAdd (&counters[1], n_unique);
+}
+
 cudaError_t launch_k2a_split (const LaunchCtx& L, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
-                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc)
+                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc, const uint32_t* bin_list, uint32_t n_list)
+{
+    const uint32_t grid = bin_list ? n_list : nb1;
+    if (grid == 0) return cudaSuccess;
+    if (W == 1) k2a_fine_split<1><<<grid, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, bin_list);
+    else        k2a_fine_split<2><<<grid, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, bin_list);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
+// k <= 31: dedup + split of all bins; counters[0] = bins listed in big_list (more than rmax records), counters[1] = distinct records written
+uint32_t k2a_dedup_rmax (uint32_t max_bin_records, int fine_bits)
+{
+    // records + table (next power of two >= 1.3 rmax) + counters within 200 KB; at most 8191 (multiplicities keep 15 bits, indices 16)
+    uint32_t rmax = max_bin_records < 8191 ? max_bin_records : 8191;
+    for (;;)
+    {
+        uint32_t ts = 256; while (ts < rmax + rmax / 3) ts <<= 1;
+        const size_t bytes = (size_t)rmax * 16 + (size_t)ts * 4 + 3 * ((size_t)4 << fine_bits);
+        if (bytes <= 200 * 1024 || rmax <= 256) return rmax;
+        rmax -= 256;
+    }
+}
+cudaError_t launch_k2a_dedup_split (const LaunchCtx& L, const K2aSrc& src, void* dst, const uint64_t* coarse_off, uint32_t nb1, uint32_t cap,
+                                    int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t* big_list, unsigned long long* counters)
 {
     if (nb1 == 0) return cudaSuccess;
-    if (W == 1) k2a_fine_split<1><<<nb1, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, cap, fine_bits, bin_desc);
-    else        k2a_fine_split<2><<<nb1, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, cap, fine_bits, bin_desc);
+    constexpr int NT = 512;
+    uint32_t ts = 256; while (ts < rmax + rmax / 3) ts <<= 1;
+    const size_t smem = (size_t)rmax * 16 + (size_t)ts * 4 + 3 * ((size_t)4 << fine_bits);
+    cudaError_t e = cudaFuncSetAttribute (k2a_dedup_split<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k2a_dedup_split<NT>, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)L.sm_count * per_sm;
+    if (grid > nb1) grid = nb1;
+    k2a_dedup_split<NT><<<(unsigned)grid, NT, smem, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, big_list, counters);
     (*L.launches)++;
     return cudaGetLastError ();
 }
@@ -156,10 +289,7 @@ __device__ __forceinline__ uint32_t slot_hash64 (uint64_t key, int log2)
 __device__ __forceinline__ uint32_t slot_hash128 (u128 key, int log2)
 { return slot_hash64 (key.lo ^ (key.hi * 0xC2B2AE3D27D4EB4FULL), log2); }
 
-#define EMPTY64 0xFFFFFFFFFFFFFFFFULL
 #define K2_THREADS 256
-#define K2_HB      256        // histogram bins kept in shared memory (larger abundances go to global atomics)
-#define K2_MAXPROBE 512
 #define K2_ROUNDS  6          // table-scan rounds: occupied-slot list capacity (3T/4) <= K2_ROUNDS * K2_THREADS  => T <= 4096
 #define K2_OUT_BLOCK 8192     // output slots a CTA reserves with one global atomic
 template<int W> struct K2Cfg;
@@ -172,7 +302,7 @@ __device__ __forceinline__ uint32_t smem_slot64 (uint64_t key, int log2)
 
 // ---- insertion into an open-addressed table in GLOBAL memory (fallback path) -----------------------------------
 // W=1: the key word itself is claimed with a 64-bit CAS.
-__device__ __forceinline__ bool table_insert_w1 (unsigned long long* keys, uint32_t* cnts, int log2, uint64_t key, int maxprobe)
+__device__ __forceinline__ bool table_insert_w1 (unsigned long long* keys, uint32_t* cnts, int log2, uint64_t key, int maxprobe, uint32_t add = 1u)
 {
     const uint32_t tmask = (1u << log2) - 1;
     uint32_t slot = slot_hash64 (key, log2);
@@ -180,7 +310,7 @@ __device__ __forceinline__ bool table_insert_w1 (unsigned long long* keys, uint3
     {
         unsigned long long cur = keys[slot];
         if (cur == EMPTY64) cur = atomicCAS (&keys[slot], EMPTY64, (unsigned long long)key);
-        if (cur == EMPTY64 || cur == key) { atomicAdd (&cnts[slot], 1u); return true; }
+        if (cur == EMPTY64 || cur == key) { atomicAdd (&cnts[slot], add); return true; }
         slot = (slot + 1) & tmask;
     }
     return false;
@@ -380,12 +510,13 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
                             const uint64_t lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
                             const uint64_t hi = ((uint64_t)q.z | ((uint64_t)q.w << 32)) & ((1ULL << DEV_LEN_SHIFT_W1) - 1);
                             const uint64_t key = rec_kmer_w1 (lo, hi, j, k);
+                            const uint32_t mult = q.w >> (DEV_FINE_SHIFT_W1 - 32);          // multiplicity of the record (k2a)
                             uint32_t slot = smem_slot64 (key, P.table_log2);
                             int probe = 0;
                             for (;;)
                             {
                                 unsigned long long cur = s_klo[slot];
-                                if (cur == key) { atomicAdd (&s_cnt[slot], 1u); break; }
+                                if (cur == key) { atomicAdd (&s_cnt[slot], mult); break; }
                                 if (cur == EMPTY64)
                                 {
                                     cur = atomicCAS (&s_klo[slot], EMPTY64, (unsigned long long)key);
@@ -393,9 +524,9 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
                                     {   // first occurrence in this bin: remember the slot
                                         const uint32_t qn = atomicAdd (&s_nocc[st], 1u);
                                         if (qn < (uint32_t)OCC_CAP) s_occ[qn] = (uint16_t)slot; else s_ovf = 1;
-                                        atomicAdd (&s_cnt[slot], 1u); break;
+                                        atomicAdd (&s_cnt[slot], mult); break;
                                     }
-                                    if (cur == key) { atomicAdd (&s_cnt[slot], 1u); break; }
+                                    if (cur == key) { atomicAdd (&s_cnt[slot], mult); break; }
                                 }
                                 slot = (slot + 1) & (T - 1);
                                 if (++probe >= K2_MAXPROBE) { s_ovf = 1; break; }
@@ -508,24 +639,6 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
 //     register: no atomics); k-mers whose first slot holds another key go to the warp's retry list and are re-inserted
 //     32 at a time with the general probing loop, so the rare long probe never stalls 31 other lanes.
 // After the block barrier each warp walks its own claimed-slot list: histogram, statistics, emission, slot cleanup.
-__device__ __forceinline__ uint32_t k2_slot32 (uint32_t lo, uint32_t hi, int shift)
-{ return (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> shift; }
-
-// general open-addressing insert starting at 'slot'; returns the slot (bit 31 set when this call claimed it), or -1
-__device__ __forceinline__ int k2_probe_loop (unsigned long long* s_klo, uint32_t* s_cnt, uint32_t slot, unsigned long long key, uint32_t tmask, uint32_t add = 1u)
-{
-    #pragma unroll 1
-    for (int probe = 0; probe < K2_MAXPROBE; probe++)
-    {
-        unsigned long long cur = s_klo[slot];
-        if (cur == EMPTY64) cur = atomicCAS (&s_klo[slot], EMPTY64, key);
-        if (cur == EMPTY64) { atomicAdd (&s_cnt[slot], add); return (int)(slot | 0x80000000u); }
-        if (cur == key)     { atomicAdd (&s_cnt[slot], add); return (int)slot; }
-        slot = (slot + 1) & tmask;
-    }
-    return -1;
-}
-
 #define K2_RETRY_CAP 160        // per warp: 31 left over + 4 steps x 32 lanes at the very worst
 
 template<int NT>
@@ -546,6 +659,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
     uint32_t* s_hist = s_cnt + T;
     uint64_t* s_bar  = (uint64_t*)(s_hist + K2_HB);                          // [2]
     uint16_t* s_occ  = (uint16_t*)(s_bar + 2);                               // [NWARP][OCC_W]
+    __shared__ uint16_t s_retry_m[NWARP * K2_RETRY_CAP];                     // multiplicities of the retry entries
     __shared__ uint32_t s_bin[2], s_n[2];
     __shared__ unsigned long long s_base[2];
     __shared__ int s_ovf;
@@ -557,6 +671,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
     for (int i = tid; i < K2_HB; i += NT) s_hist[i] = 0;
     uint16_t* occ_w = s_occ + (size_t)wid * OCC_W;
     unsigned long long* retry_w = s_retry + wid * K2_RETRY_CAP;
+    uint16_t* retry_m = s_retry_m + wid * K2_RETRY_CAP;
 
     auto fetch = [&] (int st)
     {
@@ -626,7 +741,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
                 if (e < rn)
                 {
                     const unsigned long long key = retry_w[e];
-                    res = k2_probe_loop (s_klo, s_cnt, k2_slot32 ((uint32_t)key, (uint32_t)(key >> 32), hshift), key, tmask);
+                    res = k2_probe_loop (s_klo, s_cnt, k2_slot32 ((uint32_t)key, (uint32_t)(key >> 32), hshift), key, tmask, (uint32_t)retry_m[e]);
                     if (res == -1) w_ovf = true;
                 }
                 __syncwarp ();
@@ -677,6 +792,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
                     const int nkc = act ? (int)((q.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
                     K2Chunk C;
                     k2_chunk_begin (C, q.x, q.y, q.z, q.w & ((1u << (DEV_LEN_SHIFT_W1 - 32)) - 1), c, k);
+                    const uint32_t mult = q.w >> (DEV_FINE_SHIFT_W1 - 32);                  // multiplicity of the record (k2a)
                     uint32_t lo[4], hi[4], slot[4];
                     k2_chunk_kmer<0> (C, lo[0], hi[0]); k2_chunk_kmer<1> (C, lo[1], hi[1]);
                     k2_chunk_kmer<2> (C, lo[2], hi[2]); k2_chunk_kmer<3> (C, lo[3], hi[3]);
@@ -693,13 +809,13 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
                         if (isE) cv = atomicCAS (&s_klo[slot[i]], EMPTY64, key);
                         const bool isnew = isE && cv == EMPTY64;
                         const bool hit = valid && (isnew || cv == key);
-                        if (hit) atomicAdd (&s_cnt[slot[i]], 1u);
+                        if (hit && mult > (isnew ? 1u : 0u)) atomicAdd (&s_cnt[slot[i]], isnew ? mult - 1u : mult);     // a claim counts one by itself
                         append_new (isnew, slot[i]);
                         const bool miss = valid && !hit;
                         const unsigned mm = __ballot_sync (FULL_MASK, miss);
                         if (mm)
                         {
-                            if (miss) retry_w[rn + __popc (mm & lt_mask)] = key;
+                            if (miss) { retry_w[rn + __popc (mm & lt_mask)] = key; retry_m[rn + __popc (mm & lt_mask)] = (uint16_t)mult; }
                             rn += __popc (mm);
                         }
                     }
@@ -728,7 +844,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
             if (q < wn)
             {
                 const uint32_t slot = occ_w[q];
-                c = s_cnt[slot]; klo = s_klo[slot];
+                c = s_cnt[slot] + 1u; klo = s_klo[slot];                    // the claim itself counts one (k2_common.cuh)
                 s_klo[slot] = EMPTY64; s_cnt[slot] = 0;
                 n_distinct++;
                 const uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
@@ -826,20 +942,20 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
     const uint32_t lt_mask = (1u << lane) - 1;
     const int k = P.k;
     // per warp: keys T*8 | retry K2_RETRY_CAP*8 | counts T*4 | claimed OCC_W*2 | retry multiplicities ; per CTA: histogram
-    const size_t per_warp = (size_t)T * 8 + K2_RETRY_CAP * 8 + (size_t)T * 4 + (((size_t)OCC_W * 2 + 15) & ~(size_t)15) + K2_RETRY_CAP;
+    const size_t per_warp = (size_t)T * 8 + K2_RETRY_CAP * 8 + (size_t)T * 4 + (((size_t)OCC_W * 2 + 15) & ~(size_t)15) + K2_RETRY_CAP * 2;
     unsigned char* wbase = smem_raw + per_warp * wid;
     unsigned long long* s_klo = (unsigned long long*)wbase;
     unsigned long long* retry_w = s_klo + T;
     uint32_t* s_cnt = (uint32_t*)(retry_w + K2_RETRY_CAP);
     uint16_t* occ_w = (uint16_t*)(s_cnt + T);
-    uint8_t* retry_m = (uint8_t*)wbase + per_warp - K2_RETRY_CAP;
+    uint16_t* retry_m = (uint16_t*)(wbase + per_warp - K2_RETRY_CAP * 2);
     uint32_t* s_hist = (uint32_t*)(smem_raw + per_warp * NWARP);
 
     for (int i = lane; i < T; i += 32) { s_klo[i] = EMPTY64; s_cnt[i] = 0; }
     for (int i = tid; i < K2_HB; i += NT) s_hist[i] = 0;
     __syncthreads ();
 
-    unsigned long long n_distinct = 0, n_solid = 0, n_emitted = 0;
+    unsigned long long n_distinct = 0, n_solid = 0, n_emitted = 0, n_once = 0;    // n_once: k-mers seen once (most of them: kept out of the shared histogram)
     unsigned long long out_pos = 0, out_end = 0;
     const uint32_t G = gridDim.x * NWARP;
     const uint4 zero4 = make_uint4 (0, 0, 0, 0);
@@ -893,7 +1009,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                     if (e < rn)
                     {
                         const unsigned long long key = retry_w[e];
-                        res = k2_probe_loop (s_klo, s_cnt, k2_slot32 ((uint32_t)key, (uint32_t)(key >> 32), hshift), key, tmask, ORI ? (uint32_t)retry_m[e] : 1u);
+                        res = k2_probe_loop (s_klo, s_cnt, k2_slot32 ((uint32_t)key, (uint32_t)(key >> 32), hshift), key, tmask, (uint32_t)retry_m[e]);
                         if (res == -1) w_ovf = true;
                     }
                     __syncwarp ();
@@ -907,14 +1023,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
             {
                 uint4 rec = rec0;
                 if (g0) rec = (g0 + lane < n) ? __ldg ((const uint4*)P.recs + base0 + g0 + lane) : zero4;
-                uint32_t nch = (((rec.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;            // 0 for the zero record
-                if (ORI)
-                {   // identical records -> the lowest lane keeps the record with the multiplicity in place of the fine-bin id
-                    const unsigned same = __match_any_sync (FULL_MASK, rec.x) & __match_any_sync (FULL_MASK, rec.y)
-                                        & __match_any_sync (FULL_MASK, rec.z) & __match_any_sync (FULL_MASK, rec.w);
-                    if ((same & lt_mask) != 0) nch = 0;
-                    rec.w = (rec.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | ((uint32_t)__popc (same) << (DEV_FINE_SHIFT_W1 - 32));
-                }
+                const uint32_t nch = (((rec.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) + 3u) >> 2;      // 0 for the zero record
                 uint32_t incl = nch;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (lane >= o) incl += y; }
@@ -938,7 +1047,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                     const int nkc = act ? (int)((q.w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) - 4 * c : 0;      // k-mers of this chunk
                     K2Chunk C;
                     uint32_t lo[4], hi[4], slot[4];
-                    const uint32_t mult = ORI ? (q.w >> (DEV_FINE_SHIFT_W1 - 32)) : 1u;
+                    const uint32_t mult = q.w >> (DEV_FINE_SHIFT_W1 - 32);                  // multiplicity of the record (k2a)
                     if (ORI)
                     {
                         k2_chunk_begin_raw (C, q.x, q.y, q.z, q.w & ((1u << (DEV_LEN_SHIFT_W1 - 32)) - 1), c, k);
@@ -964,13 +1073,13 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                         if (isE) cv = atomicCAS (&s_klo[slot[i]], EMPTY64, key);
                         const bool isnew = isE && cv == EMPTY64;
                         const bool hit = valid && (isnew || cv == key);
-                        if (hit) atomicAdd (&s_cnt[slot[i]], mult);
+                        if (hit && mult > (isnew ? 1u : 0u)) atomicAdd (&s_cnt[slot[i]], isnew ? mult - 1u : mult);     // a claim counts one by itself
                         append_new (isnew, slot[i]);
                         const bool miss = valid && !hit;
                         const unsigned mm = __ballot_sync (FULL_MASK, miss);
                         if (mm)
                         {
-                            if (miss) { retry_w[rn + __popc (mm & lt_mask)] = key; if (ORI) retry_m[rn + __popc (mm & lt_mask)] = (uint8_t)mult; }
+                            if (miss) { retry_w[rn + __popc (mm & lt_mask)] = key; retry_m[rn + __popc (mm & lt_mask)] = (uint16_t)mult; }
                             rn += __popc (mm);
                         }
                     }
@@ -996,11 +1105,11 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
                     if (q < wn)
                     {
                         const uint32_t slot = occ_w[q];
-                        c = s_cnt[slot]; klo = s_klo[slot];
+                        c = s_cnt[slot] + 1u; klo = s_klo[slot];            // the claim itself counts one (k2_common.cuh)
                         s_klo[slot] = EMPTY64; s_cnt[slot] = 0;
                         n_distinct++;
                         const uint32_t hb = c >= (uint32_t)P.histo_max ? (uint32_t)P.histo_max : c;
-                        if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
+                        if (hb == 1) n_once++; else if (hb < K2_HB) atomicAdd (&s_hist[hb], 1u); else atomicAdd (&P.histogram[hb], 1ULL);
                         if (c >= P.solid_min && c <= P.solid_max) n_solid++;
                         emit = (c >= P.emit_min && c <= P.emit_max);
                     }
@@ -1040,10 +1149,11 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
     for (int o = 16; o > 0; o >>= 1)
     {
         n_distinct += __shfl_xor_sync (FULL_MASK, n_distinct, o); n_solid += __shfl_xor_sync (FULL_MASK, n_solid, o);
-        n_emitted += __shfl_xor_sync (FULL_MASK, n_emitted, o);
+        n_emitted += __shfl_xor_sync (FULL_MASK, n_emitted, o); n_once += __shfl_xor_sync (FULL_MASK, n_once, o);
     }
     if (lane == 0)
     {
+        if (n_once) atomicAdd (&P.histogram[P.histo_max >= 1 ? 1 : P.histo_max], n_once);
         if (n_distinct) atomicAdd (&P.counters[1], n_distinct);
         if (n_solid)    atomicAdd (&P.counters[2], n_solid);
         if (n_emitted)  atomicAdd (&P.counters[6], n_emitted);
@@ -1052,7 +1162,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
 static size_t k2b_warp_smem_bytes (int table_log2, int nt)
 {
     const size_t T = (size_t)1 << table_log2, occ = (T * 3) / 4;
-    const size_t per_warp = T * 8 + K2_RETRY_CAP * 8 + T * 4 + ((occ * 2 + 15) & ~(size_t)15) + K2_RETRY_CAP;
+    const size_t per_warp = T * 8 + K2_RETRY_CAP * 8 + T * 4 + ((occ * 2 + 15) & ~(size_t)15) + K2_RETRY_CAP * 2;
     return per_warp * (nt / 32) + K2_HB * 4;
 }
 template<int NT, bool ORI>
@@ -1444,9 +1554,10 @@ __global__ void __launch_bounds__(256) k2c_insert (const K2Params P, uint32_t n_
                 uint4 r = __ldg (&base[i]);
                 uint64_t lo = (uint64_t)r.x | ((uint64_t)r.y << 32), hi = (uint64_t)r.z | ((uint64_t)r.w << 32);
                 const int len = (int)((hi >> DEV_LEN_SHIFT_W1) & 31);
+                const uint32_t mult = (uint32_t)(hi >> DEV_FINE_SHIFT_W1);              // multiplicity of the record (k2a)
                 hi &= (1ULL << DEV_LEN_SHIFT_W1) - 1;
                 for (int j = 0; j < len; j++)
-                    table_insert_w1 ((unsigned long long*)P.g_lo, P.g_cnt, P.g_log2, rec_kmer_w1 (lo, hi, j, k), 1 << 30);
+                    table_insert_w1 ((unsigned long long*)P.g_lo, P.g_cnt, P.g_log2, rec_kmer_w1 (lo, hi, j, k), 1 << 30, mult);
             }
             else
             {

@@ -273,3 +273,57 @@ cudaError_t launch_pack_ascii (const LaunchCtx& L, const char* ascii, uint64_t n
     (*L.launches)++;
     return cudaGetLastError ();
 }
+
+// ------------------------------------------------------------------------------------------------ ASCII packer, appending
+// The streaming input path (gatb_gpu_reads_push_ascii): a batch of n characters is packed into the stream at nucleotide
+// offset 'base' (any value).  One thread produces the 32 stream positions [32g, 32g+32): two nucleotide words and one
+// mask word; the first and the last group of a batch share their words with the neighbouring batches, so they are OR-ed
+// in (the buffers are zero beyond the last nucleotide written).  Same encoding as k_pack_ascii (Data::ConvertASCII).
+__global__ void __launch_bounds__(256) k_pack_ascii_at (const char* __restrict__ ascii, uint64_t n, uint64_t base, uint32_t* words, uint32_t* nmask,
+                                                        unsigned long long* n_invalid)
+{
+    unsigned long long bad = 0;
+    const uint64_t g_first = base / 32, g_last = (base + n - 1) / 32;
+    for (uint64_t g = g_first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= g_last; g += (uint64_t)gridDim.x * blockDim.x)
+    {
+        uint32_t w0 = 0, w1 = 0, mk = 0;
+        for (int t = 0; t < 32; t++)
+        {
+            const uint64_t pos = g * 32 + t;
+            if (pos < base || pos >= base + n) continue;
+            const unsigned char c = (unsigned char)ascii[pos - base];
+            const uint32_t code = (c >> 1) & 3u;
+            const bool ok = (c=='A'||c=='C'||c=='G'||c=='T'||c=='a'||c=='c'||c=='g'||c=='t');
+            if (!ok) { mk |= 1u << t; bad++; }
+            if (t < 16) w0 |= code << (2*t); else w1 |= code << (2*(t-16));
+        }
+        if (g == g_first || g == g_last) { atomicOr (&words[2*g], w0); atomicOr (&words[2*g+1], w1); atomicOr (&nmask[g], mk); }
+        else { words[2*g] = w0; words[2*g+1] = w1; nmask[g] = mk; }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync (FULL_MASK, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd (n_invalid, bad);
+}
+cudaError_t launch_pack_ascii_at (const LaunchCtx& L, const char* ascii, uint64_t n, uint64_t base, uint32_t* packed_words, uint32_t* nmask,
+                                  unsigned long long* n_invalid)
+{
+    if (n == 0) return cudaSuccess;
+    const uint64_t groups = (base + n - 1) / 32 - base / 32 + 1;
+    const uint64_t blocks = (groups + 255) / 256; const unsigned grid = (unsigned)(blocks < (uint64_t)L.sm_count * 32 ? blocks : (uint64_t)L.sm_count * 32);
+    k_pack_ascii_at<<<grid, 256, 0, L.stream>>> (ascii, n, base, packed_words, nmask, n_invalid);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+// offsets of a pushed batch: out[i] = in[i] - in[0] + base
+__global__ void k_rebase_offsets (const uint64_t* in, uint64_t n, uint64_t base, uint64_t* out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] - in[0] + base;
+}
+cudaError_t launch_rebase_offsets (const LaunchCtx& L, const uint64_t* in, uint64_t n, uint64_t base, uint64_t* out)
+{
+    if (n == 0) return cudaSuccess;
+    k_rebase_offsets<<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>> (in, n, base, out);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}

@@ -120,7 +120,10 @@ bool        k1_oriented (int k, int m, int w, int path_flags);   // does launch_
 // k2_count.cu
 struct K2aSrc { const uint4* bins[16]; const uint32_t* cursors[16]; int n; };     // the same coarse bins gathered from n sources
 cudaError_t launch_k2a_split (const LaunchCtx&, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
-                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc);
+                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc, const uint32_t* bin_list = 0, uint32_t n_list = 0);
+uint32_t    k2a_dedup_rmax (uint32_t max_bin_records, int fine_bits);
+cudaError_t launch_k2a_dedup_split (const LaunchCtx&, const K2aSrc& src, void* dst, const uint64_t* coarse_off, uint32_t nb1, uint32_t cap,
+                                    int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t* big_list, unsigned long long* counters);
 cudaError_t launch_k2b_count (const LaunchCtx&, const K2Params&);
 cudaError_t launch_k2b_count_list (const LaunchCtx&, const K2Params&);     // CTA-per-bin kernel over P.bin_list (k <= 31)
 int         k2b_variant (int path_flags);            // 1 warp per bin, 128 / 256 CTA per bin (chunked insert), 0 one k-mer per lane
@@ -154,3 +157,9 @@ cudaError_t launch_synth_reads (const LaunchCtx&, uint64_t seed, uint64_t genome
                                 int L, uint8_t* packed);
 cudaError_t launch_pack_ascii (const LaunchCtx&, const char* ascii, uint64_t n, uint32_t* packed_words, uint32_t* nmask,
                                unsigned long long* n_invalid);
+cudaError_t launch_pack_ascii_at (const LaunchCtx&, const char* ascii, uint64_t n, uint64_t base, uint32_t* packed_words, uint32_t* nmask,
+                                  unsigned long long* n_invalid);
+cudaError_t launch_rebase_offsets (const LaunchCtx&, const uint64_t* in, uint64_t n, uint64_t base, uint64_t* out);
+// k2_fused.cu
+size_t      k2f_smem_bytes (int table_log2, int nwarp);
+cudaError_t launch_k2f_count (const LaunchCtx&, const K2Params&, const K2aSrc&, uint32_t nb, uint32_t cap, uint32_t n_bins, int dedup);

@@ -54,14 +54,15 @@ typedef struct gatb_gpu_params
     int32_t  minimizer_type;     /* _minimizerType   0 = lexicographic (supported); 1 = frequency (not yet)     */
     int32_t  emit_all;           /* 1: return EVERY distinct k-mer (for custom ICountProcessor chains); 0: solid only */
     int32_t  read_len;           /* >0: all reads have this length and read_offsets_nt may be NULL               */
-    int32_t  table_log2;         /* 0 = default (9 for kmer_size < 32: one warp per bin; 11 otherwise); log2 slots of the
-                                    first-tier per-bin shared-memory table, 5..13                                  */
+    int32_t  table_log2;         /* 0 = default (9 for kmer_size < 32: one warp per fine bin; 11 otherwise; 13 with GATB_PATH_FUSED);
+                                    log2 slots of the first-tier shared-memory table, 5..13                        */
     int32_t  path_flags;         /* 0 = the product path.  Selectors of the alternate code paths (GATB_PATH_*), so that one
                                     process can run the parity suite through every kernel variant                    */
     int32_t  k3_dir_rounds;      /* 0 = default; >0: rounds of the block directory of the bucket scatter (a tiny one forces the
                                     exact two-pass fallback)                                                         */
     int32_t  bin_load_pct;       /* 0 = default; planned k-mer occurrences per fine bin in % of the first-tier table slots */
-    int32_t  reserved[2];
+    int32_t  fine_bits;          /* 0 = default (7); k <= 31: log2 of the fine bins per coarse bin on one GPU (experiments)  */
+    int32_t  reserved[1];
 } gatb_gpu_params;
 /* gatb_gpu_params.path_flags */
 enum {
@@ -73,7 +74,10 @@ enum {
     GATB_PATH_K2B_W2_WARP  = 8,      /* 32 <= k <= 63: warp-per-bin kernel instead of CTA per bin                          */
     GATB_PATH_NO_TIER2     = 16,     /* overflowing bins go straight to the global-memory table                            */
     GATB_PATH_K3_NO_POOL   = 32,     /* exact two-pass bucket scatter instead of the pooled single pass                    */
-    GATB_PATH_CANONICAL    = 64      /* register scanner without orientation: k2b rebuilds min(forward, revcomp) per k-mer  */
+    GATB_PATH_CANONICAL    = 64,     /* register scanner without orientation: k2b rebuilds min(forward, revcomp) per k-mer  */
+    GATB_PATH_NO_DEDUP     = 128,    /* identical records are not collapsed (every multiplicity is 1)                       */
+    GATB_PATH_FUSED        = 256     /* k <= 31: one CTA counts a whole coarse bin straight out of the partition buffers (k2_fused.cu:
+                                        TMA-streamed tiles, CTA-wide table) instead of fine split + warp-per-fine-bin counting  */
 };
 
 enum { GATB_GPU_NSTATS = 16, GATB_GPU_MAX_RANKS = 8, GATB_GPU_MAX_SOURCES = 16 };   /* sources = ranks x pieces per rank */
@@ -91,7 +95,8 @@ enum {
                                     overflowed the second-tier (per-CTA, 8192 slots) table and went to the global table,
                                     stats[11] = k-mer occurrences in the latter */
     GATB_STAT_RETRIES = 9,       /* partition-kernel re-runs after a bucket overflow    */
-    GATB_STAT_RECORD_BYTES = 10  /* bytes of super-k-mer records (S of SURVEY.md 8d)    */
+    GATB_STAT_RECORD_BYTES = 10, /* bytes of super-k-mer records (S of SURVEY.md 8d)    */
+    GATB_STAT_UNIQUE_RECORDS = 13 /* records left after identical ones were collapsed (k <= 31) */
 };
 
 typedef struct gatb_gpu_result
@@ -132,6 +137,19 @@ int gatb_gpu_count_dev (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* r
                         const uint8_t* d_packed_reads, const uint64_t* d_read_offsets_nt, uint64_t n_reads,
                         const uint32_t* d_n_mask, gatb_gpu_result* out);
 void gatb_gpu_result_free (gatb_gpu_ctx*, gatb_gpu_result*);
+
+/* ---- streaming input (SURVEY.md 8b "push_reads / finish"): the bank is pushed batch by batch as ASCII, packed to 2 bits on
+ * the device as it arrives (row A1; replaces the per-sequence Data::ConvertASCII of bank::Sequence, tools/misc/api/Data.hpp:185,
+ * inside the IteratorCommand loop tools/designpattern/impl/ICommand.hpp:304-330), and counted once at the end.  The host never
+ * holds more than one batch.
+ *   gatb_gpu_reads_begin        forgets the reads pushed so far (expected_nt: capacity hint, may be 0)
+ *   gatb_gpu_reads_push_ascii   n_seqs sequences concatenated without separators in ascii[seq_offsets[0] .. seq_offsets[n_seqs]);
+ *                               characters other than ACGTacgt are invalid nucleotides (their k-mers are dropped)
+ *   gatb_gpu_reads_count        gatb_gpu_count over everything pushed: host arrays out, same ownership rules */
+int gatb_gpu_reads_begin (gatb_gpu_ctx*, uint64_t expected_nt);
+int gatb_gpu_reads_push_ascii (gatb_gpu_ctx*, const char* ascii, const uint64_t* seq_offsets, uint64_t n_seqs);
+int gatb_gpu_reads_count (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* repart_table, const uint32_t* freq_order,
+                          gatb_gpu_result* out);
 
 /* ---- the same path in stages, for multi-GPU runs (one process per GPU) -------------------------------------------
  * The device binning: every rank partitions ITS reads into nb1 coarse bins with the SAME geometry;

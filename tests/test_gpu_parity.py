@@ -125,11 +125,18 @@ def test_small_tables_force_the_global_fallback(gpu, oracle, table_log2):
 # small for the pooled scatter, the register scanner without orientation, and other bin loads
 def path_variants():
     import gatb_core_b200 as g
-    return [("general_k1", dict(path_flags=g.PATH_K1_GENERAL)), ("cta128", dict(path_flags=g.PATH_K2B_CTA128)),
+    F = g.PATH_FUSED
+    return [("general_k1", dict(path_flags=g.PATH_K1_GENERAL)), ("general_k1_fused", dict(path_flags=g.PATH_K1_GENERAL | F)),
+            ("fused", dict(path_flags=F)), ("fused_no_dedup", dict(path_flags=F | g.PATH_NO_DEDUP)),
+            ("fused_canonical", dict(path_flags=F | g.PATH_CANONICAL)),
+            ("fused_overflow_to_tiers", dict(path_flags=F, table_log2=7)), ("fused_overflow_to_global", dict(table_log2=5, path_flags=F | g.PATH_NO_TIER2)),
+            ("fused_dense", dict(path_flags=F, bin_load_pct=350)), ("cta128", dict(path_flags=g.PATH_K2B_CTA128)),
             ("cta256", dict(path_flags=g.PATH_K2B_CTA256)), ("lane", dict(path_flags=g.PATH_K2B_LANE)),
             ("no_tier2_small_table", dict(path_flags=g.PATH_NO_TIER2, table_log2=6)), ("k3_no_pool", dict(path_flags=g.PATH_K3_NO_POOL)),
             ("k3_tiny_directory", dict(k3_dir_rounds=1)), ("canonical_records", dict(path_flags=g.PATH_CANONICAL)),
             ("canonical_cta128", dict(path_flags=g.PATH_CANONICAL | g.PATH_K2B_CTA128)),
+            ("no_dedup", dict(path_flags=g.PATH_NO_DEDUP)), ("no_dedup_canonical", dict(path_flags=g.PATH_NO_DEDUP | g.PATH_CANONICAL)),
+            ("fine_bits_5", dict(fine_bits=5)), ("fine_bits_9_dense", dict(fine_bits=9, bin_load_pct=120)),
             ("dense_bins", dict(bin_load_pct=150)), ("sparse_bins", dict(bin_load_pct=10)), ("tier_tables", dict(table_log2=6))]
 
 
@@ -192,6 +199,25 @@ def test_oriented_records_on_both_strands_hairpins_and_palindromes(gpu, oracle, 
         check_parts(got, want["solid"], 1, 1)
         assert (got["histogram"] == want["histogram"]).all()
         assert got["stats"]["kmers_nb_distinct"] == int(want["stats"][2])
+
+
+@pytest.mark.parametrize("name", ["dsk_k31_parts", "dsk_k63_w16"])
+def test_streaming_input_equals_one_shot(gpu, oracle, name):
+    # gatb_gpu_reads_begin / _push_ascii / _count: ragged batches of ASCII sequences (with N), packed on the device at
+    # arbitrary nucleotide offsets, must give the same result as the one-shot host call
+    fx = fixtures.Fixture(name, oracle)
+    rng = np.random.default_rng(3)
+    seqs = list(fx.seqs) + [b"", b"ACGTN" * 7, b"acgtacgtacgtacgtacgtacgtacgtacgtacgtacgtacgtacgtacgtacgtacgtacgtacgt", b"A"]
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, nb_passes=fx.nb_passes, abundance_min=fx.abundance_min)
+    packed, offs, mask = pack_seqs(oracle, seqs)
+    want = gpu.count(packed, offs, len(seqs), params, repart=fx.repart, n_mask=mask)
+    cuts = sorted(set([0, len(seqs)] + [int(c) for c in rng.integers(0, len(seqs), 9)]))
+    batches = [seqs[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    got = gpu.count_pushed(batches, params, repart=fx.repart)
+    nkeys = fx.nb_partitions * fx.nb_passes
+    check_parts(got, want["parts"], nkeys, fx.words)
+    assert (got["histogram"] == want["histogram"]).all()
+    assert got["stats"] == want["stats"] or all(got["stats"][k] == want["stats"][k] for k in ("kmers_nb_valid", "kmers_nb_invalid", "kmers_nb_distinct", "kmers_nb_solid", "sequences", "nucleotides"))
 
 
 def test_reference_golden_vectors_dsk(gpu, oracle):
