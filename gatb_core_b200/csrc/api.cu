@@ -253,7 +253,9 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
     const uint64_t T = 1ULL << table_log2;
     if (p->bin_load_pct < 0 || p->bin_load_pct > 400) return fail (ctx, "bin_load_pct must be in [0,400]");
-    int fine_bits = (W == 1) ? FINE_BITS_W1 : FINE_BITS_W2;
+    // k <= 31: 64 fine bins per coarse bin (measured best on B200: the dedup split stages a ~2300-record coarse bin in 37 KB of
+    // shared memory, several CTAs per SM); the record keeps up to 10 bits of fine-bin id for multi-GPU geometries
+    int fine_bits = (W == 1) ? 6 : FINE_BITS_W2;
     if (fused) fine_bits = 5;
     if (W == 1 && p->fine_bits > 0)
     {
@@ -270,7 +272,7 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     }
     else
     {
-        const uint64_t occ_per_bin = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : 55)) / 100 + 1;
+        const uint64_t occ_per_bin = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : (W == 1 ? 80 : 55))) / 100 + 1;
         // k <= 31: one more fine-bin bit per doubling of the ranks, so that nb1 (the coarse bins every rank scatters into) stays put
         if (W == 1) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
         uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
@@ -539,7 +541,10 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
 
     // ---- k3: partition id + ascending order ----
     int t_bits = 0;
-    { uint64_t per_key = n_items / n_keys + 1; while (t_bits < 2*k && t_bits < 24 && (per_key >> t_bits) > 1024) t_bits++; }
+    // buckets of ~256 k-mers on average: the top bits of CANONICAL values are far from uniform (a value starts with A or C far more
+    // often than with T or G), the fullest bucket of a key holds several times the average and must stay below the 4096 items a CTA
+    // sorts in shared memory / the block directory of the pooled scatter covers (measured: at 1024 the scatter fell back to two passes)
+    { uint64_t per_key = n_items / n_keys + 1; while (t_bits < 2*k && t_bits < 24 && (per_key >> t_bits) > 256) t_bits++; }
     while (t_bits > 0 && (n_keys << t_bits) > (1ULL << 30)) t_bits--;
     const uint64_t n_buckets = n_keys << t_bits;
     // result arrays live in context-owned slots (valid until the next count on this context): no per-call cudaMalloc
@@ -665,8 +670,8 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     // part_offsets[key] = bucket_off[key << t_bits]
     {
         std::vector<uint64_t> offs (n_keys + 1);
-        for (uint64_t key = 0; key <= n_keys; key++)
-            CK (cudaMemcpyAsync (&offs[key], (const uint64_t*)ctx->slot[S_BUCKETOFF] + (key << t_bits), 8, cudaMemcpyDeviceToHost, ctx->stream));
+        // one strided copy: entry key << t_bits of the bucket offsets for every key (and the total at the end)
+        CK (cudaMemcpy2DAsync (offs.data (), 8, ctx->slot[S_BUCKETOFF], (size_t)8 << t_bits, 8, n_keys + 1, cudaMemcpyDeviceToHost, ctx->stream));
         CK (cudaStreamSynchronize (ctx->stream));
         CK (cudaMemcpyAsync (d_offs, offs.data (), (n_keys + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK (cudaMemcpyAsync (d_hist, ctx->slot[S_HISTO], (size_t)(histo_max + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -177,6 +177,38 @@ API RefDsk* ref_dsk_run (const char* input, int k, int m, int abundance_min, int
     catch (...)                 { g_error = "unknown exception"; return 0; }
 }
 
+/* The reference's minimizer -> partition table (Repartitor) for a GIVEN number of partitions, computed by the reference's own
+ * RepartitorAlgorithm (kmer/impl/RepartitionAlgorithm.cpp:286-492: samples the bank, balances the minimizer bins) on 'input'.
+ * bench.py uses it with the partition count ConfigurationAlgorithm's arithmetic gives for the full-size workload. */
+#include <gatb/kmer/impl/RepartitionAlgorithm.hpp>
+template<size_t span>
+static int run_repartition (const char* input, int k, int m, int nb_partitions, int nb_passes, int nb_cores, const char* tmp_prefix, uint16_t* table)
+{
+    IBank* bank = Bank::open (input);  LOCAL (bank);
+    Configuration config;
+    config._kmerSize = k; config._minim_size = m; config._nb_partitions = nb_partitions; config._nb_passes = nb_passes;
+    config._repartitionType = 0; config._minimizerType = 0; config._nbCores = nb_cores; config._nb_banks = 1;
+    u_int64_t nbSeq = 0, totalSize = 0, maxSize = 0;
+    bank->estimate (nbSeq, totalSize, maxSize);
+    config._estimateSeqNb = nbSeq; config._estimateSeqTotalSize = totalSize; config._estimateSeqMaxSize = maxSize;
+    config._isComputed = true;
+    Storage* storage = StorageFactory (STORAGE_FILE).create (tmp_prefix, true, true);  LOCAL (storage);
+    RepartitorAlgorithm<span> repart (bank, storage->getGroup ("minimizers"), config, nb_cores);
+    repart.execute ();
+    Repartitor rep (storage->getGroup ("minimizers"));
+    const uint64_t nbm = (uint64_t)1 << (2*m);
+    for (uint64_t i=0; i<nbm; i++)  table[i] = rep (i);
+    return 0;
+}
+API int ref_repartition (const char* input, int k, int m, int nb_partitions, int nb_passes, int nb_cores, const char* tmp_prefix, uint16_t* table)
+{
+    try { return k < 32 ? run_repartition<32> (input, k, m, nb_partitions, nb_passes, nb_cores, tmp_prefix, table)
+                        : run_repartition<64> (input, k, m, nb_partitions, nb_passes, nb_cores, tmp_prefix, table); }
+    catch (Exception& e)        { g_error = e.getMessage(); return 1; }
+    catch (std::exception& e)   { g_error = e.what();       return 1; }
+    catch (...)                 { g_error = "unknown exception"; return 1; }
+}
+
 API int      ref_dsk_nb_partitions (RefDsk* r) { return r->nb_partitions; }
 API int      ref_dsk_nb_passes     (RefDsk* r) { return r->nb_passes; }
 API double   ref_dsk_seconds       (RefDsk* r) { return r->seconds; }

@@ -228,6 +228,7 @@ class Reference:
         L.ref_dsk_get_part.argtypes = [VP, C.c_uint32, VP, VP, VP]
         L.ref_dsk_get_repart.argtypes = [VP, u16p]
         L.ref_dsk_free.argtypes = [VP]
+        L.ref_repartition.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, u16p]
         L.ref_histogram.argtypes = [i32p, C.c_uint64, C.c_int, C.c_int, u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.ref_kmers.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p, u64p, u32p, u8p, u8p]
         L.ref_superkmers.argtypes = [C.c_char_p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, u16p, C.c_int,
@@ -242,6 +243,53 @@ class Reference:
         L.ref_nbits_per_kmer.argtypes = [C.c_int]
         L.ref_bloom.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, VP, VP, C.c_uint64, VP,
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+
+    def repartition(self, fasta_path, k, m, nb_partitions, nb_passes=1, nb_cores=1):
+        """The reference's Repartitor table (u16[4^m]) for a given partition count, sampled from the bank by RepartitorAlgorithm."""
+        table = np.zeros(4 ** m, np.uint16)
+        with tempfile.TemporaryDirectory() as tmp:
+            cwd = os.getcwd()
+            os.chdir(tmp)
+            try:
+                rc = self.L.ref_repartition(os.fsencode(fasta_path), k, m, nb_partitions, nb_passes, nb_cores,
+                                            os.fsencode(os.path.join(tmp, "repart")), table)
+            finally:
+                os.chdir(cwd)
+        if rc:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        return table
+
+    @staticmethod
+    def configuration(n_kmers, kmer_bytes=8, nb_cores=1, max_memory_mb=5000, max_disk_mb=None, max_open_files=None):
+        """nb_passes / nb_partitions as ConfigurationAlgorithm computes them (kmer/impl/ConfigurationAlgorithm.cpp:316-417):
+        volume = kmers * sizeof(Type) / MB; volume_minim = volume * 0.5 * 1.2; nb_passes = (volume/4)/max_disk + 1;
+        nb_partitions = (volume_per_pass * nb_partitions_in_parallel) / max_memory + 1, halving the partitions in parallel
+        (then adding passes) while the count reaches the open-file limit; finally rounded up to a multiple of the partitions
+        in parallel.  Defaults: 5000 MB, all cores in parallel."""
+        import resource
+        volume = max(n_kmers * kmer_bytes // (1 << 20), 1)
+        volume_minim = max(int(volume * 0.5 * 1.2), 1)
+        if max_disk_mb is None:
+            st = os.statvfs(os.getcwd())
+            avail = st.f_bavail * st.f_frsize // (1 << 20)
+            max_disk_mb = max(75 * avail // 100, avail - 2000) or 10000
+        if max_open_files is None:
+            max_open_files = resource.getrlimit(resource.RLIMIT_NOFILE)[0] // 2
+        nb_passes = (volume // 4) // max_disk_mb + 1
+        in_parallel = max(nb_cores, 1)
+        while True:
+            per_pass = volume_minim // nb_passes
+            nb_partitions = (per_pass * in_parallel) // max_memory_mb + 1
+            if nb_partitions >= max_open_files and in_parallel > 1:
+                in_parallel //= 2
+            elif nb_partitions >= max_open_files:
+                nb_passes += 1
+            else:
+                break
+        inc = (in_parallel - nb_partitions % in_parallel) % in_parallel        # rounded up to a multiple of the partitions in parallel (:422-425)
+        if max_open_files - nb_partitions > inc:
+            nb_partitions += inc
+        return nb_passes, nb_partitions
 
     def dsk(self, fasta_path, k, m, abundance_min=2, nb_cores=1, max_memory_mb=5000, minimizer_type=0, repartition_type=0):
         """Runs SortingCountAlgorithm on a FASTA/FASTQ file.  Returns dict(parts, repart, nb_partitions, ...)."""

@@ -123,3 +123,21 @@ def test_bloom_bytes_identical(oracle, reference, kind, words, k):
         b, bbits = reference.bloom(kind, bit_size, 4, k, words, lo, hi)
         assert abits == bbits and len(a) == len(b)
         assert (a == b).all(), (kind, bit_size)
+
+
+def test_configuration_arithmetic_matches_the_reference(reference, oracle, tmp_path):
+    # bench.py sizes its partitions with oracle_lib.Reference.configuration: it must give what ConfigurationAlgorithm gives
+    import oracle_lib
+    n, L, k = 30000, 100, 31
+    codes = oracle.synth_reads(9, n * L // 30, 0, n, L).reshape(n, L)
+    fa = tmp_path / "r.fa"
+    with open(fa, "wb") as f:
+        for i, r in enumerate(codes):
+            f.write(b">r%d\n" % i + oracle.codes_to_ascii(r) + b"\n")
+    for cores, mem in ((1, 5000), (4, 5000), (3, 1)):
+        res = reference.dsk(str(fa), k, 10, nb_cores=cores, max_memory_mb=mem)
+        want = (res["nb_passes"], res["nb_partitions"])
+        got = oracle_lib.Reference.configuration(n * (L - k + 1), 8, cores, max_memory_mb=mem, max_disk_mb=10 ** 7, max_open_files=10 ** 6)
+        assert got == want, (cores, mem, got, want)
+    table = reference.repartition(str(fa), k, 10, 24, 1, 2)
+    assert table.shape == (4 ** 10,) and int(table.max()) == 23 and len(np.unique(table)) == 24
