@@ -494,7 +494,8 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         if (n_ovf && W == 1 && (fused || k2b_variant (p->path_flags) == 1) && !no_tier2)
         {   // ---- further tiers: the bins a warp's 2^table_log2-slot table could not hold are counted by CTAs with 2048,
             //      then 8192 slots (k2b_count_w1 over a bin list); what still overflows goes to the global table ----
-            const int tier_log2[2] = { 11, 13 }, tier_counter[2] = { 7, 12 };
+            // (the claimed-slot lists of k2b_count_w1 are per warp, 3/32 of the table each: 4096 slots leave a warp 384 of them)
+            const int tier_log2[2] = { 12, 13 }, tier_counter[2] = { 7, 12 };
             for (int t = 0; t < 2 && n_ovf; t++)
             {
                 if (!fused && tier_log2[t] <= table_log2) continue;
@@ -541,10 +542,12 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
 
     // ---- k3: partition id + ascending order ----
     int t_bits = 0;
-    // buckets of ~256 k-mers on average: the top bits of CANONICAL values are far from uniform (a value starts with A or C far more
-    // often than with T or G), the fullest bucket of a key holds several times the average and must stay below the 4096 items a CTA
-    // sorts in shared memory / the block directory of the pooled scatter covers (measured: at 1024 the scatter fell back to two passes)
-    { uint64_t per_key = n_items / n_keys + 1; while (t_bits < 2*k && t_bits < 24 && (per_key >> t_bits) > 256) t_bits++; }
+    // buckets cut along the distribution of canonical values (k3_range_of).  One key: 512..1024 k-mers on average.  Several keys
+    // (GATB partitions): the k-mers of a partition share minimizers, their leading nucleotides are skewed key by key, and the
+    // fullest bucket must stay below the 4096 items a CTA sorts in shared memory / the block directory of the pooled scatter
+    // covers (measured at 176 partitions: an average of 768 or 1024 falls back to the two-pass scatter, 256 does not)
+    { const uint64_t avg = n_keys > 1 ? 256 : 1024;
+      uint64_t per_key = n_items / n_keys + 1; while (t_bits < 2*k - 1 && t_bits < 24 && (per_key >> t_bits) > avg) t_bits++; }
     while (t_bits > 0 && (n_keys << t_bits) > (1ULL << 30)) t_bits--;
     const uint64_t n_buckets = n_keys << t_bits;
     // result arrays live in context-owned slots (valid until the next count on this context): no per-call cudaMalloc

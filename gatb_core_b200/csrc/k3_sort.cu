@@ -56,10 +56,30 @@ __device__ __forceinline__ uint32_t gatb_minimizer_w2 (u128 v, int k, int m, uin
     return best;
 }
 
-// bucket = (partition key << t_bits) | top t_bits of the k-mer value
+// Value range of a bucket.  A canonical k-mer is the smaller of two (nearly) independent values, so as a fraction u of the value
+// range its density is 2(1-u): buckets cut at equal steps of the top bits would hold up to twice the average at the low end and
+// almost nothing at the high end.  Any MONOTONE map of the value keeps the concatenation of sorted buckets sorted, so the
+// bucket index follows the distribution function F(u) = 1 - (1-u)^2 = 2u - u^2 instead: u = the top U = min(2k, 31) bits,
+// F in 2U bits (strictly increasing in u), the top 'bits' of it.  The sorting kernel takes its sub-buckets from the SAME F with
+// more bits, so buckets and sub-buckets nest.  Exact integer arithmetic, one function for every kernel that needs it.
+__device__ __forceinline__ int k3_range_U (int k) { return 2 * k < 31 ? 2 * k : 31; }
+__device__ __forceinline__ uint64_t k3_range_of (uint32_t u, int U, int bits)
+{
+    const uint64_t F = (((uint64_t)u << (U + 1)) - (uint64_t)u * u);      // < 2^(2U)
+    return F >> (2 * U - bits);
+}
+// the top U bits of a 2k-bit value
+template<int W> __device__ __forceinline__ uint32_t k3_top_bits (uint64_t lo, uint64_t hi, int k, int U)
+{
+    const int s = 2 * k - U;
+    if (W == 1) return (uint32_t)(lo >> s);
+    return (uint32_t)(s >= 64 ? (hi >> (s - 64)) : (s ? ((lo >> s) | (hi << (64 - s))) : lo)) & (uint32_t)((1ULL << U) - 1);
+}
+// bucket = (partition key << t_bits) | range (top bits of the k-mer value)
 __device__ __forceinline__ uint32_t k3_bucket_of (const K3Params& P, uint64_t lo, uint64_t hi)
 {
     const int k = P.k, t = P.t_bits;
+    const int U = k3_range_U (k);
     uint32_t key = 0, topbits = 0;
     if (P.W == 1)
     {
@@ -68,7 +88,7 @@ __device__ __forceinline__ uint32_t k3_bucket_of (const K3Params& P, uint64_t lo
             const uint32_t mini = gatb_minimizer_w1 (lo, k, P.m, P.mmask, P.mask_ma1);
             key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
         }
-        if (t) topbits = (uint32_t)(lo >> (2*k - t));
+        if (t) topbits = (uint32_t) k3_range_of (k3_top_bits<1> (lo, 0, k, U), U, t);
     }
     else
     {
@@ -78,7 +98,7 @@ __device__ __forceinline__ uint32_t k3_bucket_of (const K3Params& P, uint64_t lo
             const uint32_t mini = gatb_minimizer_w2 (v, k, P.m, P.mmask, P.mask_ma1);
             key = (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
         }
-        if (t) { const int s = 2*k - t; topbits = (uint32_t)(s >= 64 ? (v.hi >> (s - 64)) : ((v.lo >> s) | (v.hi << (64 - s)))); }
+        if (t) topbits = (uint32_t) k3_range_of (k3_top_bits<2> (v.lo, v.hi, k, U), U, t);
     }
     return (key << t) | topbits;
 }
@@ -207,19 +227,17 @@ __global__ void __launch_bounds__(256) k3b_scatter (const K3Params P)
 }
 
 // ---- per-bucket sort in shared memory ------------------------------------------------------------------------------
-// The k-mers of a bucket share their top t_bits; below them the values are close to uniform.  So the bucket is sorted by
-// DISTRIBUTION: the next B bits (2^B >= n) pick a sub-bucket (shared-memory histogram, in-place scan, scatter with the
+// The k-mers of a bucket share the top t_bits of the distribution function of canonical values (k3_range_of); below them
+// it is close to uniform.  So the bucket is sorted by DISTRIBUTION: its next B bits (2^B >= n) pick a sub-bucket (shared-memory histogram, in-place scan, scatter with the
 // scanned counters as cursors), and inside a sub-bucket (about one k-mer on average) every k-mer finds its rank by
 // comparing itself with its few neighbours -- k-mers are distinct, so ranks are unique.  O(n) work, two block barriers.
 // A bucket with a crowded sub-bucket (skewed values) takes the bitonic network instead.
 #define K3_SUB_MAX 48
 template<int W>
-__device__ __forceinline__ uint32_t k3_sub_bucket (uint64_t lo, uint64_t hi, int shift, uint32_t mask)
+__device__ __forceinline__ uint32_t k3_sub_bucket (uint64_t lo, uint64_t hi, int k, int U, int bits, uint32_t mask)
 {
-    // bits [shift, shift+B) of the (hi:lo) value
-    if (W == 1) return (uint32_t)(lo >> shift) & mask;
-    if (shift >= 64) return (uint32_t)(hi >> (shift - 64)) & mask;
-    return (uint32_t)((shift ? ((lo >> shift) | (hi << (64 - shift))) : lo)) & mask;
+    // the B bits of the distribution function below the bucket's own t_bits (bits = t_bits + B): monotone in the value
+    return (uint32_t) k3_range_of (k3_top_bits<W> (lo, hi, k, U), U, bits) & mask;
 }
 
 template<int W>
@@ -256,8 +274,9 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
         }
         const int n = (int)n64;
         int np = 1, B = 0; while (np < n) { np <<= 1; B++; }
-        // value bits below the bucket's own t_bits: 2k - t_bits of them; the sub-bucket takes the top B of those
-        const int free_bits = 2 * P.k - P.t_bits;
+        // bits of the distribution function below the bucket's own t_bits: 2U - t_bits of them; the sub-bucket takes the top B of those
+        const int U = k3_range_U (P.k);
+        const int free_bits = 2 * U - P.t_bits;
         bool ranked = false;
         if (n == 1)
         {
@@ -266,14 +285,14 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
         }
         if (free_bits >= B)
         {
-            const int shift = free_bits - B; const uint32_t mask = (uint32_t)np - 1;
+            const int sbits = P.t_bits + B; const uint32_t mask = (uint32_t)np - 1;
             for (int i = tid; i < np; i += 256) s_off[i] = 0;
             if (tid == 0) s_max = 0;
             __syncthreads ();
             for (int i = tid; i < n; i += 256)
             {
                 uint64_t lo, hi; uint32_t c; fetch (b, beg, i, lo, hi, c);
-                atomicAdd (&s_off[k3_sub_bucket<W> (lo, hi, shift, mask)], 1u);
+                atomicAdd (&s_off[k3_sub_bucket<W> (lo, hi, P.k, U, sbits, mask)], 1u);
             }
             __syncthreads ();
             // in-place exclusive scan of np counters: every thread owns np/256 consecutive ones (np >= 256) or one (np < 256)
@@ -302,14 +321,14 @@ __global__ void __launch_bounds__(256) k3c_sort (const K3Params P)
                 for (int i = tid; i < n; i += 256)
                 {
                     uint64_t lo, hi; uint32_t c; fetch (b, beg, i, lo, hi, c);
-                    const uint32_t pos = atomicAdd (&s_off[k3_sub_bucket<W> (lo, hi, shift, mask)], 1u);
+                    const uint32_t pos = atomicAdd (&s_off[k3_sub_bucket<W> (lo, hi, P.k, U, sbits, mask)], 1u);
                     s_lo[pos] = lo; if (W == 2) s_hi[pos] = hi; s_c[pos] = c;
                 }
                 __syncthreads ();
                 for (int i = tid; i < n; i += 256)
                 {
                     const uint64_t lo = s_lo[i], hi = (W == 2) ? s_hi[i] : 0;
-                    const uint32_t sb = k3_sub_bucket<W> (lo, hi, shift, mask);
+                    const uint32_t sb = k3_sub_bucket<W> (lo, hi, P.k, U, sbits, mask);
                     const uint32_t e = s_off[sb], st0 = sb ? s_off[sb - 1] : 0;
                     uint32_t rank = 0;
                     for (uint32_t j = st0; j < e; j++)
