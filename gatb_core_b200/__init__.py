@@ -24,7 +24,7 @@ EXPORTS = ["gatb_gpu_create", "gatb_gpu_destroy", "gatb_gpu_last_error", "gatb_g
            "gatb_gpu_histogram_cutoff", "gatb_gpu_malloc", "gatb_gpu_free", "gatb_gpu_memcpy_h2d", "gatb_gpu_memcpy_d2h",
            "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii", "gatb_gpu_plan",
            "gatb_gpu_partition_into", "gatb_gpu_partition_range_into", "gatb_gpu_count_bins", "gatb_gpu_reads_begin",
-           "gatb_gpu_reads_push_ascii", "gatb_gpu_reads_count"]
+           "gatb_gpu_reads_push_ascii", "gatb_gpu_reads_count", "gatb_gpu_reads_push_text", "gatb_gpu_reads_info"]
 
 
 class GatbGpuError(RuntimeError):
@@ -80,6 +80,8 @@ def load_library():
     L.gatb_gpu_reads_begin.argtypes = [VP, U64]
     L.gatb_gpu_reads_push_ascii.argtypes = [VP, C.c_char_p, VP, U64]
     L.gatb_gpu_reads_count.argtypes = [VP, C.POINTER(Params), VP, VP, C.POINTER(Result)]
+    L.gatb_gpu_reads_push_text.argtypes = [VP, C.c_char_p, U64, I32]
+    L.gatb_gpu_reads_info.argtypes = [VP, VP]
     L.gatb_gpu_superkmers.argtypes = [VP, C.POINTER(Params), VP, VP, VP, U64, VP, C.POINTER(VP), VP, VP]
     L.gatb_gpu_free_host.argtypes = [VP]
     L.gatb_gpu_bloom_params.argtypes = [I32, U64, C.POINTER(U64), C.POINTER(C.c_int32)]
@@ -186,6 +188,23 @@ class GatbGpu:
             return self._unpack_host(res, params)
         finally:
             self.L.gatb_gpu_result_free(self.ctx, C.byref(res))
+
+    def count_text(self, batches, fmt, params, repart=None):
+        """FASTA (fmt=0) / FASTQ (fmt=1) text batches, cut at record boundaries, parsed and packed on the device; returns
+        (result like count(), info = [sequences, nucleotides, shortest, longest, sum of squares (float), invalid])."""
+        self._check(self.L.gatb_gpu_reads_begin(self.ctx, 0))
+        for text in batches:
+            self._check(self.L.gatb_gpu_reads_push_text(self.ctx, text, len(text), fmt))
+        info = np.zeros(6, np.uint64)
+        self._check(self.L.gatb_gpu_reads_info(self.ctx, _ptr(info)))
+        res = Result()
+        rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
+        self._check(self.L.gatb_gpu_reads_count(self.ctx, C.byref(params), _ptr(rp), None, C.byref(res)))
+        try:
+            out = self._unpack_host(res, params)
+        finally:
+            self.L.gatb_gpu_result_free(self.ctx, C.byref(res))
+        return out, [int(info[0]), int(info[1]), int(info[2]), int(info[3]), float(info[4:5].view(np.float64)[0]), int(info[5])]
 
     def count_dev(self, d_packed, d_offsets, n_reads, params, repart=None, d_n_mask=None):
         """Device pointers (ints) in; returns the raw Result (device arrays) -- free with result_free()."""

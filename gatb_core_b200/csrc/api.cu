@@ -947,6 +947,87 @@ int gatb_gpu_reads_push_ascii (gatb_gpu_ctx* ctx, const char* ascii, const uint6
     return 0;
 }
 
+// FASTA / FASTQ text parsed on the device (k_parse.cu): lines, records, offsets, packing
+int gatb_gpu_reads_push_text (gatb_gpu_ctx* ctx, const char* text, uint64_t n, int format)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (n == 0) return 0;
+    if (!text) return fail (ctx, "reads_push_text: NULL buffer");
+    if (format != GATB_TEXT_FASTA && format != GATB_TEXT_FASTQ) return fail (ctx, "reads_push_text: unknown format %d", format);
+    if (n >= (1ULL << 32)) return fail (ctx, "reads_push_text: batches of 4 GiB and more are not supported (cut the file into smaller batches)");
+    LaunchCtx L = lctx (ctx);
+    const uint64_t nblk = text_blocks (n);
+    // ---- text to the device, newline census ----
+    if (ensure (ctx, S_MISC, n + 64)) return 1;
+    if (ensure (ctx, S_TOTCUR, nblk * 4 + 64)) return 1;
+    if (ensure (ctx, S_COARSEOFF, (nblk + 1) * 8 + 64)) return 1;
+    if (ensure (ctx, S_SCAN, scan_scratch_elems (nblk > (n / 16 + 2) ? nblk : (n / 16 + 2)) * 8)) return 1;
+    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
+    char* d_text = (char*)ctx->slot[S_MISC];
+    CK (cudaMemcpyAsync (d_text, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK (launch_text_count_newlines (L, d_text, n, (uint32_t*)ctx->slot[S_TOTCUR]));
+    CK (launch_scan_u32_to_u64 (L, (const uint32_t*)ctx->slot[S_TOTCUR], (uint64_t*)ctx->slot[S_COARSEOFF], nblk, (uint64_t*)ctx->slot[S_SCAN]));
+    uint64_t n_newlines = 0; char last = 0;
+    CK (cudaMemcpyAsync (&n_newlines, (const uint64_t*)ctx->slot[S_COARSEOFF] + nblk, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    last = text[n - 1];
+    const uint64_t n_lines = n_newlines + (last == '\n' ? 0 : 1);
+    if (n_lines == 0) return 0;
+    // ---- line table: starts, sequence lengths, header flags; destinations and record indices by two scans ----
+    if (ensure (ctx, S_BUCKETOFF, (n_lines + 2) * 8)) return 1;            // line_start
+    if (ensure (ctx, S_BUCKETCNT, (n_lines + 2) * 4)) return 1;            // seq_len
+    if (ensure (ctx, S_BUCKETOF,  (n_lines + 2) * 4)) return 1;            // is_header
+    if (ensure (ctx, S_BIGLIST,   (n_lines + 2) * 8)) return 1;            // line_dst
+    if (ensure (ctx, S_MISC2,     (n_lines + 2) * 8)) return 1;            // line_rec
+    if (ensure (ctx, S_SCAN, scan_scratch_elems (n_lines + 1) * 8)) return 1;
+    uint64_t* d_ls = (uint64_t*)ctx->slot[S_BUCKETOFF];
+    CK (cudaMemsetAsync (d_ls, 0, 8, ctx->stream));
+    CK (launch_text_line_starts (L, d_text, n, (const uint64_t*)ctx->slot[S_COARSEOFF], d_ls));
+    uint32_t* d_len = (uint32_t*)ctx->slot[S_BUCKETCNT]; uint32_t* d_hdr = (uint32_t*)ctx->slot[S_BUCKETOF];
+    uint64_t* d_dst = (uint64_t*)ctx->slot[S_BIGLIST];   uint64_t* d_rec = (uint64_t*)ctx->slot[S_MISC2];
+    CK (launch_text_lines (L, d_text, n, d_ls, n_lines, format, d_len, d_hdr));
+    CK (launch_scan_u32_to_u64 (L, d_len, d_dst, n_lines, (uint64_t*)ctx->slot[S_SCAN]));
+    CK (launch_scan_u32_to_u64 (L, d_hdr, d_rec, n_lines, (uint64_t*)ctx->slot[S_SCAN]));
+    uint64_t tot[2] = { 0, 0 };
+    CK (cudaMemcpyAsync (&tot[0], d_dst + n_lines, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaMemcpyAsync (&tot[1], d_rec + n_lines, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    const uint64_t total_nt = tot[0], n_recs = tot[1];
+    if (n_recs == 0) return total_nt ? fail (ctx, "reads_push_text: sequence data without a record header (batches must start at a record)") : 0;
+    // ---- append: offsets, packed nucleotides, invalid mask ----
+    const uint64_t base = ctx->push_nt, total = base + total_nt;
+    if (grow_keep (ctx, S_READS, total / 4 + 256, base / 4 + 8)) return 1;
+    if (grow_keep (ctx, S_NMASK, total / 8 + 256, base / 8 + 8)) return 1;
+    if (grow_keep (ctx, S_OFFSETS, (ctx->push_seqs + n_recs + 1) * 8 + 64, (ctx->push_seqs + 1) * 8)) return 1;
+    unsigned long long* d_bad = (unsigned long long*)ctx->slot[S_STATS] + 40;
+    CK (cudaMemsetAsync (d_bad, 0, 8, ctx->stream));
+    CK (launch_text_offsets (L, d_hdr, d_dst, d_rec, n_lines, base, (uint64_t*)ctx->slot[S_OFFSETS] + ctx->push_seqs, n_recs, total_nt));
+    CK (launch_text_pack (L, d_text, d_ls, d_dst, n_lines, total_nt, base, (uint32_t*)ctx->slot[S_READS], (uint32_t*)ctx->slot[S_NMASK], d_bad));
+    unsigned long long bad = 0;
+    CK (cudaMemcpyAsync (&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    ctx->push_invalid += bad; ctx->push_nt = total; ctx->push_seqs += n_recs;
+    return 0;
+}
+
+// what was pushed so far: [0] sequences [1] nucleotides [2] shortest [3] longest [4] sum of squared lengths (double) [5] invalid nucleotides
+int gatb_gpu_reads_info (gatb_gpu_ctx* ctx, uint64_t* info6)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (!info6) return fail (ctx, "reads_info: NULL output");
+    if (ensure (ctx, S_STATS, 64 * 8)) return 1;
+    unsigned long long* d = (unsigned long long*)ctx->slot[S_STATS] + 44;
+    unsigned long long h[3] = { ~0ULL, 0, 0 };
+    CK (cudaMemcpyAsync (d, h, 24, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->push_seqs) CK (launch_text_stats (lctx (ctx), (const uint64_t*)ctx->slot[S_OFFSETS], ctx->push_seqs, d));
+    CK (cudaMemcpyAsync (h, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    info6[0] = ctx->push_seqs; info6[1] = ctx->push_nt; info6[2] = ctx->push_seqs ? h[0] : 0; info6[3] = h[1]; info6[4] = h[2]; info6[5] = ctx->push_invalid;
+    return 0;
+}
+
 int gatb_gpu_reads_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_table, const uint32_t* freq_order, gatb_gpu_result* out)
 {
     if (!ctx) return 1;

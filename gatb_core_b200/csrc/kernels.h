@@ -163,3 +163,14 @@ cudaError_t launch_rebase_offsets (const LaunchCtx&, const uint64_t* in, uint64_
 // k2_fused.cu
 size_t      k2f_smem_bytes (int table_log2, int nwarp);
 cudaError_t launch_k2f_count (const LaunchCtx&, const K2Params&, const K2aSrc&, uint32_t nb, uint32_t cap, uint32_t n_bins, int dedup);
+// k_parse.cu (FASTA / FASTQ text on the device)
+uint64_t    text_blocks (uint64_t n);
+cudaError_t launch_text_count_newlines (const LaunchCtx&, const char* text, uint64_t n, uint32_t* block_counts);
+cudaError_t launch_text_line_starts (const LaunchCtx&, const char* text, uint64_t n, const uint64_t* block_off, uint64_t* line_start);
+cudaError_t launch_text_lines (const LaunchCtx&, const char* text, uint64_t n, const uint64_t* line_start, uint64_t n_lines, int format,
+                               uint32_t* seq_len, uint32_t* is_header);
+cudaError_t launch_text_offsets (const LaunchCtx&, const uint32_t* is_header, const uint64_t* line_dst, const uint64_t* line_rec, uint64_t n_lines,
+                                 uint64_t base, uint64_t* out, uint64_t n_recs, uint64_t total_nt);
+cudaError_t launch_text_pack (const LaunchCtx&, const char* text, const uint64_t* line_start, const uint64_t* line_dst, uint64_t n_lines,
+                              uint64_t total_nt, uint64_t base, uint32_t* words, uint32_t* nmask, unsigned long long* n_invalid);
+cudaError_t launch_text_stats (const LaunchCtx&, const uint64_t* offsets, uint64_t n, unsigned long long* out);

@@ -145,8 +145,16 @@ void gatb_gpu_result_free (gatb_gpu_ctx*, gatb_gpu_result*);
  *   gatb_gpu_reads_begin        forgets the reads pushed so far (expected_nt: capacity hint, may be 0)
  *   gatb_gpu_reads_push_ascii   n_seqs sequences concatenated without separators in ascii[seq_offsets[0] .. seq_offsets[n_seqs]);
  *                               characters other than ACGTacgt are invalid nucleotides (their k-mers are dropped)
- *   gatb_gpu_reads_count        gatb_gpu_count over everything pushed: host arrays out, same ownership rules */
+ *   gatb_gpu_reads_count        gatb_gpu_count over everything pushed: host arrays out, same ownership rules
+ *   gatb_gpu_reads_push_text    a batch of FASTA (multi-line records) or FASTQ (four-line records) TEXT, cut by the caller at record
+ *                               boundaries; lines, records, offsets and the packing are found on the device (k_parse.cu) -- the
+ *                               device-side replacement of the reference's line parser bank/impl/BankFasta.cpp:391-620
+ *   gatb_gpu_reads_info         what was pushed so far: [0] sequences [1] nucleotides [2] shortest [3] longest record
+ *                               [4] sum of squared lengths (bits of a double) [5] invalid nucleotides (BankStats, kmer/impl/BankKmers.hpp:164-215) */
+enum { GATB_TEXT_FASTA = 0, GATB_TEXT_FASTQ = 1 };
 int gatb_gpu_reads_begin (gatb_gpu_ctx*, uint64_t expected_nt);
+int gatb_gpu_reads_push_text (gatb_gpu_ctx*, const char* text, uint64_t n_bytes, int format);
+int gatb_gpu_reads_info (gatb_gpu_ctx*, uint64_t* info6);
 int gatb_gpu_reads_push_ascii (gatb_gpu_ctx*, const char* ascii, const uint64_t* seq_offsets, uint64_t n_seqs);
 int gatb_gpu_reads_count (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* repart_table, const uint32_t* freq_order,
                           gatb_gpu_result* out);

@@ -96,6 +96,63 @@ static void push_bank (gatb_gpu_ctx* ctx, tools::dp::Iterator<bank::Sequence>* i
     itSeq->finalize ();
 }
 
+/* ---- stage 1, fast path: the bank is ONE plain FASTA / FASTQ file.  The file is read in batches cut at record boundaries and
+ * parsed on the device (gatb_gpu_reads_push_text): the serial line parser of the reference (BankFasta.cpp:391-620, under the
+ * iterator lock of ICommand.hpp:313-319) is out of the way.  Returns false when the bank is something else (gzip, album,
+ * several files, in-memory bank): the caller then iterates it through the reference's own iterator. ---- */
+static bool push_plain_file (gatb_gpu_ctx* ctx, bank::IBank* bank, BankStats& stats, tools::dp::IteratorListener* progress)
+{
+    if (getenv ("GATB_GPU_NO_TEXT_PARSER")) return false;
+    const std::string path = bank->getId ();
+    if (path.empty () || path.find (',') != std::string::npos) return false;
+    if (bank->getCompositionNb () > 1) return false;
+    FILE* f = fopen (path.c_str (), "rb");
+    if (!f) return false;
+    unsigned char magic[2] = { 0, 0 };
+    const size_t got = fread (magic, 1, 2, f);
+    int format = -1;
+    if (got == 2 && magic[0] == '>') format = GATB_TEXT_FASTA; else if (got == 2 && magic[0] == '@') format = GATB_TEXT_FASTQ;
+    if (format < 0) { fclose (f); return false; }                          /* gzip (1f 8b), empty, binary bank, album ... */
+    fseek (f, 0, SEEK_SET);
+    const size_t BATCH = 256u << 20;
+    std::vector<char> buf (BATCH + (8u << 20));
+    size_t have = 0; bool eof = false;
+    check (ctx, gatb_gpu_reads_begin (ctx, 0), "gatb_gpu_reads_begin");
+    while (!eof || have)
+    {
+        if (!eof) { const size_t r = fread (buf.data () + have, 1, BATCH - have, f); have += r; if (r == 0 || have < BATCH) eof = true; }
+        if (have == 0) break;
+        size_t cut = have;
+        if (!eof)
+        {   /* last record boundary inside the batch: "\n>" (FASTA) / a line starting with '@' whose line after next starts with '+' (FASTQ) */
+            cut = 0;
+            for (size_t i = have - 1; i > 0; i--)
+            {
+                if (buf[i - 1] != '\n') continue;
+                if (format == GATB_TEXT_FASTA) { if (buf[i] == '>') { cut = i; break; } continue; }
+                if (buf[i] != '@') continue;
+                const char* l1 = (const char*) memchr (buf.data () + i, '\n', have - i);
+                if (!l1) continue;
+                const char* l2 = (const char*) memchr (l1 + 1, '\n', buf.data () + have - (l1 + 1));
+                if (!l2 || l2 + 1 >= buf.data () + have) continue;
+                if (l2[1] == '+') { cut = i; break; }
+            }
+            if (cut == 0) { fclose (f); throw system::Exception ("GPU k-mer counting: no record boundary inside a %zu-byte batch of %s", have, path.c_str ()); }
+        }
+        check (ctx, gatb_gpu_reads_push_text (ctx, buf.data (), cut, format), "gatb_gpu_reads_push_text");
+        if (progress) progress->inc (cut);
+        memmove (buf.data (), buf.data () + cut, have - cut);
+        have -= cut;
+    }
+    fclose (f);
+    uint64_t info[6];
+    check (ctx, gatb_gpu_reads_info (ctx, info), "gatb_gpu_reads_info");
+    stats.sequencesNb = info[0]; stats.sequencesTotalLength = info[1];
+    stats.sequencesMinLength = info[0] ? info[2] : ~0; stats.sequencesMaxLength = info[3];
+    double sq; memcpy (&sq, &info[4], 8); stats.sequencesTotalLengthSquare = (u_int64_t) sq;
+    return true;
+}
+
 /* ---- stage 2: one partition replayed through a processor clone (one command per partition, like PartitionsCommand) ---- */
 template<size_t span>
 class ReplayCommand : public tools::dp::ICommand, public system::SmartPointer
@@ -144,7 +201,9 @@ template<> void SortingCountAlgorithm<SPAN>::fillPartitions (size_t pass, Iterat
         run.close ();                                                                                                                \
         run.ctx = gatb_gpu_create (gpu_dsk::device_id ());                                                                           \
         if (run.ctx == 0)  throw Exception ("GPU k-mer counting: %s", gatb_gpu_last_error (0));                                      \
-        gpu_dsk::push_bank (run.ctx, itSeq, _bankStats, _progress);                                                                  \
+        if (!gpu_dsk::push_plain_file (run.ctx, _bank, _bankStats, _progress))                                                       \
+            gpu_dsk::push_bank (run.ctx, itSeq, _bankStats, _progress);                                                              \
+        else  itSeq->finalize ();                                                                                                    \
         gatb_gpu_params p;  memset (&p, 0, sizeof(p));                                                                               \
         p.kmer_size = _config._kmerSize;  p.minimizer_size = _config._minim_size;                                                    \
         p.nb_partitions = _config._nb_partitions;  p.nb_passes = _config._nb_passes;                                                 \

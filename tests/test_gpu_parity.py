@@ -220,6 +220,40 @@ def test_streaming_input_equals_one_shot(gpu, oracle, name):
     assert got["stats"] == want["stats"] or all(got["stats"][k] == want["stats"][k] for k in ("kmers_nb_valid", "kmers_nb_invalid", "kmers_nb_distinct", "kmers_nb_solid", "sequences", "nucleotides"))
 
 
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+def test_text_parsed_on_the_device_equals_packed_input(gpu, oracle, fmt):
+    # gatb_gpu_reads_push_text: FASTA (multi-line records, CRLF, lower case, N, empty records, blank lines) and four-line FASTQ,
+    # in several batches cut at record boundaries, against the same sequences packed on the host
+    fx = fixtures.Fixture("dsk_k31_parts", oracle)
+    rng = np.random.default_rng(11)
+    seqs = [s if i % 5 else s.lower() for i, s in enumerate(fx.seqs)] + [b"", b"ACGTNNNNACGT" * 9, b"a", b"ACGT" * 40]
+    recs = []
+    for i, sq in enumerate(seqs):
+        if fmt == "fasta":
+            w = int(rng.integers(20, 90)) if i % 3 == 0 else 10 ** 6
+            eol = b"\r\n" if i % 7 == 0 else b"\n"
+            body = b"".join(sq[a:a + w] + eol for a in range(0, len(sq), w)) if sq else b""
+            recs.append(b">read_%d some text > with @ signs" % i + eol + body + (b"\n" if i % 13 == 0 else b""))
+        else:
+            recs.append(b"@read_%d\n" % i + sq + b"\n+\n" + bytes(rng.integers(33, 74, len(sq), dtype=np.uint8)) + b"\n")
+    if fmt == "fasta":
+        recs[-1] = recs[-1].rstrip(b"\n")                     # a file that does not end with a newline
+    cuts = sorted(set([0, len(recs)] + [int(c) for c in rng.integers(0, len(recs), 5)]))
+    batches = [b"".join(recs[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, nb_passes=fx.nb_passes, abundance_min=fx.abundance_min)
+    got, info = gpu.count_text(batches, 0 if fmt == "fasta" else 1, params, repart=fx.repart)
+    up = [s.upper() for s in seqs]
+    packed, offs, mask = pack_seqs(oracle, up)
+    want = gpu.count(packed, offs, len(up), params, repart=fx.repart, n_mask=mask)
+    nkeys = fx.nb_partitions * fx.nb_passes
+    check_parts(got, want["parts"], nkeys, fx.words)
+    assert (got["histogram"] == want["histogram"]).all()
+    lens = [len(s) for s in seqs]
+    assert info[:4] == [len(seqs), sum(lens), min(lens), max(lens)] and info[4] == float(sum(l * l for l in lens))
+    assert info[5] == sum(c not in b"ACGTacgt" for s in seqs for c in s)
+    assert got["stats"]["sequences"] == len(seqs) and got["stats"]["kmers_nb_invalid"] == want["stats"]["kmers_nb_invalid"]
+
+
 def test_reference_golden_vectors_dsk(gpu, oracle):
     # TestDSK.cpp:147-241 (solid counts) and :244-341 (exact set + checksum)
     for seqs, k, nks, expected in G.DSK1_CASES:

@@ -25,7 +25,7 @@ def build():
         pytest.skip("integration/_build lacks %s (built where /root/reference exists)" % missing)
 
 
-def write_fasta(oracle, path, n, L, seed, with_n=False):
+def write_fasta(oracle, path, n, L, seed, with_n=False, fastq=False):
     codes = oracle.synth_reads(seed, n * L // 30, 0, n, L).reshape(n, L)
     rng = np.random.default_rng(seed)
     with open(path, "wb") as f:
@@ -33,16 +33,18 @@ def write_fasta(oracle, path, n, L, seed, with_n=False):
             s = bytearray(oracle.codes_to_ascii(r))
             if with_n and i % 7 == 0:
                 s[int(rng.integers(0, L))] = ord("N")
-            if i % 11 == 0:                                   # multi-line records, like real FASTA files
+            if fastq:
+                f.write(b"@r%d\n" % i + bytes(s) + b"\n+\n" + bytes(rng.integers(33, 74, len(s), dtype=np.uint8)) + b"\n")
+            elif i % 11 == 0:                                 # multi-line records, like real FASTA files
                 f.write(b">r%d some comment\n" % i + bytes(s[:60]) + b"\n" + bytes(s[60:]) + b"\n")
             else:
                 f.write(b">r%d\n" % i + bytes(s) + b"\n")
 
 
-def run_tool(tool, fasta, out, k, extra, abundance_min=2):
+def run_tool(tool, fasta, out, k, extra, abundance_min=2, env=None):
     cmd = [os.path.join(BUILD, tool), "-in", fasta, "-kmer-size", str(k), "-abundance-min", str(abundance_min), "-out", out,
            "-out-dir", os.path.dirname(out), "-out-tmp", os.path.dirname(out), "-storage-type", "file", "-verbose", "0"] + extra
-    return subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(out))
+    return subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(out), env=dict(os.environ, **(env or {})))
 
 
 def test_integration_builds_and_has_no_cpu_fallback(oracle, tmp_path):
@@ -73,7 +75,11 @@ def test_integration_builds_and_has_no_cpu_fallback(oracle, tmp_path):
     assert int(info["kmers_nb_distinct"]) == int(want["stats"][2]) and int(info["kmers_nb_solid"]) == int(want["stats"][3])
 
 
+# the GPU build reads a plain FASTA / FASTQ file itself and parses it on the device; "_bank_iterator" cases force the other
+# route (the reference's own bank iterator feeding ASCII batches), which is what gzip files, albums and in-memory banks take
 CASES = [("k21_cores4", 21, 100, ["-nb-cores", "4"], False),
+         ("k31_fastq", 31, 150, ["-nb-cores", "4"], True),
+         ("k31_bank_iterator", 31, 150, ["-nb-cores", "2"], True),
          ("k31_default", 31, 150, [], False),
          ("k31_three_passes_with_N", 31, 150, ["-max-disk", "1", "-nb-cores", "2"], True),
          ("k31_m8_small_memory", 31, 150, ["-minimizer-size", "8", "-max-memory", "100", "-nb-cores", "3"], True),
@@ -85,13 +91,14 @@ CASES = [("k21_cores4", 21, 100, ["-nb-cores", "4"], False),
 @pytest.mark.parametrize("name,k,L,extra,with_n", CASES, ids=[c[0] for c in CASES])
 def test_gatb_tool_on_gpu_equals_reference_build(oracle, tmp_path, name, k, L, extra, with_n):
     build()
-    fa = str(tmp_path / "reads.fa")
-    write_fasta(oracle, fa, 20000, L, 100 + k, with_n)
+    fastq = name.endswith("fastq")
+    fa = str(tmp_path / ("reads.fq" if fastq else "reads.fa"))
+    write_fasta(oracle, fa, 20000, L, 100 + k, with_n, fastq)
     outs = {}
     for tool in ("dsk_tool_cpu", "dsk_tool_gpu"):
         d = tmp_path / tool
         d.mkdir()
-        r = run_tool(tool, fa, str(d / "x"), k, extra)
+        r = run_tool(tool, fa, str(d / "x"), k, extra, env={"GATB_GPU_NO_TEXT_PARSER": "1"} if name.endswith("bank_iterator") else None)
         assert r.returncode == 0, tool + ": " + r.stdout + r.stderr
         outs[tool] = str(d / "x")
     for suffix in (".solid.txt", ".histo.txt", ".info.txt", ".all.txt"):
