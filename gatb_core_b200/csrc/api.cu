@@ -273,8 +273,9 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     else
     {
         const uint64_t occ_per_bin = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : (W == 1 ? 80 : 55))) / 100 + 1;
-        // k <= 31: one more fine-bin bit per doubling of the ranks, so that nb1 (the coarse bins every rank scatters into) stays put
-        if (W == 1) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
+        // k <= 31: the coarse bins keep their size whatever the number of ranks (a gathered bin must fit the shared memory of the
+        // dedup split, k2a_dedup_split), so nb1 -- the bins every rank scatters into -- grows with the job: 3.7 million at 8 GPUs
+        // and 8*10^8 reads, a rank's piece of a bin is a few blocks of 64 records.  (Round 1 kept nb1 fixed and grew the bins.)
         uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
         nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits;
     }

@@ -210,11 +210,22 @@ def bench(args, rank, world, local):
     torch.cuda.synchronize()          # the zero fill runs on torch's stream, the library works on its own: order them
     gpu.synth_reads_dev(SEED, genome, rank * n, n, L, reads.data_ptr())
     gpu.synchronize()
-    params = gpu.make_params(K, M, abundance_min=ABUNDANCE_MIN, read_len=L)
+    # the partitioning the reference would use for the WHOLE job (bench.reference_configuration: ConfigurationAlgorithm's
+    # arithmetic + the reference's RepartitorAlgorithm on a sample), computed on rank 0 outside the timed region and broadcast
+    from bench import reference_configuration
     total_kmers = n_global * (L - K + 1)
+    if rank == 0:
+        cfg = reference_configuration(gpu, n_global, args)
+    else:
+        cfg = None
+    box = [cfg]
+    dist.broadcast_object_list(box, src=0)
+    nb_passes, nb_partitions, repart, repart_src = box[0]
+    params = gpu.make_params(K, M, nb_partitions=nb_partitions, nb_passes=nb_passes, abundance_min=ABUNDANCE_MIN, read_len=L,
+                             path_flags=args.path_flags, bin_load_pct=args.bin_load_pct, table_log2=args.table_log2, fine_bits=args.fine_bits)
 
     def step(timers=None):
-        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, timers=timers)
+        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, timers=timers)
         gpu.result_free(res)
         return stats
 
@@ -252,13 +263,13 @@ def bench(args, rank, world, local):
         reads.copy_(h_reads, non_blocking=True)
         torch.cuda.synchronize()
         t1 = time.time()
-        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world)
+        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart)
         t2 = time.time()
         host = result_to_pinned(gpu, res, params)
         gpu.result_free(res)
         if rank == 0 and os.environ.get("GATB_BENCH_DEBUG"):
             print("e2e step %d: h2d %.1f ms, count %.1f ms, d2h %.1f ms" % (i, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.time() - t2) * 1e3), file=__import__("sys").stderr)
-        d2h_bytes = int(host["n_items"]) * 12 + (10001 + 2) * 8
+        d2h_bytes = int(host["n_items"]) * 12 + (10001 + nb_passes * nb_partitions + 1) * 8
         el2 = torch.tensor([time.time() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(el2, op=dist.ReduceOp.MAX)
         if i >= 1:
@@ -272,7 +283,9 @@ def bench(args, rank, world, local):
         hist = np.asarray(host["histogram"], dtype=np.int64)
         ni = int(host["n_items"])
         cnt, lo = host["counts"][:ni], host["kmers_lo"][:ni]
-        asc = ni < 2 or bool((lo[1:] > lo[:-1]).all())       # k <= 31: one 64-bit word per k-mer
+        offs = np.asarray(host["part_offsets"], dtype=np.int64)
+        desc = np.nonzero(lo[1:] <= lo[:-1])[0] + 1 if ni > 1 else np.zeros(0, np.int64)
+        asc = bool(np.isin(desc, offs).all())                # ascending inside every partition key (k <= 31: one word per k-mer)
         local = [int(hist.sum()), sum(c * int(hist[c]) for c in range(ABUNDANCE_MIN)) + int(cnt.sum(dtype=np.int64)),
                  int(hist[ABUNDANCE_MIN:].sum()), ni, 0 if asc else 1]
     except Exception:                                        # never let the checker take the measurement down
@@ -298,8 +311,9 @@ def bench(args, rank, world, local):
         line = {"metric": METRIC, "value": stats["kmers_nb_distinct"] / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic",
-                "config": {"workload": "k=31, %d synthetic 150bp reads (%d per GPU), %dxB200, minimizer buckets sharded via NCCL all-to-all, m=10, abundance-min=2" % (n_global, n, world),
-                           "reads": n_global, "genome_nt": genome, "coverage": COVERAGE, "error_rate": 0.01,
+                "config": {"workload": "k=31, %d synthetic 150bp reads (%d per GPU), %dxB200, minimizer buckets sharded via NCCL all-to-all, m=10, abundance-min=2, "
+                                       "%d partitions x %d pass(es) (the reference's own configuration)" % (n_global, n, world, nb_partitions, nb_passes),
+                           "reads": n_global, "nb_partitions": nb_partitions, "nb_passes": nb_passes, "repartitor": repart_src, "genome_nt": genome, "coverage": COVERAGE, "error_rate": 0.01,
                            "l2": "per-GPU inputs (%.1f GB packed reads) far exceed the 126 MB L2" % (nbytes / 1e9)},
                 "input_bases_per_s": n_global * L / per_step, "kmer_occurrences_per_s": stats["kmers_nb_valid"] / per_step,
                 "distinct": stats["kmers_nb_distinct"], "solid": stats["kmers_nb_solid"], "records": stats["records"],

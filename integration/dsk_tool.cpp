@@ -10,6 +10,8 @@
  *     <out>.solid.txt   partition by partition, "p kmer abundance" of Partition<Count>* getSolidCounts()
  *     <out>.histo.txt   the histogram collection the default chain saved into the storage
  *     <out>.info.txt    kmers_nb_valid / kmers_nb_invalid / kmers_nb_distinct / kmers_nb_solid / nb_partitions / nb_passes
+ * With -storage-type hdf5 (the default) the <out>.h5 file is then re-opened from disk and dumped:
+ *     <out>.h5dump.txt  dsk/solid/<p> datasets, dsk attributes, histogram/histogram, a checksum of minimizers/minimRepart
  * Run 2 (a custom ICountProcessor added with addProcessor(), the kmer12 pattern): every distinct k-mer with its count
  *     <out>.all.txt     "key kmer count", key = pass * nb_partitions + partition, in the order process() was called
  */
@@ -80,6 +82,30 @@ template<size_t span>  struct MainLoop  {  void operator () (IProperties* option
         fi << "nb_partitions " << algo.getConfig()._nb_partitions << "\nnb_passes " << algo.getConfig()._nb_passes << "\n";
         fi << "solid_iterated " << nbSolid << "\n";
         cout << "run 1 (default chain): " << nbSolid << " solid k-mers in " << solid->size() << " partitions" << endl;
+    }
+    /* ---- the .h5 file itself, re-opened from disk the way Graph::load / Graph::create -in x.h5 consume it
+     *      (debruijn/impl/Graph.cpp:151-235, 778-803): dsk/solid/<p> datasets + group attributes, histogram, minimizers/minimRepart ---- */
+    if (options->getStr (STR_STORAGE_TYPE) == "hdf5")
+    {
+        Storage* storage = StorageFactory (STORAGE_HDF5).load (out);  LOCAL (storage);
+        ofstream fd ((out + ".h5dump.txt").c_str());
+        Group& dsk = storage->getGroup ("dsk");
+        fd << "dsk.kmer_size " << dsk.getProperty ("kmer_size") << "\n";
+        Partition<Count>& solid = dsk.getPartition<Count> ("solid");
+        fd << "dsk/solid partitions " << solid.size() << " items " << solid.getNbItems() << "\n";
+        for (size_t p = 0; p < solid.size(); p++)
+        {
+            Iterator<Count>* it = solid[p].iterator ();  LOCAL (it);
+            for (it->first(); !it->isDone(); it->next())  { fd << p << " " << it->item().value.toString (k) << " " << it->item().abundance << "\n"; }
+        }
+        Iterable<gatb::core::tools::misc::IHistogram::Entry>& histo = storage->getGroup ("histogram").getCollection<gatb::core::tools::misc::IHistogram::Entry> ("histogram");
+        Iterator<gatb::core::tools::misc::IHistogram::Entry>* ih = histo.iterator ();  LOCAL (ih);
+        for (ih->first(); !ih->isDone(); ih->next())  { if (ih->item().abundance) fd << "histogram " << ih->item().index << " " << ih->item().abundance << "\n"; }
+        Repartitor repart;  repart.load (storage->getGroup ("minimizers"));
+        u_int64_t sum = 0;  const u_int64_t nbm = (u_int64_t)1 << (2 * options->getInt (STR_MINIMIZER_SIZE));
+        for (u_int64_t i = 0; i < nbm; i++)  { sum = sum * 1000003ULL + repart (i); }
+        fd << "minimRepart passes " << repart.getNbPasses() << " checksum " << sum << "\n";
+        cout << "re-opened " << out << ".h5: " << solid.getNbItems() << " solid k-mers in " << solid.size() << " datasets" << endl;
     }
     /* ---- run 2: a custom count processor (kmer12.cpp pattern) ---- */
     {

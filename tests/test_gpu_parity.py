@@ -427,3 +427,46 @@ def test_staged_multi_gpu_path_on_one_rank(gpu, oracle):
     check_parts(got, want["parts"], fx.nb_partitions, 1)
     assert (got["histogram"] == want["histogram"]).all()
     assert stats["kmers_nb_distinct"] == want["stats"]["kmers_nb_distinct"]
+
+
+# ---- BASELINE.json configs 3 and 4 at a down-sampled size, against the REFERENCE itself (oracle/_ref: SortingCountAlgorithm on all
+#      host cores with its own configuration and Repartitor table): same generator and seeds as SURVEY.md 8d, n / 1000 ----
+@pytest.mark.parametrize("name,k,L,n,seed", [("cfg3_k31", 31, 150, 1000000, 43), ("cfg4_k63", 63, 250, 500000, 44)])
+def test_downsampled_configs_against_the_reference(gpu, oracle, reference, tmp_path, name, k, L, n, seed):
+    codes = oracle.synth_reads(seed, n * L // 30, 0, n, L)
+    fa = tmp_path / "reads.fa"
+    with open(fa, "wb") as f:
+        block = np.empty((n, 3 + L + 1), np.uint8)
+        block[:, :3] = np.frombuffer(b">r\n", np.uint8)
+        block[:, 3:3 + L] = np.frombuffer(b"ACTG", np.uint8)[codes].reshape(n, L)
+        block[:, -1] = ord("\n")
+        f.write(block.tobytes())
+    ref = reference.dsk(str(fa), k, 10, abundance_min=2, nb_cores=4)
+    nparts, npass = ref["nb_partitions"], ref["nb_passes"]
+    packed = pad(oracle.pack_2bit(codes))
+    params = gpu.make_params(k, 10, nb_partitions=nparts, nb_passes=npass, abundance_min=2, read_len=L, emit_all=True)
+    got = gpu.count(packed, None, n, params, repart=ref["repart"])
+    assert got["stats"]["kmers_nb_distinct"] == ref["nb_distinct"]
+    for key in range(nparts * npass):
+        lo, hi, cn = ref["parts"][key]
+        glo, ghi, gcn = got["parts"][key]
+        assert len(lo) == len(glo) and (lo == glo).all() and (cn == gcn).all(), (name, key)
+        if k > 31:
+            assert (hi == ghi).all(), (name, key)
+
+
+def test_multi_gpu_equals_single_gpu():
+    """torchrun of tools/check_multigpu.py on every visible GPU (at most 8): the sharded count, merged per partition, must equal
+    the single-GPU count bit for bit, k = 31 and k = 63.  Skipped on a one-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    if n < 2:
+        pytest.skip("one GPU visible")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                        "--master-port", "29733", os.path.join(root, "tools", "check_multigpu.py")], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("GPUs == 1 GPU") == 2, r.stdout[-2000:]

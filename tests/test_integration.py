@@ -41,9 +41,9 @@ def write_fasta(oracle, path, n, L, seed, with_n=False, fastq=False):
                 f.write(b">r%d\n" % i + bytes(s) + b"\n")
 
 
-def run_tool(tool, fasta, out, k, extra, abundance_min=2, env=None):
+def run_tool(tool, fasta, out, k, extra, abundance_min=2, env=None, storage="hdf5"):
     cmd = [os.path.join(BUILD, tool), "-in", fasta, "-kmer-size", str(k), "-abundance-min", str(abundance_min), "-out", out,
-           "-out-dir", os.path.dirname(out), "-out-tmp", os.path.dirname(out), "-storage-type", "file", "-verbose", "0"] + extra
+           "-out-dir", os.path.dirname(out), "-out-tmp", os.path.dirname(out), "-storage-type", storage, "-verbose", "0"] + extra
     return subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(out), env=dict(os.environ, **(env or {})))
 
 
@@ -58,6 +58,7 @@ def test_integration_builds_and_has_no_cpu_fallback(oracle, tmp_path):
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
     # the reference build of the same tool agrees with the oracle port on the number of distinct / solid k-mers
     r = run_tool("dsk_tool_cpu", fa, str(tmp_path / "c"), 21, ["-nb-cores", "2"])
+    assert os.path.getsize(str(tmp_path / "c.h5dump.txt")) > 0
     assert r.returncode == 0, r.stdout + r.stderr
     info = dict(l.split() for l in open(str(tmp_path / "c.info.txt")))
     seqs = [l.strip() for l in open(fa, "rb") if not l.startswith(b">")]
@@ -98,10 +99,15 @@ def test_gatb_tool_on_gpu_equals_reference_build(oracle, tmp_path, name, k, L, e
     for tool in ("dsk_tool_cpu", "dsk_tool_gpu"):
         d = tmp_path / tool
         d.mkdir()
-        r = run_tool(tool, fa, str(d / "x"), k, extra, env={"GATB_GPU_NO_TEXT_PARSER": "1"} if name.endswith("bank_iterator") else None)
+        storage = "file" if name == "k21_cores4" else "hdf5"            # .h5 is the reference's default output; one case keeps the file storage
+        r = run_tool(tool, fa, str(d / "x"), k, extra, env={"GATB_GPU_NO_TEXT_PARSER": "1"} if name.endswith("bank_iterator") else None, storage=storage)
         assert r.returncode == 0, tool + ": " + r.stdout + r.stderr
         outs[tool] = str(d / "x")
-    for suffix in (".solid.txt", ".histo.txt", ".info.txt", ".all.txt"):
+        if storage == "hdf5":
+            assert open(str(d / "x.h5"), "rb").read(8) == b"\x89HDF\r\n\x1a\n"            # a real HDF5 file
+    # .h5dump.txt: the .h5 re-opened from disk with the reference's Storage classes (what Graph::load consumes): every dsk/solid/<p>
+    # dataset, the dsk attributes, the histogram and the Repartitor table -- identical dataset by dataset
+    for suffix in (".solid.txt", ".histo.txt", ".info.txt", ".all.txt") + ((".h5dump.txt",) if storage == "hdf5" else ()):
         a, b = outs["dsk_tool_cpu"] + suffix, outs["dsk_tool_gpu"] + suffix
         assert os.path.getsize(a) > 0
         assert filecmp.cmp(a, b, shallow=False), "%s differs between the reference build and the GPU build (%s)" % (suffix, name)
@@ -115,7 +121,7 @@ def test_reference_example_kmer12_unchanged_on_gpu(oracle, tmp_path):
     fa = str(tmp_path / "reads.fa")
     write_fasta(oracle, fa, 20000, 150, 5)
     r = subprocess.run([os.path.join(BUILD, "kmer12_gpu"), "-in", fa, "-kmer-size", "31", "-abundance-min", "3", "-out-dir", str(tmp_path),
-                        "-out-tmp", str(tmp_path), "-storage-type", "file"], capture_output=True, text=True, cwd=str(tmp_path))
+                        "-out-tmp", str(tmp_path)], capture_output=True, text=True, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout + r.stderr
     c = run_tool("dsk_tool_cpu", fa, str(tmp_path / "c"), 31, [], abundance_min=3)
     assert c.returncode == 0, c.stdout + c.stderr
