@@ -545,9 +545,9 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     int t_bits = 0;
     // buckets cut along the distribution of canonical values (k3_range_of).  One key: 512..1024 k-mers on average.  Several keys
     // (GATB partitions): the k-mers of a partition share minimizers, their leading nucleotides are skewed key by key, and the
-    // fullest bucket must stay below the 4096 items a CTA sorts in shared memory / the block directory of the pooled scatter
-    // covers (measured at 176 partitions: an average of 768 or 1024 falls back to the two-pass scatter, 256 does not)
-    { const uint64_t avg = n_keys > 1 ? 256 : 1024;
+    // fullest buckets reach several times the average: up to 4096 items a CTA sorts them in shared memory, up to 16384 (the block
+    // directory of the pooled scatter) they are sorted in place in global memory, beyond that the exact two-pass scatter takes over
+    { const uint64_t avg = n_keys > 1 ? 768 : 1024;
       uint64_t per_key = n_items / n_keys + 1; while (t_bits < 2*k - 1 && t_bits < 24 && (per_key >> t_bits) > avg) t_bits++; }
     while (t_bits > 0 && (n_keys << t_bits) > (1ULL << 30)) t_bits--;
     const uint64_t n_buckets = n_keys << t_bits;
@@ -588,7 +588,9 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     bool pooled = false;
     if (!no_pool && n_items)
     {
-        const uint32_t dir_rounds = p->k3_dir_rounds > 0 ? (uint32_t)p->k3_dir_rounds : k3_sort_cap () / K3_BLK;   // a tiny directory forces the fallback
+        // the directory covers buckets of up to 16384 items (those above the 4096 a CTA sorts in shared memory are sorted in place
+        // in global memory, k3d); a tiny directory (test selector) forces the exact two-pass fallback
+        const uint32_t dir_rounds = p->k3_dir_rounds > 0 ? (uint32_t)p->k3_dir_rounds : 4 * k3_sort_cap () / K3_BLK;
         const uint64_t pool_blocks = n_items / K3_BLK + n_buckets + 1;
         if (pool_blocks < (1ULL << 32))
         {
@@ -639,10 +641,22 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
             CK (cudaMemcpyAsync (&chunk_off[c], (const uint64_t*)ctx->slot[S_BUCKETOFF] + chunk_bucket[c], 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK (cudaStreamSynchronize (ctx->stream));
     }
+    unsigned long long n_big = 0, n_big_done = 0;
     for (int c = 0; c < n_chunks; c++)
     {
         k3.bucket_begin = (uint32_t)chunk_bucket[c]; k3.bucket_end = (uint32_t)chunk_bucket[c+1];
         CK (launch_k3c_sort (L, k3));
+        if (to_host || c == n_chunks - 1)
+        {   // buckets of this chunk too large for the shared-memory sort: sorted in place now, so that the chunk leaves complete
+            CK (cudaMemcpyAsync (&n_big, d_cnt + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+            if (n_big > n_big_done)
+            {
+                K3Params k3d = k3; k3d.big_list = k3.big_list + n_big_done;
+                CK (launch_k3d_sort_big (L, k3d, (uint32_t)(n_big - n_big_done)));
+                n_big_done = n_big;
+            }
+        }
         if (to_host)
         {
             CK (cudaEventRecord (ctx->cev[20 + c], ctx->stream));
@@ -657,20 +671,6 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         }
     }
     cudaEventRecord (ctx->kev[7], ctx->stream);
-    unsigned long long n_big = 0;
-    CK (cudaMemcpyAsync (&n_big, d_cnt + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK (cudaStreamSynchronize (ctx->stream));
-    if (n_big)
-    {
-        CK (launch_k3d_sort_big (L, k3, (uint32_t)n_big));
-        if (to_host && n_items)
-        {   // rare: oversized buckets were sorted after their chunk left; send the arrays again
-            CK (cudaStreamSynchronize (ctx->copy_stream));
-            CK (cudaMemcpyAsync (h_lo, dr->lo, n_items * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            if (W == 2) CK (cudaMemcpyAsync (h_hi, dr->hi, n_items * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK (cudaMemcpyAsync (h_cnt32, dr->cnt, n_items * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-    }
     // part_offsets[key] = bucket_off[key << t_bits]
     {
         std::vector<uint64_t> offs (n_keys + 1);

@@ -389,6 +389,17 @@ __global__ void __launch_bounds__(1024) k3d_sort_big (const K3Params P, uint32_t
         const uint64_t beg = P.bucket_off[b], n = P.bucket_off[b+1] - beg;
         uint64_t np = 1; while (np < n) np <<= 1;
         uint64_t* lo = P.tmp_lo + beg; uint64_t* hi = (W == 2) ? P.tmp_hi + beg : 0; uint32_t* cn = P.tmp_cnt + beg;
+        if (P.pool)
+        {   // pooled scatter: the bucket's items sit in 32-item blocks; gather them into the output range and sort there
+            lo = P.out_lo + beg; hi = (W == 2) ? P.out_hi + beg : 0; cn = (uint32_t*)P.out_cnt + beg;
+            for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+            {
+                const uint64_t at = (uint64_t)P.dir[(uint64_t)(i / K3_BLK) * P.n_buckets + b] * K3_BLK + (i % K3_BLK);
+                if (W == 1) { const uint4 q4 = P.pool[at]; lo[i] = (uint64_t)q4.x | ((uint64_t)q4.y << 32); cn[i] = q4.z; }
+                else { const uint4 q4 = P.pool[2 * at]; lo[i] = (uint64_t)q4.x | ((uint64_t)q4.y << 32); hi[i] = (uint64_t)q4.z | ((uint64_t)q4.w << 32); cn[i] = P.pool[2 * at + 1].x; }
+            }
+            __syncthreads ();
+        }
         for (uint64_t size = 2; size <= np; size <<= 1)
             for (uint64_t stride = size >> 1; stride > 0; stride >>= 1)
             {
@@ -411,8 +422,9 @@ __global__ void __launch_bounds__(1024) k3d_sort_big (const K3Params P, uint32_t
                 }
                 __syncthreads ();
             }
-        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
-        { P.out_lo[beg + i] = lo[i]; if (W == 2) P.out_hi[beg + i] = hi[i]; P.out_cnt[beg + i] = (int32_t)cn[i]; }
+        if (!P.pool)
+            for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+            { P.out_lo[beg + i] = lo[i]; if (W == 2) P.out_hi[beg + i] = hi[i]; P.out_cnt[beg + i] = (int32_t)cn[i]; }
         __syncthreads ();
     }
 }
