@@ -41,7 +41,7 @@ class Params(C.Structure):
 
 # gatb_gpu_params.path_flags (include/gatb_gpu.h): selectors of the alternate code paths, 0 = the product path
 PATH_K1_GENERAL, PATH_K2B_CTA128, PATH_K2B_CTA256, PATH_K2B_LANE = 1, 2, 4, 6
-PATH_K2B_W2_WARP, PATH_NO_TIER2, PATH_K3_NO_POOL, PATH_CANONICAL, PATH_NO_DEDUP, PATH_FUSED = 8, 16, 32, 64, 128, 256
+PATH_K2B_W2_WARP, PATH_NO_TIER2, PATH_K3_NO_POOL, PATH_CANONICAL, PATH_NO_DEDUP, PATH_FUSED, PATH_K1_STAGING = 8, 16, 32, 64, 128, 256, 512
 
 
 class Result(C.Structure):

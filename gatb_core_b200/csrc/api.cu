@@ -248,7 +248,11 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
 {
     const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
     const bool fused = path_fused (p);
-    const int table_log2 = p->table_log2 > 0 ? p->table_log2 : (fused ? 13 : k2b_default_table_log2 (W, p->path_flags));
+    int table_log2 = p->table_log2 > 0 ? p->table_log2 : (fused ? 13 : k2b_default_table_log2 (W, p->path_flags));
+    // multi-Gb inputs crowd the 16-mer minimizer space of the register scanner (4*10^9 nt: every minimizer value marks ~3 loci),
+    // the fine-bin loads get a heavy tail and 9 % of the bins overflowed a warp's 512-slot table (measured on 8 GPUs: 69 ms in
+    // the tier kernels).  1024-slot tables cost the first tier 35 % but absorb the tail.
+    if (p->table_log2 == 0 && W == 1 && !fused && table_log2 == 9 && total_kmers > 40000000000ULL) table_log2 = 10;
     if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
     if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
     const uint64_t T = 1ULL << table_log2;
@@ -329,7 +333,7 @@ struct ReadChunks { int n; uint64_t first[17]; cudaEvent_t* ready; };
 static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
                            const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
                            void* d_bins, uint32_t* d_cursors, unsigned long long* h_stats,
-                           const ReadChunks* chunks = 0, uint64_t first_read = 0)
+                           const ReadChunks* chunks = 0, uint64_t first_read = 0, uint64_t max_len = 0)
 {
     LaunchCtx L = lctx (ctx);
     if (ensure (ctx, S_STATS, 64 * 8)) return 1;
@@ -341,6 +345,7 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
     k1.k = p->kmer_size; k1.m = g->m_device; k1.w = g->w; k1.maxlen = g->maxlen;
     k1.mmask = (g->m_device >= 16) ? 0xFFFFFFFFu : ((1u << (2 * g->m_device)) - 1); k1.mask_ma1 = 0;
     k1.force_general = (p->path_flags & GATB_PATH_K1_GENERAL) ? 1 : 0;
+    k1.max_len = (int)max_len; k1.no_staging = (p->path_flags & GATB_PATH_K1_STAGING) ? 0 : 1;
     k1.oriented = k1_oriented (p->kmer_size, g->m_device, g->w, p->path_flags) ? 1 : 0;
     k1.mode = K1_MODE_DEVICE; k1.nb1 = g->nb1; k1.n_regions = g->n_ranks; k1.bins_per_region = g->bins_per_rank;
     if (g->cap % COARSE_BLK) return fail (ctx, "geometry: cap %u is not a multiple of %d", g->cap, (int)COARSE_BLK); k1.fine_bits = g->fine_bits; k1.count_only = 0;
@@ -735,7 +740,7 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
         if ((uint64_t)g.cap * g.nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %u x %u bins)", g.cap, g.nb1);
         if (ensure (ctx, S_COARSE, (size_t)g.nb1 * g.cap * g.record_bytes)) return 1;
         if (partition_impl (ctx, p, &g, d_reads, d_offsets, n_reads, d_nmask, ctx->slot[S_COARSE], (uint32_t*)ctx->slot[S_CURSORS],
-                            h_stats, chunks)) return 1;
+                            h_stats, chunks, 0, max_len)) return 1;
         if (h_stats[3] == 0) break;
         // a bin overflowed: the cursors hold the true demand -> size for the largest and run again
         std::vector<uint32_t> cur (g.nb1);
@@ -785,15 +790,17 @@ int gatb_gpu_partition_range_into (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, 
     cudaSetDevice (ctx->device);
     if (check_params (ctx, p, (const uint16_t*)1)) return 1;
     if (check_geometry (ctx, p, g)) return 1;
+    uint64_t range_max_len = 0;
     {   // the limits of the partition kernels are enforced here too (the event word keeps 21, oriented 20, bits of k-mer index)
         uint64_t tk = 0, tn = 0, max_len = 0;
         if (workload_size (ctx, p, d_read_offsets_nt ? d_read_offsets_nt + first_read : 0, n_reads, &tk, &tn, &max_len)) return 1;
         if (max_len >= (1ULL << 21)) return fail (ctx, "reads longer than 2^21-1 nucleotides are not supported by the partition kernel yet (longest: %llu)", (unsigned long long)max_len);
         if (max_len >= (1ULL << 20) && !(p->path_flags & GATB_PATH_K1_GENERAL))
             return fail (ctx, "reads of 2^20 nucleotides and more need path_flags |= GATB_PATH_K1_GENERAL on every rank (plan, partition and count)");
+        range_max_len = max_len;
     }
     unsigned long long h[4];
-    if (partition_impl (ctx, p, g, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, d_bins, d_cursors, h, 0, first_read)) return 1;
+    if (partition_impl (ctx, p, g, d_packed_reads, d_read_offsets_nt, n_reads, d_n_mask, d_bins, d_cursors, h, 0, first_read, range_max_len)) return 1;
     for (int i = 0; i < 4; i++) stats4[i] = h[i];
     return 0;
 }

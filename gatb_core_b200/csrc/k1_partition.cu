@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "k1_scan.cuh"
+#include "k2_common.cuh"      // mbarrier / TMA bulk copy helpers
 
 #define K1_THREADS 128
 #define K1_QCAP    384        // events per warp queue: flush threshold 96 + 8 steps x 32 lanes + slack
@@ -375,12 +376,19 @@ struct K1Emit
     }
 };
 
-template<int WIN, int W, bool HAS_N, bool ORI>
-__global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params P)
+// SM: the packed reads of a warp (32 consecutive reads = one contiguous byte range of the stream) are staged in shared memory
+// by ONE TMA bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP) issued by lane 0 one tile ahead (two buffers per warp); the scan
+// reads its words with ld.shared.  Every input byte crosses HBM -> SM once, in 16-byte-aligned bursts, instead of being
+// fetched word by word at a 37.5-byte stride per thread.  tile_bytes = dynamic shared memory per warp and buffer.
+template<int WIN, int W, bool HAS_N, bool ORI, bool SM>
+__global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params P, const uint32_t tile_bytes)
 {
     __shared__ __align__(16) uint32_t s_q[K1_THREADS / 32][K1F_QCAP * 2];
     __shared__ uint32_t s_ring[K1S_RING * K1_THREADS];
     __shared__ uint32_t s_tail[K1_THREADS / 32];
+    __shared__ __align__(8) uint64_t s_bar[K1_THREADS / 32][2];
+    __shared__ unsigned long long s_lo[K1_THREADS / 32][2];              // first stream byte held by the buffer
+    extern __shared__ __align__(16) unsigned char k1_tiles[];            // [warp][2][tile_bytes]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = P.k, m = P.m;
     uint32_t* q = s_q[wid];
@@ -410,7 +418,32 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
     };
 
     const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    // lane 0: one bulk copy for the 32 reads this warp scans in 'tile' (nothing when the slice is empty)
+    auto stage = [&] (uint64_t tile, int buf)
+    {
+        const uint64_t ra = tile * K1_THREADS + (uint64_t)wid * 32;
+        if (ra >= P.n_reads) { s_lo[wid][buf] = ~0ULL; return; }
+        const uint64_t rb = (ra + 32 < P.n_reads) ? ra + 32 : P.n_reads;
+        const uint64_t oa = P.offsets ? P.offsets[P.first_read + ra] : (P.first_read + ra) * (uint64_t)P.read_len;
+        const uint64_t ob = P.offsets ? P.offsets[P.first_read + rb] : (P.first_read + rb) * (uint64_t)P.read_len;
+        const uint64_t lo = (oa >> 2) & ~15ULL;
+        uint64_t hi = (((ob + 3) >> 2) + 9 + 15) & ~15ULL;              // the scan looks two words past the last nucleotide
+        if (hi - lo > tile_bytes) hi = lo + tile_bytes;                  // (cannot happen: the launcher sized tile_bytes for the longest read)
+        s_lo[wid][buf] = lo;
+        fence_proxy_async ();
+        mbar_expect_tx (&s_bar[wid][buf], (uint32_t)(hi - lo));
+        tma_bulk_g2s (k1_tiles + ((size_t)wid * 2 + buf) * tile_bytes, (const unsigned char*)P.words + lo, (uint32_t)(hi - lo), &s_bar[wid][buf]);
+    };
+    if (SM)
+    {
+        if (lane == 0) { mbar_init (&s_bar[wid][0], 1); mbar_init (&s_bar[wid][1], 1); }
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp ();
+        if (lane == 0 && blockIdx.x < n_tiles) stage (blockIdx.x, 0);
+        __syncwarp ();
+    }
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++)
     {
         const uint64_t ri = tile * K1_THREADS + tid;
         const uint64_t r = P.first_read + ri;
@@ -422,11 +455,23 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
         }
         const int nm = (len >= k) ? (len - m + 1) : 0;      // reads shorter than k are skipped (Sequence2SuperKmer.hpp:144)
         const int nm_max = __reduce_max_sync (FULL_MASK, nm);
-        K1Scanner<WIN, K1_THREADS, HAS_N, ORI> sc;
+        K1Scanner<WIN, K1_THREADS, HAS_N, ORI, SM> sc;
+        uint32_t tile_saddr = 0; unsigned long long tile_lo = 0;
+        if (SM)
+        {
+            const int buf = (int)(it & 1);
+            __syncwarp ();                                   // everybody is done with the other buffer (previous tile)
+            if (lane == 0 && tile + gridDim.x < n_tiles) stage (tile + gridDim.x, buf ^ 1);
+            __syncwarp ();
+            tile_lo = s_lo[wid][buf];
+            if (tile_lo != ~0ULL) mbar_wait (&s_bar[wid][buf], (it >> 1) & 1u);
+            tile_saddr = smem_u32 (k1_tiles + ((size_t)wid * 2 + buf) * tile_bytes);
+        }
         if (nm > 0)
         {
             nvalid += (unsigned long long)(len - k + 1);
-            sc.begin ((const uint32_t*)P.words, roff, len, m, s_ring + tid, P.nmask);
+            if (SM) sc.begin_shared (tile_saddr + (uint32_t)((((2 * roff) >> 5) << 2) - tile_lo), roff, len, m, s_ring + tid, P.nmask);
+            else    sc.begin ((const uint32_t*)P.words, roff, len, m, s_ring + tid, P.nmask);
             if (sc.j >= nm) sc.finish (emit);
         }
         int j0 = WIN;
@@ -467,20 +512,32 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
     }
 }
 
-template<int WIN, int W, bool HAS_N, bool ORI>
-static cudaError_t k1_fast_launch_n (const LaunchCtx& L, const K1Params& P)
+template<int WIN, int W, bool HAS_N, bool ORI, bool SM>
+static cudaError_t k1_fast_launch_s (const LaunchCtx& L, const K1Params& P, uint32_t tile_bytes)
 {
+    const size_t smem = SM ? (size_t)tile_bytes * 2 * (K1_THREADS / 32) : 0;
+    cudaError_t e = cudaFuncSetAttribute (k1_superkmer_fast<WIN,W,HAS_N,ORI,SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W,HAS_N,ORI>, K1_THREADS, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W,HAS_N,ORI,SM>, K1_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
     uint64_t grid = (uint64_t)L.sm_count * per_sm;                 // persistent: a multiple of the SM count
     if (grid > n_tiles) grid = n_tiles;
     if (grid == 0) return cudaSuccess;
-    k1_superkmer_fast<WIN,W,HAS_N,ORI><<<(unsigned)grid, K1_THREADS, 0, L.stream>>> (P);
+    k1_superkmer_fast<WIN,W,HAS_N,ORI,SM><<<(unsigned)grid, K1_THREADS, smem, L.stream>>> (P, tile_bytes);
     (*L.launches)++;
     return cudaGetLastError ();
+}
+// staged in shared memory when the longest read is known and 32 of them fit 12 KB (reads of up to ~1500 nucleotides)
+template<int WIN, int W, bool HAS_N, bool ORI>
+static cudaError_t k1_fast_launch_n (const LaunchCtx& L, const K1Params& P)
+{
+    const uint64_t longest = P.offsets ? (uint64_t)P.max_len : (uint64_t)P.read_len;
+    const uint64_t tile_bytes = (32 * ((longest + 3) / 4) + 64 + 15) & ~15ULL;
+    if (longest > 0 && tile_bytes <= 12288 && !P.no_staging) return k1_fast_launch_s<WIN, W, HAS_N, ORI, true> (L, P, (uint32_t)tile_bytes);
+    return k1_fast_launch_s<WIN, W, HAS_N, ORI, false> (L, P, 0);
 }
 template<int WIN, int W>
 static cudaError_t k1_fast_launch_t (const LaunchCtx& L, const K1Params& P)

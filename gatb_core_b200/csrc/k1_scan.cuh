@@ -107,7 +107,9 @@ constexpr int k1s_gcd (int a, int b) { return b ? k1s_gcd (b, a % b) : a; }
 // keeps the number of nucleotides since the last invalid one; the keys are computed as usual (an invalid nucleotide is
 // encoded like G), only the k-mers are masked.
 // ORI: oriented scan (see above); emit gets a fourth argument: true when some k-mer of the super-k-mer is ambiguous.
-template<int WIN, int RS = 0, bool HAS_N = false, bool ORI = false>
+// SM: the packed words of the read were staged in shared memory (k1_partition.cu stages a warp's reads with one TMA bulk
+// copy per 32 reads); the scanner then takes its words with ld.shared from the 32-bit shared address 'wps'.
+template<int WIN, int RS = 0, bool HAS_N = false, bool ORI = false, bool SM = false>
 struct K1Scanner
 {
     static constexpr int LCM    = WIN / k1s_gcd (WIN, 16) * 16;   // positions after which (window slot, word phase) repeat
@@ -121,6 +123,7 @@ struct K1Scanner
     uint32_t raw;                 // last raw word consumed
     uint32_t ahead;               // raw word loaded one step early (its latency hides behind 16 positions of work)
     const uint32_t* wp;           // next raw word
+    uint32_t wps;                 // SM: shared-memory address of the next raw word
     uint32_t* ring;               // this thread's column of the word ring (RS != 0)
     uint32_t nw;                  // normalised words produced so far
     uint32_t sh;                  // bit offset of the read inside its first raw word
@@ -146,10 +149,17 @@ struct K1Scanner
     // the nucleotide entering the window at word position u is nucleotide 16t+u+m-1 of the read
     K1S_HD void note_nucleotide (int u) { since_bad = ((bb >> (u + m1)) & 1u) ? 0 : since_bad + 1; }
 
+    K1S_HD uint32_t load_raw ()
+    {
+#if defined(__CUDA_ARCH__)
+        if constexpr (SM) { uint32_t v; asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(wps)); wps += 4; return v; }
+#endif
+        const uint32_t v = K1S_LDG (wp); wp++; return v;
+    }
     K1S_HD uint32_t next_word ()
     {
         const uint32_t r = ahead;
-        ahead = K1S_LDG (wp); wp++;
+        ahead = load_raw ();
         const uint32_t n = K1S_FSHR (raw, r, sh);
         raw = r;
         if (RS) { ring[(nw & (K1S_RING - 1)) * RS] = n; nw++; }
@@ -248,6 +258,9 @@ struct K1Scanner
 
     // ---- the read starts at nucleotide 'roff' of the packed stream 'words32'; len >= k = m+WIN-1 is required -------
     // Processes the first block (m-mer positions 0..WIN-1): afterwards the super-k-mer of k-mer 0 is open.
+    uintptr_t ring_shared_word0;  // SM: shared address of the raw word that holds the read's first nucleotide
+    K1S_HD void begin_shared (uint32_t word0_saddr, uint64_t roff, int len, int m, uint32_t* ring_column, const uint32_t* n_mask)
+    { ring_shared_word0 = word0_saddr; begin ((const uint32_t*)0, roff, len, m, ring_column, n_mask); }
     K1S_HD void begin (const uint32_t* words32, uint64_t roff, int len, int m, uint32_t* ring_column = 0, const uint32_t* n_mask = 0)
     {
         ring = ring_column; nw = 0;
@@ -264,8 +277,9 @@ struct K1Scanner
         nm = len - m + 1;
         const uint64_t b0 = 2 * roff;
         wp = words32 + (b0 >> 5); sh = (uint32_t)(b0 & 31);
-        raw = K1S_LDG (wp); wp++;
-        ahead = K1S_LDG (wp); wp++;
+        if (SM) wps = (uint32_t)(uintptr_t)ring_shared_word0;       // set by begin_shared
+        raw = load_raw ();
+        ahead = load_raw ();
         na = next_word (); ra = k1s_pair_reverse (na);
         nb = next_word (); rb = k1s_pair_reverse (nb);
         first_block (Int<0> ());

@@ -62,6 +62,8 @@ struct K1Params
     int      count_only;            // 1: only count demand (cursors), store nothing
     int      force_general;         // 1: never take the register-scanner kernel (GATB_PATH_K1_GENERAL, reads of 2^20 nucleotides and more)
     int      oriented;              // 1: records oriented by the strand of their minimizer (k1_scan.cuh); see k1_oriented()
+    int      max_len;               // longest read of the batch when offsets are given (0 = unknown: no shared-memory staging)
+    int      no_staging;            // 1 (default): the register scanner reads the stream from global memory; 0: TMA-staged tiles (GATB_PATH_K1_STAGING)
 };
 
 struct K2Params

@@ -23,7 +23,7 @@
  *     significant position (kmer/impl/Model.hpp:636-657); canonical = min(forward, reverse complement).
  *   - packed reads: 2 bits per nucleotide, nucleotide i of the stream in bits [2(i%4), 2(i%4)+2) of byte i/4; read r
  *     occupies stream positions [read_offsets_nt[r], read_offsets_nt[r+1]).  Buffers must be 16-byte aligned and
- *     readable for 16 bytes past the last nucleotide (gatb_gpu_count copies host input into such a buffer itself).
+ *     readable for 32 bytes past the last nucleotide (gatb_gpu_count copies host input into such a buffer itself).
  *   - n_mask (optional, may be NULL): 1 bit per stream position, bit (i%32) of 32-bit word i/32, set = the
  *     nucleotide is not A/C/G/T (k-mers overlapping it are invalid and dropped, Sequence2SuperKmer.hpp:95-108).
  *   - k-mers are returned as (lo, hi) 64-bit halves; hi arrays are NULL when kmer_size < 32 (Kmer<32>).
@@ -76,6 +76,8 @@ enum {
     GATB_PATH_K3_NO_POOL   = 32,     /* exact two-pass bucket scatter instead of the pooled single pass                    */
     GATB_PATH_CANONICAL    = 64,     /* register scanner without orientation: k2b rebuilds min(forward, revcomp) per k-mer  */
     GATB_PATH_NO_DEDUP     = 128,    /* identical records are not collapsed (every multiplicity is 1)                       */
+    GATB_PATH_K1_STAGING   = 512,    /* the register scanner reads TMA-staged tiles (one bulk copy per 32 reads) instead of the global
+                                        stream: measured 5 ms slower and the same DRAM traffic, kept as a tested variant */
     GATB_PATH_FUSED        = 256     /* k <= 31: one CTA counts a whole coarse bin straight out of the partition buffers (k2_fused.cu:
                                         TMA-streamed tiles, CTA-wide table) instead of fine split + warp-per-fine-bin counting  */
 };

@@ -127,7 +127,7 @@ def path_variants():
     import gatb_core_b200 as g
     F = g.PATH_FUSED
     return [("general_k1", dict(path_flags=g.PATH_K1_GENERAL)), ("general_k1_fused", dict(path_flags=g.PATH_K1_GENERAL | F)),
-            ("fused", dict(path_flags=F)), ("fused_no_dedup", dict(path_flags=F | g.PATH_NO_DEDUP)),
+            ("k1_tma_staging", dict(path_flags=g.PATH_K1_STAGING)), ("fused", dict(path_flags=F)), ("fused_no_dedup", dict(path_flags=F | g.PATH_NO_DEDUP)),
             ("fused_canonical", dict(path_flags=F | g.PATH_CANONICAL)),
             ("fused_overflow_to_tiers", dict(path_flags=F, table_log2=7)), ("fused_overflow_to_global", dict(table_log2=5, path_flags=F | g.PATH_NO_TIER2)),
             ("fused_dense", dict(path_flags=F, bin_load_pct=350)), ("cta128", dict(path_flags=g.PATH_K2B_CTA128)),
