@@ -24,7 +24,7 @@ EXPORTS = ["gatb_gpu_create", "gatb_gpu_destroy", "gatb_gpu_last_error", "gatb_g
            "gatb_gpu_histogram_cutoff", "gatb_gpu_malloc", "gatb_gpu_free", "gatb_gpu_memcpy_h2d", "gatb_gpu_memcpy_d2h",
            "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii", "gatb_gpu_plan",
            "gatb_gpu_partition_into", "gatb_gpu_partition_range_into", "gatb_gpu_count_bins", "gatb_gpu_reads_begin",
-           "gatb_gpu_reads_push_ascii", "gatb_gpu_reads_count", "gatb_gpu_reads_push_text", "gatb_gpu_reads_info"]
+           "gatb_gpu_reads_push_ascii", "gatb_gpu_reads_count", "gatb_gpu_reads_push_text", "gatb_gpu_reads_info", "gatb_gpu_synth_zipf_dev"]
 
 
 class GatbGpuError(RuntimeError):
@@ -96,6 +96,7 @@ def load_library():
     L.gatb_gpu_memcpy_d2h.argtypes = [VP, VP, VP, U64]
     L.gatb_gpu_synchronize.argtypes = [VP]
     L.gatb_gpu_synth_reads_dev.argtypes = [VP, U64, U64, U64, U64, I32, VP]
+    L.gatb_gpu_synth_zipf_dev.argtypes = [VP, U64, U64, VP, VP, U64, U64, I32, VP]
     L.gatb_gpu_pack_ascii.argtypes = [VP, C.c_char_p, U64, VP, VP, C.POINTER(U64)]
     L.gatb_gpu_plan.argtypes = [VP, C.POINTER(Params), U64, U64, I32, C.POINTER(Geometry)]
     L.gatb_gpu_partition_into.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), VP, VP, U64, VP, VP, VP, VP]
@@ -343,6 +344,9 @@ class GatbGpu:
 
     def synchronize(self):
         self._check(self.L.gatb_gpu_synchronize(self.ctx))
+
+    def synth_zipf_dev(self, seed, cdf, genome_off, first_read, n_reads, L, d_packed):
+        self._check(self.L.gatb_gpu_synth_zipf_dev(self.ctx, seed, len(cdf), _ptr(cdf), _ptr(genome_off), first_read, n_reads, L, C.c_void_p(d_packed)))
 
     def synth_reads_dev(self, seed, genome_len, first_read, n_reads, L, d_packed):
         self._check(self.L.gatb_gpu_synth_reads_dev(self.ctx, seed, genome_len, first_read, n_reads, L, _ptr(d_packed)))

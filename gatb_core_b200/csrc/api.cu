@@ -17,7 +17,7 @@ static std::string g_create_error;
 
 // device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
 enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
-            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_OVFLIST2, S_NSLOTS };
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_OVFLIST2, S_BINOFF, S_NSLOTS };
 
 struct gatb_gpu_ctx
 {
@@ -123,6 +123,21 @@ int gatb_gpu_synth_reads_dev (gatb_gpu_ctx* ctx, uint64_t seed, uint64_t genome_
     cudaSetDevice (ctx->device);
     if (genome_len < (uint64_t)L) return fail (ctx, "genome_len < read length");
     CK (launch_synth_reads (lctx (ctx), seed, genome_len, first_read, n_reads, L, d_packed));
+    return 0;
+}
+
+int gatb_gpu_synth_zipf_dev (gatb_gpu_ctx* ctx, uint64_t seed, uint64_t n_species, const uint64_t* cdf, const uint64_t* genome_off,
+                             uint64_t first_read, uint64_t n_reads, int L, uint8_t* d_packed)
+{
+    cudaSetDevice (ctx->device);
+    if (n_species == 0 || !cdf || !genome_off) return fail (ctx, "synth_zipf: tables missing");
+    for (uint64_t s = 0; s < n_species; s++) if (genome_off[s+1] - genome_off[s] < (uint64_t)L) return fail (ctx, "synth_zipf: a genome is shorter than the reads");
+    if (ensure (ctx, S_MISC2, (2 * n_species + 1) * 8 + 64)) return 1;
+    uint64_t* d_cdf = (uint64_t*)ctx->slot[S_MISC2]; uint64_t* d_off = d_cdf + n_species;
+    CK (cudaMemcpyAsync (d_cdf, cdf, n_species * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK (cudaMemcpyAsync (d_off, genome_off, (n_species + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK (launch_synth_reads_zipf (lctx (ctx), seed, n_species, d_cdf, d_off, first_read, n_reads, L, d_packed));
+    CK (cudaStreamSynchronize (ctx->stream));
     return 0;
 }
 
@@ -333,14 +348,14 @@ struct ReadChunks { int n; uint64_t first[17]; cudaEvent_t* ready; };
 static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g,
                            const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads, const uint32_t* d_nmask,
                            void* d_bins, uint32_t* d_cursors, unsigned long long* h_stats,
-                           const ReadChunks* chunks = 0, uint64_t first_read = 0, uint64_t max_len = 0)
+                           const ReadChunks* chunks = 0, uint64_t first_read = 0, uint64_t max_len = 0, const uint64_t* d_bin_off = 0)
 {
     LaunchCtx L = lctx (ctx);
     if (ensure (ctx, S_STATS, 64 * 8)) return 1;
     unsigned long long* d_stats = (unsigned long long*)ctx->slot[S_STATS];
     const uint64_t nbins = (uint64_t)g->nb1 << g->fine_bits;
-    if ((uint64_t)g->cap * g->nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %u x %u bins)", g->cap, g->nb1);
     K1Params k1; memset (&k1, 0, sizeof(k1));
+    k1.bin_off = d_bin_off;
     k1.words = (const uint64_t*)d_reads; k1.offsets = d_offsets; k1.nmask = d_nmask; k1.n_reads = n_reads; k1.read_len = p->read_len;
     k1.k = p->kmer_size; k1.m = g->m_device; k1.w = g->w; k1.maxlen = g->maxlen;
     k1.mmask = (g->m_device >= 16) ? 0xFFFFFFFFu : ((1u << (2 * g->m_device)) - 1); k1.mask_ma1 = 0;
@@ -373,14 +388,14 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
 static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
                             const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
                             uint32_t nb1_local, const uint16_t* repart_host, uint64_t total_kmers_bound, gatb_gpu_result* out,
-                            bool to_host = false)
+                            bool to_host = false, const uint64_t* const* d_src_off = 0)
 {
     LaunchCtx L = lctx (ctx);
     const int k = p->kmer_size, W = g->words;
     const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
     const int histo_max = p->histo_max, fine_bits = g->fine_bits, table_log2 = g->table_log2;
     const uint64_t nbins = (uint64_t)nb1_local << fine_bits;
-    const uint32_t cap = g->cap;
+    const uint32_t cap = d_src_off ? 0xFFFFFFFFu : g->cap;        // dense sources hold exactly what their cursors say
     const size_t rec_bytes = 16 * W;
     if (n_src < 1 || n_src > GATB_GPU_MAX_SOURCES) return fail (ctx, "n_src must be in [1,%d]", GATB_GPU_MAX_SOURCES);
 
@@ -405,7 +420,8 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     const bool fused = path_fused (p);
     const int dedup = (p->path_flags & GATB_PATH_NO_DEDUP) ? 0 : 1;
     if (!fused && ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
-    K2aSrc S2; S2.n = n_src; for (int s = 0; s < n_src; s++) { S2.bins[s] = (const uint4*)d_src_bins[s]; S2.cursors[s] = d_src_cursors[s]; }
+    K2aSrc S2; memset (&S2, 0, sizeof(S2)); S2.n = n_src;
+    for (int s = 0; s < n_src; s++) { S2.bins[s] = (const uint4*)d_src_bins[s]; S2.cursors[s] = d_src_cursors[s]; S2.off[s] = d_src_off ? d_src_off[s] : 0; }
     cudaEventRecord (ctx->kev[2], ctx->stream);
     uint64_t n_unique_records = n_records;
     if (fused) cudaEventRecord (ctx->kev[3], ctx->stream);
@@ -735,23 +751,37 @@ static int count_dev_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ui
     if (ensure (ctx, S_CURSORS, (size_t)g.nb1 * 4)) return 1;
     uint64_t retries = 0;
     unsigned long long h_stats[4];
-    for (;;)
+    const uint64_t* d_bin_off = 0;
     {
-        if ((uint64_t)g.cap * g.nb1 >= (1ULL << 32)) return fail (ctx, "record index space exceeds 2^32 (cap %u x %u bins)", g.cap, g.nb1);
-        if (ensure (ctx, S_COARSE, (size_t)g.nb1 * g.cap * g.record_bytes)) return 1;
+        // first attempt: bins of the planned fixed capacity (round-interleaved layout).  If any bin overflows -- skewed inputs: a
+        // metagenome whose dominant species is covered thousands of times puts 15x the average into some bins -- the cursors hold
+        // the exact demand of every bin: the second run lays the bins out DENSELY at their exact sizes (no capacity to guess, no
+        // memory wasted on the largest bin), and the readers follow the offset table.
+        const size_t planned = (size_t)g.nb1 * g.cap * g.record_bytes;
+        if (planned > ((size_t)150 << 30)) return fail (ctx, "partition buffer of %zu bytes does not fit the device", planned);
+        if (ensure (ctx, S_COARSE, planned)) return 1;
         if (partition_impl (ctx, p, &g, d_reads, d_offsets, n_reads, d_nmask, ctx->slot[S_COARSE], (uint32_t*)ctx->slot[S_CURSORS],
                             h_stats, chunks, 0, max_len)) return 1;
-        if (h_stats[3] == 0) break;
-        // a bin overflowed: the cursors hold the true demand -> size for the largest and run again
-        std::vector<uint32_t> cur (g.nb1);
-        CK (cudaMemcpy (cur.data (), ctx->slot[S_CURSORS], (size_t)g.nb1 * 4, cudaMemcpyDeviceToHost));
-        uint32_t mx = 0; for (uint64_t i = 0; i < g.nb1; i++) if (cur[i] > mx) mx = cur[i];
-        g.cap = (uint32_t)(((uint64_t)mx + COARSE_BLK - 1) / COARSE_BLK * COARSE_BLK);
-        if (++retries > 3) return fail (ctx, "partition kernel still overflows after %llu retries", (unsigned long long)retries);
+        if (h_stats[3] != 0)
+        {
+            retries = 1;
+            if (ensure (ctx, S_BINOFF, ((size_t)g.nb1 + 1) * 8)) return 1;
+            if (ensure (ctx, S_SCAN, scan_scratch_elems (g.nb1) * 8)) return 1;
+            CK (launch_scan_u32_to_u64 (lctx (ctx), (const uint32_t*)ctx->slot[S_CURSORS], (uint64_t*)ctx->slot[S_BINOFF], g.nb1, (uint64_t*)ctx->slot[S_SCAN]));
+            uint64_t total_records = 0;
+            CK (cudaMemcpyAsync (&total_records, (const uint64_t*)ctx->slot[S_BINOFF] + g.nb1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+            if (ensure (ctx, S_COARSE, (total_records + 1) * g.record_bytes)) return 1;
+            d_bin_off = (const uint64_t*)ctx->slot[S_BINOFF];
+            if (partition_impl (ctx, p, &g, d_reads, d_offsets, n_reads, d_nmask, ctx->slot[S_COARSE], (uint32_t*)ctx->slot[S_CURSORS],
+                                h_stats, chunks, 0, max_len, d_bin_off)) return 1;
+            if (h_stats[3] != 0) return fail (ctx, "partition kernel dropped %llu records in the exact layout", (unsigned long long)h_stats[3]);
+        }
     }
     const void* src_bins[1] = { ctx->slot[S_COARSE] };
     const uint32_t* src_cur[1] = { (const uint32_t*)ctx->slot[S_CURSORS] };
-    if (count_bins_impl (ctx, p, &g, 1, src_bins, src_cur, g.nb1, repart_host, total_kmers, out, to_host)) return 1;
+    const uint64_t* src_off[1] = { d_bin_off };
+    if (count_bins_impl (ctx, p, &g, 1, src_bins, src_cur, g.nb1, repart_host, total_kmers, out, to_host, d_bin_off ? src_off : 0)) return 1;
     out->stats[GATB_STAT_KMERS_VALID] = h_stats[0]; out->stats[GATB_STAT_KMERS_INVALID] = h_stats[1];
     out->stats[GATB_STAT_SEQUENCES] = n_reads; out->stats[GATB_STAT_NUCLEOTIDES] = total_nt; out->stats[GATB_STAT_RETRIES] = retries;
     float ms;

@@ -58,12 +58,21 @@ __device__ __forceinline__ void k1_store_record (const K1Params& P, uint32_t key
     }
     uint32_t slot = atomicAdd (&P.cursors[bin], 1u);
     if (P.count_only) return;
-    if (slot >= P.cap) { dropped++; return; }
     uint64_t ridx = (uint64_t)bin * P.cap + slot;                         // GATB mode: bin-major
-    if (P.mode == K1_MODE_DEVICE)
+    if (P.bin_off)
     {
-        const uint32_t region = bin / P.bins_per_region;
-        ridx = (uint64_t)region * P.bins_per_region * P.cap + coarse_index (bin - region * P.bins_per_region, slot, P.bins_per_region);
+        const uint64_t o = P.bin_off[bin];
+        if (slot >= P.bin_off[bin + 1] - o) { dropped++; return; }
+        ridx = o + slot;
+    }
+    else
+    {
+        if (slot >= P.cap) { dropped++; return; }
+        if (P.mode == K1_MODE_DEVICE)
+        {
+            const uint32_t region = bin / P.bins_per_region;
+            ridx = (uint64_t)region * P.bins_per_region * P.cap + coarse_index (bin - region * P.bins_per_region, slot, P.bins_per_region);
+        }
     }
     stored++;
     // ---- record: nn = k+len-1 nucleotides starting at stream position roff+start ----
@@ -261,12 +270,23 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_partition (const K1Pa
 struct K1fBin { uint32_t bin, fine, lbin; uint64_t rbase; };
 
 // one record: l k-mers from k-mer 'st' of the owner's read on; cls 0 = as read, 1 = reverse-complemented
-template<int W, bool ORI>
+template<int W, bool ORI, bool DENSE>
 __device__ __forceinline__ void k1f_put (const K1Params& P, const K1fBin& B, const uint32_t* col, uint32_t st, int l, int cls,
                                          unsigned long long& stored, unsigned long long& dropped)
 {
     const uint32_t slot = atomicAdd (&P.cursors[B.bin], 1u);
-    if (slot >= P.cap) { dropped++; return; }
+    uint64_t ridx;
+    if (DENSE)
+    {   // dense layout (second run after a counting run): exact room for every bin
+        const uint64_t o = P.bin_off[B.bin];
+        if (slot >= P.bin_off[B.bin + 1] - o) { dropped++; return; }
+        ridx = o + slot;
+    }
+    else
+    {
+        if (slot >= P.cap) { dropped++; return; }
+        ridx = B.rbase + coarse_index (B.lbin, slot, P.bins_per_region);
+    }
     stored++;
     const uint32_t w0 = st >> 4;
     const int sh = 2 * (int)(st & 15);
@@ -284,7 +304,7 @@ __device__ __forceinline__ void k1f_put (const K1Params& P, const K1fBin& B, con
         if (nn <= 32) { lo &= mask2k64 (nn); hi = 0; } else { hi &= mask2k64 (nn - 32); }
         if (ORI && cls) k1s_revcomp_span (lo, hi, nn);
         hi |= ((uint64_t)l << DEV_LEN_SHIFT_W1) | ((uint64_t)B.fine << DEV_FINE_SHIFT_W1);
-        ((uint4*)P.bins)[B.rbase + coarse_index (B.lbin, slot, P.bins_per_region)] = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+        ((uint4*)P.bins)[ridx] = make_uint4 ((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
     }
     else
     {
@@ -297,7 +317,7 @@ __device__ __forceinline__ void k1f_put (const K1Params& P, const K1fBin& B, con
             if (nn <= lo_nt) q[i] = 0; else if (nn < lo_nt + 32) q[i] &= mask2k64 (nn - lo_nt);
         }
         q[3] |= ((uint64_t)l << REC_LEN_SHIFT_W2) | ((uint64_t)B.fine << REC_FINE_SHIFT_W2);
-        uint4* dst = (uint4*)P.bins + 2 * (B.rbase + coarse_index (B.lbin, slot, P.bins_per_region));
+        uint4* dst = (uint4*)P.bins + 2 * ridx;
         dst[0] = make_uint4 ((uint32_t)q[0], (uint32_t)(q[0] >> 32), (uint32_t)q[1], (uint32_t)(q[1] >> 32));
         dst[1] = make_uint4 ((uint32_t)q[2], (uint32_t)(q[2] >> 32), (uint32_t)q[3], (uint32_t)(q[3] >> 32));
     }
@@ -306,7 +326,7 @@ __device__ __forceinline__ void k1f_put (const K1Params& P, const K1fBin& B, con
 // A super-k-mer flagged ambiguous (rare: hairpins, palindromic minimizers) is taken apart: every k-mer is classified
 // exactly (k1s_classify_kmer) and leaves as a record of its own, ambiguous k-mers in their canonical orientation
 // min(K, revcomp K) like kmer/impl/Model.hpp:857-884.  Kept out of line so that it costs the scan no registers.
-template<int WIN>
+template<int WIN, bool DENSE>
 __device__ __noinline__ void k1f_store_ambiguous (const K1Params& P, const K1fBin& B, const uint32_t* col, uint32_t start, int len,
                                                   unsigned long long& stored, unsigned long long& dropped)
 {
@@ -324,13 +344,13 @@ __device__ __noinline__ void k1f_store_ambiguous (const K1Params& P, const K1fBi
             const uint64_t fwv = pair_reverse64 (xs) >> (64 - 2 * P.k);
             cls = (rcv < fwv) ? 1 : 0;
         }
-        k1f_put<1, true> (P, B, col, st, 1, cls, stored, dropped);
+        k1f_put<1, true, DENSE> (P, B, col, st, 1, cls, stored, dropped);
     }
 }
 
 // ORI (k <= 31 only): 'key' is the strand-tagged window minimum t of k1_scan.cuh (bin from its rank t >> 1, class R when t is
 // odd: the record holds the reverse complement of the span), meta = start << 12 | ambiguous << 11 | len << 5 | lane.
-template<int W, bool ORI, int WIN>
+template<int W, bool ORI, int WIN, bool DENSE>
 __device__ __forceinline__ void k1f_store (const K1Params& P, uint32_t key, uint32_t meta, const uint32_t* ring_w,
                                            unsigned long long& stored, unsigned long long& dropped)
 {
@@ -346,11 +366,11 @@ __device__ __forceinline__ void k1f_store (const K1Params& P, uint32_t key, uint
     B.lbin = B.bin - region * P.bins_per_region;
     const uint32_t* col = ring_w + olane;                   // the owner's column: word t at col[(t % K1S_RING) * K1_THREADS]
     if constexpr (ORI)
-        if ((meta >> 11) & 1u) { k1f_store_ambiguous<WIN> (P, B, col, start, len, stored, dropped); return; }
+        if ((meta >> 11) & 1u) { k1f_store_ambiguous<WIN, DENSE> (P, B, col, start, len, stored, dropped); return; }
     while (len > 0)
     {
         const int l = len < P.maxlen ? len : P.maxlen;
-        k1f_put<W, ORI> (P, B, col, start, l, ORI ? (int)(key & 1u) : 0, stored, dropped);
+        k1f_put<W, ORI, DENSE> (P, B, col, start, l, ORI ? (int)(key & 1u) : 0, stored, dropped);
         start += l; len -= l;
     }
 }
@@ -380,7 +400,7 @@ struct K1Emit
 // by ONE TMA bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP) issued by lane 0 one tile ahead (two buffers per warp); the scan
 // reads its words with ld.shared.  Every input byte crosses HBM -> SM once, in 16-byte-aligned bursts, instead of being
 // fetched word by word at a 37.5-byte stride per thread.  tile_bytes = dynamic shared memory per warp and buffer.
-template<int WIN, int W, bool HAS_N, bool ORI, bool SM>
+template<int WIN, int W, bool HAS_N, bool ORI, bool SM, bool DENSE>
 __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params P, const uint32_t tile_bytes)
 {
     __shared__ __align__(16) uint32_t s_q[K1_THREADS / 32][K1F_QCAP * 2];
@@ -409,7 +429,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
             if (e < n)
             {
                 const uint2 ev = *(const uint2*)(q + 2 * e);
-                k1f_store<W, ORI, WIN> (P, ev.x, ev.y, ring_w, stored, dropped);
+                k1f_store<W, ORI, WIN, DENSE> (P, ev.x, ev.y, ring_w, stored, dropped);
             }
         }
         __syncwarp ();
@@ -512,21 +532,21 @@ __global__ void __launch_bounds__(K1_THREADS) k1_superkmer_fast (const K1Params 
     }
 }
 
-template<int WIN, int W, bool HAS_N, bool ORI, bool SM>
+template<int WIN, int W, bool HAS_N, bool ORI, bool SM, bool DENSE>
 static cudaError_t k1_fast_launch_s (const LaunchCtx& L, const K1Params& P, uint32_t tile_bytes)
 {
     const size_t smem = SM ? (size_t)tile_bytes * 2 * (K1_THREADS / 32) : 0;
-    cudaError_t e = cudaFuncSetAttribute (k1_superkmer_fast<WIN,W,HAS_N,ORI,SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute (k1_superkmer_fast<WIN,W,HAS_N,ORI,SM,DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W,HAS_N,ORI,SM>, K1_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_superkmer_fast<WIN,W,HAS_N,ORI,SM,DENSE>, K1_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const uint64_t n_tiles = (P.n_reads + K1_THREADS - 1) / K1_THREADS;
     uint64_t grid = (uint64_t)L.sm_count * per_sm;                 // persistent: a multiple of the SM count
     if (grid > n_tiles) grid = n_tiles;
     if (grid == 0) return cudaSuccess;
-    k1_superkmer_fast<WIN,W,HAS_N,ORI,SM><<<(unsigned)grid, K1_THREADS, smem, L.stream>>> (P, tile_bytes);
+    k1_superkmer_fast<WIN,W,HAS_N,ORI,SM,DENSE><<<(unsigned)grid, K1_THREADS, smem, L.stream>>> (P, tile_bytes);
     (*L.launches)++;
     return cudaGetLastError ();
 }
@@ -536,8 +556,9 @@ static cudaError_t k1_fast_launch_n (const LaunchCtx& L, const K1Params& P)
 {
     const uint64_t longest = P.offsets ? (uint64_t)P.max_len : (uint64_t)P.read_len;
     const uint64_t tile_bytes = (32 * ((longest + 3) / 4) + 64 + 15) & ~15ULL;
-    if (longest > 0 && tile_bytes <= 12288 && !P.no_staging) return k1_fast_launch_s<WIN, W, HAS_N, ORI, true> (L, P, (uint32_t)tile_bytes);
-    return k1_fast_launch_s<WIN, W, HAS_N, ORI, false> (L, P, 0);
+    if (P.bin_off) return k1_fast_launch_s<WIN, W, HAS_N, ORI, false, true> (L, P, 0);          // dense layout (second run of a skewed input)
+    if (longest > 0 && tile_bytes <= 12288 && !P.no_staging) return k1_fast_launch_s<WIN, W, HAS_N, ORI, true, false> (L, P, (uint32_t)tile_bytes);
+    return k1_fast_launch_s<WIN, W, HAS_N, ORI, false, false> (L, P, 0);
 }
 template<int WIN, int W>
 static cudaError_t k1_fast_launch_t (const LaunchCtx& L, const K1Params& P)

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
         #pragma unroll
         for (int u = 8; u > 0; u >>= 1) if (s + u < 16 && g >= s_first[s + u]) s += u;
         src = S.bins[s];
-        ci = coarse_index (b, g - s_first[s], nb);
+        ci = k2a_record_index (S, s, b, g - s_first[s], nb);
     };
     // pass 1: records per fine bin (the second pass finds the same lines in L2)
     for (uint32_t g = tid; g < n_all; g += blockDim.x)
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __
             int s = 0;
             #pragma unroll
             for (int u = 8; u > 0; u >>= 1) if (s + u < 16 && g >= s_first[s + u]) s += u;
-            return S.bins[s] + coarse_index (b, g - s_first[s], nb);
+            return S.bins[s] + k2a_record_index (S, s, b, g - s_first[s], nb);
         };
         for (uint32_t g0 = tid; g0 < n_all; g0 += 4 * NT)
         {

@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(NWARP * 32 + 32) k2f_count_coarse (const K2Par
             while (filled < n)
             {
                 while (p_off >= p_cnt[p_src]) { p_src++; p_off = 0; }
-                uint32_t c = COARSE_BLK - (p_off % COARSE_BLK);
+                uint32_t c = S.off[p_src] ? 1024u : COARSE_BLK - (p_off % COARSE_BLK);      // dense sources are contiguous
                 if (c > p_cnt[p_src] - p_off) c = p_cnt[p_src] - p_off;
                 if (c > n - filled) c = n - filled;
-                tma_bulk_g2s (dst + filled, S.bins[p_src] + coarse_index (p_bin, p_off, nb), c * 16, &s_bar[buf]);
+                tma_bulk_g2s (dst + filled, S.bins[p_src] + k2a_record_index (S, (int)p_src, p_bin, p_off, nb), c * 16, &s_bar[buf]);
                 filled += c; p_off += c;
             }
             p_left -= n;

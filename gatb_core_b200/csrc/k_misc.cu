@@ -238,6 +238,51 @@ cudaError_t launch_synth_reads (const LaunchCtx& L, uint64_t seed, uint64_t geno
     return cudaGetLastError ();
 }
 
+// metagenome-like reads (BASELINE config 5): species by Zipf through the host-built threshold table; mirrors orc_synth_reads_zipf
+__device__ __forceinline__ uint32_t synth_base_zipf (uint64_t seed, uint64_t sR, uint64_t sE, uint64_t n_species, const uint64_t* __restrict__ cdf,
+                                                     const uint64_t* __restrict__ goff, uint64_t r, int L, int j)
+{
+    const uint64_t h0 = splitmix64 (sR + 3*r), h1 = splitmix64 (sR + 3*r + 1), h2 = splitmix64 (sR + 3*r + 2);
+    uint64_t lo = 0, hi = n_species - 1;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (h2 <= cdf[mid]) hi = mid; else lo = mid + 1; }
+    const uint64_t glen = goff[lo+1] - goff[lo];
+    const uint64_t start = goff[lo] + h0 % (glen - L + 1);
+    const int flip = (int)(h1 >> 63);
+    const int jj = flip ? (L - 1 - j) : j;
+    uint32_t b = (uint32_t)(splitmix64 (seed * 0x100000001B3ULL + start + jj) >> 61) & 3u;
+    const uint64_t e = splitmix64 (sE + r * (uint64_t)L + jj);
+    if ((e % 100) == 0) b = (b + 1 + (uint32_t)((e >> 32) % 3)) & 3u;
+    return flip ? (b ^ 2u) : b;
+}
+__global__ void __launch_bounds__(256) k_synth_reads_zipf (uint64_t seed, uint64_t sR, uint64_t sE, uint64_t n_species, const uint64_t* __restrict__ cdf,
+                                                           const uint64_t* __restrict__ goff, uint64_t first_read, uint64_t n_reads, int L,
+                                                           uint32_t* words, uint64_t n_words)
+{
+    for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (uint64_t)gridDim.x * blockDim.x)
+    {
+        uint32_t word = 0;
+        uint64_t p = wi * 16;
+        uint64_t r = p / L; int j = (int)(p - r * L);
+        for (int t = 0; t < 16; t++)
+        {
+            if (r < n_reads) word |= synth_base_zipf (seed, sR, sE, n_species, cdf, goff, first_read + r, L, j) << (2*t);
+            if (++j == L) { j = 0; r++; }
+        }
+        words[wi] = word;
+    }
+}
+cudaError_t launch_synth_reads_zipf (const LaunchCtx& L, uint64_t seed, uint64_t n_species, const uint64_t* d_cdf, const uint64_t* d_goff,
+                                     uint64_t first_read, uint64_t n_reads, int len, uint8_t* packed)
+{
+    uint64_t n_words = (n_reads * (uint64_t)len + 15) / 16;
+    if (n_words == 0) return cudaSuccess;
+    uint64_t sR = splitmix64 (seed ^ 0x5EEDC0DE00000001ULL), sE = splitmix64 (seed ^ 0x5EEDC0DE00000002ULL);
+    uint64_t blocks = (n_words + 255) / 256; unsigned grid = (unsigned)(blocks < (uint64_t)L.sm_count * 32 ? blocks : (uint64_t)L.sm_count * 32);
+    k_synth_reads_zipf<<<grid, 256, 0, L.stream>>> (seed, sR, sE, n_species, d_cdf, d_goff, first_read, n_reads, len, (uint32_t*)packed, n_words);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+
 // ------------------------------------------------------------------------------------------------ ASCII packer
 // one thread packs 32 characters -> one 64-bit... kept at 16 characters -> one u32 of nucleotides and half a mask word
 __global__ void __launch_bounds__(256) k_pack_ascii (const char* __restrict__ ascii, uint64_t n, uint32_t* words, uint32_t* nmask, unsigned long long* n_invalid)

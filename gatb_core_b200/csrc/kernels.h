@@ -54,6 +54,8 @@ struct K1Params
     uint32_t nb1;                   // number of (coarse) bins
     uint32_t n_regions, bins_per_region;   // device mode: nb1 = n_regions * bins_per_region; region r (one per owner rank) is a
                                     // contiguous block of bins_per_region*cap records laid out by coarse_index()
+    const uint64_t* bin_off;        // NULL: bins of fixed capacity 'cap' laid out by coarse_index; else DENSE layout: bin b owns the
+                                    // records [bin_off[b], bin_off[b+1]) (exact sizes from a counting run: skewed inputs)
     uint32_t cap;                   // records per bin
     int      fine_bits;
     void*    bins;                  // nb1*cap records
@@ -120,7 +122,11 @@ cudaError_t launch_k1 (const LaunchCtx&, const K1Params&);
 int         k1_fast_window (int k);      // window (k-m+1) the register-scanner kernel is compiled for, 0 = none
 bool        k1_oriented (int k, int m, int w, int path_flags);   // does launch_k1 write oriented records for these parameters?
 // k2_count.cu
-struct K2aSrc { const uint4* bins[16]; const uint32_t* cursors[16]; int n; };     // the same coarse bins gathered from n sources
+// the same coarse bins gathered from n sources.  off[s] == NULL: source s is laid out by coarse_index (fixed capacity per bin);
+// off[s] != NULL: DENSE layout, bin b of source s holds its records at [off[s][b], off[s][b+1]) (exact sizes: skewed inputs)
+struct K2aSrc { const uint4* bins[16]; const uint32_t* cursors[16]; const uint64_t* off[16]; int n; };
+__host__ __device__ __forceinline__ uint64_t k2a_record_index (const K2aSrc& S, int s, uint32_t b, uint32_t slot, uint32_t nb)
+{ return S.off[s] ? S.off[s][b] + slot : coarse_index (b, slot, nb); }
 cudaError_t launch_k2a_split (const LaunchCtx&, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
                               uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc, const uint32_t* bin_list = 0, uint32_t n_list = 0);
 uint32_t    k2a_dedup_rmax (uint32_t max_bin_records, int fine_bits);
@@ -176,3 +182,5 @@ cudaError_t launch_text_offsets (const LaunchCtx&, const uint32_t* is_header, co
 cudaError_t launch_text_pack (const LaunchCtx&, const char* text, const uint64_t* line_start, const uint64_t* line_dst, uint64_t n_lines,
                               uint64_t total_nt, uint64_t base, uint32_t* words, uint32_t* nmask, unsigned long long* n_invalid);
 cudaError_t launch_text_stats (const LaunchCtx&, const uint64_t* offsets, uint64_t n, unsigned long long* out);
+cudaError_t launch_synth_reads_zipf (const LaunchCtx&, uint64_t seed, uint64_t n_species, const uint64_t* d_cdf, const uint64_t* d_goff,
+                                     uint64_t first_read, uint64_t n_reads, int len, uint8_t* packed);

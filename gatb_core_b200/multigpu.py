@@ -75,6 +75,33 @@ def merge_sorted_runs(runs):
     return lo[order], hi[order], cn[order]
 
 
+def bloom_distributed(gpu, kind, k, res, n_solid_global, world):
+    """Bloom filter of the solid k-mers of a distributed count (BloomAlgorithm::execute, kmer/impl/BloomAlgorithm.cpp:155-203):
+    sized from the GLOBAL number of solid k-mers exactly like the reference (float32 product), every rank inserts the solid
+    k-mers it owns into a private full-size bit array on its GPU (gatb_gpu_bloom_dev, byte-exact hash functions), the arrays are
+    all-gathered over NCCL and OR-ed.  Returns (uint8 device tensor with the reference's byte layout, bit size).
+    `res` is the device Result of count_distributed (emit range = solid range)."""
+    import gatb_core_b200
+    dev = torch.device("cuda", gpu.device)
+    size, nh = gpu.bloom_params(k, n_solid_global)
+    nbytes, bits = gpu.bloom_layout(kind, size)
+    padded = (nbytes + 3) // 4 * 4
+    mine = torch.zeros(padded, dtype=torch.uint8, device=dev)
+    torch.cuda.current_stream().synchronize()
+    n = int(res.n_items)
+    gpu._check(gpu.L.gatb_gpu_bloom_dev(gpu.ctx, gatb_core_b200.BLOOM_KINDS[kind], size, nh, k, res.kmers_lo, res.kmers_hi, n, mine.data_ptr()))
+    gpu.synchronize()
+    if world > 1:
+        allb = torch.empty(world * padded, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        v = allb.view(world, padded).view(torch.int32)
+        out = v[0].clone()
+        for r in range(1, world):
+            out |= v[r]
+        mine = out.view(torch.uint8)
+    return mine[:nbytes], bits
+
+
 N_PIECES = 2      # a rank partitions its reads in this many pieces: piece i travels while piece i+1 is being partitioned
 
 

@@ -234,6 +234,11 @@ int   gatb_gpu_synchronize (gatb_gpu_ctx*);
  * writes reads [first_read, first_read+n_reads) of length L, packed back to back, into d_packed. */
 int   gatb_gpu_synth_reads_dev (gatb_gpu_ctx*, uint64_t seed, uint64_t genome_len, uint64_t first_read,
                                 uint64_t n_reads, int L, uint8_t* d_packed);
+/* Metagenome-like reads (BASELINE.json config 5; bit-identical to oracle/kmer_oracle.c orc_synth_reads_zipf): n_species genomes laid
+ * end to end (genome_off[n_species+1], host), the species of a read drawn through the threshold table cdf[n_species] (host,
+ * built by the caller, e.g. Zipf with exponent 1.1), then start / strand / 1 % substitutions as above. */
+int   gatb_gpu_synth_zipf_dev (gatb_gpu_ctx*, uint64_t seed, uint64_t n_species, const uint64_t* cdf, const uint64_t* genome_off,
+                               uint64_t first_read, uint64_t n_reads, int L, uint8_t* d_packed);
 /* 2-bit packer for ASCII reads concatenated without separators (host in, host out; n_mask_out may be NULL):
  * the device-side analogue of bank::Sequence -> Data::ConvertASCII (tools/misc/api/Data.hpp:185). */
 int   gatb_gpu_pack_ascii (gatb_gpu_ctx*, const char* ascii, uint64_t n, uint8_t* packed_out, uint32_t* n_mask_out,

@@ -667,6 +667,48 @@ void orc_synth_reads (uint64_t seed, uint64_t genome_len, uint64_t first_read, u
         }
     }
 }
+/* ---- metagenome-like workload (BASELINE.json config 5): n_species genomes of 10^5..10^6 nt laid end to end in one
+ * coordinate space (genome_off[s] .. genome_off[s+1]), the species of a read drawn from Zipf(exponent) through a table of
+ * 64-bit thresholds (species = first s with h < cdf[s]); otherwise like orc_synth_reads (start, strand flip, 1 % substitutions).
+ * The tables are computed ONCE on the host (doubles, pow) and handed to the device generator as they are, so both sides use the
+ * same bits. ---- */
+void orc_zipf_tables (uint64_t seed, uint64_t n_species, double exponent, uint64_t* cdf, uint64_t* genome_off)
+{
+    double total = 0, run = 0;
+    for (uint64_t s=0; s<n_species; s++)  total += 1.0 / pow ((double)(s+1), exponent);
+    genome_off[0] = 0;
+    for (uint64_t s=0; s<n_species; s++)
+    {
+        run += 1.0 / pow ((double)(s+1), exponent);
+        double f = run / total;
+        cdf[s] = (s+1 == n_species || f >= 1.0) ? ~0ULL : (uint64_t)(f * 18446744073709551615.0);
+        genome_off[s+1] = genome_off[s] + 100000 + orc_splitmix64 ((seed ^ 0x5EEDC0DE00000003ULL) + s) % 900001;
+    }
+}
+void orc_synth_reads_zipf (uint64_t seed, uint64_t n_species, const uint64_t* cdf, const uint64_t* genome_off, uint64_t first_read,
+                           uint64_t n_reads, int L, uint8_t* codes)
+{
+    uint64_t sR = orc_splitmix64 (seed ^ 0x5EEDC0DE00000001ULL), sE = orc_splitmix64 (seed ^ 0x5EEDC0DE00000002ULL);
+    #pragma omp parallel for schedule(static)
+    for (uint64_t i=0; i<n_reads; i++)
+    {
+        uint64_t r = first_read + i;
+        uint64_t h0 = orc_splitmix64 (sR + 3*r), h1 = orc_splitmix64 (sR + 3*r + 1), h2 = orc_splitmix64 (sR + 3*r + 2);
+        uint64_t lo = 0, hi = n_species - 1;                       /* first s with h2 <= cdf[s] */
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (h2 <= cdf[mid]) hi = mid; else lo = mid + 1; }
+        uint64_t glen = genome_off[lo+1] - genome_off[lo];
+        uint64_t start = genome_off[lo] + h0 % (glen - L + 1);
+        int flip = (int)(h1 >> 63);
+        uint8_t* out = codes + i * (uint64_t)L;
+        for (int j=0; j<L; j++)
+        {
+            uint8_t b = genome_base (seed, start + j);
+            uint64_t e = orc_splitmix64 (sE + r * (uint64_t)L + j);
+            if ((e % 100) == 0)  b = (uint8_t)((b + 1 + ((e >> 32) % 3)) & 3);
+            if (flip)  out[L-1-j] = b ^ 2;  else out[j] = b;
+        }
+    }
+}
 void orc_pack_2bit (const uint8_t* codes, uint64_t n, uint8_t* packed)
 {
     memset (packed, 0, (n + 3)/4);

@@ -80,6 +80,9 @@ uint64_t orc_splitmix64 (uint64_t x);
 /* codes A=0 C=1 T=2 G=3, one byte per nucleotide, n_reads*L bytes */
 void orc_synth_reads (uint64_t seed, uint64_t genome_len, uint64_t first_read, uint64_t n_reads, int L, uint8_t* codes);
 /* packs codes (one per byte) to the 2-bit little-endian stream used by the C-ABI: nt i -> bits [2(i%4), 2(i%4)+2) of byte i/4 */
+void orc_zipf_tables (uint64_t seed, uint64_t n_species, double exponent, uint64_t* cdf, uint64_t* genome_off);
+void orc_synth_reads_zipf (uint64_t seed, uint64_t n_species, const uint64_t* cdf, const uint64_t* genome_off, uint64_t first_read,
+                           uint64_t n_reads, int L, uint8_t* codes);
 void orc_pack_2bit (const uint8_t* codes, uint64_t n, uint8_t* packed);
 void orc_codes_to_ascii (const uint8_t* codes, uint64_t n, char* ascii);
 

@@ -70,6 +70,8 @@ class Oracle:
         L.orc_splitmix64.argtypes = [C.c_uint64]
         L.orc_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, u8p]
         L.orc_pack_2bit.argtypes = [u8p, C.c_uint64, u8p]
+        L.orc_zipf_tables.argtypes = [C.c_uint64, C.c_uint64, C.c_double, u64p, u64p]
+        L.orc_synth_reads_zipf.argtypes = [C.c_uint64, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint64, C.c_int, u8p]
         L.orc_codes_to_ascii.argtypes = [u8p, C.c_uint64, VP]
 
     # ---- helpers -------------------------------------------------------------------------------------
@@ -147,6 +149,17 @@ class Oracle:
     def synth_reads(self, seed, genome_len, first_read, n_reads, L):
         codes = np.zeros(n_reads * L, np.uint8)
         self.L.orc_synth_reads(seed, genome_len, first_read, n_reads, L, codes)
+        return codes
+
+    def zipf_tables(self, seed, n_species, exponent=1.1):
+        """(cdf thresholds u64[n_species], genome offsets u64[n_species+1]) of the metagenome-like generator (config 5)."""
+        cdf, off = np.zeros(n_species, np.uint64), np.zeros(n_species + 1, np.uint64)
+        self.L.orc_zipf_tables(seed, n_species, exponent, cdf, off)
+        return cdf, off
+
+    def synth_reads_zipf(self, seed, cdf, off, first_read, n_reads, L):
+        codes = np.zeros(n_reads * L, np.uint8)
+        self.L.orc_synth_reads_zipf(seed, len(cdf), cdf, off, first_read, n_reads, L, codes)
         return codes
 
     def pack_2bit(self, codes):

@@ -470,3 +470,37 @@ def test_multi_gpu_equals_single_gpu():
                         "--master-port", "29733", os.path.join(root, "tools", "check_multigpu.py")], capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("GPUs == 1 GPU") == 2, r.stdout[-2000:]
+
+
+# ---- BASELINE.json config 5 (metagenome-like Zipf skew) at a reduced size: generator parity, counts against the oracle, overflow
+#      statistics, and the Bloom filter of the solid k-mers ----
+def test_zipf_metagenome_generator_and_counts(gpu, oracle):
+    n_species, n, L, k, m = 300, 60000, 150, 31, 10
+    cdf, off = oracle.zipf_tables(45, n_species, 1.1)
+    codes = oracle.synth_reads_zipf(45, cdf, off, 1234, n, L)
+    want_packed = oracle.pack_2bit(codes)
+    d = gpu.malloc(len(want_packed) + 64)
+    gpu.synth_zipf_dev(45, cdf, off, 1234, n, L, d)
+    got_packed = np.zeros((len(want_packed) + 3) // 4 * 4, np.uint8)
+    gpu.d2h(got_packed, d)
+    assert (got_packed[:len(want_packed)] == want_packed).all()
+    # the species sizes follow the table: the first species holds the Zipf share of the reads
+    share0 = float(cdf[0]) / 2.0 ** 64
+    assert 0.1 < share0 < 0.3
+    params = gpu.make_params(k, m, nb_partitions=4, abundance_min=2, read_len=L)
+    repart = (np.arange(4 ** m) * 2654435761 % 4).astype(np.uint16)
+    res = gpu.count_dev(d, None, n, params, repart=repart)
+    got = gpu.result_to_host(res, params)
+    gpu.result_free(res)
+    gpu.free(d)
+    seqs = [oracle.codes_to_ascii(r) for r in codes.reshape(n, L)]
+    want = oracle.dsk(seqs, k, m, repart, 4, abundance_min=2)
+    check_parts(got, want["solid"], 4, 1)
+    assert (got["histogram"] == want["histogram"]).all()
+    # the dominant species is covered several times, most others less than once
+    assert max(int(c.max()) for _, _, c in got["parts"].values() if len(c)) > 5
+    lo = np.concatenate([got["parts"][key][0] for key in range(4)])
+    size, nh = gpu.bloom_params(k, len(lo))
+    b, _ = gpu.bloom("neighbor", size, nh, k, lo)
+    ob, _ = oracle.bloom("neighbor", size, nh, k, 1, lo)
+    assert (b == ob).all()

@@ -32,6 +32,8 @@ def main():
         gpu.synchronize()
         res, stats = multigpu.count_distributed(gpu, params, reads.data_ptr(), n, n_global, n_global * (L - k + 1), rank, world, repart=repart)
         mine = gpu.result_to_host(res, params)
+        bloom, bloom_bits = multigpu.bloom_distributed(gpu, "neighbor", k, res, stats["kmers_nb_solid"], world)
+        bloom = bloom.cpu().numpy()
         gpu.result_free(res)
         gathered = [None] * world
         dist.all_gather_object(gathered, {"parts": mine["parts"], "hist": mine["histogram"]})
@@ -51,7 +53,13 @@ def main():
             hist = sum(g["hist"].astype(np.int64) for g in gathered)
             assert (hist == want["histogram"].astype(np.int64)).all()
             assert stats["kmers_nb_distinct"] == want["stats"]["kmers_nb_distinct"]
-            print("k=%d: %d GPUs == 1 GPU: %d distinct, %d solid k-mers, histogram identical" % (k, world, stats["kmers_nb_distinct"], stats["kmers_nb_solid"]))
+            # Bloom filter of ALL solid k-mers on one GPU == per-rank filters gathered and OR-ed
+            lo1 = np.concatenate([want["parts"][key][0] for key in range(nparts)])
+            hi1 = np.concatenate([want["parts"][key][1] for key in range(nparts)]) if k > 31 else None
+            size, nh = gpu.bloom_params(k, len(lo1))
+            b1, bits1 = gpu.bloom("neighbor", size, nh, k, lo1, hi1)
+            assert bits1 == bloom_bits and len(b1) == len(bloom) and (b1 == bloom).all(), "distributed Bloom filter differs"
+            print("k=%d: %d GPUs == 1 GPU: %d distinct, %d solid k-mers, histogram identical, Bloom filter (%d bytes) identical" % (k, world, stats["kmers_nb_distinct"], stats["kmers_nb_solid"], len(bloom)))
         dist.barrier()
     gpu.close()
     dist.destroy_process_group()
