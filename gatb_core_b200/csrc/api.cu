@@ -292,9 +292,11 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     else
     {
         const uint64_t occ_per_bin = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : (W == 1 ? 80 : 55))) / 100 + 1;
-        // k <= 31: the coarse bins keep their size whatever the number of ranks (a gathered bin must fit the shared memory of the
-        // dedup split, k2a_dedup_split), so nb1 -- the bins every rank scatters into -- grows with the job: 3.7 million at 8 GPUs
-        // and 8*10^8 reads, a rank's piece of a bin is a few blocks of 64 records.  (Round 1 kept nb1 fixed and grew the bins.)
+        // k <= 31: one more fine-bin bit per doubling of the ranks, so that nb1 (the coarse bins every rank scatters into) stays
+        // put: the partition kernel's scattered 16-byte stores are combined in L2, one open 128-byte line per bin, and 3.7 million
+        // bins (measured on 8 GPUs with bins of constant size) thrash it: k1 49 -> 94 ms.  The gathered bins grow instead; the
+        // dedup split takes them in several passes over ranges of fine-bin ids.
+        if (W == 1) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
         uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
         nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits;
     }
@@ -435,11 +437,13 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
                                     (uint2*)ctx->slot[S_BINDESC], rmax, (uint32_t*)ctx->slot[S_OVFLIST], d_k2a));
         unsigned long long h_k2a[2] = { 0, 0 };
         if (max_bin > rmax)
-        {   // bins too large for shared memory: the plain two-pass split (multiplicity 1)
+        {   // bins larger than the staging area take several passes inside the kernel; those it gave up on (a skewed range of fine
+            // ids, or more passes than fine bins) go through the plain two-pass split (multiplicity 1)
             CK (cudaMemcpyAsync (h_k2a, d_k2a, 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK (cudaStreamSynchronize (ctx->stream));
-            CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
-                                  (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)h_k2a[0]));
+            if (h_k2a[0])
+                CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
+                                      (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)h_k2a[0]));
         }
         CK (cudaMemcpyAsync (h_k2a, d_k2a, 16, cudaMemcpyDeviceToHost, ctx->stream));
         cudaEventRecord (ctx->kev[3], ctx->stream);

@@ -125,28 +125,32 @@ __global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __
     uint32_t* s_cur = s_off + nf;
     uint32_t* s_tmp = s_cur + nf;
     __shared__ uint32_t s_first[17];
+    __shared__ uint32_t s_staged, s_written;
     const int tid = threadIdx.x;
     const uint32_t tmask = ts - 1;
     unsigned long long n_unique = 0;
     for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x)
     {
         __syncthreads ();
-        for (uint32_t i = tid; i < ts; i += NT) tbl[i] = 0xFFFFFFFFu;
-        for (int i = tid; i < nf; i += NT) { s_tmp[i] = 0; s_cur[i] = 0; }
         if (tid == 0)
         {
             uint32_t run = 0;
             for (int s = 0; s < S.n; s++) { s_first[s] = run; run += min (S.cursors[s][b], cap); }
             for (int s = S.n; s <= 16; s++) s_first[s] = run;
+            s_written = 0;
         }
         __syncthreads ();
         const uint32_t n_all = s_first[16];
-        if (n_all > rmax)
-        {   // rare: handed to the two-pass kernel
+        // A bin that fits the staging area is done in one pass.  A larger one (several ranks gather into one bin; dense bin loads)
+        // takes P passes over ranges of fine-bin ids: pass j stages only the records of its range -- the passes after the first
+        // find the bin in L2 -- so that identical records still collapse whatever the size of the bin.  (fine ids are hashed:
+        // a range holds n_all / P records give or take a few per cent; 80 % of the staging area is planned.)
+        const uint32_t P = n_all <= rmax ? 1u : (uint32_t)(((uint64_t)n_all * 5 + 4 * rmax - 1) / (4 * (uint64_t)rmax));
+        if (P > (uint32_t)nf)
+        {   // more passes than fine bins: handed to the two-pass kernel
             if (tid == 0) { const uint32_t idx = (uint32_t) atomicAdd (&counters[0], 1ULL); big_list[idx] = b; }
             continue;
         }
-        // ---- stage the bin: four independent 16-byte loads in flight per thread ----
         auto src_of = [&] (uint32_t g) -> const uint4*
         {
             int s = 0;
@@ -154,67 +158,108 @@ __global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __
             for (int u = 8; u > 0; u >>= 1) if (s + u < 16 && g >= s_first[s + u]) s += u;
             return S.bins[s] + k2a_record_index (S, s, b, g - s_first[s], nb);
         };
-        for (uint32_t g0 = tid; g0 < n_all; g0 += 4 * NT)
-        {
-            uint4 r[4];
-            #pragma unroll
-            for (int u = 0; u < 4; u++) { const uint32_t g = g0 + u * NT; if (g < n_all) r[u] = __ldg (src_of (g)); }
-            #pragma unroll
-            for (int u = 0; u < 4; u++) { const uint32_t g = g0 + u * NT; if (g < n_all) recs[g] = r[u]; }
-        }
-        __syncthreads ();
-        // ---- collapse identical records ----
-        for (uint32_t g = tid; g < n_all; g += NT)
-        {
-            const uint4 r = recs[g];
-            uint32_t h = (r.x * 0x9E3779B1u) ^ (r.y * 0x85EBCA77u) ^ (r.z * 0xC2B2AE3Du) ^ (r.w * 0x27D4EB2Fu);
-            h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
-            h &= tmask;
-            for (;;)
-            {
-                uint32_t e = *(volatile uint32_t*)&tbl[h];
-                if (e == 0xFFFFFFFFu) { e = atomicCAS (&tbl[h], 0xFFFFFFFFu, g | (1u << 16)); if (e == 0xFFFFFFFFu) break; }
-                const uint4 o = recs[e & 0xFFFFu];
-                if (o.x == r.x && o.y == r.y && o.z == r.z && o.w == r.w) { atomicAdd (&tbl[h], 1u << 16); break; }
-                h = (h + 1) & tmask;
-            }
-        }
-        __syncthreads ();
-        // ---- distinct records per fine bin ----
-        for (uint32_t i = tid; i < ts; i += NT)
-        {
-            const uint32_t e = tbl[i];
-            if (e != 0xFFFFFFFFu) atomicAdd (&s_tmp[recs[e & 0xFFFFu].w >> (DEV_FINE_SHIFT_W1 - 32)], 1u);
-        }
-        __syncthreads ();
-        if (tid < 32)
-        {
-            const int per = nf > 32 ? nf / 32 : 1;
-            uint32_t sum = 0;
-            for (int i = 0; i < per; i++) { const int idx = tid * per + i; if (idx < nf) sum += s_tmp[idx]; }
-            uint32_t incl = sum;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (tid >= o) incl += y; }
-            uint32_t run = incl - sum;
-            for (int i = 0; i < per; i++)
-            {
-                const int idx = tid * per + i;
-                if (idx < nf) { const uint32_t v = s_tmp[idx]; s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v); run += v; }
-            }
-            if (tid == 31) n_unique += run;
-        }
-        __syncthreads ();
-        // ---- write them in fine-bin order, multiplicity in place of the fine-bin id ----
         const uint64_t dbase = coarse_off[b];
-        for (uint32_t i = tid; i < ts; i += NT)
+        bool failed = false;
+        for (uint32_t pass = 0; pass < P && !failed; pass++)
         {
-            const uint32_t e = tbl[i];
-            if (e == 0xFFFFFFFFu) continue;
-            uint4 r = recs[e & 0xFFFFu];
-            const uint32_t f = r.w >> (DEV_FINE_SHIFT_W1 - 32);
-            const uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
-            r.w = (r.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | ((e >> 16) << (DEV_FINE_SHIFT_W1 - 32));
-            dst[dbase + p] = r;
+            const uint32_t f_lo = (uint32_t)((uint64_t)nf * pass / P), f_hi = (uint32_t)((uint64_t)nf * (pass + 1) / P);
+            for (uint32_t i = tid; i < ts; i += NT) tbl[i] = 0xFFFFFFFFu;
+            for (uint32_t i = f_lo + tid; i < f_hi; i += NT) { s_tmp[i] = 0; s_cur[i] = 0; }
+            if (tid == 0) s_staged = 0;
+            __syncthreads ();
+            // ---- stage the records of this pass: four independent 16-byte loads in flight per thread ----
+            uint32_t n_st;
+            if (P == 1)
+            {
+                for (uint32_t g0 = tid; g0 < n_all; g0 += 4 * NT)
+                {
+                    uint4 r[4];
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++) { const uint32_t g = g0 + u * NT; if (g < n_all) r[u] = __ldg (src_of (g)); }
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++) { const uint32_t g = g0 + u * NT; if (g < n_all) recs[g] = r[u]; }
+                }
+                __syncthreads ();
+                n_st = n_all;
+            }
+            else
+            {
+                for (uint32_t g0 = tid; g0 < n_all; g0 += 4 * NT)
+                {
+                    uint4 r[4];
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++) { const uint32_t g = g0 + u * NT; if (g < n_all) r[u] = __ldg (src_of (g)); }
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++)
+                    {
+                        const uint32_t g = g0 + u * NT;
+                        const uint32_t f = (g < n_all) ? (r[u].w >> (DEV_FINE_SHIFT_W1 - 32)) : 0xFFFFFFFFu;
+                        if (f >= f_lo && f < f_hi) { const uint32_t at = atomicAdd (&s_staged, 1u); if (at < rmax) recs[at] = r[u]; }
+                    }
+                }
+                __syncthreads ();
+                n_st = s_staged;
+                if (n_st > rmax) { failed = true; break; }                  // CTA-uniform
+            }
+            // ---- collapse identical records ----
+            for (uint32_t g = tid; g < n_st; g += NT)
+            {
+                const uint4 r = recs[g];
+                uint32_t h = (r.x * 0x9E3779B1u) ^ (r.y * 0x85EBCA77u) ^ (r.z * 0xC2B2AE3Du) ^ (r.w * 0x27D4EB2Fu);
+                h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+                h &= tmask;
+                for (;;)
+                {
+                    uint32_t e = *(volatile uint32_t*)&tbl[h];
+                    if (e == 0xFFFFFFFFu) { e = atomicCAS (&tbl[h], 0xFFFFFFFFu, g | (1u << 16)); if (e == 0xFFFFFFFFu) break; }
+                    const uint4 o = recs[e & 0xFFFFu];
+                    if (o.x == r.x && o.y == r.y && o.z == r.z && o.w == r.w) { atomicAdd (&tbl[h], 1u << 16); break; }
+                    h = (h + 1) & tmask;
+                }
+            }
+            __syncthreads ();
+            // ---- distinct records per fine bin ----
+            for (uint32_t i = tid; i < ts; i += NT)
+            {
+                const uint32_t e = tbl[i];
+                if (e != 0xFFFFFFFFu) atomicAdd (&s_tmp[recs[e & 0xFFFFu].w >> (DEV_FINE_SHIFT_W1 - 32)], 1u);
+            }
+            __syncthreads ();
+            if (tid < 32)
+            {   // exclusive scan of the counters of this pass' range by one warp; offsets continue after the previous passes
+                const uint32_t nr = f_hi - f_lo;
+                const uint32_t per = (nr + 31) / 32;
+                uint32_t sum = 0;
+                for (uint32_t i = 0; i < per; i++) { const uint32_t idx = f_lo + tid * per + i; if (idx < f_hi) sum += s_tmp[idx]; }
+                uint32_t incl = sum;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (tid >= o) incl += y; }
+                uint32_t run = s_written + incl - sum;
+                for (uint32_t i = 0; i < per; i++)
+                {
+                    const uint32_t idx = f_lo + tid * per + i;
+                    if (idx < f_hi) { const uint32_t v = s_tmp[idx]; s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v); run += v; }
+                }
+                __syncwarp ();
+                if (tid == 31) { n_unique += run - s_written; s_written = run; }
+            }
+            __syncthreads ();
+            // ---- write them in fine-bin order, multiplicity in place of the fine-bin id ----
+            for (uint32_t i = tid; i < ts; i += NT)
+            {
+                const uint32_t e = tbl[i];
+                if (e == 0xFFFFFFFFu) continue;
+                uint4 r = recs[e & 0xFFFFu];
+                const uint32_t f = r.w >> (DEV_FINE_SHIFT_W1 - 32);
+                const uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+                r.w = (r.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | ((e >> 16) << (DEV_FINE_SHIFT_W1 - 32));
+                dst[dbase + p] = r;
+            }
+            __syncthreads ();
+        }
+        if (failed)
+        {   // a range overfilled the staging area (skewed fine ids): the two-pass kernel redoes the whole bin
+            if (tid == 0) { const uint32_t idx = (uint32_t) atomicAdd (&counters[0], 1ULL); big_list[idx] = b; }
         }
     }
     if (tid == 31 && n_unique) atomicAdd (&counters[1], n_unique);
@@ -231,7 +276,7 @@ cudaError_t launch_k2a_split (const LaunchCtx& L, int W, const K2aSrc& src, void
     return cudaGetLastError ();
 }
 
-// k <= 31: dedup + split of all bins; counters[0] = bins listed in big_list (more than rmax records), counters[1] = distinct records written
+// k <= 31: dedup + split of all bins; counters[0] = bins listed in big_list (handed to the two-pass kernel), counters[1] = distinct records written
 uint32_t k2a_dedup_rmax (uint32_t max_bin_records, int fine_bits)
 {
     // records + table (next power of two >= 1.3 rmax) + counters within 200 KB; at most 8191 (multiplicities keep 15 bits, indices 16)
@@ -244,13 +289,10 @@ uint32_t k2a_dedup_rmax (uint32_t max_bin_records, int fine_bits)
         rmax -= 256;
     }
 }
-cudaError_t launch_k2a_dedup_split (const LaunchCtx& L, const K2aSrc& src, void* dst, const uint64_t* coarse_off, uint32_t nb1, uint32_t cap,
-                                    int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t* big_list, unsigned long long* counters)
+template<int NT>
+static cudaError_t k2a_dedup_launch (const LaunchCtx& L, const K2aSrc& src, void* dst, const uint64_t* coarse_off, uint32_t nb1, uint32_t cap,
+                                     int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t ts, size_t smem, uint32_t* big_list, unsigned long long* counters)
 {
-    if (nb1 == 0) return cudaSuccess;
-    constexpr int NT = 512;
-    uint32_t ts = 256; while (ts < rmax + rmax / 3) ts <<= 1;
-    const size_t smem = (size_t)rmax * 16 + (size_t)ts * 4 + 3 * ((size_t)4 << fine_bits);
     cudaError_t e = cudaFuncSetAttribute (k2a_dedup_split<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -262,6 +304,16 @@ cudaError_t launch_k2a_dedup_split (const LaunchCtx& L, const K2aSrc& src, void*
     k2a_dedup_split<NT><<<(unsigned)grid, NT, smem, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, big_list, counters);
     (*L.launches)++;
     return cudaGetLastError ();
+}
+cudaError_t launch_k2a_dedup_split (const LaunchCtx& L, const K2aSrc& src, void* dst, const uint64_t* coarse_off, uint32_t nb1, uint32_t cap,
+                                    int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t* big_list, unsigned long long* counters)
+{
+    if (nb1 == 0) return cudaSuccess;
+    uint32_t ts = 256; while (ts < rmax + rmax / 3) ts <<= 1;
+    const size_t smem = (size_t)rmax * 16 + (size_t)ts * 4 + 3 * ((size_t)4 << fine_bits);
+    // a staging area so large that only one CTA fits an SM (bins gathered from several ranks): 1024 threads keep the SM busy
+    if (smem > 113 * 1024) return k2a_dedup_launch<1024> (L, src, dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, smem, big_list, counters);
+    return k2a_dedup_launch<512> (L, src, dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, smem, big_list, counters);
 }
 
 // ------------------------------------------------------------------------------------------------ record decoding
