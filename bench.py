@@ -263,7 +263,7 @@ def run_ours(args):
     gpu.synchronize()
     nb_passes, nb_partitions, repart, repart_src = reference_configuration(gpu, n, args)
     params = gpu.make_params(K, M, nb_partitions=nb_partitions, nb_passes=nb_passes, abundance_min=ABUNDANCE_MIN, read_len=L,
-                             path_flags=args.path_flags, bin_load_pct=args.bin_load_pct, table_log2=args.table_log2, fine_bits=args.fine_bits)
+                             path_flags=args.path_flags, bin_load_pct=args.bin_load_pct, table_log2=args.table_log2, fine_bits=args.fine_bits, bin_target_pct=args.bin_target_pct)
     stream = torch.cuda.ExternalStream(gpu.stream, device=torch.device("cuda", local))
 
     def step():
@@ -443,6 +443,7 @@ def main():
     ap.add_argument("--path-flags", type=int, default=0, help="gatb_gpu_params.path_flags (experiments; 0 = the product path)")
     ap.add_argument("--bin-load-pct", type=int, default=0, help="gatb_gpu_params.bin_load_pct (experiments; 0 = default)")
     ap.add_argument("--fine-bits", type=int, default=0, help="gatb_gpu_params.fine_bits (experiments; 0 = default)")
+    ap.add_argument("--bin-target-pct", type=int, default=0, help="gatb_gpu_params.bin_target_pct (experiments; 0 = default)")
     ap.add_argument("--table-log2", type=int, default=0, help="gatb_gpu_params.table_log2 (experiments; 0 = default)")
     ap.add_argument("--staged", action="store_true", help="N=1 through the staged multi-GPU code path (debugging aid)")
     args = ap.parse_args()

@@ -36,12 +36,13 @@ class Params(C.Structure):
                 ("nb_passes", C.c_int32), ("abundance_min", C.c_int32), ("abundance_max", C.c_int32),
                 ("histo_max", C.c_int32), ("minimizer_type", C.c_int32), ("emit_all", C.c_int32),
                 ("read_len", C.c_int32), ("table_log2", C.c_int32), ("path_flags", C.c_int32),
-                ("k3_dir_rounds", C.c_int32), ("bin_load_pct", C.c_int32), ("fine_bits", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("k3_dir_rounds", C.c_int32), ("bin_load_pct", C.c_int32), ("fine_bits", C.c_int32), ("bin_target_pct", C.c_int32)]
 
 
 # gatb_gpu_params.path_flags (include/gatb_gpu.h): selectors of the alternate code paths, 0 = the product path
 PATH_K1_GENERAL, PATH_K2B_CTA128, PATH_K2B_CTA256, PATH_K2B_LANE = 1, 2, 4, 6
 PATH_K2B_W2_WARP, PATH_NO_TIER2, PATH_K3_NO_POOL, PATH_CANONICAL, PATH_NO_DEDUP, PATH_FUSED, PATH_K1_STAGING = 8, 16, 32, 64, 128, 256, 512
+PATH_K2A_SMALL_STAGE, PATH_K2A_PRESPLIT = 1024, 2048
 
 
 class Result(C.Structure):
@@ -154,9 +155,10 @@ class GatbGpu:
     # ---- DSK ---------------------------------------------------------------------------------------------------
     @staticmethod
     def make_params(k, m, nb_partitions=1, nb_passes=1, abundance_min=2, abundance_max=2**31 - 1, histo_max=10000,
-                    emit_all=False, read_len=0, table_log2=0, path_flags=0, k3_dir_rounds=0, bin_load_pct=0, fine_bits=0):
+                    emit_all=False, read_len=0, table_log2=0, path_flags=0, k3_dir_rounds=0, bin_load_pct=0, fine_bits=0, bin_target_pct=0):
         p = Params()
         p.path_flags, p.k3_dir_rounds, p.bin_load_pct, p.fine_bits = path_flags, k3_dir_rounds, bin_load_pct, fine_bits
+        p.bin_target_pct = bin_target_pct
         p.kmer_size, p.minimizer_size, p.nb_partitions, p.nb_passes = k, m, nb_partitions, nb_passes
         p.abundance_min, p.abundance_max, p.histo_max, p.minimizer_type = abundance_min, abundance_max, histo_max, 0
         p.emit_all, p.read_len, p.table_log2 = int(emit_all), read_len, table_log2

@@ -17,7 +17,7 @@ static std::string g_create_error;
 
 // device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
 enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
-            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_OVFLIST2, S_BINOFF, S_NSLOTS };
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_OVFLIST2, S_BINOFF, S_PRESPLIT, S_SUBOFF, S_SUBCNT, S_NSLOTS };
 
 struct gatb_gpu_ctx
 {
@@ -264,18 +264,20 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
     const bool fused = path_fused (p);
     int table_log2 = p->table_log2 > 0 ? p->table_log2 : (fused ? 13 : k2b_default_table_log2 (W, p->path_flags));
-    // multi-Gb inputs crowd the 16-mer minimizer space of the register scanner (4*10^9 nt: every minimizer value marks ~3 loci),
-    // the fine-bin loads get a heavy tail and 9 % of the bins overflowed a warp's 512-slot table (measured on 8 GPUs: 69 ms in
-    // the tier kernels).  1024-slot tables cost the first tier 35 % but absorb the tail.
-    if (p->table_log2 == 0 && W == 1 && !fused && table_log2 == 9 && total_kmers > 40000000000ULL) table_log2 = 10;
     if (table_log2 < 5 || table_log2 > 13) return fail (ctx, "table_log2 must be in [5,13]");
     if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
     const uint64_t T = 1ULL << table_log2;
     if (p->bin_load_pct < 0 || p->bin_load_pct > 400) return fail (ctx, "bin_load_pct must be in [0,400]");
-    // k <= 31: 64 fine bins per coarse bin (measured best on B200: the dedup split stages a ~2300-record coarse bin in 37 KB of
-    // shared memory, several CTAs per SM); the record keeps up to 10 bits of fine-bin id for multi-GPU geometries
-    int fine_bits = (W == 1) ? 6 : FINE_BITS_W2;
+    // k <= 31: a coarse bin is planned for 64 counting bins (measured best on B200: the dedup split stages a ~3300-record coarse bin
+    // in shared memory, several CTAs per SM) and carries 512 fine ids: the dedup split merges consecutive ids into counting bins of
+    // even load (k2a_dedup_split, "adaptive bins").  One more id bit per doubling of the ranks, so that nb1 (the coarse bins every
+    // rank scatters into) stays put: the partition kernel's scattered 16-byte stores are combined in L2, one open 128-byte line per
+    // bin, and 3.7 million bins (measured on 8 GPUs with bins of constant size) thrash it: k1 49 -> 94 ms.  The gathered bins grow
+    // instead; the dedup split takes them in several passes over ranges of fine ids.
+    const int coarse_log2 = 6;                                                  // planned counting bins per coarse bin and rank
+    int fine_bits = (W == 1) ? 9 : FINE_BITS_W2;
     if (fused) fine_bits = 5;
+    if (W == 1 && !fused) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
     if (W == 1 && p->fine_bits > 0)
     {
         if (p->fine_bits > DEV_FINE_BITS_MAX_W1) return fail (ctx, "fine_bits must be in [1,%d]", (int)DEV_FINE_BITS_MAX_W1);
@@ -292,13 +294,10 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
     else
     {
         const uint64_t occ_per_bin = (T * (p->bin_load_pct > 0 ? p->bin_load_pct : (W == 1 ? 80 : 55))) / 100 + 1;
-        // k <= 31: one more fine-bin bit per doubling of the ranks, so that nb1 (the coarse bins every rank scatters into) stays
-        // put: the partition kernel's scattered 16-byte stores are combined in L2, one open 128-byte line per bin, and 3.7 million
-        // bins (measured on 8 GPUs with bins of constant size) thrash it: k1 49 -> 94 ms.  The gathered bins grow instead; the
-        // dedup split takes them in several passes over ranges of fine-bin ids.
-        if (W == 1) for (int r = 1; r < n_ranks && fine_bits < DEV_FINE_BITS_MAX_W1; r <<= 1) fine_bits++;
         uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
-        nb1 = (nbins_fine + (1ULL << fine_bits) - 1) >> fine_bits;
+        int split_log2 = fine_bits;                                             // k >= 32: the fine ids ARE the counting bins
+        if (W == 1) { split_log2 = coarse_log2; for (int r = 1; r < n_ranks; r <<= 1) split_log2++; }    // nb1 stays put, the gathered bins grow
+        nb1 = (nbins_fine + (1ULL << split_log2) - 1) >> split_log2;
     }
     if (nb1 < 1) nb1 = 1;
     nb1 = (nb1 + n_ranks - 1) / n_ranks * n_ranks;                              // every rank owns nb1/n_ranks consecutive coarse bins
@@ -405,7 +404,8 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     if (ensure (ctx, S_TOTCUR, (size_t)nb1_local * 4)) return 1;
     if (ensure (ctx, S_COARSEOFF, ((size_t)nb1_local + 1) * 8)) return 1;
     if (ensure (ctx, S_SCAN, scan_scratch_elems (nb1_local > (n_keys << 24) ? nb1_local : (n_keys << 24)) * 8)) return 1;
-    if (ensure (ctx, S_BINDESC, nbins * 8)) return 1;
+    const uint64_t desc_cap = nbins + nbins / 8 + 1024;          // (adaptive bins: at most one per fine id, plus the bins of the two-pass fallback)
+    if (ensure (ctx, S_BINDESC, desc_cap * 8)) return 1;
     CursorList CL; CL.n = n_src; for (int s = 0; s < n_src; s++) CL.cur[s] = d_src_cursors[s];
     if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
     uint32_t* d_maxbin = (uint32_t*)((unsigned long long*)ctx->slot[S_COUNTERS] + 15);
@@ -426,29 +426,70 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     for (int s = 0; s < n_src; s++) { S2.bins[s] = (const uint4*)d_src_bins[s]; S2.cursors[s] = d_src_cursors[s]; S2.off[s] = d_src_off ? d_src_off[s] : 0; }
     cudaEventRecord (ctx->kev[2], ctx->stream);
     uint64_t n_unique_records = n_records;
+    uint64_t nbins_count = nbins;                  // bins the counting kernels see (the dedup split forms its own: adaptive bins)
+    bool desc_abs = false;                         // their descriptors hold absolute record offsets
     if (fused) cudaEventRecord (ctx->kev[3], ctx->stream);
     else if (W == 1 && dedup && n_records)
     {   // ---- k <= 31: the bin is staged in shared memory once, identical records collapse, multiplicities travel with the records ----
+        if (n_records >= (1ULL << 32)) return fail (ctx, "too many super-k-mer records for one device (%llu): use more passes or more GPUs", (unsigned long long)n_records);
         if (ensure (ctx, S_OVFLIST, (nbins > nb1_local ? nbins : nb1_local) * 4)) return 1;
         unsigned long long* d_k2a = (unsigned long long*)ctx->slot[S_COUNTERS] + 12;
-        CK (cudaMemsetAsync (d_k2a, 0, 2 * 8, ctx->stream));
-        const uint32_t rmax = k2a_dedup_rmax (max_bin, fine_bits);
-        CK (launch_k2a_dedup_split (L, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
-                                    (uint2*)ctx->slot[S_BINDESC], rmax, (uint32_t*)ctx->slot[S_OVFLIST], d_k2a));
-        unsigned long long h_k2a[2] = { 0, 0 };
-        if (max_bin > rmax)
-        {   // bins larger than the staging area take several passes inside the kernel; those it gave up on (a skewed range of fine
-            // ids, or more passes than fine bins) go through the plain two-pass split (multiplicity 1)
-            CK (cudaMemcpyAsync (h_k2a, d_k2a, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK (cudaStreamSynchronize (ctx->stream));
-            if (h_k2a[0])
-                CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
-                                      (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)h_k2a[0]));
+        CK (cudaMemsetAsync (d_k2a, 0, 3 * 8, ctx->stream));
+        // ---- bins gathered from several ranks are several times larger than a CTA's staging area: instead of taking them in as many
+        //      passes (each reads the whole bin again: 66 ms for 5 passes on 8 GPUs), a plain two-pass split by the leading bits of the
+        //      fine id first cuts them into sub-bins of single-GPU size (one more copy of the records, ~18 ms), which the dedup split
+        //      then takes from that dense copy in one pass each ----
+        uint32_t nb_d = nb1_local, cap_d = cap, max_bin_d = max_bin; int fine_bits_d = fine_bits;
+        const uint64_t* coarse_off_d = (const uint64_t*)ctx->slot[S_COARSEOFF];
+        K2aSrc S2d = S2;
+        {
+            const uint32_t mean_bin = (uint32_t)(n_records / (nb1_local ? nb1_local : 1)) + 1;
+            int sub_bits = 0;
+            if (n_src > 1 || (p->path_flags & GATB_PATH_K2A_PRESPLIT))
+                while (sub_bits < fine_bits - 6 && ((mean_bin >> sub_bits) * 5) / 4 > k2a_two_cta_capacity (fine_bits - sub_bits)) sub_bits++;
+            if ((p->path_flags & GATB_PATH_K2A_PRESPLIT) && sub_bits == 0 && fine_bits > 2) sub_bits = 2;        // test selector
+            if (sub_bits)
+            {
+                const uint64_t nsub = (uint64_t)nb1_local << sub_bits;
+                if (ensure (ctx, S_PRESPLIT, (n_records + 1) * rec_bytes)) return 1;
+                if (ensure (ctx, S_SUBOFF, (nsub + 1) * 8)) return 1;
+                if (ensure (ctx, S_SUBCNT, nsub * 4)) return 1;
+                K2aPresplit PS; PS.sub_off = (uint64_t*)ctx->slot[S_SUBOFF]; PS.sub_cnt = (uint32_t*)ctx->slot[S_SUBCNT]; PS.shift = fine_bits - sub_bits;
+                CK (launch_k2a_split (L, W, S2, ctx->slot[S_PRESPLIT], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, sub_bits, 0, 0, 0, 0, 0, &PS));
+                CursorList C1; C1.n = 1; C1.cur[0] = PS.sub_cnt;
+                CK (cudaMemsetAsync (d_maxbin, 0, 8, ctx->stream));
+                if (ensure (ctx, S_TOTCUR, nsub * 4)) return 1;
+                k_sum_cursors<<<(unsigned)((nsub + 255) / 256), 256, 0, ctx->stream>>> (C1, (uint32_t)nsub, 0xFFFFFFFFu, (uint32_t*)ctx->slot[S_TOTCUR], d_maxbin); ctx->launches++;
+                CK (cudaMemcpyAsync (&max_bin_d, d_maxbin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK (cudaStreamSynchronize (ctx->stream));
+                memset (&S2d, 0, sizeof(S2d)); S2d.n = 1; S2d.bins[0] = (const uint4*)ctx->slot[S_PRESPLIT]; S2d.cursors[0] = PS.sub_cnt; S2d.off[0] = PS.sub_off;
+                nb_d = (uint32_t)nsub; cap_d = 0xFFFFFFFFu; fine_bits_d = fine_bits - sub_bits; coarse_off_d = PS.sub_off;
+            }
         }
-        CK (cudaMemcpyAsync (h_k2a, d_k2a, 16, cudaMemcpyDeviceToHost, ctx->stream));
-        cudaEventRecord (ctx->kev[3], ctx->stream);
+        const uint32_t rmax = (p->path_flags & GATB_PATH_K2A_SMALL_STAGE) ? 256u : k2a_dedup_rmax (max_bin_d, (uint32_t)(n_records / (nb_d ? nb_d : 1)) + 1, fine_bits_d);
+        // counting bins of <= target k-mers of surviving records (+ one fine id's worth): the distinct k-mers of a bin (at most
+        // that many) must stay below 3/4 of the table, and a fuller table probes longer: 45 % measured best
+        // (k2b 62.2 + 1.1 ms for the 0.2 % of bins that still overflow; 60 %: 65.4 + 3.8, 30 %: 63.0 + 0.4)
+        const uint32_t target = (uint32_t)((((uint64_t)1 << table_log2) * (p->bin_target_pct > 0 ? p->bin_target_pct : 45)) / 100);
+        // the distinct k-mers of a bin are at most the k-mers of its records, typically 3/4 of them: a bin whose records hold more than
+        // 0.95 T k-mers (one fine id = one minimizer value holds several loci of a multi-Gb genome) will not fit 3/4 T slots
+        const uint32_t big_load = (k2b_variant (p->path_flags) == 1) ? (uint32_t)((((uint64_t)1 << table_log2) * 95) / 100) : 0u;
+        CK (launch_k2a_dedup_split (L, S2d, ctx->slot[S_FINE], coarse_off_d, nb_d, cap_d, fine_bits_d,
+                                    (uint2*)ctx->slot[S_BINDESC], rmax, (uint32_t*)ctx->slot[S_OVFLIST], d_k2a, target, big_load));
+        unsigned long long h_k2a[3] = { 0, 0, 0 };
+        CK (cudaMemcpyAsync (h_k2a, d_k2a, 24, cudaMemcpyDeviceToHost, ctx->stream));
         CK (cudaStreamSynchronize (ctx->stream));
+        if (h_k2a[0])
+        {   // bins the kernel gave up on (a skewed range of fine ids, more passes than it tracks) go through the plain two-pass
+            // split (multiplicity 1, one counting bin per fine id), their descriptors appended after the adaptive ones
+            if (h_k2a[2] + (h_k2a[0] << fine_bits_d) > desc_cap) return fail (ctx, "bin descriptors exhausted");
+            CK (launch_k2a_split (L, W, S2d, ctx->slot[S_FINE], coarse_off_d, nb_d, cap_d, fine_bits_d,
+                                  (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)h_k2a[0], 1, h_k2a[2]));
+        }
+        cudaEventRecord (ctx->kev[3], ctx->stream);
         n_unique_records = h_k2a[1];                 // (bins of the two-pass kernel are not in this figure)
+        nbins_count = h_k2a[2] + (h_k2a[0] << fine_bits_d);
+        desc_abs = true;
     }
     else
     {
@@ -471,8 +512,9 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     if (out_cap < ctx->slot_cap[S_OUT] / item_bytes) out_cap = ctx->slot_cap[S_OUT] / item_bytes;   // never shrink: no re-allocation per call
 
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
-    if (ensure (ctx, S_OVFLIST, (nbins > nb1_local ? nbins : nb1_local) * 4)) return 1;
-    if (ensure (ctx, S_OVFLIST2, nbins * 4)) return 1;
+    { const uint64_t nl = nbins_count > nbins ? nbins_count : nbins;
+      if (ensure (ctx, S_OVFLIST, (nl > nb1_local ? nl : nb1_local) * 4)) return 1;
+      if (ensure (ctx, S_OVFLIST2, nl * 4)) return 1; }
     unsigned long long* d_cnt = (unsigned long long*)ctx->slot[S_COUNTERS];
     unsigned long long h_cnt[16];
     uint64_t n_ovf = 0, n_ovf_first = 0;
@@ -487,8 +529,9 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         CK (cudaMemsetAsync (ctx->slot[S_HISTO], 0, (size_t)(histo_max + 1) * 8, ctx->stream));
         CK (cudaMemsetAsync (d_cnt, 0, 16 * 8, ctx->stream));
         memset (&k2, 0, sizeof(k2));
-        k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins;
-        k2.coarse_off = (const uint64_t*)ctx->slot[S_COARSEOFF]; k2.fine_bits = fine_bits; k2.table_log2 = table_log2;
+        k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins_count;
+        // (absolute descriptors: every bin takes coarse_off[bin >> 31] = coarse_off[0] = 0 as its base)
+        k2.coarse_off = (const uint64_t*)ctx->slot[S_COARSEOFF]; k2.fine_bits = desc_abs ? 31 : fine_bits; k2.table_log2 = table_log2;
         k2.path_flags = p->path_flags; k2.oriented = k1_oriented (k, g->m_device, g->w, p->path_flags) ? 1 : 0;
         k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
         k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
@@ -521,10 +564,13 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         {   // ---- further tiers: the bins a warp's 2^table_log2-slot table could not hold are counted by CTAs with 2048,
             //      then 8192 slots (k2b_count_w1 over a bin list); what still overflows goes to the global table ----
             // (the claimed-slot lists of k2b_count_w1 are per warp, 3/32 of the table each: 4096 slots leave a warp 384 of them)
-            const int tier_log2[2] = { 12, 13 }, tier_counter[2] = { 7, 12 };
-            for (int t = 0; t < 2 && n_ovf; t++)
+            // (first, warps again with 2048-slot tables -- k2b_warp_bins over the bin list, at the rate of the first tier: on multi-Gb
+            //  inputs one bin in eleven overflows 512 slots, and CTA tiers took 69 ms for them on 8 GPUs)
+            const int tier_log2[3] = { 10, 12, 13 }, tier_counter[3] = { 13, 7, 12 };
+            for (int t = 0; t < 3 && n_ovf; t++)
             {
                 if (!fused && tier_log2[t] <= table_log2) continue;
+                if (fused && tier_log2[t] < 12) continue;
                 const int other = (cur_list == S_OVFLIST) ? S_OVFLIST2 : S_OVFLIST;
                 K2Params k2t = k2;
                 k2t.bin_list = (const uint32_t*)ctx->slot[cur_list]; k2t.n_list = (uint32_t)n_ovf;
@@ -725,7 +771,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         out->part_offsets = h_offs; out->kmers_lo = h_lo; out->kmers_hi = h_hi; out->counts = h_cnt32; out->histogram = h_hist;
     }
     out->stats[GATB_STAT_DISTINCT] = h_cnt[1]; out->stats[GATB_STAT_SOLID] = h_cnt[2];
-    out->stats[GATB_STAT_RECORDS] = n_records; out->stats[GATB_STAT_BINS] = nbins; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf_first; out->stats[12] = n_ovf;
+    out->stats[GATB_STAT_RECORDS] = n_records; out->stats[GATB_STAT_BINS] = nbins_count; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf_first; out->stats[12] = n_ovf;
     out->stats[GATB_STAT_RECORD_BYTES] = n_records * rec_bytes; out->stats[GATB_STAT_UNIQUE_RECORDS] = n_unique_records;
     float ms;
     cudaEventElapsedTime (&ms, ctx->ev[2], ctx->ev[3]); out->seconds[2] = ms * 1e-3;

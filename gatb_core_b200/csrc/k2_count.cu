@@ -29,32 +29,40 @@
 // ------------------------------------------------------------------------------------------------ k2a
 // After the fine split the fine-bin id of a 16-byte record is implied by its position: the field carries the MULTIPLICITY of
 // the record instead (1 here; k2a_dedup_split collapses identical records).  Every k <= 31 counting kernel adds it.
+// PRE-SPLIT mode (PS.sub_off != NULL, k <= 31, several ranks): 'fine_bits' is the number of LEADING id bits to split by (the id
+// shifted right by PS.shift); the records are copied verbatim, and instead of descriptors the kernel writes the first record
+// (absolute) and the record count of every sub-bin -- the dense source k2a_dedup_split then takes its bins from.
+// desc_abs == 0: descriptor of fine bin f of coarse bin b at bin_desc[b << fine_bits | f] = {offset inside the coarse bin, records}
+// desc_abs != 0: (bins listed in bin_list, after k2a_dedup_split gave up on them) descriptors at bin_desc[desc_base +
+//                (blockIdx.x << fine_bits | f)] = {ABSOLUTE record offset, records}, like the ones k2a_dedup_split writes itself.
 template<int W>
 __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __restrict__ dst, const uint64_t* __restrict__ coarse_off,
-                                                        uint32_t nb, uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc, const uint32_t* __restrict__ bin_list)
+                                                        uint32_t nb, uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc, const uint32_t* __restrict__ bin_list,
+                                                        int desc_abs, uint64_t desc_base, K2aPresplit PS)
 {
     // nb = bins of a source region (laid out by coarse_index, kernels.h)
-    __shared__ uint32_t s_off[1024], s_cur[1024], s_tmp[1024];         // 1 << fine_bits <= 1024 fine bins per coarse bin
-    __shared__ uint32_t s_first[17];                        // record range of every source inside the gathered bin
-    const uint32_t b = bin_list ? bin_list[blockIdx.x] : blockIdx.x;
+    extern __shared__ uint32_t k2a_fs_smem[];                             // 3 << fine_bits counters
     const int nf = 1 << fine_bits;
+    uint32_t* s_off = k2a_fs_smem; uint32_t* s_cur = s_off + nf; uint32_t* s_tmp = s_cur + nf;
+    __shared__ uint32_t s_first[K2A_MAXSRC + 1];                        // record range of every source inside the gathered bin
+    const uint32_t b = bin_list ? bin_list[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x;
     for (int i = tid; i < nf; i += blockDim.x) { s_tmp[i] = 0; s_cur[i] = 0; }
     if (tid == 0)
     {
         uint32_t run = 0;
         for (int s = 0; s < S.n; s++) { s_first[s] = run; run += min (S.cursors[s][b], cap); }
-        for (int s = S.n; s <= 16; s++) s_first[s] = run;
+        for (int s = S.n; s <= K2A_MAXSRC; s++) s_first[s] = run;
     }
     __syncthreads ();
-    const uint32_t n_all = s_first[16];
+    const uint32_t n_all = s_first[K2A_MAXSRC];
     // record g of the gathered bin: the pieces of all sources laid end to end, so that the threads stay busy however
-    // small a single piece is (16 sources of a few hundred records each on 8 GPUs)
+    // small a single piece is (32 sources of a few hundred records each on 8 GPUs)
     auto locate = [&] (uint32_t g, const uint4*& src, uint64_t& ci)
     {
         int s = 0;
         #pragma unroll
-        for (int u = 8; u > 0; u >>= 1) if (s + u < 16 && g >= s_first[s + u]) s += u;
+        for (int u = K2A_MAXSRC / 2; u > 0; u >>= 1) if (s + u < K2A_MAXSRC && g >= s_first[s + u]) s += u;
         src = S.bins[s];
         ci = k2a_record_index (S, s, b, g - s_first[s], nb);
     };
@@ -63,9 +71,10 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
     {
         const uint4* src; uint64_t ci; locate (g, src, ci);
         const uint32_t top = __ldg (&src[ci * W + (W - 1)]).w;
-        atomicAdd (&s_tmp[W == 1 ? (top >> (DEV_FINE_SHIFT_W1 - 32)) : (top >> (32 - FINE_BITS_W2))], 1u);
+        atomicAdd (&s_tmp[W == 1 ? (((top >> (DEV_FINE_SHIFT_W1 - 32)) >> PS.shift) & (nf - 1)) : (top >> (32 - FINE_BITS_W2))], 1u);
     }
     __syncthreads ();
+    const uint64_t dbase = coarse_off[b];
     if (tid < 32)
     {   // exclusive scan of the nf counters by one warp (nf/32 consecutive ones per lane, at least one)
         const int per = nf > 32 ? nf / 32 : 1;
@@ -78,20 +87,26 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
         for (int i = 0; i < per; i++)
         {
             const int idx = tid * per + i;
-            if (idx < nf) { const uint32_t v = s_tmp[idx]; s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v); run += v; }
+            if (idx < nf)
+            {
+                const uint32_t v = s_tmp[idx]; s_off[idx] = run;
+                if (PS.sub_off) { PS.sub_off[((uint64_t)b << fine_bits) + idx] = dbase + run; PS.sub_cnt[((uint64_t)b << fine_bits) + idx] = v; }
+                else if (desc_abs) bin_desc[desc_base + ((uint64_t)blockIdx.x << fine_bits) + idx] = make_uint2 ((uint32_t)(dbase + run), v);
+                else          bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v);
+                run += v;
+            }
         }
     }
     __syncthreads ();
-    const uint64_t dbase = coarse_off[b];
     for (uint32_t g = tid; g < n_all; g += blockDim.x)
     {
         const uint4* src; uint64_t ci; locate (g, src, ci);
         if (W == 1)
         {
             uint4 rec = __ldg (&src[ci]);
-            uint32_t f = rec.w >> (DEV_FINE_SHIFT_W1 - 32);
+            uint32_t f = ((rec.w >> (DEV_FINE_SHIFT_W1 - 32)) >> PS.shift) & (nf - 1);
             uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
-            rec.w = (rec.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | (1u << (DEV_FINE_SHIFT_W1 - 32));
+            if (!PS.sub_off) rec.w = (rec.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | (1u << (DEV_FINE_SHIFT_W1 - 32));     // (pre-split: the id stays)
             dst[dbase + p] = rec;
         }
         else
@@ -107,27 +122,40 @@ __global__ void __launch_bounds__(256) k2a_fine_split (const K2aSrc S, uint4* __
 // ------------------------------------------------------------------------------------------------ k2a with deduplication
 // k <= 31.  One CTA stages a whole gathered coarse bin in shared memory (read ONCE from HBM), collapses identical records
 // (oriented records of the reads that cover one locus without an error in the span are bit-identical, whatever the
-// strand: about half of all records), and writes every distinct record once, in fine-bin order, with its multiplicity
-// in place of the fine-bin id.  The counting kernels then insert a record's k-mers once, adding the multiplicity.
+// strand: about half of all records), and writes every distinct record once, ordered by fine id, with its multiplicity
+// in place of the fine id.  The counting kernels then insert a record's k-mers once, adding the multiplicity.
 //   dedup table: TS slots of {record index : 16, count : 16}; a slot is claimed with a 32-bit CAS, duplicates add 1 << 16.
-// Shared memory: records rmax * 16 | table ts * 4 | fine-bin counters 3 * nf * 4.  Bins with more than rmax records are
-// listed for the plain two-pass kernel above.
+// ADAPTIVE BINS: the fine ids written by the partition kernel are several times finer than a counting bin.  Knowing the k-mers
+// of the surviving records per fine id, the CTA cuts the sequence of ids wherever the running sum passes a multiple of
+// 'target': consecutive ids are merged into bins of <= target k-mer occurrences plus one id's worth, so the counting kernel
+// sees bins of even load (hashed minimizers alone give bins whose load is a compound Poisson sum of a few loci: one in a
+// hundred used to overflow a warp's table on one GPU, one in eleven on multi-Gb inputs) and the tables can be planned fuller.
+// A bin that still ends up with more than 'big_load' k-mers (one fine id can hold several loci of a multi-Gb genome) is flagged
+// (K2_DESC_BIG in the count): the first-tier counting kernel hands it to the next tier without trying.
+// Descriptors {absolute record offset, records} are appended to bin_desc through counters[2] (the order of the bins is free).
+// Shared memory: records rmax * 16 | table ts * 4 | per-id arrays 4 * nf * 4.  A bin larger than the staging area is taken in
+// several passes over ranges of fine ids; bins the kernel gives up on are listed for the plain two-pass kernel above.
 template<int NT>
-__global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __restrict__ dst, const uint64_t* __restrict__ coarse_off,
+__global__ void __launch_bounds__(NT, 1024 / NT) k2a_dedup_split (const K2aSrc S, uint4* __restrict__ dst, const uint64_t* __restrict__ coarse_off,
                                                        uint32_t nb, uint32_t cap, int fine_bits, uint2* __restrict__ bin_desc,
-                                                       uint32_t rmax, uint32_t ts, uint32_t* __restrict__ big_list, unsigned long long* __restrict__ counters)
+                                                       uint32_t rmax, uint32_t ts, uint32_t* __restrict__ big_list, unsigned long long* __restrict__ counters,
+                                                       uint32_t target, uint32_t big_load)
 {
     extern __shared__ __align__(16) unsigned char k2a_smem[];
     uint4*    recs  = (uint4*)k2a_smem;
     uint32_t* tbl   = (uint32_t*)(recs + rmax);
     const int nf = 1 << fine_bits;
-    uint32_t* s_off = tbl + ts;
-    uint32_t* s_cur = s_off + nf;
-    uint32_t* s_tmp = s_cur + nf;
-    __shared__ uint32_t s_first[17];
-    __shared__ uint32_t s_staged, s_written;
+    const uint32_t idmask = (uint32_t)nf - 1;          // (after a pre-split the leading id bits are implied by the bin)
+    uint32_t* s_off = tbl + ts;          // first record of the id inside the coarse bin
+    uint32_t* s_cur = s_off + nf;        // k-mers of the surviving records of the id -> their exclusive prefix inside a chunk of 32 ids
+    uint32_t* s_tmp = s_cur + nf;        // surviving records of the id -> write cursor of the id
+    uint32_t* s_q   = s_tmp + nf;        // 1: the id starts a counting bin
+    __shared__ uint32_t s_first[K2A_MAXSRC + 1];
+    __shared__ uint32_t s_staged, s_written, s_nb, s_nb2;
+    __shared__ uint32_t s_ct[128], s_ckt[128];                  // per chunk of 32 fine ids: surviving records, their k-mers
+    __shared__ unsigned long long s_gbase;
+    __shared__ unsigned long long s_pass_base[16]; __shared__ uint32_t s_pass_nb[16];      // descriptors appended by every pass of the current bin
     const int tid = threadIdx.x;
-    const uint32_t tmask = ts - 1;
     unsigned long long n_unique = 0;
     for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x)
     {
@@ -136,18 +164,18 @@ __global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __
         {
             uint32_t run = 0;
             for (int s = 0; s < S.n; s++) { s_first[s] = run; run += min (S.cursors[s][b], cap); }
-            for (int s = S.n; s <= 16; s++) s_first[s] = run;
+            for (int s = S.n; s <= K2A_MAXSRC; s++) s_first[s] = run;
             s_written = 0;
         }
         __syncthreads ();
-        const uint32_t n_all = s_first[16];
+        const uint32_t n_all = s_first[K2A_MAXSRC];
         // A bin that fits the staging area is done in one pass.  A larger one (several ranks gather into one bin; dense bin loads)
-        // takes P passes over ranges of fine-bin ids: pass j stages only the records of its range -- the passes after the first
+        // takes P passes over ranges of fine ids: pass j stages only the records of its range -- the passes after the first
         // find the bin in L2 -- so that identical records still collapse whatever the size of the bin.  (fine ids are hashed:
-        // a range holds n_all / P records give or take a few per cent; 80 % of the staging area is planned.)
-        const uint32_t P = n_all <= rmax ? 1u : (uint32_t)(((uint64_t)n_all * 5 + 4 * rmax - 1) / (4 * (uint64_t)rmax));
-        if (P > (uint32_t)nf)
-        {   // more passes than fine bins: handed to the two-pass kernel
+        // a range holds n_all / P records give or take a few per cent; 75 % of the staging area is planned.)
+        const uint32_t P = n_all <= rmax ? 1u : (uint32_t)(((uint64_t)n_all * 4 + 3 * rmax - 1) / (3 * (uint64_t)rmax));
+        if (P > (uint32_t)nf || P > 16u)
+        {   // more passes than fine ids (or than this CTA keeps track of): handed to the two-pass kernel
             if (tid == 0) { const uint32_t idx = (uint32_t) atomicAdd (&counters[0], 1ULL); big_list[idx] = b; }
             continue;
         }
@@ -155,17 +183,18 @@ __global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __
         {
             int s = 0;
             #pragma unroll
-            for (int u = 8; u > 0; u >>= 1) if (s + u < 16 && g >= s_first[s + u]) s += u;
+            for (int u = K2A_MAXSRC / 2; u > 0; u >>= 1) if (s + u < K2A_MAXSRC && g >= s_first[s + u]) s += u;
             return S.bins[s] + k2a_record_index (S, s, b, g - s_first[s], nb);
         };
         const uint64_t dbase = coarse_off[b];
         bool failed = false;
+        uint32_t n_done = 0;                                                   // passes completed (CTA-uniform)
         for (uint32_t pass = 0; pass < P && !failed; pass++)
         {
             const uint32_t f_lo = (uint32_t)((uint64_t)nf * pass / P), f_hi = (uint32_t)((uint64_t)nf * (pass + 1) / P);
             for (uint32_t i = tid; i < ts; i += NT) tbl[i] = 0xFFFFFFFFu;
             for (uint32_t i = f_lo + tid; i < f_hi; i += NT) { s_tmp[i] = 0; s_cur[i] = 0; }
-            if (tid == 0) s_staged = 0;
+            if (tid == 0) { s_staged = 0; s_nb = 0; s_nb2 = 0; }
             __syncthreads ();
             // ---- stage the records of this pass: four independent 16-byte loads in flight per thread ----
             uint32_t n_st;
@@ -184,8 +213,9 @@ __global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __
             }
             else
             {
-                for (uint32_t g0 = tid; g0 < n_all; g0 += 4 * NT)
+                for (uint32_t g00 = 0; g00 < n_all; g00 += 4 * NT)            // warp-uniform bounds: the ballots below need whole warps
                 {
+                    const uint32_t g0 = g00 + tid;
                     uint4 r[4];
                     #pragma unroll
                     for (int u = 0; u < 4; u++) { const uint32_t g = g0 + u * NT; if (g < n_all) r[u] = __ldg (src_of (g)); }
@@ -193,8 +223,16 @@ __global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __
                     for (int u = 0; u < 4; u++)
                     {
                         const uint32_t g = g0 + u * NT;
-                        const uint32_t f = (g < n_all) ? (r[u].w >> (DEV_FINE_SHIFT_W1 - 32)) : 0xFFFFFFFFu;
-                        if (f >= f_lo && f < f_hi) { const uint32_t at = atomicAdd (&s_staged, 1u); if (at < rmax) recs[at] = r[u]; }
+                        const uint32_t f = (g < n_all) ? ((r[u].w >> (DEV_FINE_SHIFT_W1 - 32)) & idmask) : 0xFFFFFFFFu;
+                        const bool keep = f >= f_lo && f < f_hi;
+                        const unsigned km = __ballot_sync (FULL_MASK, keep);            // one shared atomic per warp, not per record
+                        if (km)
+                        {
+                            uint32_t at = 0;
+                            if ((tid & 31) == 0) at = atomicAdd (&s_staged, (uint32_t)__popc (km));
+                            at = __shfl_sync (FULL_MASK, at, 0) + __popc (km & ((1u << (tid & 31)) - 1));
+                            if (keep && at < rmax) recs[at] = r[u];
+                        }
                     }
                 }
                 __syncthreads ();
@@ -207,91 +245,168 @@ __global__ void __launch_bounds__(NT) k2a_dedup_split (const K2aSrc S, uint4* __
                 const uint4 r = recs[g];
                 uint32_t h = (r.x * 0x9E3779B1u) ^ (r.y * 0x85EBCA77u) ^ (r.z * 0xC2B2AE3Du) ^ (r.w * 0x27D4EB2Fu);
                 h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
-                h &= tmask;
+                h = __umulhi (h, ts);
                 for (;;)
                 {
                     uint32_t e = *(volatile uint32_t*)&tbl[h];
                     if (e == 0xFFFFFFFFu) { e = atomicCAS (&tbl[h], 0xFFFFFFFFu, g | (1u << 16)); if (e == 0xFFFFFFFFu) break; }
                     const uint4 o = recs[e & 0xFFFFu];
                     if (o.x == r.x && o.y == r.y && o.z == r.z && o.w == r.w) { atomicAdd (&tbl[h], 1u << 16); break; }
-                    h = (h + 1) & tmask;
+                    h = (h + 1 == ts) ? 0u : h + 1;
                 }
             }
             __syncthreads ();
-            // ---- distinct records per fine bin ----
+            // ---- surviving records and their k-mers per fine id ----
             for (uint32_t i = tid; i < ts; i += NT)
             {
                 const uint32_t e = tbl[i];
-                if (e != 0xFFFFFFFFu) atomicAdd (&s_tmp[recs[e & 0xFFFFu].w >> (DEV_FINE_SHIFT_W1 - 32)], 1u);
-            }
-            __syncthreads ();
-            if (tid < 32)
-            {   // exclusive scan of the counters of this pass' range by one warp; offsets continue after the previous passes
-                const uint32_t nr = f_hi - f_lo;
-                const uint32_t per = (nr + 31) / 32;
-                uint32_t sum = 0;
-                for (uint32_t i = 0; i < per; i++) { const uint32_t idx = f_lo + tid * per + i; if (idx < f_hi) sum += s_tmp[idx]; }
-                uint32_t incl = sum;
-                #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o); if (tid >= o) incl += y; }
-                uint32_t run = s_written + incl - sum;
-                for (uint32_t i = 0; i < per; i++)
+                if (e != 0xFFFFFFFFu)
                 {
-                    const uint32_t idx = f_lo + tid * per + i;
-                    if (idx < f_hi) { const uint32_t v = s_tmp[idx]; s_off[idx] = run; bin_desc[((uint64_t)b << fine_bits) + idx] = make_uint2 (run, v); run += v; }
+                    const uint32_t w = recs[e & 0xFFFFu].w;
+                    const uint32_t f = (w >> (DEV_FINE_SHIFT_W1 - 32)) & idmask;
+                    atomicAdd (&s_tmp[f], 1u);
+                    atomicAdd (&s_cur[f], (w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u);
                 }
-                __syncwarp ();
-                if (tid == 31) { n_unique += run - s_written; s_written = run; }
             }
             __syncthreads ();
-            // ---- write them in fine-bin order, multiplicity in place of the fine-bin id ----
+            // ---- exclusive scans (records, k-mers of the survivors) over the ids of this pass: every warp scans chunks of 32 ids ... ----
+            const uint32_t nr = f_hi - f_lo, nch = (nr + 31) >> 5;                       // nch <= 128
+            const uint32_t lane = tid & 31;
+            for (uint32_t c = tid >> 5; c < nch; c += NT / 32)
+            {
+                const uint32_t idx = f_lo + 32 * c + lane;
+                const uint32_t v = idx < f_hi ? s_tmp[idx] : 0u, kv = idx < f_hi ? s_cur[idx] : 0u;
+                uint32_t incl = v, kincl = kv;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const uint32_t y = __shfl_up_sync (FULL_MASK, incl, o), ky = __shfl_up_sync (FULL_MASK, kincl, o);
+                    if (lane >= (uint32_t)o) { incl += y; kincl += ky; }
+                }
+                if (idx < f_hi) { s_off[idx] = incl - v; s_cur[idx] = kincl - kv; }
+                if (lane == 31) { s_ct[c] = incl; s_ckt[c] = kincl; }
+            }
+            __syncthreads ();
+            // ---- ... and every thread adds the totals of the chunks before its own (a handful: summed on the spot).  Record offsets
+            //      continue after the previous passes; the k-mer prefix divided by 'target' is the id's bin quotient: ids with equal
+            //      quotients form one bin, an id whose quotient differs from its predecessor's starts one (s_q: quotient | start flag).
+            //      s_tmp becomes the write cursor of the id. ----
+            const uint32_t written = s_written;
+            uint32_t starts = 0, pass_total = 0, pass_kmers = 0;
+            {
+                uint32_t c_done = 0, roff = 0, koff = 0;                                     // totals of the chunks [0, c_done)
+                for (uint32_t idx = f_lo + tid; idx < f_hi; idx += NT)
+                {
+                    const uint32_t c = (idx - f_lo) >> 5;
+                    for (; c_done < c; c_done++) { roff += s_ct[c_done]; koff += s_ckt[c_done]; }
+                    const uint32_t q = target ? (s_cur[idx] + koff) / target : idx;
+                    bool start = (idx == f_lo);
+                    if (!start)
+                    {   // the predecessor's prefix: same chunk, or the last id of the previous chunk (lane 0; NT is a multiple of 32)
+                        const uint32_t kp = s_cur[idx - 1] + (lane == 0 ? koff - s_ckt[c - 1] : koff);
+                        start = (target ? kp / target : idx - 1) != q;
+                    }
+                    s_q[idx - f_lo] = ((s_cur[idx] + koff) << 1) | (start ? 1u : 0u);       // k-mers before the id | start flag
+                    s_off[idx] += written + roff;
+                    s_tmp[idx] = 0;
+                    starts += start ? 1u : 0u;
+                }
+                for (; c_done < nch; c_done++) { roff += s_ct[c_done]; koff += s_ckt[c_done]; }
+                pass_total = roff; pass_kmers = koff;
+            }
+            if (starts) atomicAdd (&s_nb, starts);
+            __syncthreads ();
+            const uint32_t end_all = written + pass_total;
+            if (tid == 0)
+            {   // (the global reservation travels while the CTA writes its survivors)
+                s_gbase = atomicAdd (&counters[2], (unsigned long long)s_nb); s_pass_base[pass] = s_gbase; s_pass_nb[pass] = s_nb;
+                s_written = end_all; n_unique += pass_total;
+            }
+            // ---- write the survivors ordered by fine id, multiplicity in place of the id ----
             for (uint32_t i = tid; i < ts; i += NT)
             {
                 const uint32_t e = tbl[i];
                 if (e == 0xFFFFFFFFu) continue;
                 uint4 r = recs[e & 0xFFFFu];
-                const uint32_t f = r.w >> (DEV_FINE_SHIFT_W1 - 32);
-                const uint32_t p = s_off[f] + atomicAdd (&s_cur[f], 1u);
+                const uint32_t f = (r.w >> (DEV_FINE_SHIFT_W1 - 32)) & idmask;
+                const uint32_t p = s_off[f] + atomicAdd (&s_tmp[f], 1u);
                 r.w = (r.w & ((1u << (DEV_FINE_SHIFT_W1 - 32)) - 1)) | ((e >> 16) << (DEV_FINE_SHIFT_W1 - 32));
                 dst[dbase + p] = r;
             }
             __syncthreads ();
+            // ---- descriptors: a bin ends where the next one starts (a bin without records -- possible at the start of a pass -- is
+            //      written with a zero count: the counting kernels skip it); slots from a shared counter, the order of the bins is free ----
+            {
+                const unsigned long long gbase = s_gbase;
+                for (uint32_t idx = f_lo + tid; idx < f_hi; idx += NT)
+                {
+                    const uint32_t qs = s_q[idx - f_lo];
+                    if (!(qs & 1u)) continue;
+                    uint32_t e = idx + 1; while (e < f_hi && !(s_q[e - f_lo] & 1u)) e++;
+                    const uint32_t first = s_off[idx], cnt = (e < f_hi ? s_off[e] : end_all) - first;
+                    const uint32_t load = (e < f_hi ? (s_q[e - f_lo] >> 1) : pass_kmers) - (qs >> 1);       // k-mers of the bin's records
+                    bin_desc[gbase + atomicAdd (&s_nb2, 1u)] = make_uint2 ((uint32_t)(dbase + first), cnt | ((big_load && load > big_load) ? K2_DESC_BIG : 0u));
+                }
+            }
+            __syncthreads ();
+            n_done = pass + 1;
         }
         if (failed)
-        {   // a range overfilled the staging area (skewed fine ids): the two-pass kernel redoes the whole bin
+        {   // a range overfilled the staging area (skewed fine ids): the two-pass kernel redoes the whole bin; the descriptors the
+            // earlier passes appended are emptied (their records are about to be rewritten: they must not be counted twice)
             if (tid == 0) { const uint32_t idx = (uint32_t) atomicAdd (&counters[0], 1ULL); big_list[idx] = b; }
+            // ('failed' was raised in pass index = number of completed passes; recompute it: passes done = those with a base recorded)
+            for (uint32_t pp = 0; pp < n_done; pp++)
+                for (uint32_t i = tid; i < s_pass_nb[pp]; i += NT) bin_desc[s_pass_base[pp] + i].y = 0;
         }
     }
-    if (tid == 31 && n_unique) atomicAdd (&counters[1], n_unique);
+    if (tid == 0 && n_unique) atomicAdd (&counters[1], n_unique);
 }
 
+// W: records of 16*W bytes.  bin_list == NULL: all nb1 coarse bins, descriptors indexed by (coarse bin, fine id); else the listed bins
+// only (bins k2a_dedup_split gave up on), descriptors in its format appended at desc_base
 cudaError_t launch_k2a_split (const LaunchCtx& L, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
-                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc, const uint32_t* bin_list, uint32_t n_list)
+                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc, const uint32_t* bin_list, uint32_t n_list,
+                              int desc_abs, uint64_t desc_base, const K2aPresplit* presplit)
 {
+    K2aPresplit PS; PS.sub_off = 0; PS.sub_cnt = 0; PS.shift = 0;
+    if (presplit) PS = *presplit;
     const uint32_t grid = bin_list ? n_list : nb1;
     if (grid == 0) return cudaSuccess;
-    if (W == 1) k2a_fine_split<1><<<grid, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, bin_list);
-    else        k2a_fine_split<2><<<grid, 256, 0, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, bin_list);
+    const size_t smem = (size_t)12 << fine_bits;
+    if (smem > 40 * 1024)
+    {
+        cudaError_t e = cudaFuncSetAttribute (W == 1 ? (const void*)k2a_fine_split<1> : (const void*)k2a_fine_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    if (W == 1) k2a_fine_split<1><<<grid, 256, smem, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, bin_list, desc_abs, desc_base, PS);
+    else        k2a_fine_split<2><<<grid, 256, smem, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, bin_list, desc_abs, desc_base, PS);
     (*L.launches)++;
     return cudaGetLastError ();
 }
 
-// k <= 31: dedup + split of all bins; counters[0] = bins listed in big_list (handed to the two-pass kernel), counters[1] = distinct records written
-uint32_t k2a_dedup_rmax (uint32_t max_bin_records, int fine_bits)
+// k <= 31: dedup + split of all bins; counters[0] = bins listed in big_list (handed to the two-pass kernel), counters[1] = distinct
+// records written, counters[2] = bin descriptors appended
+// dedup table: 1.25 slots per staged record (not a power of two: the slot is umulhi (hash, ts)); about half of the staged records
+// are duplicates, so the table runs at 35..45 % load, 80 % at the very worst
+static uint32_t k2a_table_slots (uint32_t rmax) { return rmax + rmax / 4 + 32; }
+static size_t k2a_dedup_smem (uint32_t rmax, int fine_bits) { return (size_t)rmax * 16 + (size_t)k2a_table_slots (rmax) * 4 + 4 * ((size_t)4 << fine_bits); }
+// records a CTA can stage with two CTAs per SM
+uint32_t k2a_two_cta_capacity (int fine_bits) { uint32_t r2 = 256; while (k2a_dedup_smem (r2 + 64, fine_bits) <= 111 * 1024) r2 += 64; return r2; }
+uint32_t k2a_dedup_rmax (uint32_t max_bin_records, uint32_t mean_bin_records, int fine_bits)
 {
-    // records + table (next power of two >= 1.3 rmax) + counters within 200 KB; at most 8191 (multiplicities keep 15 bits, indices 16)
-    uint32_t rmax = max_bin_records < 8191 ? max_bin_records : 8191;
-    for (;;)
-    {
-        uint32_t ts = 256; while (ts < rmax + rmax / 3) ts <<= 1;
-        const size_t bytes = (size_t)rmax * 16 + (size_t)ts * 4 + 3 * ((size_t)4 << fine_bits);
-        if (bytes <= 200 * 1024 || rmax <= 256) return rmax;
-        rmax -= 256;
-    }
+    // Two CTAs of 512 threads per SM (111 KB each) when the typical bin fits with a quarter of head-room: the few larger bins take two
+    // passes.  Otherwise one CTA of 1024 threads with up to 200 KB; at most 8191 records (multiplicities keep 15 bits, indices 16).
+    uint32_t r2 = 256; while (k2a_dedup_smem (r2 + 64, fine_bits) <= 111 * 1024) r2 += 64;
+    if (max_bin_records <= r2) return max_bin_records < 256 ? 256 : max_bin_records;
+    if (mean_bin_records + mean_bin_records / 4 <= r2) return r2;
+    uint32_t r1 = r2; while (r1 + 64 <= 8191 && k2a_dedup_smem (r1 + 64, fine_bits) <= 200 * 1024) r1 += 64;
+    return max_bin_records < r1 ? max_bin_records : r1;
 }
 template<int NT>
 static cudaError_t k2a_dedup_launch (const LaunchCtx& L, const K2aSrc& src, void* dst, const uint64_t* coarse_off, uint32_t nb1, uint32_t cap,
-                                     int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t ts, size_t smem, uint32_t* big_list, unsigned long long* counters)
+                                     int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t ts, size_t smem, uint32_t* big_list, unsigned long long* counters,
+                                     uint32_t target, uint32_t big_load)
 {
     cudaError_t e = cudaFuncSetAttribute (k2a_dedup_split<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -301,19 +416,19 @@ static cudaError_t k2a_dedup_launch (const LaunchCtx& L, const K2aSrc& src, void
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)L.sm_count * per_sm;
     if (grid > nb1) grid = nb1;
-    k2a_dedup_split<NT><<<(unsigned)grid, NT, smem, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, big_list, counters);
+    k2a_dedup_split<NT><<<(unsigned)grid, NT, smem, L.stream>>> (src, (uint4*)dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, big_list, counters, target, big_load);
     (*L.launches)++;
     return cudaGetLastError ();
 }
 cudaError_t launch_k2a_dedup_split (const LaunchCtx& L, const K2aSrc& src, void* dst, const uint64_t* coarse_off, uint32_t nb1, uint32_t cap,
-                                    int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t* big_list, unsigned long long* counters)
+                                    int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t* big_list, unsigned long long* counters, uint32_t target, uint32_t big_load)
 {
     if (nb1 == 0) return cudaSuccess;
-    uint32_t ts = 256; while (ts < rmax + rmax / 3) ts <<= 1;
-    const size_t smem = (size_t)rmax * 16 + (size_t)ts * 4 + 3 * ((size_t)4 << fine_bits);
+    const uint32_t ts = k2a_table_slots (rmax);
+    const size_t smem = k2a_dedup_smem (rmax, fine_bits);
     // a staging area so large that only one CTA fits an SM (bins gathered from several ranks): 1024 threads keep the SM busy
-    if (smem > 113 * 1024) return k2a_dedup_launch<1024> (L, src, dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, smem, big_list, counters);
-    return k2a_dedup_launch<512> (L, src, dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, smem, big_list, counters);
+    if (smem > 113 * 1024) return k2a_dedup_launch<1024> (L, src, dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, smem, big_list, counters, target, big_load);
+    return k2a_dedup_launch<512> (L, src, dst, coarse_off, nb1, cap, fine_bits, bin_desc, rmax, ts, smem, big_list, counters, target, big_load);
 }
 
 // ------------------------------------------------------------------------------------------------ record decoding
@@ -477,7 +592,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
         {   // skip empty bins here so that the CTA never synchronises for nothing
             bin = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
             if (bin >= P.nbins) break;
-            d = P.bin_desc[bin];
+            d = P.bin_desc[bin]; d.y &= K2_DESC_COUNT;
             if (d.y) break;
         }
         s_bin[st] = bin; s_nocc[st] = 0;
@@ -733,7 +848,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_count_w1 (const K2Params P)
             const uint32_t idx = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
             if (P.bin_list) { if (idx >= P.n_list) { bin = P.nbins; break; } bin = P.bin_list[idx]; }
             else            { bin = idx; if (bin >= P.nbins) break; }
-            d = P.bin_desc[bin];
+            d = P.bin_desc[bin]; d.y &= K2_DESC_COUNT;
             if (d.y) break;
         }
         s_bin[st] = bin;
@@ -1012,30 +1127,42 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
     const uint32_t G = gridDim.x * NWARP;
     const uint4 zero4 = make_uint4 (0, 0, 0, 0);
 
-    // software pipeline over this warp's bins: (bin0, d0, base0, rec0) is current; d1/co1 of the next bin are in flight
-    uint32_t bin0 = blockIdx.x * NWARP + wid;
-    uint2 d0 = bin0 < P.nbins ? P.bin_desc[bin0] : make_uint2 (0, 0);
-    unsigned long long base0 = bin0 < P.nbins ? P.coarse_off[bin0 >> P.fine_bits] + d0.x : 0;
-    uint4 rec0 = ((uint32_t)lane < d0.y) ? __ldg ((const uint4*)P.recs + base0 + lane) : zero4;
-    uint32_t bin1 = bin0 + G;
-    uint2 d1 = bin1 < P.nbins ? P.bin_desc[bin1] : make_uint2 (0, 0);
-    unsigned long long co1 = bin1 < P.nbins ? P.coarse_off[bin1 >> P.fine_bits] : 0;
+    // software pipeline over this warp's bins: (bin0, d0, base0, rec0) is current; d1/co1 of the next bin are in flight.
+    // With a bin list (the warp tier of the overflow path: the bins a smaller table could not hold) work item g is bin_list[g].
+    constexpr uint32_t NOBIN = 0xFFFFFFFFu;
+    const uint32_t n_work = P.bin_list ? P.n_list : P.nbins;
+    auto bin_of = [&] (uint32_t g) -> uint32_t { return g < n_work ? (P.bin_list ? __ldg (P.bin_list + g) : g) : NOBIN; };
+    uint32_t g1 = blockIdx.x * NWARP + wid;
+    uint32_t bin0 = bin_of (g1);
+    // (descriptor counts keep a flag in the top bit: the dedup split marks the bins it knows to be too large for a first-tier
+    //  table; the first-tier run -- no bin list -- hands them to the next tier untouched, the runs over a list ignore the flag)
+    const uint32_t ymask = P.bin_list ? K2_DESC_COUNT : 0xFFFFFFFFu;
+    auto desc_of = [&] (uint32_t bin) -> uint2 { uint2 d = make_uint2 (0, 0); if (bin != NOBIN) { d = P.bin_desc[bin]; d.y &= ymask; } return d; };
+    uint2 d0 = desc_of (bin0);
+    unsigned long long base0 = bin0 != NOBIN ? P.coarse_off[bin0 >> P.fine_bits] + d0.x : 0;
+    uint4 rec0 = ((uint32_t)lane < d0.y && !(d0.y & K2_DESC_BIG)) ? __ldg ((const uint4*)P.recs + base0 + lane) : zero4;
+    g1 += G;
+    uint32_t bin1 = bin_of (g1);
+    uint2 d1 = desc_of (bin1);
+    unsigned long long co1 = bin1 != NOBIN ? P.coarse_off[bin1 >> P.fine_bits] : 0;
 
-    while (bin0 < P.nbins)
+    while (bin0 != NOBIN)
     {
         // ---- requests for the following bins ----
         const unsigned long long base1 = co1 + d1.x;
-        const uint4 rec1 = ((uint32_t)lane < d1.y) ? __ldg ((const uint4*)P.recs + base1 + lane) : zero4;
-        const uint32_t bin2 = bin1 + G;
-        const uint2 d2 = bin2 < P.nbins ? P.bin_desc[bin2] : make_uint2 (0, 0);
-        const unsigned long long co2 = bin2 < P.nbins ? P.coarse_off[bin2 >> P.fine_bits] : 0;
+        const uint4 rec1 = ((uint32_t)lane < d1.y && !(d1.y & K2_DESC_BIG)) ? __ldg ((const uint4*)P.recs + base1 + lane) : zero4;
+        g1 += G;
+        const uint32_t bin2 = bin_of (g1);
+        const uint2 d2 = desc_of (bin2);
+        const unsigned long long co2 = bin2 != NOBIN ? P.coarse_off[bin2 >> P.fine_bits] : 0;
 
         const uint32_t n = d0.y;
         // a bin with this many records (five times the planned load) practically never fits the warp's table: hand it to the
-        // next tier untouched instead of filling the table first (any bin may go there, this only saves the wasted attempt)
+        // next tier untouched instead of filling the table first (any bin may go there, this only saves the wasted attempt);
+        // likewise the bins the dedup split flagged (n has the flag bit then)
         if (n > (uint32_t)T / 3)
         {
-            if (lane == 0) { const uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin0; }
+            if (lane == 0) { const uint32_t idx = (uint32_t) atomicAdd (&P.counters[P.ovf_counter], 1ULL); P.ovf_list[idx] = bin0; }
         }
         else if (n)
         {
@@ -1143,8 +1270,8 @@ __global__ void __launch_bounds__(NT, 768 / NT) k2b_warp_bins (const K2Params P)
             if (rn) drain_retries ();
             __syncwarp ();
             if (__any_sync (FULL_MASK, w_ovf) || wn > OCC_W)
-            {   // the bin goes to the global-memory fallback (k2c): wipe the warp's table
-                if (lane == 0) { const uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin0; }
+            {   // the bin goes to the next tier: wipe the warp's table
+                if (lane == 0) { const uint32_t idx = (uint32_t) atomicAdd (&P.counters[P.ovf_counter], 1ULL); P.ovf_list[idx] = bin0; }
                 for (int i = lane; i < T; i += 32) { s_klo[i] = EMPTY64; s_cnt[i] = 0; }
                 __syncwarp ();
             }
@@ -1228,7 +1355,8 @@ static cudaError_t k2b_warp_launch (const LaunchCtx& L, const K2Params& P)
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)L.sm_count * per_sm;
-    const uint64_t need = (P.nbins + NT / 32 - 1) / (NT / 32);
+    const uint64_t n_work = P.bin_list ? P.n_list : P.nbins;
+    const uint64_t need = (n_work + NT / 32 - 1) / (NT / 32);
     if (grid > need) grid = need;
     k2b_warp_bins<NT, ORI><<<(unsigned)grid, NT, smem, L.stream>>> (P);
     (*L.launches)++;
@@ -1508,6 +1636,9 @@ static cudaError_t k2b_warp_w2_launch (const LaunchCtx& L, const K2Params& P)
 cudaError_t launch_k2b_count_list (const LaunchCtx& L, const K2Params& P)
 {
     if (P.n_list == 0) return cudaSuccess;
+    // tables of up to 2048 slots still belong to one warp each (k2b_warp_bins over the bin list): five times the rate of the CTA tiers
+    if (P.W == 1 && P.table_log2 <= 11 && k2b_variant (P.path_flags) == 1)
+        return P.oriented ? k2b_warp_launch<128, true> (L, P) : k2b_warp_launch<128, false> (L, P);
     const size_t smem = k2b_w1_smem_bytes (P.table_log2, 256);
     cudaError_t e = cudaFuncSetAttribute (k2b_count_w1<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1576,7 +1707,7 @@ __global__ void __launch_bounds__(256) k2c_measure (const K2Params P, uint32_t n
     for (uint32_t o = blockIdx.x; o < n_ovf; o += gridDim.x)
     {
         const uint32_t bin = P.ovf_list[o];
-        const uint2 d = P.bin_desc[bin];
+        uint2 d = P.bin_desc[bin]; d.y &= K2_DESC_COUNT;
         const uint4* base = (const uint4*)P.recs + (P.coarse_off[bin >> P.fine_bits] + d.x) * W;
         for (uint32_t i = threadIdx.x; i < d.y; i += blockDim.x)
         {
@@ -1597,7 +1728,7 @@ __global__ void __launch_bounds__(256) k2c_insert (const K2Params P, uint32_t n_
     for (uint32_t o = blockIdx.y; o < n_ovf; o += gridDim.y)
     {
         const uint32_t bin = P.ovf_list[o];
-        const uint2 d = P.bin_desc[bin];
+        uint2 d = P.bin_desc[bin]; d.y &= K2_DESC_COUNT;
         const uint4* base = (const uint4*)P.recs + (P.coarse_off[bin >> P.fine_bits] + d.x) * W;
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.y; i += gridDim.x * blockDim.x)
         {

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(NWARP * 32 + 32) k2f_count_coarse (const K2Par
 
     // ---- producer state: the tiles of this CTA's bins, in order ----
     uint32_t p_bin = blockIdx.x, p_src = 0, p_off = 0, p_left = 0; bool p_open = false;
-    uint32_t p_cnt[16];
+    uint32_t p_cnt[K2A_MAXSRC];
     auto issue_tile = [&] (int buf)
     {   // only lane 0 of the producer warp runs this
         for (;;)
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NWARP * 32 + 32) k2f_count_coarse (const K2Par
                 if (p_bin >= n_bins) { s_tflags[buf] = K2F_END; s_tn[buf] = 0; s_tbin[buf] = 0; return; }
                 uint32_t tot = 0;
                 #pragma unroll
-                for (int s = 0; s < 16; s++) { p_cnt[s] = (s < S.n) ? min (__ldg (&S.cursors[s][p_bin]), cap) : 0u; tot += p_cnt[s]; }
+                for (int s = 0; s < K2A_MAXSRC; s++) { p_cnt[s] = (s < S.n) ? min (__ldg (&S.cursors[s][p_bin]), cap) : 0u; tot += p_cnt[s]; }
                 if (tot == 0) { p_bin += gridDim.x; continue; }
                 p_left = tot; p_src = 0; p_off = 0; p_open = true;
             }

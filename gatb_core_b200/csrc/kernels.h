@@ -17,10 +17,11 @@
 enum { REC_LEN_SHIFT_W1 = 52, REC_FINE_SHIFT_W1 = 57, FINE_BITS_W1 = 7,
        REC_LEN_SHIFT_W2 = 52, REC_FINE_SHIFT_W2 = 58, FINE_BITS_W2 = 6 };
 // Device-mode records of k <= 31 trade nucleotides for fine-bin bits: at most DEV_MAXLEN_W1 = 24 k-mers (54 nucleotides,
-// bits [0,108)), nbK in bits [108,113), fine-bin id in bits [113,128) (up to 15 bits; the planner uses 7 on one GPU and
-// one more per doubling of the ranks, so that the number of COARSE bins a partition kernel scatters into stays put).
+// bits [0,108)), nbK in bits [108,113), fine id in bits [113,128) (up to 15 bits; the planner uses 9 on one GPU -- eight ids per planned counting
+// bin, merged into bins of even load by k2a_dedup_split -- and one more per doubling of the ranks, so that the number of COARSE
+// bins a partition kernel scatters into stays put).
 // The shifts below are relative to the upper 64-bit half, like the ones above.
-enum { DEV_LEN_SHIFT_W1 = 44, DEV_FINE_SHIFT_W1 = 49, DEV_MAXLEN_W1 = 24, DEV_FINE_BITS_MAX_W1 = 10 };
+enum { DEV_LEN_SHIFT_W1 = 44, DEV_FINE_SHIFT_W1 = 49, DEV_MAXLEN_W1 = 24, DEV_FINE_BITS_MAX_W1 = 12 };
 
 // ----------------------------------------------------------------------------------------------------------------
 // Layout of a region of coarse bins (device mode): ROUNDS of COARSE_BLK (= 64) records.  Record 'slot' of bin 'b' of a region
@@ -124,14 +125,22 @@ bool        k1_oriented (int k, int m, int w, int path_flags);   // does launch_
 // k2_count.cu
 // the same coarse bins gathered from n sources.  off[s] == NULL: source s is laid out by coarse_index (fixed capacity per bin);
 // off[s] != NULL: DENSE layout, bin b of source s holds its records at [off[s][b], off[s][b+1]) (exact sizes: skewed inputs)
-struct K2aSrc { const uint4* bins[16]; const uint32_t* cursors[16]; const uint64_t* off[16]; int n; };
+#define K2A_MAXSRC 32           // = GATB_GPU_MAX_SOURCES (ranks x pieces per rank)
+struct K2aSrc { const uint4* bins[K2A_MAXSRC]; const uint32_t* cursors[K2A_MAXSRC]; const uint64_t* off[K2A_MAXSRC]; int n; };
 __host__ __device__ __forceinline__ uint64_t k2a_record_index (const K2aSrc& S, int s, uint32_t b, uint32_t slot, uint32_t nb)
 { return S.off[s] ? S.off[s][b] + slot : coarse_index (b, slot, nb); }
+// pre-split of gathered bins by the leading bits of the fine id (k2a_fine_split): first record and record count of every sub-bin
+struct K2aPresplit { uint64_t* sub_off; uint32_t* sub_cnt; int shift; };
 cudaError_t launch_k2a_split (const LaunchCtx&, int W, const K2aSrc& src, void* dst, const uint64_t* coarse_off,
-                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc, const uint32_t* bin_list = 0, uint32_t n_list = 0);
-uint32_t    k2a_dedup_rmax (uint32_t max_bin_records, int fine_bits);
+                              uint32_t nb1, uint32_t cap, int fine_bits, uint2* bin_desc, const uint32_t* bin_list = 0, uint32_t n_list = 0,
+                              int desc_abs = 0, uint64_t desc_base = 0, const K2aPresplit* presplit = 0);
+uint32_t    k2a_dedup_rmax (uint32_t max_bin_records, uint32_t mean_bin_records, int fine_bits);
+uint32_t    k2a_two_cta_capacity (int fine_bits);
 cudaError_t launch_k2a_dedup_split (const LaunchCtx&, const K2aSrc& src, void* dst, const uint64_t* coarse_off, uint32_t nb1, uint32_t cap,
-                                    int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t* big_list, unsigned long long* counters);
+                                    int fine_bits, uint2* bin_desc, uint32_t rmax, uint32_t* big_list, unsigned long long* counters,
+                                    uint32_t target /* k-mers of surviving records per counting bin; 0: one bin per fine id */,
+                                    uint32_t big_load /* bins with more k-mers are flagged K2_DESC_BIG; 0: none */);
+enum : uint32_t { K2_DESC_BIG = 0x80000000u, K2_DESC_COUNT = 0x7FFFFFFFu };      // bin descriptor .y = record count | flag
 cudaError_t launch_k2b_count (const LaunchCtx&, const K2Params&);
 cudaError_t launch_k2b_count_list (const LaunchCtx&, const K2Params&);     // CTA-per-bin kernel over P.bin_list (k <= 31)
 int         k2b_variant (int path_flags);            // 1 warp per bin, 128 / 256 CTA per bin (chunked insert), 0 one k-mer per lane

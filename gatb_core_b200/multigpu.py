@@ -102,29 +102,68 @@ def bloom_distributed(gpu, kind, k, res, n_solid_global, world):
     return mine[:nbytes], bits
 
 
-N_PIECES = 2      # a rank partitions its reads in this many pieces: piece i travels while piece i+1 is being partitioned
+N_PIECES = 4      # a rank partitions its reads in this many pieces: piece i travels while piece i+1 is being partitioned
+MAX_SOURCES = 32  # GATB_GPU_MAX_SOURCES (include/gatb_gpu.h): ranks x pieces
+
+
+def pieces_per_rank(world, n_reads_local):
+    """Pieces a rank cuts its reads into (only the last piece's exchange is exposed, so more pieces hide more of it)"""
+    if world <= 1 or n_reads_local < 1024:
+        return 1
+    npc = N_PIECES
+    while npc > 1 and world * npc > MAX_SOURCES:
+        npc //= 2
+    return npc
+
+
+def piece_bounds(n_reads_local, npc):
+    """First read of every piece (multiples of 32 reads) and the end"""
+    return [(n_reads_local * i // npc) & ~31 for i in range(npc)] + [n_reads_local]
+
+
+def bind_to_gpu_numa(local):
+    """Pins this process to the CPUs next to its GPU (NVML affinity) BEFORE it allocates pinned host memory: eight ranks whose
+    staging buffers sit on the wrong socket share one inter-socket link for all their host<->device copies."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
 
 
 def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total_kmers_global, rank, world, repart=None,
-                      d_offsets=None, timers=None):
+                      d_offsets=None, timers=None, ready=None):
     """One distributed counting pass.  Returns (device Result of this rank's bins, stats dict with GLOBAL sums).
 
-    partition piece 0 -> [send piece 0 || partition piece 1] -> send piece 1 -> count: every (source rank, piece) is one
-    source of the owner's fine split (gatb_gpu_count_bins, at most 16 sources)."""
+    partition piece 0 -> [send piece 0 || partition piece 1] -> ... -> send the last piece -> count: every (source rank, piece)
+    is one source of the owner's fine split (gatb_gpu_count_bins, at most 32 sources).
+    ready: optional list of torch events, one per piece (piece_bounds): the reads of piece i are on the device once ready[i] has
+    completed (the caller's host->device copies run on their own stream while the earlier pieces are being partitioned)."""
     dev = torch.device("cuda", gpu.device)
     geom = gpu.plan(params, total_kmers_global, n_reads_global, world)
-    npc = N_PIECES if (world > 1 and world * N_PIECES <= 16 and n_reads_local >= 1024) else 1
+    npc = pieces_per_rank(world, n_reads_local)
     t = {"partition": 0.0, "exchange_wait": 0.0}
     nb1, rb, bpr, blk = geom.nb1, geom.record_bytes, geom.bins_per_rank, geom.coarse_blk
     if npc > 1:                                          # a piece holds 1/npc of the records of a bin: shrink the capacity with it
         geom.cap = (int(geom.cap / npc * 1.15) + 64 + blk - 1) // blk * blk
-    firsts = [(n_reads_local * i // npc) & ~31 for i in range(npc)] + [n_reads_local]      # multiples of 32 reads
+    firsts = piece_bounds(n_reads_local, npc)
     st_sum = [0, 0, 0, 0]
     all_pieces, all_cur, keep, used_total = [], [], [], 0
     pending = None
     t_begin = time.time()
     for i in range(npc):
         n_i = firsts[i + 1] - firsts[i]
+        if ready is not None:
+            ready[i].synchronize()
         while True:
             cap = geom.cap
             bins = torch.empty(nb1 * cap * rb, dtype=torch.uint8, device=dev)
@@ -227,6 +266,7 @@ def bench(args, rank, world, local):
     """bench.py --gpus N (N>1): weak scaling, args.reads reads per GPU out of one genome sized for all of them."""
     import gatb_core_b200
     from bench import K, M, L, ABUNDANCE_MIN, COVERAGE, SEED, METRIC, UNIT, ClockSampler, measured_peak
+    bind_to_gpu_numa(local)
     gpu = gatb_core_b200.GatbGpu(local)
     dev = torch.device("cuda", local)
     n = args.reads
@@ -249,7 +289,7 @@ def bench(args, rank, world, local):
     dist.broadcast_object_list(box, src=0)
     nb_passes, nb_partitions, repart, repart_src = box[0]
     params = gpu.make_params(K, M, nb_partitions=nb_partitions, nb_passes=nb_passes, abundance_min=ABUNDANCE_MIN, read_len=L,
-                             path_flags=args.path_flags, bin_load_pct=args.bin_load_pct, table_log2=args.table_log2, fine_bits=args.fine_bits)
+                             path_flags=args.path_flags, bin_load_pct=args.bin_load_pct, table_log2=args.table_log2, fine_bits=args.fine_bits, bin_target_pct=args.bin_target_pct)
 
     def step(timers=None):
         res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, timers=timers)
@@ -281,16 +321,25 @@ def bench(args, rank, world, local):
     h_reads = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
     h_reads.copy_(reads)
     torch.cuda.synchronize()
+    copy_stream = torch.cuda.Stream(device=dev)
     e2e = []
     d2h_bytes = 0
     for i in range(1 + args.steps):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.time()
-        reads.copy_(h_reads, non_blocking=True)
-        torch.cuda.synchronize()
+        # the reads go up piece by piece on a copy stream; piece i is partitioned as soon as it has landed
+        bounds = [b * L // 4 for b in piece_bounds(n, pieces_per_rank(world, n))]
+        bounds[-1] = reads.numel()
+        ready = []
+        with torch.cuda.stream(copy_stream):
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                reads[a:b].copy_(h_reads[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                ready.append(ev)
         t1 = time.time()
-        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart)
+        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, ready=ready)
         t2 = time.time()
         host = result_to_pinned(gpu, res, params)
         gpu.result_free(res)

@@ -61,8 +61,9 @@ typedef struct gatb_gpu_params
     int32_t  k3_dir_rounds;      /* 0 = default; >0: rounds of the block directory of the bucket scatter (a tiny one forces the
                                     exact two-pass fallback)                                                         */
     int32_t  bin_load_pct;       /* 0 = default; planned k-mer occurrences per fine bin in % of the first-tier table slots */
-    int32_t  fine_bits;          /* 0 = default (7); k <= 31: log2 of the fine bins per coarse bin on one GPU (experiments)  */
-    int32_t  reserved[1];
+    int32_t  fine_bits;          /* 0 = default (9 on one GPU); k <= 31: log2 of the fine ids per coarse bin (experiments)    */
+    int32_t  bin_target_pct;     /* 0 = default (45); k <= 31: k-mers of distinct records per counting bin in % of the table slots:
+                                    the fine split merges consecutive fine ids into counting bins of that load                   */
 } gatb_gpu_params;
 /* gatb_gpu_params.path_flags */
 enum {
@@ -78,11 +79,14 @@ enum {
     GATB_PATH_NO_DEDUP     = 128,    /* identical records are not collapsed (every multiplicity is 1)                       */
     GATB_PATH_K1_STAGING   = 512,    /* the register scanner reads TMA-staged tiles (one bulk copy per 32 reads) instead of the global
                                         stream: measured 5 ms slower and the same DRAM traffic, kept as a tested variant */
+    GATB_PATH_K2A_SMALL_STAGE = 1024,/* test selector: the dedup split stages at most 256 records, so that ordinary bins take its
+                                        several-passes path and the largest ones its two-pass fallback                                  */
+    GATB_PATH_K2A_PRESPLIT = 2048,   /* test selector: the pre-split of gathered bins (several ranks) on a single source too            */
     GATB_PATH_FUSED        = 256     /* k <= 31: one CTA counts a whole coarse bin straight out of the partition buffers (k2_fused.cu:
                                         TMA-streamed tiles, CTA-wide table) instead of fine split + warp-per-fine-bin counting  */
 };
 
-enum { GATB_GPU_NSTATS = 16, GATB_GPU_MAX_RANKS = 8, GATB_GPU_MAX_SOURCES = 16 };   /* sources = ranks x pieces per rank */
+enum { GATB_GPU_NSTATS = 16, GATB_GPU_MAX_RANKS = 8, GATB_GPU_MAX_SOURCES = 32 };   /* sources = ranks x pieces per rank */
 /* indices into gatb_gpu_result.stats */
 enum {
     GATB_STAT_KMERS_VALID = 0,   /* kmers_nb_valid   (SortingCountAlgorithm.cpp:737)   */

@@ -136,7 +136,12 @@ def path_variants():
             ("k3_tiny_directory", dict(k3_dir_rounds=1)), ("canonical_records", dict(path_flags=g.PATH_CANONICAL)),
             ("canonical_cta128", dict(path_flags=g.PATH_CANONICAL | g.PATH_K2B_CTA128)),
             ("no_dedup", dict(path_flags=g.PATH_NO_DEDUP)), ("no_dedup_canonical", dict(path_flags=g.PATH_NO_DEDUP | g.PATH_CANONICAL)),
-            ("fine_bits_5", dict(fine_bits=5)), ("fine_bits_9_dense", dict(fine_bits=9, bin_load_pct=120)),
+            ("fine_bits_5", dict(fine_bits=5)), ("fine_bits_9_dense", dict(fine_bits=9, bin_load_pct=120)), ("fine_bits_12", dict(fine_bits=12)),
+            ("bin_target_tiny", dict(bin_target_pct=3)), ("bin_target_beyond_table", dict(bin_target_pct=300)),
+            ("k2a_presplit", dict(path_flags=g.PATH_K2A_PRESPLIT)), ("k2a_presplit_small_stage", dict(path_flags=g.PATH_K2A_PRESPLIT | g.PATH_K2A_SMALL_STAGE, bin_load_pct=30)),
+            ("k2a_several_passes", dict(path_flags=g.PATH_K2A_SMALL_STAGE, bin_load_pct=30)),
+            ("k2a_passes_then_fallback", dict(path_flags=g.PATH_K2A_SMALL_STAGE, bin_load_pct=50, fine_bits=3)),
+            ("k2a_two_pass_fallback", dict(path_flags=g.PATH_K2A_SMALL_STAGE, bin_load_pct=300)),
             ("dense_bins", dict(bin_load_pct=150)), ("sparse_bins", dict(bin_load_pct=10)), ("tier_tables", dict(table_log2=6))]
 
 
