@@ -297,6 +297,10 @@ static int plan_geometry (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, uint64_t 
         uint64_t nbins_fine = (total_kmers + occ_per_bin - 1) / occ_per_bin; if (nbins_fine < 1) nbins_fine = 1;
         int split_log2 = fine_bits;                                             // k >= 32: the fine ids ARE the counting bins
         if (W == 1) { split_log2 = coarse_log2; for (int r = 1; r < n_ranks; r <<= 1) split_log2++; }    // nb1 stays put, the gathered bins grow
+        // several ranks: the records arriving over NVLink pass through the same L2 that combines the partition kernel's scattered
+        // stores (k1 49 -> 72 ms on 2 GPUs while pieces travel): half as many open lines; the pre-split of the gathered bins
+        // (count_bins_impl) takes one more leading bit
+        if (W == 1 && n_ranks > 1) split_log2++;
         nb1 = (nbins_fine + (1ULL << split_log2) - 1) >> split_log2;
     }
     if (nb1 < 1) nb1 = 1;
@@ -471,8 +475,9 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         // that many) must stay below 3/4 of the table, and a fuller table probes longer: 45 % measured best
         // (k2b 62.2 + 1.1 ms for the 0.2 % of bins that still overflow; 60 %: 65.4 + 3.8, 30 %: 63.0 + 0.4)
         const uint32_t target = (uint32_t)((((uint64_t)1 << table_log2) * (p->bin_target_pct > 0 ? p->bin_target_pct : 45)) / 100);
-        // the distinct k-mers of a bin are at most the k-mers of its records, typically 3/4 of them: a bin whose records hold more than
-        // 0.95 T k-mers (one fine id = one minimizer value holds several loci of a multi-Gb genome) will not fit 3/4 T slots
+        // the distinct k-mers of a bin are at most the k-mers of its records, typically half of them (the variants of a locus' record --
+        // reads that end inside it, sequencing errors -- repeat most of its k-mers): a bin whose records hold more than 0.95 T k-mers
+        // (one fine id = one minimizer value holds several loci of a multi-Gb genome) rarely fits the 3/4 T slots a table may fill: measured on the 8-GPU geometry, a threshold of 0.95 T costs 38 + 43 ms (first tier + tiers), 1.4 T 54 + 36 ms -- a failed attempt in the first tier is dearer than a needless trip to the 1024-slot tier
         const uint32_t big_load = (k2b_variant (p->path_flags) == 1) ? (uint32_t)((((uint64_t)1 << table_log2) * 95) / 100) : 0u;
         CK (launch_k2a_dedup_split (L, S2d, ctx->slot[S_FINE], coarse_off_d, nb_d, cap_d, fine_bits_d,
                                     (uint2*)ctx->slot[S_BINDESC], rmax, (uint32_t*)ctx->slot[S_OVFLIST], d_k2a, target, big_load));
@@ -517,7 +522,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
       if (ensure (ctx, S_OVFLIST2, nl * 4)) return 1; }
     unsigned long long* d_cnt = (unsigned long long*)ctx->slot[S_COUNTERS];
     unsigned long long h_cnt[16];
-    uint64_t n_ovf = 0, n_ovf_first = 0;
+    uint64_t n_ovf = 0, n_ovf_first = 0, tier_out[3] = { 0, 0, 0 };          // bins leaving the warp tier / the two CTA tiers
     uint64_t* u_lo = 0; uint64_t* u_hi = 0; uint32_t* u_cnt = 0;
     K2Params k2;
     for (int attempt = 0; ; attempt++)
@@ -580,6 +585,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
                 CK (cudaMemcpyAsync (h_cnt, d_cnt, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
                 CK (cudaStreamSynchronize (ctx->stream));
                 n_ovf = h_cnt[tier_counter[t]];
+                tier_out[t] = n_ovf;
                 cur_list = other;
             }
             k2.ovf_list = (uint32_t*)ctx->slot[cur_list];                            // what is left goes to the global table
@@ -772,6 +778,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     }
     out->stats[GATB_STAT_DISTINCT] = h_cnt[1]; out->stats[GATB_STAT_SOLID] = h_cnt[2];
     out->stats[GATB_STAT_RECORDS] = n_records; out->stats[GATB_STAT_BINS] = nbins_count; out->stats[GATB_STAT_OVERFLOW_BINS] = n_ovf_first; out->stats[12] = n_ovf;
+    out->stats[14] = tier_out[0]; out->stats[15] = tier_out[1];
     out->stats[GATB_STAT_RECORD_BYTES] = n_records * rec_bytes; out->stats[GATB_STAT_UNIQUE_RECORDS] = n_unique_records;
     float ms;
     cudaEventElapsedTime (&ms, ctx->ev[2], ctx->ev[3]); out->seconds[2] = ms * 1e-3;

@@ -65,8 +65,8 @@ for rep in range(2):
         gpu.result_free(res)
 cur_all = torch.stack(curs).to(torch.int64)
 print("cursors per source piece: max %d mean %.1f (cap %d)" % (int(cur_all.max()), float(cur_all.float().mean()), cap))
-print("owner %d of %d ranks: records %d unique %d distinct %d solid %d bins %d overflow_bins %d to_global %d overflow_kmers %d" % (
-    owner, world, int(res.stats[4]), int(res.stats[13]), int(res.stats[2]), int(res.stats[3]), int(res.stats[7]), int(res.stats[8]), int(res.stats[12]), int(res.stats[11])))
+print("owner %d of %d ranks: records %d unique %d distinct %d solid %d bins %d overflow_bins %d (leaving the warp tier %d, the 4096-slot tier %d) to_global %d overflow_kmers %d" % (
+    owner, world, int(res.stats[4]), int(res.stats[13]), int(res.stats[2]), int(res.stats[3]), int(res.stats[7]), int(res.stats[8]), int(res.stats[14]), int(res.stats[15]), int(res.stats[12]), int(res.stats[11])))
 gpu.result_free(res)
 if len(sys.argv) > 3 and sys.argv[3] == 'noshot':
     sys.exit(0)
