@@ -445,6 +445,7 @@ def main():
     ap.add_argument("--fine-bits", type=int, default=0, help="gatb_gpu_params.fine_bits (experiments; 0 = default)")
     ap.add_argument("--bin-target-pct", type=int, default=0, help="gatb_gpu_params.bin_target_pct (experiments; 0 = default)")
     ap.add_argument("--table-log2", type=int, default=0, help="gatb_gpu_params.table_log2 (experiments; 0 = default)")
+    ap.add_argument("--no-route", action="store_true", help="N>1: skip the second exchange (per-rank ascending runs instead of whole partitions on their owner rank)")
     ap.add_argument("--staged", action="store_true", help="N=1 through the staged multi-GPU code path (debugging aid)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -24,7 +24,8 @@ EXPORTS = ["gatb_gpu_create", "gatb_gpu_destroy", "gatb_gpu_last_error", "gatb_g
            "gatb_gpu_histogram_cutoff", "gatb_gpu_malloc", "gatb_gpu_free", "gatb_gpu_memcpy_h2d", "gatb_gpu_memcpy_d2h",
            "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii", "gatb_gpu_plan",
            "gatb_gpu_partition_into", "gatb_gpu_partition_range_into", "gatb_gpu_count_bins", "gatb_gpu_reads_begin",
-           "gatb_gpu_reads_push_ascii", "gatb_gpu_reads_count", "gatb_gpu_reads_push_text", "gatb_gpu_reads_info", "gatb_gpu_synth_zipf_dev"]
+           "gatb_gpu_reads_push_ascii", "gatb_gpu_reads_count", "gatb_gpu_reads_push_text", "gatb_gpu_reads_info", "gatb_gpu_synth_zipf_dev",
+           "gatb_gpu_count_bins_routed", "gatb_gpu_sort_routed"]
 
 
 class GatbGpuError(RuntimeError):
@@ -104,6 +105,9 @@ def load_library():
     L.gatb_gpu_partition_range_into.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), VP, VP, U64, U64, VP, VP, VP, VP]
     L.gatb_gpu_count_bins.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), I32, C.POINTER(VP), C.POINTER(VP),
                                       C.c_uint32, VP, U64, C.POINTER(Result)]
+    L.gatb_gpu_count_bins_routed.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), I32, C.POINTER(VP), C.POINTER(VP),
+                                             C.c_uint32, VP, U64, I32, VP, C.POINTER(VP), C.POINTER(Result)]
+    L.gatb_gpu_sort_routed.argtypes = [VP, C.POINTER(Params), VP, VP, VP, VP, U64, C.POINTER(Result)]
     return L
 
 
@@ -283,6 +287,27 @@ class GatbGpu:
         rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
         self._check(self.L.gatb_gpu_count_bins(self.ctx, C.byref(params), C.byref(geom), n, a, b, nb1_local,
                                                _ptr(rp), kmers_bound, C.byref(res)))
+        return res
+
+    def count_bins_routed(self, params, geom, src_bins, src_cursors, nb1_local, kmers_bound, n_ranks, repart=None):
+        """Like count_bins, but instead of sorting, the emitted k-mers are grouped by the rank that owns their partition key.
+        Returns (device Result with kmers_lo / kmers_hi / counts in one region per destination rank, device pointer of the 16-bit keys,
+        items per destination, items a region can hold)."""
+        n = len(src_bins)
+        a = (C.c_void_p * n)(*src_bins)
+        b = (C.c_void_p * n)(*src_cursors)
+        res = Result()
+        rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
+        counts = np.zeros(n_ranks + 1, np.uint64)
+        keys = C.c_void_p()
+        self._check(self.L.gatb_gpu_count_bins_routed(self.ctx, C.byref(params), C.byref(geom), n, a, b, nb1_local, _ptr(rp), kmers_bound,
+                                                      n_ranks, _ptr(counts), C.byref(keys), C.byref(res)))
+        return res, keys.value, [int(x) for x in counts[:n_ranks]], int(counts[n_ranks])
+
+    def sort_routed(self, params, d_lo, d_hi, d_counts, d_keys, n_items):
+        """Partition key + ascending order of routed items (device pointers).  Returns a device Result."""
+        res = Result()
+        self._check(self.L.gatb_gpu_sort_routed(self.ctx, C.byref(params), _ptr(d_lo), _ptr(d_hi), _ptr(d_counts), _ptr(d_keys), n_items, C.byref(res)))
         return res
 
     # ---- GATB-exact super-k-mers ---------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ static std::string g_create_error;
 
 // device buffer slots cached in the context so that repeated calls (bench steps) do not re-allocate
 enum Slot { S_READS, S_OFFSETS, S_NMASK, S_COARSE, S_FINE, S_CURSORS, S_BINDESC, S_STATS, S_HISTO, S_COUNTERS,
-            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_OVFLIST2, S_BINOFF, S_PRESPLIT, S_SUBOFF, S_SUBCNT, S_NSLOTS };
+            S_OVFLIST, S_GTABLE, S_REPART, S_BUCKETOF, S_BUCKETCNT, S_BUCKETOFF, S_SCAN, S_BIGLIST, S_SORTED, S_MISC, S_MISC2, S_TOTCUR, S_COARSEOFF, S_UNSORTED, S_RESMISC, S_DIR, S_OVFLIST2, S_BINOFF, S_PRESPLIT, S_SUBOFF, S_SUBCNT, S_ROUTECNT, S_NSLOTS };
 
 struct gatb_gpu_ctx
 {
@@ -389,235 +389,20 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
     return 0;
 }
 
-// ---- stages 2-4: fine split of nb1_local coarse bins gathered from n_src sources, count, partition id + sort --------
-static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
-                            const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
-                            uint32_t nb1_local, const uint16_t* repart_host, uint64_t total_kmers_bound, gatb_gpu_result* out,
-                            bool to_host = false, const uint64_t* const* d_src_off = 0)
+// ---- stage 4 (k3): partition key + ascending order of the emitted k-mers [0, n_range) (holes carry an all-ones key) ----
+// in_key != NULL: the keys came with the items (routed items of a multi-GPU run); the result arrays live in context-owned slots
+struct SortOut { DevResult dr; uint64_t* h_lo; uint64_t* h_hi; int32_t* h_cnt32; uint64_t* h_offs; uint64_t* h_hist; };
+static int sort_stage (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint64_t* u_lo, const uint64_t* u_hi, const uint32_t* u_cnt, const uint16_t* in_key,
+                       uint64_t n_range, uint64_t n_items, const uint16_t* repart_host, bool to_host, SortOut* so)
 {
     LaunchCtx L = lctx (ctx);
-    const int k = p->kmer_size, W = g->words;
+    const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
     const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
-    const int histo_max = p->histo_max, fine_bits = g->fine_bits, table_log2 = g->table_log2;
-    const uint64_t nbins = (uint64_t)nb1_local << fine_bits;
-    const uint32_t cap = d_src_off ? 0xFFFFFFFFu : g->cap;        // dense sources hold exactly what their cursors say
-    const size_t rec_bytes = 16 * W;
-    if (n_src < 1 || n_src > GATB_GPU_MAX_SOURCES) return fail (ctx, "n_src must be in [1,%d]", GATB_GPU_MAX_SOURCES);
-
-    // ---- compact layout of the fine-split copy: coarse_off = exclusive scan of the gathered record counts ----
-    if (ensure (ctx, S_TOTCUR, (size_t)nb1_local * 4)) return 1;
-    if (ensure (ctx, S_COARSEOFF, ((size_t)nb1_local + 1) * 8)) return 1;
-    if (ensure (ctx, S_SCAN, scan_scratch_elems (nb1_local > (n_keys << 24) ? nb1_local : (n_keys << 24)) * 8)) return 1;
-    const uint64_t desc_cap = nbins + nbins / 8 + 1024;          // (adaptive bins: at most one per fine id, plus the bins of the two-pass fallback)
-    if (ensure (ctx, S_BINDESC, desc_cap * 8)) return 1;
-    CursorList CL; CL.n = n_src; for (int s = 0; s < n_src; s++) CL.cur[s] = d_src_cursors[s];
-    if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
-    uint32_t* d_maxbin = (uint32_t*)((unsigned long long*)ctx->slot[S_COUNTERS] + 15);
-    CK (cudaMemsetAsync (d_maxbin, 0, 8, ctx->stream));
-    k_sum_cursors<<<(nb1_local + 255) / 256, 256, 0, ctx->stream>>> (CL, nb1_local, cap, (uint32_t*)ctx->slot[S_TOTCUR], d_maxbin); ctx->launches++;
-    CK (launch_scan_u32_to_u64 (L, (const uint32_t*)ctx->slot[S_TOTCUR], (uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, (uint64_t*)ctx->slot[S_SCAN]));
-    uint64_t n_records = 0; uint32_t max_bin = 0;
-    CK (cudaMemcpyAsync (&n_records, (const uint64_t*)ctx->slot[S_COARSEOFF] + nb1_local, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK (cudaMemcpyAsync (&max_bin, d_maxbin, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK (cudaStreamSynchronize (ctx->stream));
-    cudaEventRecord (ctx->ev[2], ctx->stream);
-
-    // ---- k2a: fine split (not on the fused path: k <= 31 counts straight out of the coarse bins) ----
-    const bool fused = path_fused (p);
-    const int dedup = (p->path_flags & GATB_PATH_NO_DEDUP) ? 0 : 1;
-    if (!fused && ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
-    K2aSrc S2; memset (&S2, 0, sizeof(S2)); S2.n = n_src;
-    for (int s = 0; s < n_src; s++) { S2.bins[s] = (const uint4*)d_src_bins[s]; S2.cursors[s] = d_src_cursors[s]; S2.off[s] = d_src_off ? d_src_off[s] : 0; }
-    cudaEventRecord (ctx->kev[2], ctx->stream);
-    uint64_t n_unique_records = n_records;
-    uint64_t nbins_count = nbins;                  // bins the counting kernels see (the dedup split forms its own: adaptive bins)
-    bool desc_abs = false;                         // their descriptors hold absolute record offsets
-    if (fused) cudaEventRecord (ctx->kev[3], ctx->stream);
-    else if (W == 1 && dedup && n_records)
-    {   // ---- k <= 31: the bin is staged in shared memory once, identical records collapse, multiplicities travel with the records ----
-        if (n_records >= (1ULL << 32)) return fail (ctx, "too many super-k-mer records for one device (%llu): use more passes or more GPUs", (unsigned long long)n_records);
-        if (ensure (ctx, S_OVFLIST, (nbins > nb1_local ? nbins : nb1_local) * 4)) return 1;
-        unsigned long long* d_k2a = (unsigned long long*)ctx->slot[S_COUNTERS] + 12;
-        CK (cudaMemsetAsync (d_k2a, 0, 3 * 8, ctx->stream));
-        // ---- bins gathered from several ranks are several times larger than a CTA's staging area: instead of taking them in as many
-        //      passes (each reads the whole bin again: 66 ms for 5 passes on 8 GPUs), a plain two-pass split by the leading bits of the
-        //      fine id first cuts them into sub-bins of single-GPU size (one more copy of the records, ~18 ms), which the dedup split
-        //      then takes from that dense copy in one pass each ----
-        uint32_t nb_d = nb1_local, cap_d = cap, max_bin_d = max_bin; int fine_bits_d = fine_bits;
-        const uint64_t* coarse_off_d = (const uint64_t*)ctx->slot[S_COARSEOFF];
-        K2aSrc S2d = S2;
-        {
-            const uint32_t mean_bin = (uint32_t)(n_records / (nb1_local ? nb1_local : 1)) + 1;
-            int sub_bits = 0;
-            if (n_src > 1 || (p->path_flags & GATB_PATH_K2A_PRESPLIT))
-                while (sub_bits < fine_bits - 6 && ((mean_bin >> sub_bits) * 5) / 4 > k2a_two_cta_capacity (fine_bits - sub_bits)) sub_bits++;
-            if ((p->path_flags & GATB_PATH_K2A_PRESPLIT) && sub_bits == 0 && fine_bits > 2) sub_bits = 2;        // test selector
-            if (sub_bits)
-            {
-                const uint64_t nsub = (uint64_t)nb1_local << sub_bits;
-                if (ensure (ctx, S_PRESPLIT, (n_records + 1) * rec_bytes)) return 1;
-                if (ensure (ctx, S_SUBOFF, (nsub + 1) * 8)) return 1;
-                if (ensure (ctx, S_SUBCNT, nsub * 4)) return 1;
-                K2aPresplit PS; PS.sub_off = (uint64_t*)ctx->slot[S_SUBOFF]; PS.sub_cnt = (uint32_t*)ctx->slot[S_SUBCNT]; PS.shift = fine_bits - sub_bits;
-                CK (launch_k2a_split (L, W, S2, ctx->slot[S_PRESPLIT], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, sub_bits, 0, 0, 0, 0, 0, &PS));
-                CursorList C1; C1.n = 1; C1.cur[0] = PS.sub_cnt;
-                CK (cudaMemsetAsync (d_maxbin, 0, 8, ctx->stream));
-                if (ensure (ctx, S_TOTCUR, nsub * 4)) return 1;
-                k_sum_cursors<<<(unsigned)((nsub + 255) / 256), 256, 0, ctx->stream>>> (C1, (uint32_t)nsub, 0xFFFFFFFFu, (uint32_t*)ctx->slot[S_TOTCUR], d_maxbin); ctx->launches++;
-                CK (cudaMemcpyAsync (&max_bin_d, d_maxbin, 4, cudaMemcpyDeviceToHost, ctx->stream));
-                CK (cudaStreamSynchronize (ctx->stream));
-                memset (&S2d, 0, sizeof(S2d)); S2d.n = 1; S2d.bins[0] = (const uint4*)ctx->slot[S_PRESPLIT]; S2d.cursors[0] = PS.sub_cnt; S2d.off[0] = PS.sub_off;
-                nb_d = (uint32_t)nsub; cap_d = 0xFFFFFFFFu; fine_bits_d = fine_bits - sub_bits; coarse_off_d = PS.sub_off;
-            }
-        }
-        const uint32_t rmax = (p->path_flags & GATB_PATH_K2A_SMALL_STAGE) ? 256u : k2a_dedup_rmax (max_bin_d, (uint32_t)(n_records / (nb_d ? nb_d : 1)) + 1, fine_bits_d);
-        // counting bins of <= target k-mers of surviving records (+ one fine id's worth): the distinct k-mers of a bin (at most
-        // that many) must stay below 3/4 of the table, and a fuller table probes longer: 45 % measured best
-        // (k2b 62.2 + 1.1 ms for the 0.2 % of bins that still overflow; 60 %: 65.4 + 3.8, 30 %: 63.0 + 0.4)
-        const uint32_t target = (uint32_t)((((uint64_t)1 << table_log2) * (p->bin_target_pct > 0 ? p->bin_target_pct : 45)) / 100);
-        // the distinct k-mers of a bin are at most the k-mers of its records, typically half of them (the variants of a locus' record --
-        // reads that end inside it, sequencing errors -- repeat most of its k-mers): a bin whose records hold more than 0.95 T k-mers
-        // (one fine id = one minimizer value holds several loci of a multi-Gb genome) rarely fits the 3/4 T slots a table may fill: measured on the 8-GPU geometry, a threshold of 0.95 T costs 38 + 43 ms (first tier + tiers), 1.4 T 54 + 36 ms -- a failed attempt in the first tier is dearer than a needless trip to the 1024-slot tier
-        const uint32_t big_load = (k2b_variant (p->path_flags) == 1) ? (uint32_t)((((uint64_t)1 << table_log2) * 95) / 100) : 0u;
-        CK (launch_k2a_dedup_split (L, S2d, ctx->slot[S_FINE], coarse_off_d, nb_d, cap_d, fine_bits_d,
-                                    (uint2*)ctx->slot[S_BINDESC], rmax, (uint32_t*)ctx->slot[S_OVFLIST], d_k2a, target, big_load));
-        unsigned long long h_k2a[3] = { 0, 0, 0 };
-        CK (cudaMemcpyAsync (h_k2a, d_k2a, 24, cudaMemcpyDeviceToHost, ctx->stream));
-        CK (cudaStreamSynchronize (ctx->stream));
-        if (h_k2a[0])
-        {   // bins the kernel gave up on (a skewed range of fine ids, more passes than it tracks) go through the plain two-pass
-            // split (multiplicity 1, one counting bin per fine id), their descriptors appended after the adaptive ones
-            if (h_k2a[2] + (h_k2a[0] << fine_bits_d) > desc_cap) return fail (ctx, "bin descriptors exhausted");
-            CK (launch_k2a_split (L, W, S2d, ctx->slot[S_FINE], coarse_off_d, nb_d, cap_d, fine_bits_d,
-                                  (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)h_k2a[0], 1, h_k2a[2]));
-        }
-        cudaEventRecord (ctx->kev[3], ctx->stream);
-        n_unique_records = h_k2a[1];                 // (bins of the two-pass kernel are not in this figure)
-        nbins_count = h_k2a[2] + (h_k2a[0] << fine_bits_d);
-        desc_abs = true;
-    }
-    else
-    {
-        CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
-        cudaEventRecord (ctx->kev[3], ctx->stream);
-    }
-    cudaEventRecord (ctx->ev[3], ctx->stream);
-
-    // ---- k2b: count.  When the single source is the context's own coarse buffer it is dead now and becomes the output. ----
-    const uint32_t amin = p->abundance_min < 1 ? 1 : (uint32_t)p->abundance_min;
-    const uint32_t amax = p->abundance_max < 0 ? 0x7fffffffu : (uint32_t)p->abundance_max;
-    const uint32_t emin = p->emit_all ? 1u : amin, emax = p->emit_all ? 0xffffffffu : amax;
-    const int S_OUT = (!fused && n_src == 1 && d_src_bins[0] == ctx->slot[S_COARSE]) ? S_COARSE : S_UNSORTED;   // (the fused kernel reads the coarse bins while it emits)
-    uint64_t out_bound = total_kmers_bound / emin + 1;                         // a k-mer emitted needs >= emin occurrences
+    const int histo_max = p->histo_max;
     const size_t item_bytes = 8 * W + 4;
-    const uint64_t block_slack = (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;  // every warp of k2b reserves output in blocks of 2048 slots
-    uint64_t out_cap = total_kmers_bound / 8 + 4096;                           // first guess; the retry below corrects it
-    if (out_cap > out_bound) out_cap = out_bound;
-    out_cap += block_slack;
-    if (out_cap < ctx->slot_cap[S_OUT] / item_bytes) out_cap = ctx->slot_cap[S_OUT] / item_bytes;   // never shrink: no re-allocation per call
-
+    if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
     if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
-    { const uint64_t nl = nbins_count > nbins ? nbins_count : nbins;
-      if (ensure (ctx, S_OVFLIST, (nl > nb1_local ? nl : nb1_local) * 4)) return 1;
-      if (ensure (ctx, S_OVFLIST2, nl * 4)) return 1; }
     unsigned long long* d_cnt = (unsigned long long*)ctx->slot[S_COUNTERS];
-    unsigned long long h_cnt[16];
-    uint64_t n_ovf = 0, n_ovf_first = 0, tier_out[3] = { 0, 0, 0 };          // bins leaving the warp tier / the two CTA tiers
-    uint64_t* u_lo = 0; uint64_t* u_hi = 0; uint32_t* u_cnt = 0;
-    K2Params k2;
-    for (int attempt = 0; ; attempt++)
-    {
-        if (ensure (ctx, S_OUT, out_cap * item_bytes)) return 1;
-        u_lo = (uint64_t*)ctx->slot[S_OUT];
-        u_hi = (W == 2) ? u_lo + out_cap : 0;
-        u_cnt = (uint32_t*)(u_lo + out_cap * W);
-        CK (cudaMemsetAsync (ctx->slot[S_HISTO], 0, (size_t)(histo_max + 1) * 8, ctx->stream));
-        CK (cudaMemsetAsync (d_cnt, 0, 16 * 8, ctx->stream));
-        memset (&k2, 0, sizeof(k2));
-        k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins_count;
-        // (absolute descriptors: every bin takes coarse_off[bin >> 31] = coarse_off[0] = 0 as its base)
-        k2.coarse_off = (const uint64_t*)ctx->slot[S_COARSEOFF]; k2.fine_bits = desc_abs ? 31 : fine_bits; k2.table_log2 = table_log2;
-        k2.path_flags = p->path_flags; k2.oriented = k1_oriented (k, g->m_device, g->w, p->path_flags) ? 1 : 0;
-        k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
-        k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
-        k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
-        k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST]; k2.ovf_counter = 4;
-        cudaEventRecord (ctx->kev[4], ctx->stream);
-        if (fused) CK (launch_k2f_count (L, k2, S2, nb1_local, cap, nb1_local, dedup));
-        else       CK (launch_k2b_count (L, k2));
-        cudaEventRecord (ctx->kev[5], ctx->stream);
-        CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK (cudaStreamSynchronize (ctx->stream));
-        n_ovf = h_cnt[4];
-        n_ovf_first = n_ovf;
-        if (n_ovf) cudaEventRecord (ctx->kev[8], ctx->stream);
-        int cur_list = S_OVFLIST;
-        if (fused && n_ovf)
-        {   // ---- coarse bins whose distinct k-mers outgrew the CTA's table: fine split of just those bins (multiplicity 1), then
-            //      their fine bins (1 << fine_bits each) go through the tier kernels below ----
-            if (ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
-            CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
-                                  (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)n_ovf));
-            k_expand_bins<<<(unsigned)(((n_ovf << fine_bits) + 255) / 256), 256, 0, ctx->stream>>> ((const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)n_ovf, fine_bits,
-                                                                                                      (uint32_t*)ctx->slot[S_OVFLIST2]); ctx->launches++;
-            k2.recs = ctx->slot[S_FINE];
-            n_ovf <<= fine_bits; cur_list = S_OVFLIST2;
-            k2.ovf_list = (uint32_t*)ctx->slot[cur_list];
-        }
-        const bool no_tier2 = (p->path_flags & GATB_PATH_NO_TIER2) != 0;                      // test selector: straight to the global table
-        if (n_ovf && W == 1 && (fused || k2b_variant (p->path_flags) == 1) && !no_tier2)
-        {   // ---- further tiers: the bins a warp's 2^table_log2-slot table could not hold are counted by CTAs with 2048,
-            //      then 8192 slots (k2b_count_w1 over a bin list); what still overflows goes to the global table ----
-            // (the claimed-slot lists of k2b_count_w1 are per warp, 3/32 of the table each: 4096 slots leave a warp 384 of them)
-            // (first, warps again with 2048-slot tables -- k2b_warp_bins over the bin list, at the rate of the first tier: on multi-Gb
-            //  inputs one bin in eleven overflows 512 slots, and CTA tiers took 69 ms for them on 8 GPUs)
-            const int tier_log2[3] = { 10, 12, 13 }, tier_counter[3] = { 13, 7, 12 };
-            for (int t = 0; t < 3 && n_ovf; t++)
-            {
-                if (!fused && tier_log2[t] <= table_log2) continue;
-                if (fused && tier_log2[t] < 12) continue;
-                const int other = (cur_list == S_OVFLIST) ? S_OVFLIST2 : S_OVFLIST;
-                K2Params k2t = k2;
-                k2t.bin_list = (const uint32_t*)ctx->slot[cur_list]; k2t.n_list = (uint32_t)n_ovf;
-                k2t.ovf_list = (uint32_t*)ctx->slot[other]; k2t.ovf_counter = tier_counter[t]; k2t.table_log2 = tier_log2[t];
-                CK (cudaMemsetAsync (d_cnt + 3, 0, 8, ctx->stream));                 // work counter
-                CK (launch_k2b_count_list (L, k2t));
-                CK (cudaMemcpyAsync (h_cnt, d_cnt, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-                CK (cudaStreamSynchronize (ctx->stream));
-                n_ovf = h_cnt[tier_counter[t]];
-                tier_out[t] = n_ovf;
-                cur_list = other;
-            }
-            k2.ovf_list = (uint32_t*)ctx->slot[cur_list];                            // what is left goes to the global table
-            if (!n_ovf) cudaEventRecord (ctx->kev[9], ctx->stream);
-        }
-        if (n_ovf)
-        {   // ---- k2c: bins that did not fit the shared-memory table share one global table ----
-            CK (launch_k2c_measure (L, k2, (uint32_t)n_ovf));
-            CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK (cudaStreamSynchronize (ctx->stream));
-            uint64_t occ = h_cnt[5]; int g_log2 = 10; while ((1ULL << g_log2) < 2 * occ) g_log2++;
-            if (g_log2 > 31) return fail (ctx, "fallback table too large (%llu k-mers in overflowing bins)", (unsigned long long)occ);
-            size_t gT = (size_t)1 << g_log2;
-            if (ensure (ctx, S_GTABLE, gT * (8 * W + 4))) return 1;
-            k2.g_lo = (uint64_t*)ctx->slot[S_GTABLE]; k2.g_hi = (W == 2) ? k2.g_lo + gT : 0; k2.g_cnt = (uint32_t*)(k2.g_lo + gT * W); k2.g_log2 = g_log2;
-            if (W == 1) CK (cudaMemsetAsync (k2.g_lo, 0xFF, gT * 8, ctx->stream));
-            else      { CK (cudaMemsetAsync (k2.g_lo, 0, gT * 8, ctx->stream)); CK (cudaMemsetAsync (k2.g_hi, 0xFF, gT * 8, ctx->stream)); }
-            CK (cudaMemsetAsync (k2.g_cnt, 0, gT * 4, ctx->stream));
-            CK (launch_k2c_insert (L, k2, (uint32_t)n_ovf));
-            CK (launch_k2c_scan (L, k2));
-            cudaEventRecord (ctx->kev[9], ctx->stream);
-            CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK (cudaStreamSynchronize (ctx->stream));
-        }
-        if (h_cnt[0] <= out_cap) break;
-        if (attempt >= 1) return fail (ctx, "output capacity exceeded: %llu k-mers to emit, room for %llu", (unsigned long long)h_cnt[0], (unsigned long long)out_cap);
-        out_cap = h_cnt[0] + block_slack;                     // the cursor kept counting: it bounds the demand -> count again
-    }
-    const uint64_t n_items = h_cnt[6];          // k-mers emitted
-    const uint64_t n_range = h_cnt[0];          // extent of the unsorted array (block reservations leave EMPTY holes)
-    cudaEventRecord (ctx->ev[4], ctx->stream);
-
     // ---- k3: partition id + ascending order ----
     int t_bits = 0;
     // buckets cut along the distribution of canonical values (k3_range_of).  One key: 512..1024 k-mers on average.  Several keys
@@ -629,7 +414,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     while (t_bits > 0 && (n_keys << t_bits) > (1ULL << 30)) t_bits--;
     const uint64_t n_buckets = n_keys << t_bits;
     // result arrays live in context-owned slots (valid until the next count on this context): no per-call cudaMalloc
-    DevResult drs; DevResult* dr = &drs; memset (dr, 0, sizeof(*dr));
+    DevResult* dr = &so->dr; memset (so, 0, sizeof(*so));
     uint64_t n_alloc = n_items ? n_items : 1;
     if (ensure (ctx, S_SORTED, n_alloc * item_bytes + 64)) return 1;
     if (ensure (ctx, S_RESMISC, (n_keys + 1) * 8 + (size_t)(histo_max + 1) * 8 + 64)) return 1;
@@ -642,7 +427,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     if (ensure (ctx, S_BUCKETOFF, (n_buckets + 1) * 8)) return 1;
     if (ensure (ctx, S_SCAN, scan_scratch_elems (n_buckets) * 8)) return 1;
     if (ensure (ctx, S_BIGLIST, n_buckets * 8)) return 1;
-    if (n_keys > 1)
+    if (n_keys > 1 && !in_key)
     {
         uint64_t rbytes = (1ULL << (2 * p->minimizer_size)) * 2;
         if (ensure (ctx, S_REPART, rbytes)) return 1;
@@ -654,7 +439,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     k3.mmask = (1u << (2 * p->minimizer_size)) - 1; k3.mask_ma1 = gatb_mask_ma1 (p->minimizer_size);
     k3.repart = (const uint16_t*)ctx->slot[S_REPART]; k3.nb_partitions = p->nb_partitions; k3.nb_passes = p->nb_passes; k3.n_keys = (uint32_t)n_keys;
     k3.t_bits = t_bits; k3.n = n_range;
-    k3.in_lo = u_lo; k3.in_hi = u_hi; k3.in_cnt = u_cnt;
+    k3.in_lo = u_lo; k3.in_hi = u_hi; k3.in_cnt = u_cnt; k3.in_key = in_key;
     k3.bucket_count = (uint32_t*)ctx->slot[S_BUCKETCNT];
     k3.bucket_off = (const uint64_t*)ctx->slot[S_BUCKETOFF];
     k3.out_lo = (uint64_t*)dr->lo; k3.out_hi = (uint64_t*)dr->hi; k3.out_cnt = (int32_t*)dr->cnt;
@@ -763,6 +548,295 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
             CK (cudaStreamSynchronize (ctx->copy_stream));
         }
     }
+    so->h_lo = h_lo; so->h_hi = h_hi; so->h_cnt32 = h_cnt32; so->h_offs = h_offs; so->h_hist = h_hist;
+    return 0;
+}
+
+// ---- stages 2-4: fine split of nb1_local coarse bins gathered from n_src sources, count, partition id + sort --------
+static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
+                            const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
+                            uint32_t nb1_local, const uint16_t* repart_host, uint64_t total_kmers_bound, gatb_gpu_result* out,
+                            bool to_host = false, const uint64_t* const* d_src_off = 0, int route_ranks = 0, uint64_t* route_counts = 0, uint16_t** route_keys = 0)
+{
+    LaunchCtx L = lctx (ctx);
+    const int k = p->kmer_size, W = g->words;
+    const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
+    const int histo_max = p->histo_max, fine_bits = g->fine_bits, table_log2 = g->table_log2;
+    const uint64_t nbins = (uint64_t)nb1_local << fine_bits;
+    const uint32_t cap = d_src_off ? 0xFFFFFFFFu : g->cap;        // dense sources hold exactly what their cursors say
+    const size_t rec_bytes = 16 * W;
+    if (n_src < 1 || n_src > GATB_GPU_MAX_SOURCES) return fail (ctx, "n_src must be in [1,%d]", GATB_GPU_MAX_SOURCES);
+
+    // ---- compact layout of the fine-split copy: coarse_off = exclusive scan of the gathered record counts ----
+    if (ensure (ctx, S_TOTCUR, (size_t)nb1_local * 4)) return 1;
+    if (ensure (ctx, S_COARSEOFF, ((size_t)nb1_local + 1) * 8)) return 1;
+    if (ensure (ctx, S_SCAN, scan_scratch_elems (nb1_local > (n_keys << 24) ? nb1_local : (n_keys << 24)) * 8)) return 1;
+    const uint64_t desc_cap = nbins + nbins / 8 + 1024;          // (adaptive bins: at most one per fine id, plus the bins of the two-pass fallback)
+    if (ensure (ctx, S_BINDESC, desc_cap * 8)) return 1;
+    CursorList CL; CL.n = n_src; for (int s = 0; s < n_src; s++) CL.cur[s] = d_src_cursors[s];
+    if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
+    uint32_t* d_maxbin = (uint32_t*)((unsigned long long*)ctx->slot[S_COUNTERS] + 15);
+    CK (cudaMemsetAsync (d_maxbin, 0, 8, ctx->stream));
+    k_sum_cursors<<<(nb1_local + 255) / 256, 256, 0, ctx->stream>>> (CL, nb1_local, cap, (uint32_t*)ctx->slot[S_TOTCUR], d_maxbin); ctx->launches++;
+    CK (launch_scan_u32_to_u64 (L, (const uint32_t*)ctx->slot[S_TOTCUR], (uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, (uint64_t*)ctx->slot[S_SCAN]));
+    uint64_t n_records = 0; uint32_t max_bin = 0;
+    CK (cudaMemcpyAsync (&n_records, (const uint64_t*)ctx->slot[S_COARSEOFF] + nb1_local, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaMemcpyAsync (&max_bin, d_maxbin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    cudaEventRecord (ctx->ev[2], ctx->stream);
+
+    // ---- k2a: fine split (not on the fused path: k <= 31 counts straight out of the coarse bins) ----
+    const bool fused = path_fused (p);
+    const int dedup = (p->path_flags & GATB_PATH_NO_DEDUP) ? 0 : 1;
+    if (!fused && ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
+    K2aSrc S2; memset (&S2, 0, sizeof(S2)); S2.n = n_src;
+    for (int s = 0; s < n_src; s++) { S2.bins[s] = (const uint4*)d_src_bins[s]; S2.cursors[s] = d_src_cursors[s]; S2.off[s] = d_src_off ? d_src_off[s] : 0; }
+    cudaEventRecord (ctx->kev[2], ctx->stream);
+    uint64_t n_unique_records = n_records;
+    bool presplit_used = false;
+    uint64_t nbins_count = nbins;                  // bins the counting kernels see (the dedup split forms its own: adaptive bins)
+    bool desc_abs = false;                         // their descriptors hold absolute record offsets
+    if (fused) cudaEventRecord (ctx->kev[3], ctx->stream);
+    else if (W == 1 && dedup && n_records)
+    {   // ---- k <= 31: the bin is staged in shared memory once, identical records collapse, multiplicities travel with the records ----
+        if (n_records >= (1ULL << 32)) return fail (ctx, "too many super-k-mer records for one device (%llu): use more passes or more GPUs", (unsigned long long)n_records);
+        if (ensure (ctx, S_OVFLIST, (nbins > nb1_local ? nbins : nb1_local) * 4)) return 1;
+        unsigned long long* d_k2a = (unsigned long long*)ctx->slot[S_COUNTERS] + 12;
+        CK (cudaMemsetAsync (d_k2a, 0, 3 * 8, ctx->stream));
+        // ---- bins gathered from several ranks are several times larger than a CTA's staging area: instead of taking them in as many
+        //      passes (each reads the whole bin again: 66 ms for 5 passes on 8 GPUs), a plain two-pass split by the leading bits of the
+        //      fine id first cuts them into sub-bins of single-GPU size (one more copy of the records, ~18 ms), which the dedup split
+        //      then takes from that dense copy in one pass each ----
+        uint32_t nb_d = nb1_local, cap_d = cap, max_bin_d = max_bin; int fine_bits_d = fine_bits;
+        const uint64_t* coarse_off_d = (const uint64_t*)ctx->slot[S_COARSEOFF];
+        K2aSrc S2d = S2;
+        {
+            const uint32_t mean_bin = (uint32_t)(n_records / (nb1_local ? nb1_local : 1)) + 1;
+            int sub_bits = 0;
+            if (n_src > 1 || (p->path_flags & GATB_PATH_K2A_PRESPLIT))
+                while (sub_bits < fine_bits - 6 && ((mean_bin >> sub_bits) * 5) / 4 > k2a_two_cta_capacity (fine_bits - sub_bits)) sub_bits++;
+            if ((p->path_flags & GATB_PATH_K2A_PRESPLIT) && sub_bits == 0 && fine_bits > 2) sub_bits = 2;        // test selector
+            if (sub_bits)
+            {
+                const uint64_t nsub = (uint64_t)nb1_local << sub_bits;
+                if (ensure (ctx, S_PRESPLIT, (n_records + 1) * rec_bytes)) return 1;
+                if (ensure (ctx, S_SUBOFF, (nsub + 1) * 8)) return 1;
+                if (ensure (ctx, S_SUBCNT, nsub * 4)) return 1;
+                K2aPresplit PS; PS.sub_off = (uint64_t*)ctx->slot[S_SUBOFF]; PS.sub_cnt = (uint32_t*)ctx->slot[S_SUBCNT]; PS.shift = fine_bits - sub_bits;
+                CK (launch_k2a_split (L, W, S2, ctx->slot[S_PRESPLIT], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, sub_bits, 0, 0, 0, 0, 0, &PS));
+                CursorList C1; C1.n = 1; C1.cur[0] = PS.sub_cnt;
+                CK (cudaMemsetAsync (d_maxbin, 0, 8, ctx->stream));
+                if (ensure (ctx, S_TOTCUR, nsub * 4)) return 1;
+                k_sum_cursors<<<(unsigned)((nsub + 255) / 256), 256, 0, ctx->stream>>> (C1, (uint32_t)nsub, 0xFFFFFFFFu, (uint32_t*)ctx->slot[S_TOTCUR], d_maxbin); ctx->launches++;
+                CK (cudaMemcpyAsync (&max_bin_d, d_maxbin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK (cudaStreamSynchronize (ctx->stream));
+                memset (&S2d, 0, sizeof(S2d)); S2d.n = 1; S2d.bins[0] = (const uint4*)ctx->slot[S_PRESPLIT]; S2d.cursors[0] = PS.sub_cnt; S2d.off[0] = PS.sub_off;
+                presplit_used = true;
+                nb_d = (uint32_t)nsub; cap_d = 0xFFFFFFFFu; fine_bits_d = fine_bits - sub_bits; coarse_off_d = PS.sub_off;
+            }
+        }
+        const uint32_t rmax = (p->path_flags & GATB_PATH_K2A_SMALL_STAGE) ? 256u : k2a_dedup_rmax (max_bin_d, (uint32_t)(n_records / (nb_d ? nb_d : 1)) + 1, fine_bits_d);
+        // counting bins of <= target k-mers of surviving records (+ one fine id's worth): the distinct k-mers of a bin (at most
+        // that many) must stay below 3/4 of the table, and a fuller table probes longer: 45 % measured best
+        // (k2b 62.2 + 1.1 ms for the 0.2 % of bins that still overflow; 60 %: 65.4 + 3.8, 30 %: 63.0 + 0.4)
+        const uint32_t target = (uint32_t)((((uint64_t)1 << table_log2) * (p->bin_target_pct > 0 ? p->bin_target_pct : 45)) / 100);
+        // the distinct k-mers of a bin are at most the k-mers of its records, typically half of them (the variants of a locus' record --
+        // reads that end inside it, sequencing errors -- repeat most of its k-mers): a bin whose records hold more than 0.95 T k-mers
+        // (one fine id = one minimizer value holds several loci of a multi-Gb genome) rarely fits the 3/4 T slots a table may fill: measured on the 8-GPU geometry, a threshold of 0.95 T costs 38 + 43 ms (first tier + tiers), 1.4 T 54 + 36 ms -- a failed attempt in the first tier is dearer than a needless trip to the 1024-slot tier
+        const uint32_t big_load = (k2b_variant (p->path_flags) == 1) ? (uint32_t)((((uint64_t)1 << table_log2) * 95) / 100) : 0u;
+        CK (launch_k2a_dedup_split (L, S2d, ctx->slot[S_FINE], coarse_off_d, nb_d, cap_d, fine_bits_d,
+                                    (uint2*)ctx->slot[S_BINDESC], rmax, (uint32_t*)ctx->slot[S_OVFLIST], d_k2a, target, big_load));
+        unsigned long long h_k2a[3] = { 0, 0, 0 };
+        CK (cudaMemcpyAsync (h_k2a, d_k2a, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+        if (h_k2a[0])
+        {   // bins the kernel gave up on (a skewed range of fine ids, more passes than it tracks) go through the plain two-pass
+            // split (multiplicity 1, one counting bin per fine id), their descriptors appended after the adaptive ones
+            if (h_k2a[2] + (h_k2a[0] << fine_bits_d) > desc_cap) return fail (ctx, "bin descriptors exhausted");
+            CK (launch_k2a_split (L, W, S2d, ctx->slot[S_FINE], coarse_off_d, nb_d, cap_d, fine_bits_d,
+                                  (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)h_k2a[0], 1, h_k2a[2]));
+        }
+        cudaEventRecord (ctx->kev[3], ctx->stream);
+        n_unique_records = h_k2a[1];                 // (bins of the two-pass kernel are not in this figure)
+        nbins_count = h_k2a[2] + (h_k2a[0] << fine_bits_d);
+        desc_abs = true;
+    }
+    else
+    {
+        CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits, (uint2*)ctx->slot[S_BINDESC]));
+        cudaEventRecord (ctx->kev[3], ctx->stream);
+    }
+    cudaEventRecord (ctx->ev[3], ctx->stream);
+
+    // ---- k2b: count.  When the single source is the context's own coarse buffer it is dead now and becomes the output. ----
+    const uint32_t amin = p->abundance_min < 1 ? 1 : (uint32_t)p->abundance_min;
+    const uint32_t amax = p->abundance_max < 0 ? 0x7fffffffu : (uint32_t)p->abundance_max;
+    const uint32_t emin = p->emit_all ? 1u : amin, emax = p->emit_all ? 0xffffffffu : amax;
+    // (the fused kernel reads the coarse bins while it emits; after a pre-split the dense copy is dead once the dedup split has run)
+    const int S_OUT = (!fused && n_src == 1 && d_src_bins[0] == ctx->slot[S_COARSE]) ? S_COARSE : (presplit_used ? S_PRESPLIT : S_UNSORTED);
+    uint64_t out_bound = total_kmers_bound / emin + 1;                         // a k-mer emitted needs >= emin occurrences
+    const size_t item_bytes = 8 * W + 4;
+    const uint64_t block_slack = (uint64_t)(ctx->sm_count * 8 + 8) * 8 * 2048;  // every warp of k2b reserves output in blocks of 2048 slots
+    uint64_t out_cap = total_kmers_bound / 8 + 4096;                           // first guess; the retry below corrects it
+    if (out_cap > out_bound) out_cap = out_bound;
+    out_cap += block_slack;
+    if (out_cap < ctx->slot_cap[S_OUT] / item_bytes) out_cap = ctx->slot_cap[S_OUT] / item_bytes;   // never shrink: no re-allocation per call
+
+    if (ensure (ctx, S_HISTO, (size_t)(histo_max + 1) * 8)) return 1;
+    { const uint64_t nl = nbins_count > nbins ? nbins_count : nbins;
+      if (ensure (ctx, S_OVFLIST, (nl > nb1_local ? nl : nb1_local) * 4)) return 1;
+      if (ensure (ctx, S_OVFLIST2, nl * 4)) return 1; }
+    unsigned long long* d_cnt = (unsigned long long*)ctx->slot[S_COUNTERS];
+    unsigned long long h_cnt[16];
+    uint64_t n_ovf = 0, n_ovf_first = 0, tier_out[3] = { 0, 0, 0 };          // bins leaving the warp tier / the two CTA tiers
+    uint64_t* u_lo = 0; uint64_t* u_hi = 0; uint32_t* u_cnt = 0;
+    K2Params k2;
+    for (int attempt = 0; ; attempt++)
+    {
+        if (ensure (ctx, S_OUT, out_cap * item_bytes)) return 1;
+        u_lo = (uint64_t*)ctx->slot[S_OUT];
+        u_hi = (W == 2) ? u_lo + out_cap : 0;
+        u_cnt = (uint32_t*)(u_lo + out_cap * W);
+        CK (cudaMemsetAsync (ctx->slot[S_HISTO], 0, (size_t)(histo_max + 1) * 8, ctx->stream));
+        CK (cudaMemsetAsync (d_cnt, 0, 16 * 8, ctx->stream));
+        memset (&k2, 0, sizeof(k2));
+        k2.k = k; k2.W = W; k2.recs = ctx->slot[S_FINE]; k2.bin_desc = (const uint2*)ctx->slot[S_BINDESC]; k2.nbins = (uint32_t)nbins_count;
+        // (absolute descriptors: every bin takes coarse_off[bin >> 31] = coarse_off[0] = 0 as its base)
+        k2.coarse_off = (const uint64_t*)ctx->slot[S_COARSEOFF]; k2.fine_bits = desc_abs ? 31 : fine_bits; k2.table_log2 = table_log2;
+        k2.path_flags = p->path_flags; k2.oriented = k1_oriented (k, g->m_device, g->w, p->path_flags) ? 1 : 0;
+        k2.emit_min = emin; k2.emit_max = emax; k2.solid_min = amin; k2.solid_max = amax; k2.histo_max = histo_max;
+        k2.histogram = (unsigned long long*)ctx->slot[S_HISTO];
+        k2.out_lo = u_lo; k2.out_hi = u_hi; k2.out_cnt = u_cnt; k2.out_cap = out_cap;
+        k2.counters = d_cnt; k2.ovf_list = (uint32_t*)ctx->slot[S_OVFLIST]; k2.ovf_counter = 4;
+        cudaEventRecord (ctx->kev[4], ctx->stream);
+        if (fused) CK (launch_k2f_count (L, k2, S2, nb1_local, cap, nb1_local, dedup));
+        else       CK (launch_k2b_count (L, k2));
+        cudaEventRecord (ctx->kev[5], ctx->stream);
+        CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+        n_ovf = h_cnt[4];
+        n_ovf_first = n_ovf;
+        if (n_ovf) cudaEventRecord (ctx->kev[8], ctx->stream);
+        int cur_list = S_OVFLIST;
+        if (fused && n_ovf)
+        {   // ---- coarse bins whose distinct k-mers outgrew the CTA's table: fine split of just those bins (multiplicity 1), then
+            //      their fine bins (1 << fine_bits each) go through the tier kernels below ----
+            if (ensure (ctx, S_FINE, (n_records + 1) * rec_bytes)) return 1;
+            CK (launch_k2a_split (L, W, S2, ctx->slot[S_FINE], (const uint64_t*)ctx->slot[S_COARSEOFF], nb1_local, cap, fine_bits,
+                                  (uint2*)ctx->slot[S_BINDESC], (const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)n_ovf));
+            k_expand_bins<<<(unsigned)(((n_ovf << fine_bits) + 255) / 256), 256, 0, ctx->stream>>> ((const uint32_t*)ctx->slot[S_OVFLIST], (uint32_t)n_ovf, fine_bits,
+                                                                                                      (uint32_t*)ctx->slot[S_OVFLIST2]); ctx->launches++;
+            k2.recs = ctx->slot[S_FINE];
+            n_ovf <<= fine_bits; cur_list = S_OVFLIST2;
+            k2.ovf_list = (uint32_t*)ctx->slot[cur_list];
+        }
+        const bool no_tier2 = (p->path_flags & GATB_PATH_NO_TIER2) != 0;                      // test selector: straight to the global table
+        if (n_ovf && ((W == 1 && (fused || k2b_variant (p->path_flags) == 1)) || W == 2) && !no_tier2)
+        {   // ---- further tiers: the bins a warp's 2^table_log2-slot table could not hold are counted by CTAs with 2048,
+            //      then 8192 slots (k2b_count_w1 over a bin list); what still overflows goes to the global table ----
+            // (the claimed-slot lists of k2b_count_w1 are per warp, 3/32 of the table each: 4096 slots leave a warp 384 of them)
+            // (first, warps again with 2048-slot tables -- k2b_warp_bins over the bin list, at the rate of the first tier: on multi-Gb
+            //  inputs one bin in eleven overflows 512 slots, and CTA tiers took 69 ms for them on 8 GPUs)
+            const int tier_log2[3] = { 10, 12, 13 }, tier_counter[3] = { 13, 7, 12 };
+            for (int t = 0; t < 3 && n_ovf; t++)
+            {
+                if (!fused && tier_log2[t] <= table_log2) continue;
+                if ((fused || W == 2) && tier_log2[t] < 12) continue;
+                const int other = (cur_list == S_OVFLIST) ? S_OVFLIST2 : S_OVFLIST;
+                K2Params k2t = k2;
+                k2t.bin_list = (const uint32_t*)ctx->slot[cur_list]; k2t.n_list = (uint32_t)n_ovf;
+                k2t.ovf_list = (uint32_t*)ctx->slot[other]; k2t.ovf_counter = tier_counter[t]; k2t.table_log2 = tier_log2[t];
+                CK (cudaMemsetAsync (d_cnt + 3, 0, 8, ctx->stream));                 // work counter
+                CK (launch_k2b_count_list (L, k2t));
+                CK (cudaMemcpyAsync (h_cnt, d_cnt, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK (cudaStreamSynchronize (ctx->stream));
+                n_ovf = h_cnt[tier_counter[t]];
+                tier_out[t] = n_ovf;
+                cur_list = other;
+            }
+            k2.ovf_list = (uint32_t*)ctx->slot[cur_list];                            // what is left goes to the global table
+            if (!n_ovf) cudaEventRecord (ctx->kev[9], ctx->stream);
+        }
+        if (n_ovf)
+        {   // ---- k2c: bins that did not fit the shared-memory table share one global table ----
+            CK (launch_k2c_measure (L, k2, (uint32_t)n_ovf));
+            CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+            uint64_t occ = h_cnt[5]; int g_log2 = 10; while ((1ULL << g_log2) < 2 * occ) g_log2++;
+            if (g_log2 > 31) return fail (ctx, "fallback table too large (%llu k-mers in overflowing bins)", (unsigned long long)occ);
+            size_t gT = (size_t)1 << g_log2;
+            if (ensure (ctx, S_GTABLE, gT * (8 * W + 4))) return 1;
+            k2.g_lo = (uint64_t*)ctx->slot[S_GTABLE]; k2.g_hi = (W == 2) ? k2.g_lo + gT : 0; k2.g_cnt = (uint32_t*)(k2.g_lo + gT * W); k2.g_log2 = g_log2;
+            if (W == 1) CK (cudaMemsetAsync (k2.g_lo, 0xFF, gT * 8, ctx->stream));
+            else      { CK (cudaMemsetAsync (k2.g_lo, 0, gT * 8, ctx->stream)); CK (cudaMemsetAsync (k2.g_hi, 0xFF, gT * 8, ctx->stream)); }
+            CK (cudaMemsetAsync (k2.g_cnt, 0, gT * 4, ctx->stream));
+            CK (launch_k2c_insert (L, k2, (uint32_t)n_ovf));
+            CK (launch_k2c_scan (L, k2));
+            cudaEventRecord (ctx->kev[9], ctx->stream);
+            CK (cudaMemcpyAsync (h_cnt, d_cnt, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+        }
+        if (h_cnt[0] <= out_cap) break;
+        if (attempt >= 1) return fail (ctx, "output capacity exceeded: %llu k-mers to emit, room for %llu", (unsigned long long)h_cnt[0], (unsigned long long)out_cap);
+        out_cap = h_cnt[0] + block_slack;                     // the cursor kept counting: it bounds the demand -> count again
+    }
+    const uint64_t n_items = h_cnt[6];          // k-mers emitted
+    const uint64_t n_range = h_cnt[0];          // extent of the unsorted array (block reservations leave EMPTY holes)
+    cudaEventRecord (ctx->ev[4], ctx->stream);
+
+    SortOut so; memset (&so, 0, sizeof(so));
+    if (route_ranks > 0)
+    {   // ---- several GPUs, second exchange: instead of sorting here, the emitted k-mers are grouped by the rank that owns their
+        //      partition (key % route_ranks) together with their keys; the caller exchanges the groups and every rank sorts the
+        //      partitions it owns (gatb_gpu_sort_routed) ----
+        if (route_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "route_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
+        if (ensure (ctx, S_ROUTECNT, 24 * 8)) return 1;
+        unsigned long long* d_rc = (unsigned long long*)ctx->slot[S_ROUTECNT];
+        K3Params k3; memset (&k3, 0, sizeof(k3));
+        k3.k = k; k3.m = p->minimizer_size; k3.W = W;
+        k3.mmask = (1u << (2 * p->minimizer_size)) - 1; k3.mask_ma1 = gatb_mask_ma1 (p->minimizer_size);
+        k3.nb_partitions = p->nb_partitions; k3.nb_passes = p->nb_passes; k3.n_keys = (uint32_t)n_keys; k3.n = n_range;
+        k3.in_lo = u_lo; k3.in_hi = u_hi; k3.in_cnt = u_cnt;
+        if (n_keys > 1)
+        {
+            uint64_t rbytes = (1ULL << (2 * p->minimizer_size)) * 2;
+            if (ensure (ctx, S_REPART, rbytes)) return 1;
+            CK (cudaMemcpyAsync (ctx->slot[S_REPART], repart_host, rbytes, cudaMemcpyHostToDevice, ctx->stream));
+            k3.repart = (const uint16_t*)ctx->slot[S_REPART];
+        }
+        cudaEventRecord (ctx->kev[6], ctx->stream);
+        // regions of dest_cap items per destination: a quarter of head-room over the even share; if one fills up, once more with
+        // regions that hold everything
+        uint64_t dest_cap = n_items / route_ranks + n_items / (4 * (uint64_t)route_ranks) + 4096;
+        if (dest_cap > n_items + 1) dest_cap = n_items + 1;
+        uint64_t* o_lo = 0; uint64_t* o_hi = 0; uint32_t* o_cnt = 0; uint16_t* o_key = 0;
+        unsigned long long h_rc[9];
+        for (int attempt = 0; ; attempt++)
+        {
+            const uint64_t n_alloc = dest_cap * route_ranks;
+            // (the records k2b counted are dead by now: their buffer takes the routed items; the sort of the received items takes it next)
+            if (ensure (ctx, S_FINE, n_alloc * (8 * W + 6) + 64)) return 1;
+            o_lo = (uint64_t*)ctx->slot[S_FINE]; o_hi = (W == 2) ? o_lo + n_alloc : 0;
+            o_cnt = (uint32_t*)(o_lo + n_alloc * W); o_key = (uint16_t*)(o_cnt + n_alloc);
+            CK (cudaMemsetAsync (d_rc, 0, 24 * 8, ctx->stream));
+            CK (launch_k3r_route (L, k3, (uint32_t)route_ranks, dest_cap, d_rc, o_lo, o_hi, o_cnt, o_key, (uint32_t*)(d_rc + 8)));
+            CK (cudaMemcpyAsync (h_rc, d_rc, 9 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaStreamSynchronize (ctx->stream));
+            if (!(h_rc[8] & 1)) break;
+            if (attempt >= 1) return fail (ctx, "routing: a destination region overflowed twice");
+            dest_cap = n_items + 1;
+        }
+        unsigned long long run = 0;
+        for (int r = 0; r < route_ranks; r++) { run += h_rc[r]; if (route_counts) route_counts[r] = h_rc[r]; }
+        if (run != n_items) return fail (ctx, "routing: %llu items counted, %llu emitted", run, (unsigned long long)n_items);
+        if (route_counts) route_counts[route_ranks] = dest_cap;
+        cudaEventRecord (ctx->kev[7], ctx->stream);
+        so.dr.lo = o_lo; so.dr.hi = o_hi; so.dr.cnt = o_cnt; so.dr.offs = 0; so.dr.histo = ctx->slot[S_HISTO];
+        if (route_keys) *route_keys = o_key;
+    }
+    else if (sort_stage (ctx, p, u_lo, u_hi, u_cnt, 0, n_range, n_items, repart_host, to_host, &so)) return 1;
+    DevResult* dr = &so.dr;
+    uint64_t* h_lo = so.h_lo; uint64_t* h_hi = so.h_hi; int32_t* h_cnt32 = so.h_cnt32; uint64_t* h_offs = so.h_offs; uint64_t* h_hist = so.h_hist;
     cudaEventRecord (ctx->ev[5], ctx->stream);
     CK (cudaStreamSynchronize (ctx->stream));
 
@@ -908,6 +982,47 @@ int gatb_gpu_count_bins (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb
     cudaEventRecord (ctx->ev[1], ctx->stream);
     if (count_bins_impl (ctx, p, g, n_src, d_src_bins, d_src_cursors, nb1_local, repart_table, kmers_bound, out)) return 1;
     float ms; cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[5]); out->seconds[6] = ms * 1e-3;
+    return 0;
+}
+
+int gatb_gpu_count_bins_routed (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const gatb_gpu_geometry* g, int n_src,
+                                const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
+                                uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, int n_ranks,
+                                uint64_t* send_counts, uint16_t** d_keys, gatb_gpu_result* out)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (!out || !send_counts || !d_keys) return fail (ctx, "out, send_counts or d_keys is NULL");
+    if (check_params (ctx, p, repart_table)) return 1;
+    if (check_geometry (ctx, p, g)) return 1;
+    if (nb1_local > g->nb1) return fail (ctx, "nb1_local %u exceeds the geometry's %u coarse bins", nb1_local, g->nb1);
+    if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "n_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
+    cudaEventRecord (ctx->ev[1], ctx->stream);
+    if (count_bins_impl (ctx, p, g, n_src, d_src_bins, d_src_cursors, nb1_local, repart_table, kmers_bound, out, false, 0, n_ranks, send_counts, d_keys)) return 1;
+    float ms; cudaEventElapsedTime (&ms, ctx->ev[1], ctx->ev[5]); out->seconds[6] = ms * 1e-3;
+    return 0;
+}
+
+int gatb_gpu_sort_routed (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint64_t* d_lo, const uint64_t* d_hi, const uint32_t* d_counts,
+                          const uint16_t* d_keys, uint64_t n_items, gatb_gpu_result* out)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (!out) return fail (ctx, "out is NULL");
+    if (p->kmer_size < 1 || p->kmer_size > 63 || p->nb_partitions < 1 || p->nb_passes < 1 || p->histo_max < 1) return fail (ctx, "bad parameters");
+    if (n_items && (!d_lo || !d_counts || !d_keys || (p->kmer_size >= 32 && !d_hi))) return fail (ctx, "item arrays are NULL");
+    cudaEventRecord (ctx->ev[4], ctx->stream);
+    SortOut so;
+    if (sort_stage (ctx, p, d_lo, d_hi, d_counts, d_keys, n_items, n_items, 0, false, &so)) return 1;
+    cudaEventRecord (ctx->ev[5], ctx->stream);
+    CK (cudaStreamSynchronize (ctx->stream));
+    memset (out, 0, sizeof(*out));
+    out->n_keys = (uint64_t)p->nb_partitions * p->nb_passes; out->n_items = n_items; out->on_device = 1;
+    out->part_offsets = (uint64_t*)so.dr.offs; out->kmers_lo = (uint64_t*)so.dr.lo; out->kmers_hi = (uint64_t*)so.dr.hi;
+    out->counts = (int32_t*)so.dr.cnt; out->histogram = (uint64_t*)so.dr.histo;
+    float ms;
+    cudaEventElapsedTime (&ms, ctx->ev[4], ctx->ev[5]); out->seconds[4] = ms * 1e-3;
+    cudaEventElapsedTime (&ms, ctx->kev[6], ctx->kev[7]); out->kernel_seconds[3] = ms * 1e-3;
     return 0;
 }
 

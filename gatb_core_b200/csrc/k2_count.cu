@@ -591,6 +591,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
         for (;;)
         {   // skip empty bins here so that the CTA never synchronises for nothing
             bin = (uint32_t) atomicAdd (&P.counters[3], 1ULL);
+            if (P.bin_list) bin = bin < P.n_list ? P.bin_list[bin] : 0xFFFFFFFFu;       // tier run: the bins an earlier table could not hold
             if (bin >= P.nbins) break;
             d = P.bin_desc[bin]; d.y &= K2_DESC_COUNT;
             if (d.y) break;
@@ -722,7 +723,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2b_bucket_hash_count (const K2Par
         const bool ovf = s_ovf != 0;
         if (ovf)
         {   // the bin goes to the global-memory fallback (k2c): wipe the whole table
-            if (tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[4], 1ULL); P.ovf_list[idx] = bin; }
+            if (tid == 0) { uint32_t idx = (uint32_t) atomicAdd (&P.counters[P.ovf_counter], 1ULL); P.ovf_list[idx] = bin; }
             for (int i = tid; i < T; i += K2_THREADS) { if (W == 1) s_klo[i] = EMPTY64; else s_khi[i] = EMPTY64; s_cnt[i] = 0; }
             __syncthreads ();
             if (tid == 0) s_ovf = 0;
@@ -1632,10 +1633,26 @@ static cudaError_t k2b_warp_w2_launch (const LaunchCtx& L, const K2Params& P)
     return cudaGetLastError ();
 }
 
+static size_t k2b_smem_bytes (int W, int table_log2);
 // second tier: the bins the warp kernel could not hold, counted by CTAs with the table size of P.table_log2
 cudaError_t launch_k2b_count_list (const LaunchCtx& L, const K2Params& P)
 {
     if (P.n_list == 0) return cudaSuccess;
+    if (P.W == 2)
+    {   // 32 <= k <= 63: the CTA-per-bin kernel with a larger table over the list
+        const size_t smem2 = k2b_smem_bytes (2, P.table_log2);
+        cudaError_t e2 = cudaFuncSetAttribute (k2b_bucket_hash_count<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) return e2;
+        int per_sm2 = 0;
+        e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm2, k2b_bucket_hash_count<2>, K2_THREADS, smem2);
+        if (e2 != cudaSuccess) return e2;
+        if (per_sm2 < 1) per_sm2 = 1;
+        uint64_t grid2 = (uint64_t)L.sm_count * per_sm2;
+        if (grid2 > P.n_list) grid2 = P.n_list;
+        k2b_bucket_hash_count<2><<<(unsigned)grid2, K2_THREADS, smem2, L.stream>>> (P);
+        (*L.launches)++;
+        return cudaGetLastError ();
+    }
     // tables of up to 2048 slots still belong to one warp each (k2b_warp_bins over the bin list): five times the rate of the CTA tiers
     if (P.W == 1 && P.table_log2 <= 11 && k2b_variant (P.path_flags) == 1)
         return P.oriented ? k2b_warp_launch<128, true> (L, P) : k2b_warp_launch<128, false> (L, P);

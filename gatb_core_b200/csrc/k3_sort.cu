@@ -103,6 +103,27 @@ __device__ __forceinline__ uint32_t k3_bucket_of (const K3Params& P, uint64_t lo
     return (key << t) | topbits;
 }
 
+// partition key of an emitted k-mer: pass * nb_partitions + repart[GATB minimizer]
+__device__ __forceinline__ uint32_t k3_key_of (const K3Params& P, uint64_t lo, uint64_t hi)
+{
+    uint32_t mini;
+    if (P.W == 1) mini = gatb_minimizer_w1 (lo, P.k, P.m, P.mmask, P.mask_ma1);
+    else { u128 v; v.lo = lo; v.hi = hi; mini = gatb_minimizer_w2 (v, P.k, P.m, P.mmask, P.mask_ma1); }
+    return (mini % (uint32_t)P.nb_passes) * (uint32_t)P.nb_partitions + P.repart[mini];
+}
+// (i = index of the item: with P.in_key the key travels with the item -- it was computed when the item was routed to the rank
+//  that owns its partition, k3r_* below -- and is not computed again)
+__device__ __forceinline__ uint32_t k3_bucket_of (const K3Params& P, uint64_t lo, uint64_t hi, uint64_t i)
+{
+    if (P.in_key)
+    {
+        const int U = k3_range_U (P.k);
+        const uint32_t topbits = P.t_bits ? (uint32_t) k3_range_of (P.W == 1 ? k3_top_bits<1> (lo, 0, P.k, U) : k3_top_bits<2> (lo, hi, P.k, U), U, P.t_bits) : 0u;
+        return ((uint32_t)P.in_key[i] << P.t_bits) | topbits;
+    }
+    return k3_bucket_of (P, lo, hi);
+}
+
 // ---- k3s: classify + scatter in ONE pass over the emitted k-mers ------------------------------------------------------
 // Scattering 6*10^8 items into 10^6 buckets with exact offsets keeps one open line per bucket and array, spread over
 // the whole multi-GB copy: every store is an address-translation miss (measured: the same scatter folded into a
@@ -135,7 +156,7 @@ __global__ void __launch_bounds__(256) k3s_pool_scatter (const K3Params P)
         ok[j] = (P.W == 1 ? lo[j] : hi[j]) != 0xFFFFFFFFFFFFFFFFULL;
         if (ok[j])
         {
-            b[j] = k3_bucket_of (P, lo[j], hi[j]);
+            b[j] = k3_bucket_of (P, lo[j], hi[j], base + 256 * j);
             slot[j] = atomicAdd (&P.bucket_count[b[j]], 1u);
             if (slot[j] >= cap) { ok[j] = false; atomicOr (P.ovf_flag, 1u); }
         }
@@ -192,7 +213,7 @@ __global__ void __launch_bounds__(256) k3a_classify (const K3Params P)
         if (i >= P.n) continue;
         // holes left by k2b's block-wise output reservation carry an all-ones key: skip them
         if ((P.W == 1 ? lo[j] : hi[j]) == 0xFFFFFFFFFFFFFFFFULL) { P.bucket_of[i] = 0xFFFFFFFFu; continue; }
-        const uint32_t b = k3_bucket_of (P, lo[j], hi[j]);
+        const uint32_t b = k3_bucket_of (P, lo[j], hi[j], i);
         P.bucket_of[i] = b;
         atomicAdd (&P.bucket_count[b], 1u);
     }
@@ -440,6 +461,66 @@ cudaError_t launch_k3b_scatter (const LaunchCtx& L, const K3Params& P)
 {
     if (P.n == 0) return cudaSuccess;
     k3b_scatter<<<(unsigned)((P.n + 256 * K3_ILP - 1) / (256 * K3_ILP)), 256, 0, L.stream>>> (P);
+    (*L.launches)++;
+    return cudaGetLastError ();
+}
+// ---- k3r: routing of the emitted k-mers to the rank that owns their partition (several GPUs) ---------------------------------
+// A k-mer lives in one device bin, hence on one rank; its GATB partition (key) is unrelated to that bin.  For the result of a
+// partition to be ONE ascending sequence (what ICountProcessor::process sees in the reference) the k-mers are moved once more:
+// key -> owner rank key % n_ranks.  k3r_route computes the key of every item (once: it travels with the item, 16 bits) and writes the
+// items grouped by destination (SoA: value, count, key) into regions of dest_cap items each -- a block reserves its share of every
+// destination with one atomic; the Repartitor balances the partitions, so the destinations fill evenly and a quarter of head-room
+// suffices (a full region raises ovf_flag: the caller retries with regions that hold everything).  The caller exchanges the groups
+// (all-to-all) and runs the sort stage on what it received.
+__global__ void __launch_bounds__(256) k3r_route (const K3Params P, uint32_t n_ranks, uint64_t dest_cap, unsigned long long* __restrict__ dest_cursor,
+                                                  uint64_t* __restrict__ o_lo, uint64_t* __restrict__ o_hi, uint32_t* __restrict__ o_cnt, uint16_t* __restrict__ o_key,
+                                                  uint32_t* __restrict__ ovf_flag)
+{
+    __shared__ uint32_t s_cnt[8];
+    __shared__ unsigned long long s_base[8];
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    __syncthreads ();
+    const uint64_t base = (uint64_t)blockIdx.x * (256 * K3_ILP) + threadIdx.x;
+    uint64_t lo[K3_ILP], hi[K3_ILP];
+    uint32_t key[K3_ILP], at[K3_ILP];
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+    {
+        const uint64_t i = base + 256 * j;
+        lo[j] = i < P.n ? P.in_lo[i] : 0xFFFFFFFFFFFFFFFFULL;
+        hi[j] = (P.W == 2) ? (i < P.n ? P.in_hi[i] : 0xFFFFFFFFFFFFFFFFULL) : 0;
+    }
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+    {
+        key[j] = 0xFFFFFFFFu;                                  // holes left by k2b's block-wise output reservation: skipped
+        if ((P.W == 1 ? lo[j] : hi[j]) != 0xFFFFFFFFFFFFFFFFULL)
+        {
+            key[j] = P.n_keys > 1 ? k3_key_of (P, lo[j], hi[j]) : 0u;
+            at[j] = atomicAdd (&s_cnt[key[j] % n_ranks], 1u);
+        }
+    }
+    __syncthreads ();
+    if (threadIdx.x < n_ranks) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd (&dest_cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]) : 0ULL;
+    __syncthreads ();
+    #pragma unroll
+    for (int j = 0; j < K3_ILP; j++)
+    {
+        if (key[j] == 0xFFFFFFFFu) continue;
+        const uint32_t d = key[j] % n_ranks;
+        const unsigned long long slot = s_base[d] + at[j];
+        if (slot >= dest_cap) { atomicOr (ovf_flag, 1u); continue; }           // the region of this destination is full: the caller retries with exact sizes
+        const unsigned long long pos = (unsigned long long)d * dest_cap + slot;
+        o_lo[pos] = lo[j]; if (P.W == 2) o_hi[pos] = hi[j];
+        o_cnt[pos] = P.in_cnt[base + 256 * j]; o_key[pos] = (uint16_t)key[j];
+    }
+}
+cudaError_t launch_k3r_route (const LaunchCtx& L, const K3Params& P, uint32_t n_ranks, uint64_t dest_cap, unsigned long long* dest_cursor,
+                              uint64_t* o_lo, uint64_t* o_hi, uint32_t* o_cnt, uint16_t* o_key, uint32_t* ovf_flag)
+{
+    if (P.n == 0) return cudaSuccess;
+    const uint64_t grid = (P.n + 256 * K3_ILP - 1) / (256 * K3_ILP);
+    k3r_route<<<(unsigned)grid, 256, 0, L.stream>>> (P, n_ranks, dest_cap, dest_cursor, o_lo, o_hi, o_cnt, o_key, ovf_flag);
     (*L.launches)++;
     return cudaGetLastError ();
 }

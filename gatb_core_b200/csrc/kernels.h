@@ -101,6 +101,7 @@ struct K3Params
     int t_bits;                     // value-range bits per key: bucket = key << t_bits | top t_bits of the k-mer
     uint64_t n;
     const uint64_t* in_lo; const uint64_t* in_hi; const uint32_t* in_cnt;
+    const uint16_t* in_key;         // NULL: the partition key is computed from the k-mer; else it came with the item (routed items, k3r_*)
     uint32_t* bucket_of;            // [n]
     uint32_t* bucket_count;         // [n_buckets]   -> cursors during scatter
     const uint64_t* bucket_off;     // [n_buckets+1]
@@ -151,6 +152,8 @@ cudaError_t launch_k2c_scan (const LaunchCtx&, const K2Params&);
 // k3_sort.cu
 cudaError_t launch_k3a_classify (const LaunchCtx&, const K3Params&);
 cudaError_t launch_k3b_scatter (const LaunchCtx&, const K3Params&);
+cudaError_t launch_k3r_route (const LaunchCtx&, const K3Params&, uint32_t n_ranks, uint64_t dest_cap, unsigned long long* dest_cursor,
+                              uint64_t* o_lo, uint64_t* o_hi, uint32_t* o_cnt, uint16_t* o_key, uint32_t* ovf_flag);
 cudaError_t launch_k3s_pool_scatter (const LaunchCtx&, const K3Params&);
 uint32_t    k3_sort_cap ();
 cudaError_t launch_k3s_pool_scatter (const LaunchCtx&, const K3Params&);

@@ -102,6 +102,60 @@ def bloom_distributed(gpu, kind, k, res, n_solid_global, world):
     return mine[:nbytes], bits
 
 
+class _DevArray:
+    """A device array owned by the library, as torch sees it (zero copy, __cuda_array_interface__)"""
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr if count else 0, False), "version": 2}
+
+
+def _as_tensor(ptr, count, dtype, dev):
+    if count == 0:
+        return torch.empty(0, dtype=dtype, device=dev)
+    typestr = {torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_DevArray(ptr, count, typestr), device=dev)
+
+
+def _count_and_route(gpu, params, geom, src_bins, src_cur, bpr, kmers_bound, repart, rank, world, dev, t):
+    """count -> route by partition owner -> all-to-all of the emitted k-mers (values, counts, keys) -> sort of the owned partitions.
+    The result of partition key k is ONE ascending sequence on rank k % world, like the reference's (every other rank holds nothing
+    for k); histogram and statistics stay per rank (they combine by sum)."""
+    W = 1 if params.kmer_size < 32 else 2
+    res1, d_keys, send, cap = gpu.count_bins_routed(params, geom, src_bins, src_cur, bpr, kmers_bound, world, repart=repart)
+    t0 = time.time()
+    send_t = torch.tensor(send, dtype=torch.int64, device=dev)
+    recv_t = torch.empty_like(send_t)
+    dist.all_to_all_single(recv_t, send_t)
+    recv = [int(x) for x in recv_t.tolist()]
+    n_recv = sum(recv)
+    starts = [sum(recv[:r]) for r in range(world)]
+    # (element size in bytes: the 16-bit keys travel as bytes, NCCL has no 16-bit integer type)
+    arrays = [(res1.kmers_lo, torch.int64, 1)] + ([(res1.kmers_hi, torch.int64, 1)] if W == 2 else []) + [(res1.counts, torch.int32, 1), (d_keys, torch.uint8, 2)]
+    got, works = [], []
+    for ptr, dt, sc in arrays:
+        src = _as_tensor(ptr, cap * world * sc, dt, dev)      # one region of 'cap' items per destination rank
+        dst = torch.empty(max(n_recv, 1) * sc, dtype=dt, device=dev)
+        works.append(dist.all_to_all([dst[starts[r] * sc:(starts[r] + recv[r]) * sc] for r in range(world)],
+                                     [src[r * cap * sc:(r * cap + send[r]) * sc] for r in range(world)], async_op=True))
+        got.append(dst)
+    for w in works:
+        w.wait()
+    torch.cuda.current_stream().synchronize()
+    t["route_exchange"] = time.time() - t0
+    t["routed_bytes"] = (sum(send) - send[rank]) * (8 * W + 6)
+    d_hi = got[1].data_ptr() if W == 2 else None
+    res = gpu.sort_routed(params, got[0].data_ptr(), d_hi, got[-2].data_ptr(), got[-1].data_ptr(), n_recv)
+    for i in range(len(res.stats)):
+        res.stats[i] = res1.stats[i]
+    for i in range(8):
+        res.seconds[i] = res1.seconds[i]
+    ks = [float(x) for x in res1.kernel_seconds]
+    ks[3] += float(res.kernel_seconds[3])                 # routing kernels + sort
+    for i in range(8):
+        res.kernel_seconds[i] = ks[i]
+    res._keep = got                                       # (nothing of it is referenced by the result, but keep the order of frees simple)
+    return res
+
+
 N_PIECES = 4      # a rank partitions its reads in this many pieces: piece i travels while piece i+1 is being partitioned
 MAX_SOURCES = 32  # GATB_GPU_MAX_SOURCES (include/gatb_gpu.h): ranks x pieces
 
@@ -141,13 +195,14 @@ def bind_to_gpu_numa(local):
 
 
 def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total_kmers_global, rank, world, repart=None,
-                      d_offsets=None, timers=None, ready=None):
+                      d_offsets=None, timers=None, ready=None, route=True):
     """One distributed counting pass.  Returns (device Result of this rank's bins, stats dict with GLOBAL sums).
 
     partition piece 0 -> [send piece 0 || partition piece 1] -> ... -> send the last piece -> count: every (source rank, piece)
     is one source of the owner's fine split (gatb_gpu_count_bins, at most 32 sources).
     ready: optional list of torch events, one per piece (piece_bounds): the reads of piece i are on the device once ready[i] has
-    completed (the caller's host->device copies run on their own stream while the earlier pieces are being partitioned)."""
+    completed (the caller's host->device copies run on their own stream while the earlier pieces are being partitioned).
+    route: second exchange (_count_and_route): every partition key ends up whole and ascending on rank key % world."""
     dev = torch.device("cuda", gpu.device)
     geom = gpu.plan(params, total_kmers_global, n_reads_global, world)
     npc = pieces_per_rank(world, n_reads_local)
@@ -215,7 +270,10 @@ def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total
     # k-mers in the bins this rank owns: estimate with 25 % head-room, never above the hard bound
     kmers_bound = int(min(gathered * geom.maxlen, gathered * avg_len * 1.25 + 65536))
     t0 = time.time()
-    res = gpu.count_bins(params, geom, src_bins, src_cur, bpr, kmers_bound, repart=repart)
+    if world > 1 and route:
+        res = _count_and_route(gpu, params, geom, src_bins, src_cur, bpr, kmers_bound, repart, rank, world, dev, t)
+    else:
+        res = gpu.count_bins(params, geom, src_bins, src_cur, bpr, kmers_bound, repart=repart)
     t["count"] = time.time() - t0
     t["count_kernels"] = [float(x) for x in res.kernel_seconds][:5]
     t["overflow_kmers"] = int(res.stats[11])
@@ -292,7 +350,7 @@ def bench(args, rank, world, local):
                              path_flags=args.path_flags, bin_load_pct=args.bin_load_pct, table_log2=args.table_log2, fine_bits=args.fine_bits, bin_target_pct=args.bin_target_pct)
 
     def step(timers=None):
-        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, timers=timers)
+        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, timers=timers, route=not args.no_route)
         gpu.result_free(res)
         return stats
 
@@ -339,7 +397,7 @@ def bench(args, rank, world, local):
                 ev.record(copy_stream)
                 ready.append(ev)
         t1 = time.time()
-        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, ready=ready)
+        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, ready=ready, route=not args.no_route)
         t2 = time.time()
         host = result_to_pinned(gpu, res, params)
         gpu.result_free(res)
@@ -362,15 +420,18 @@ def bench(args, rank, world, local):
         offs = np.asarray(host["part_offsets"], dtype=np.int64)
         desc = np.nonzero(lo[1:] <= lo[:-1])[0] + 1 if ni > 1 else np.zeros(0, np.int64)
         asc = bool(np.isin(desc, offs).all())                # ascending inside every partition key (k <= 31: one word per k-mer)
+        sizes = np.diff(offs)
+        owned = (np.arange(len(sizes)) % world) == rank      # second exchange: a partition lives whole on rank key % world
+        whole = bool((sizes[~owned] == 0).all())
         local = [int(hist.sum()), sum(c * int(hist[c]) for c in range(ABUNDANCE_MIN)) + int(cnt.sum(dtype=np.int64)),
-                 int(hist[ABUNDANCE_MIN:].sum()), ni, 0 if asc else 1]
+                 int(hist[ABUNDANCE_MIN:].sum()), ni, 0 if (asc and whole) else 1]
     except Exception:                                        # never let the checker take the measurement down
         err = 1
     loc = torch.tensor(local + [err], dtype=torch.int64, device=dev)
     dist.all_reduce(loc)                                     # every rank gets here, whatever happened above
     loc = [int(x) for x in loc.tolist()]
     invariants = {"sum_hist_eq_distinct": loc[0] == stats["kmers_nb_distinct"], "occurrences_accounted": loc[1] == stats["kmers_nb_valid"],
-                  "solid_is_histogram_tail": loc[2] == loc[3] == stats["kmers_nb_solid"], "strictly_ascending_per_rank": loc[4] == 0,
+                  "solid_is_histogram_tail": loc[2] == loc[3] == stats["kmers_nb_solid"], "partitions_whole_and_ascending_on_their_owner": loc[4] == 0,
                   "checker_errors": loc[5]}
     invariants["all"] = all(v is True for k, v in invariants.items() if k != "checker_errors") and loc[5] == 0
     if rank == 0:
@@ -388,7 +449,8 @@ def bench(args, rank, world, local):
                 "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic",
                 "config": {"workload": "k=31, %d synthetic 150bp reads (%d per GPU), %dxB200, minimizer buckets sharded via NCCL all-to-all, m=10, abundance-min=2, "
-                                       "%d partitions x %d pass(es) (the reference's own configuration)" % (n_global, n, world, nb_partitions, nb_passes),
+                                       "%d partitions x %d pass(es) (the reference's own configuration)%s" % (n_global, n, world, nb_partitions, nb_passes,
+                                          "" if args.no_route else "; second all-to-all: every partition whole and ascending on rank key %% %d" % world),
                            "reads": n_global, "nb_partitions": nb_partitions, "nb_passes": nb_passes, "repartitor": repart_src, "genome_nt": genome, "coverage": COVERAGE, "error_rate": 0.01,
                            "l2": "per-GPU inputs (%.1f GB packed reads) far exceed the 126 MB L2" % (nbytes / 1e9)},
                 "input_bases_per_s": n_global * L / per_step, "kmer_occurrences_per_s": stats["kmers_nb_valid"] / per_step,

@@ -202,6 +202,22 @@ int gatb_gpu_count_bins (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_g
                          const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
                          uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, gatb_gpu_result* out);
 
+/* Second exchange of a multi-GPU run: the result of a partition must be ONE ascending sequence (what ICountProcessor::process sees in
+ * the reference, kmer/impl/PartitionsCommand.cpp:1599-1805), but a k-mer's device bin -- hence the rank that counted it -- is unrelated
+ * to its GATB partition.  gatb_gpu_count_bins_routed counts like gatb_gpu_count_bins and, instead of sorting, groups the emitted
+ * k-mers by the rank that owns their partition key (key % n_ranks): out->kmers_lo / kmers_hi / counts and *d_keys (16-bit keys) are
+ * DEVICE arrays of n_ranks regions of send_counts[n_ranks] items each, the first send_counts[r] items of region r going to rank r
+ * (send_counts: host [n_ranks + 1]); out->n_items is their total, out->part_offsets is NULL, out->histogram the device histogram of
+ * this rank's bins.  The caller exchanges the groups (all-to-all) and hands what it received to gatb_gpu_sort_routed: ascending order
+ * of the partitions this rank owns, result as gatb_gpu_count_bins (every key not owned is empty; the keys travel with the items and are
+ * not computed twice). */
+int gatb_gpu_count_bins_routed (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_geometry*, int n_src,
+                                const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
+                                uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, int n_ranks,
+                                uint64_t* send_counts, uint16_t** d_keys, gatb_gpu_result* out);
+int gatb_gpu_sort_routed (gatb_gpu_ctx*, const gatb_gpu_params*, const uint64_t* d_kmers_lo, const uint64_t* d_kmers_hi,
+                          const uint32_t* d_counts, const uint16_t* d_keys, uint64_t n_items, gatb_gpu_result* out);
+
 /* ---- GATB-exact super-k-mer partitioning (rows A3-A6): per key, the record stream [u8 nbK][packed bytes]... that
  *      the reference writes to its SuperKmerBinFiles (order of records inside a key is unspecified).
  *      streams[key] is malloc'ed host memory (gatb_gpu_free_host); stats_out: [0] nb super-k-mers [1] nb k-mers

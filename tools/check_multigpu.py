@@ -35,6 +35,14 @@ def main():
         bloom, bloom_bits = multigpu.bloom_distributed(gpu, "neighbor", k, res, stats["kmers_nb_solid"], world)
         bloom = bloom.cpu().numpy()
         gpu.result_free(res)
+        if k == 31:     # the same without the second exchange: per-rank ascending runs of disjoint k-mers, merged on the host
+            res_b, _ = multigpu.count_distributed(gpu, params, reads.data_ptr(), n, n_global, n_global * (L - k + 1), rank, world, repart=repart, route=False)
+            runs = gpu.result_to_host(res_b, params)
+            gpu.result_free(res_b)
+            box = [None] * world
+            dist.all_gather_object(box, runs["parts"])
+            if rank == 0:
+                unrouted = [multigpu.merge_sorted_runs([b[key] for b in box]) for key in range(nparts)]
         gathered = [None] * world
         dist.all_gather_object(gathered, {"parts": mine["parts"], "hist": mine["histogram"]})
         if rank == 0:
@@ -47,9 +55,16 @@ def main():
             want = gpu.result_to_host(single, params)
             gpu.result_free(single)
             for key in range(nparts):
-                lo, hi, cn = multigpu.merge_sorted_runs([g["parts"][key] for g in gathered])
+                # second exchange: the partition is whole and ascending on its owner rank, every other rank holds nothing of it
+                for r in range(world):
+                    if r != key % world:
+                        assert len(gathered[r]["parts"][key][0]) == 0, (k, key, r)
+                lo, hi, cn = gathered[key % world]["parts"][key]
                 wlo, whi, wcn = want["parts"][key]
                 assert len(lo) == len(wlo) and (lo == wlo).all() and (hi == whi).all() and (cn == wcn).all(), (k, key)
+                if k == 31:
+                    ulo, uhi, ucn = unrouted[key]
+                    assert len(ulo) == len(wlo) and (ulo == wlo).all() and (ucn == wcn).all(), ("unrouted", key)
             hist = sum(g["hist"].astype(np.int64) for g in gathered)
             assert (hist == want["histogram"].astype(np.int64)).all()
             assert stats["kmers_nb_distinct"] == want["stats"]["kmers_nb_distinct"]
