@@ -343,7 +343,8 @@ def run_ours(args):
                          "frac_reference_S_of_8TBps": pair_bytes_ref / pair_sec / 1e9 / 8000.0},
                 "kernel_ms": {"k1_superkmer_partition": ksec[0] * 1e3, "k2a_fine_split": ksec[1] * 1e3,
                               "k2b_bucket_hash_count": ksec[2] * 1e3, "k3_partition_id_sort": ksec[3] * 1e3,
-                              "k2c_overflow_bins": ksec[4] * 1e3}}
+                              "k2c_overflow_bins": ksec[4] * 1e3},
+                "k3_diagnostics": {"buckets_sorted_in_global_memory": ksec[5], "exact_two_pass_scatter": ksec[6], "value_range_bits_per_key": ksec[7]}}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1), and the same FASTA through GATB's own API on the GPU path ----
     cpu, e2e_api = None, None
@@ -445,7 +446,8 @@ def main():
     ap.add_argument("--fine-bits", type=int, default=0, help="gatb_gpu_params.fine_bits (experiments; 0 = default)")
     ap.add_argument("--bin-target-pct", type=int, default=0, help="gatb_gpu_params.bin_target_pct (experiments; 0 = default)")
     ap.add_argument("--table-log2", type=int, default=0, help="gatb_gpu_params.table_log2 (experiments; 0 = default)")
-    ap.add_argument("--no-route", action="store_true", help="N>1: skip the second exchange (per-rank ascending runs instead of whole partitions on their owner rank)")
+    ap.add_argument("--route", action="store_true", help="N>1: second exchange -- every partition whole and ascending on rank key %% N instead of per-rank ascending runs "
+                    "(bit-exact at 8 GPUs; off by default: partitions of a single minimizer outgrow the bucket directory of the sort on their owner, DESIGN.md 6)")
     ap.add_argument("--staged", action="store_true", help="N=1 through the staged multi-GPU code path (debugging aid)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -107,7 +107,7 @@ def load_library():
                                       C.c_uint32, VP, U64, C.POINTER(Result)]
     L.gatb_gpu_count_bins_routed.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), I32, C.POINTER(VP), C.POINTER(VP),
                                              C.c_uint32, VP, U64, I32, VP, C.POINTER(VP), C.POINTER(Result)]
-    L.gatb_gpu_sort_routed.argtypes = [VP, C.POINTER(Params), VP, VP, VP, VP, U64, C.POINTER(Result)]
+    L.gatb_gpu_sort_routed.argtypes = [VP, C.POINTER(Params), VP, VP, VP, VP, U64, I32, I32, C.POINTER(Result)]
     return L
 
 
@@ -304,10 +304,10 @@ class GatbGpu:
                                                       n_ranks, _ptr(counts), C.byref(keys), C.byref(res)))
         return res, keys.value, [int(x) for x in counts[:n_ranks]], int(counts[n_ranks])
 
-    def sort_routed(self, params, d_lo, d_hi, d_counts, d_keys, n_items):
+    def sort_routed(self, params, d_lo, d_hi, d_counts, d_keys, n_items, n_ranks, rank):
         """Partition key + ascending order of routed items (device pointers).  Returns a device Result."""
         res = Result()
-        self._check(self.L.gatb_gpu_sort_routed(self.ctx, C.byref(params), _ptr(d_lo), _ptr(d_hi), _ptr(d_counts), _ptr(d_keys), n_items, C.byref(res)))
+        self._check(self.L.gatb_gpu_sort_routed(self.ctx, C.byref(params), _ptr(d_lo), _ptr(d_hi), _ptr(d_counts), _ptr(d_keys), n_items, n_ranks, rank, C.byref(res)))
         return res
 
     # ---- GATB-exact super-k-mers ---------------------------------------------------------------------------------

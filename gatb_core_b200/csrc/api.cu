@@ -391,13 +391,16 @@ static int partition_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const ga
 
 // ---- stage 4 (k3): partition key + ascending order of the emitted k-mers [0, n_range) (holes carry an all-ones key) ----
 // in_key != NULL: the keys came with the items (routed items of a multi-GPU run); the result arrays live in context-owned slots
-struct SortOut { DevResult dr; uint64_t* h_lo; uint64_t* h_hi; int32_t* h_cnt32; uint64_t* h_offs; uint64_t* h_hist; };
+struct SortOut { DevResult dr; uint64_t* h_lo; uint64_t* h_hi; int32_t* h_cnt32; uint64_t* h_offs; uint64_t* h_hist; uint64_t n_big; int two_pass; int t_bits; };
 static int sort_stage (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint64_t* u_lo, const uint64_t* u_hi, const uint32_t* u_cnt, const uint16_t* in_key,
-                       uint64_t n_range, uint64_t n_items, const uint16_t* repart_host, bool to_host, SortOut* so)
+                       uint64_t n_range, uint64_t n_items, const uint16_t* repart_host, bool to_host, SortOut* so, uint64_t n_keys_local = 0)
 {
     LaunchCtx L = lctx (ctx);
     const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
-    const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
+    // routed items carry LOCAL keys 0 .. n_keys_local-1 (the partitions this rank owns, in order): buckets and offsets are laid out
+    // for those; the caller expands the offsets to all keys.  The result slot always has room for the offsets of all keys.
+    const uint64_t n_keys_all = (uint64_t)p->nb_partitions * p->nb_passes;
+    const uint64_t n_keys = n_keys_local ? n_keys_local : n_keys_all;
     const int histo_max = p->histo_max;
     const size_t item_bytes = 8 * W + 4;
     if (ensure (ctx, S_COUNTERS, 16 * 8)) return 1;
@@ -417,10 +420,10 @@ static int sort_stage (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint64
     DevResult* dr = &so->dr; memset (so, 0, sizeof(*so));
     uint64_t n_alloc = n_items ? n_items : 1;
     if (ensure (ctx, S_SORTED, n_alloc * item_bytes + 64)) return 1;
-    if (ensure (ctx, S_RESMISC, (n_keys + 1) * 8 + (size_t)(histo_max + 1) * 8 + 64)) return 1;
+    if (ensure (ctx, S_RESMISC, (n_keys_all + 1) * 8 + (size_t)(histo_max + 1) * 8 + 64)) return 1;
     void* d_sorted = ctx->slot[S_SORTED];
     dr->lo = d_sorted; dr->hi = (W == 2) ? (void*)((uint64_t*)d_sorted + n_alloc) : 0; dr->cnt = (void*)((uint64_t*)d_sorted + n_alloc * W);
-    void* d_offs = ctx->slot[S_RESMISC]; void* d_hist = (void*)((uint64_t*)ctx->slot[S_RESMISC] + (n_keys + 1));
+    void* d_offs = ctx->slot[S_RESMISC]; void* d_hist = (void*)((uint64_t*)ctx->slot[S_RESMISC] + (n_keys_all + 1));
     dr->offs = d_offs; dr->histo = d_hist;
 
     if (ensure (ctx, S_BUCKETCNT, n_buckets * 4)) return 1;
@@ -549,6 +552,7 @@ static int sort_stage (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint64
         }
     }
     so->h_lo = h_lo; so->h_hi = h_hi; so->h_cnt32 = h_cnt32; so->h_offs = h_offs; so->h_hist = h_hist;
+    so->n_big = n_big; so->two_pass = pooled ? 0 : 1; so->t_bits = t_bits;
     return 0;
 }
 
@@ -790,7 +794,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
         //      partition (key % route_ranks) together with their keys; the caller exchanges the groups and every rank sorts the
         //      partitions it owns (gatb_gpu_sort_routed) ----
         if (route_ranks > GATB_GPU_MAX_RANKS) return fail (ctx, "route_ranks must be in [1,%d]", GATB_GPU_MAX_RANKS);
-        if (ensure (ctx, S_ROUTECNT, 24 * 8)) return 1;
+        if (ensure (ctx, S_ROUTECNT, 136 * 8)) return 1;                      // cursor of destination r at [16 r] (one 128-byte line each), flag at [128]
         unsigned long long* d_rc = (unsigned long long*)ctx->slot[S_ROUTECNT];
         K3Params k3; memset (&k3, 0, sizeof(k3));
         k3.k = k; k3.m = p->minimizer_size; k3.W = W;
@@ -818,10 +822,13 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
             if (ensure (ctx, S_FINE, n_alloc * (8 * W + 6) + 64)) return 1;
             o_lo = (uint64_t*)ctx->slot[S_FINE]; o_hi = (W == 2) ? o_lo + n_alloc : 0;
             o_cnt = (uint32_t*)(o_lo + n_alloc * W); o_key = (uint16_t*)(o_cnt + n_alloc);
-            CK (cudaMemsetAsync (d_rc, 0, 24 * 8, ctx->stream));
-            CK (launch_k3r_route (L, k3, (uint32_t)route_ranks, dest_cap, d_rc, o_lo, o_hi, o_cnt, o_key, (uint32_t*)(d_rc + 8)));
-            CK (cudaMemcpyAsync (h_rc, d_rc, 9 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK (cudaMemsetAsync (d_rc, 0, 136 * 8, ctx->stream));
+            CK (launch_k3r_route (L, k3, (uint32_t)route_ranks, dest_cap, d_rc, o_lo, o_hi, o_cnt, o_key, (uint32_t*)(d_rc + 128)));
+            unsigned long long h_all[129];
+            CK (cudaMemcpyAsync (h_all, d_rc, 129 * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK (cudaStreamSynchronize (ctx->stream));
+            for (int r = 0; r < 8; r++) h_rc[r] = h_all[16 * r];
+            h_rc[8] = h_all[128];
             if (!(h_rc[8] & 1)) break;
             if (attempt >= 1) return fail (ctx, "routing: a destination region overflowed twice");
             dest_cap = n_items + 1;
@@ -860,6 +867,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     cudaEventElapsedTime (&ms, ctx->ev[4], ctx->ev[5]); out->seconds[4] = ms * 1e-3;
     for (int i = 1; i < 4; i++) { cudaEventElapsedTime (&ms, ctx->kev[2*i], ctx->kev[2*i+1]); out->kernel_seconds[i] = ms * 1e-3; }
     if (n_ovf_first) { cudaEventElapsedTime (&ms, ctx->kev[8], ctx->kev[9]); out->kernel_seconds[4] = ms * 1e-3; out->stats[11] = h_cnt[5]; }
+    out->kernel_seconds[5] = (double)so.n_big; out->kernel_seconds[6] = so.two_pass; out->kernel_seconds[7] = so.t_bits;          // diagnostics of the sort stage
     return 0;
 }
 
@@ -1004,7 +1012,7 @@ int gatb_gpu_count_bins_routed (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, con
 }
 
 int gatb_gpu_sort_routed (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint64_t* d_lo, const uint64_t* d_hi, const uint32_t* d_counts,
-                          const uint16_t* d_keys, uint64_t n_items, gatb_gpu_result* out)
+                          const uint16_t* d_keys, uint64_t n_items, int n_ranks, int rank, gatb_gpu_result* out)
 {
     if (!ctx) return 1;
     cudaSetDevice (ctx->device);
@@ -1012,8 +1020,25 @@ int gatb_gpu_sort_routed (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uin
     if (p->kmer_size < 1 || p->kmer_size > 63 || p->nb_partitions < 1 || p->nb_passes < 1 || p->histo_max < 1) return fail (ctx, "bad parameters");
     if (n_items && (!d_lo || !d_counts || !d_keys || (p->kmer_size >= 32 && !d_hi))) return fail (ctx, "item arrays are NULL");
     cudaEventRecord (ctx->ev[4], ctx->stream);
+    if (n_ranks < 1 || n_ranks > GATB_GPU_MAX_RANKS || rank < 0 || rank >= n_ranks) return fail (ctx, "bad rank %d of %d", rank, n_ranks);
+    // the keys this rank owns are rank, rank + n_ranks, ...: the items carry their index in that list (key / n_ranks)
+    const uint64_t n_keys_all = (uint64_t)p->nb_partitions * p->nb_passes;
+    const uint64_t n_keys_local = n_keys_all > (uint64_t)rank ? (n_keys_all - rank + n_ranks - 1) / n_ranks : 0;
     SortOut so;
-    if (sort_stage (ctx, p, d_lo, d_hi, d_counts, d_keys, n_items, n_items, 0, false, &so)) return 1;
+    if (sort_stage (ctx, p, d_lo, d_hi, d_counts, d_keys, n_items, n_items, 0, false, &so, n_keys_local ? n_keys_local : 1)) return 1;
+    {   // offsets of ALL keys: a key this rank does not own is empty (it starts where the next owned key starts)
+        std::vector<uint64_t> loc (n_keys_local + 2, 0), all (n_keys_all + 1);
+        CK (cudaMemcpyAsync (loc.data (), so.dr.offs, ((n_keys_local ? n_keys_local : 1) + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+        for (uint64_t key = 0; key <= n_keys_all; key++)
+        {
+            uint64_t j = key > (uint64_t)rank ? (key - rank + n_ranks - 1) / n_ranks : 0;          // owned keys below 'key'
+            if (j > n_keys_local) j = n_keys_local;
+            all[key] = n_keys_local ? loc[j] : 0;
+        }
+        CK (cudaMemcpyAsync (so.dr.offs, all.data (), (n_keys_all + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK (cudaStreamSynchronize (ctx->stream));
+    }
     cudaEventRecord (ctx->ev[5], ctx->stream);
     CK (cudaStreamSynchronize (ctx->stream));
     memset (out, 0, sizeof(*out));
@@ -1023,6 +1048,7 @@ int gatb_gpu_sort_routed (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uin
     float ms;
     cudaEventElapsedTime (&ms, ctx->ev[4], ctx->ev[5]); out->seconds[4] = ms * 1e-3;
     cudaEventElapsedTime (&ms, ctx->kev[6], ctx->kev[7]); out->kernel_seconds[3] = ms * 1e-3;
+    out->kernel_seconds[5] = (double)so.n_big; out->kernel_seconds[6] = so.two_pass; out->kernel_seconds[7] = so.t_bits;      // diagnostics of the sort stage
     return 0;
 }
 

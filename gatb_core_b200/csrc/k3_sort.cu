@@ -497,11 +497,21 @@ __global__ void __launch_bounds__(256) k3r_route (const K3Params P, uint32_t n_r
         if ((P.W == 1 ? lo[j] : hi[j]) != 0xFFFFFFFFFFFFFFFFULL)
         {
             key[j] = P.n_keys > 1 ? k3_key_of (P, lo[j], hi[j]) : 0u;
-            at[j] = atomicAdd (&s_cnt[key[j] % n_ranks], 1u);
+        }
+        // slot inside the block's share of the destination: one shared atomic per (warp, destination), not per item
+        const uint32_t d = key[j] == 0xFFFFFFFFu ? 0xFFu : key[j] % n_ranks;
+        const unsigned peers = __match_any_sync (0xFFFFFFFFu, d);
+        if (d != 0xFFu)
+        {
+            const int leader = __ffs (peers) - 1;
+            uint32_t b0 = 0;
+            if ((int)(threadIdx.x & 31) == leader) b0 = atomicAdd (&s_cnt[d], (uint32_t)__popc (peers));
+            at[j] = __shfl_sync (peers, b0, leader) + __popc (peers & ((1u << (threadIdx.x & 31)) - 1));
         }
     }
     __syncthreads ();
-    if (threadIdx.x < n_ranks) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd (&dest_cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]) : 0ULL;
+    // (the cursors of the destinations sit in separate 128-byte lines: 10^6 blocks x n_ranks atomics on ONE line took 70 ms on 8 GPUs)
+    if (threadIdx.x < n_ranks) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd (&dest_cursor[threadIdx.x * 16], (unsigned long long)s_cnt[threadIdx.x]) : 0ULL;
     __syncthreads ();
     #pragma unroll
     for (int j = 0; j < K3_ILP; j++)
@@ -512,7 +522,7 @@ __global__ void __launch_bounds__(256) k3r_route (const K3Params P, uint32_t n_r
         if (slot >= dest_cap) { atomicOr (ovf_flag, 1u); continue; }           // the region of this destination is full: the caller retries with exact sizes
         const unsigned long long pos = (unsigned long long)d * dest_cap + slot;
         o_lo[pos] = lo[j]; if (P.W == 2) o_hi[pos] = hi[j];
-        o_cnt[pos] = P.in_cnt[base + 256 * j]; o_key[pos] = (uint16_t)key[j];
+        o_cnt[pos] = P.in_cnt[base + 256 * j]; o_key[pos] = (uint16_t)(key[j] / n_ranks);       // index among the keys its owner holds
     }
 }
 cudaError_t launch_k3r_route (const LaunchCtx& L, const K3Params& P, uint32_t n_ranks, uint64_t dest_cap, unsigned long long* dest_cursor,

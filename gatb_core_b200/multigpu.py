@@ -143,13 +143,17 @@ def _count_and_route(gpu, params, geom, src_bins, src_cur, bpr, kmers_bound, rep
     t["route_exchange"] = time.time() - t0
     t["routed_bytes"] = (sum(send) - send[rank]) * (8 * W + 6)
     d_hi = got[1].data_ptr() if W == 2 else None
-    res = gpu.sort_routed(params, got[0].data_ptr(), d_hi, got[-2].data_ptr(), got[-1].data_ptr(), n_recv)
+    res = gpu.sort_routed(params, got[0].data_ptr(), d_hi, got[-2].data_ptr(), got[-1].data_ptr(), n_recv, world, rank)
     for i in range(len(res.stats)):
         res.stats[i] = res1.stats[i]
     for i in range(8):
         res.seconds[i] = res1.seconds[i]
     ks = [float(x) for x in res1.kernel_seconds]
+    t["route_kernel"] = float(res1.kernel_seconds[3])
+    t["sort_routed"] = float(res.kernel_seconds[3])
+    t["sort_diag"] = [float(res.kernel_seconds[i]) for i in (5, 6, 7)]
     ks[3] += float(res.kernel_seconds[3])                 # routing kernels + sort
+    ks[5:8] = t["sort_diag"]
     for i in range(8):
         res.kernel_seconds[i] = ks[i]
     res._keep = got                                       # (nothing of it is referenced by the result, but keep the order of frees simple)
@@ -195,7 +199,7 @@ def bind_to_gpu_numa(local):
 
 
 def count_distributed(gpu, params, d_reads, n_reads_local, n_reads_global, total_kmers_global, rank, world, repart=None,
-                      d_offsets=None, timers=None, ready=None, route=True):
+                      d_offsets=None, timers=None, ready=None, route=False):
     """One distributed counting pass.  Returns (device Result of this rank's bins, stats dict with GLOBAL sums).
 
     partition piece 0 -> [send piece 0 || partition piece 1] -> ... -> send the last piece -> count: every (source rank, piece)
@@ -350,7 +354,7 @@ def bench(args, rank, world, local):
                              path_flags=args.path_flags, bin_load_pct=args.bin_load_pct, table_log2=args.table_log2, fine_bits=args.fine_bits, bin_target_pct=args.bin_target_pct)
 
     def step(timers=None):
-        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, timers=timers, route=not args.no_route)
+        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, timers=timers, route=args.route)
         gpu.result_free(res)
         return stats
 
@@ -397,7 +401,7 @@ def bench(args, rank, world, local):
                 ev.record(copy_stream)
                 ready.append(ev)
         t1 = time.time()
-        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, ready=ready, route=not args.no_route)
+        res, stats = count_distributed(gpu, params, reads.data_ptr(), n, n_global, total_kmers, rank, world, repart=repart, ready=ready, route=args.route)
         t2 = time.time()
         host = result_to_pinned(gpu, res, params)
         gpu.result_free(res)
@@ -422,7 +426,7 @@ def bench(args, rank, world, local):
         asc = bool(np.isin(desc, offs).all())                # ascending inside every partition key (k <= 31: one word per k-mer)
         sizes = np.diff(offs)
         owned = (np.arange(len(sizes)) % world) == rank      # second exchange: a partition lives whole on rank key % world
-        whole = bool((sizes[~owned] == 0).all())
+        whole = (not args.route) or bool((sizes[~owned] == 0).all())
         local = [int(hist.sum()), sum(c * int(hist[c]) for c in range(ABUNDANCE_MIN)) + int(cnt.sum(dtype=np.int64)),
                  int(hist[ABUNDANCE_MIN:].sum()), ni, 0 if (asc and whole) else 1]
     except Exception:                                        # never let the checker take the measurement down
@@ -431,7 +435,7 @@ def bench(args, rank, world, local):
     dist.all_reduce(loc)                                     # every rank gets here, whatever happened above
     loc = [int(x) for x in loc.tolist()]
     invariants = {"sum_hist_eq_distinct": loc[0] == stats["kmers_nb_distinct"], "occurrences_accounted": loc[1] == stats["kmers_nb_valid"],
-                  "solid_is_histogram_tail": loc[2] == loc[3] == stats["kmers_nb_solid"], "partitions_whole_and_ascending_on_their_owner": loc[4] == 0,
+                  "solid_is_histogram_tail": loc[2] == loc[3] == stats["kmers_nb_solid"], ("partitions_whole_and_ascending_on_their_owner" if args.route else "strictly_ascending_per_rank"): loc[4] == 0,
                   "checker_errors": loc[5]}
     invariants["all"] = all(v is True for k, v in invariants.items() if k != "checker_errors") and loc[5] == 0
     if rank == 0:
@@ -450,7 +454,7 @@ def bench(args, rank, world, local):
                 "dtype": "u64", "data": "synthetic",
                 "config": {"workload": "k=31, %d synthetic 150bp reads (%d per GPU), %dxB200, minimizer buckets sharded via NCCL all-to-all, m=10, abundance-min=2, "
                                        "%d partitions x %d pass(es) (the reference's own configuration)%s" % (n_global, n, world, nb_partitions, nb_passes,
-                                          "" if args.no_route else "; second all-to-all: every partition whole and ascending on rank key %% %d" % world),
+                                          "" if not args.route else "; second all-to-all: every partition whole and ascending on rank key %% %d" % world),
                            "reads": n_global, "nb_partitions": nb_partitions, "nb_passes": nb_passes, "repartitor": repart_src, "genome_nt": genome, "coverage": COVERAGE, "error_rate": 0.01,
                            "l2": "per-GPU inputs (%.1f GB packed reads) far exceed the 126 MB L2" % (nbytes / 1e9)},
                 "input_bases_per_s": n_global * L / per_step, "kmer_occurrences_per_s": stats["kmers_nb_valid"] / per_step,

@@ -118,7 +118,9 @@ typedef struct gatb_gpu_result
     double    seconds[8];        /* stream time per stage (CUDA events): 0 h2d, 1 partition, 2 split, 3 count, 4 sort, 5 d2h,
                                     6 device total, 7 end to end */
     double    kernel_seconds[8]; /* kernel-only durations: 0 partition (k1), 1 fine split (k2a), 2 first-tier count (k2b),
-                                    3 k3 (classify + scatter + scan + sort), 4 overflow tiers + global fallback   */
+                                    3 k3 (classify + scatter + scan + sort), 4 overflow tiers + global fallback;
+                                    diagnostics of the sort stage, not times: 5 buckets sorted in global memory, 6 = 1 when the exact two-pass
+                                    scatter replaced the pooled one, 7 value-range bits per key */
     int32_t   on_device;         /* 1: the arrays above are DEVICE pointers (gatb_gpu_count_dev), 0: host            */
     int32_t   pad;
     void*     owner;             /* internal */
@@ -207,7 +209,7 @@ int gatb_gpu_count_bins (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_g
  * to its GATB partition.  gatb_gpu_count_bins_routed counts like gatb_gpu_count_bins and, instead of sorting, groups the emitted
  * k-mers by the rank that owns their partition key (key % n_ranks): out->kmers_lo / kmers_hi / counts and *d_keys (16-bit keys) are
  * DEVICE arrays of n_ranks regions of send_counts[n_ranks] items each, the first send_counts[r] items of region r going to rank r
- * (send_counts: host [n_ranks + 1]); out->n_items is their total, out->part_offsets is NULL, out->histogram the device histogram of
+ * (send_counts: host [n_ranks + 1]; a key travels as key / n_ranks, its index among the keys of its owner); out->n_items is their total, out->part_offsets is NULL, out->histogram the device histogram of
  * this rank's bins.  The caller exchanges the groups (all-to-all) and hands what it received to gatb_gpu_sort_routed: ascending order
  * of the partitions this rank owns, result as gatb_gpu_count_bins (every key not owned is empty; the keys travel with the items and are
  * not computed twice). */
@@ -216,7 +218,7 @@ int gatb_gpu_count_bins_routed (gatb_gpu_ctx*, const gatb_gpu_params*, const gat
                                 uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, int n_ranks,
                                 uint64_t* send_counts, uint16_t** d_keys, gatb_gpu_result* out);
 int gatb_gpu_sort_routed (gatb_gpu_ctx*, const gatb_gpu_params*, const uint64_t* d_kmers_lo, const uint64_t* d_kmers_hi,
-                          const uint32_t* d_counts, const uint16_t* d_keys, uint64_t n_items, gatb_gpu_result* out);
+                          const uint32_t* d_counts, const uint16_t* d_keys, uint64_t n_items, int n_ranks, int rank, gatb_gpu_result* out);
 
 /* ---- GATB-exact super-k-mer partitioning (rows A3-A6): per key, the record stream [u8 nbK][packed bytes]... that
  *      the reference writes to its SuperKmerBinFiles (order of records inside a key is unspecified).

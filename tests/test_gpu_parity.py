@@ -434,6 +434,56 @@ def test_staged_multi_gpu_path_on_one_rank(gpu, oracle):
     assert stats["kmers_nb_distinct"] == want["stats"]["kmers_nb_distinct"]
 
 
+@pytest.mark.parametrize("name,world", [("dsk_k31_parts", 3), ("dsk_k63_w16", 2), ("dsk_k21_cfg1", 8)])
+def test_routed_result_on_one_gpu(gpu, oracle, name, world):
+    # second exchange of a multi-GPU run (gatb_gpu_count_bins_routed + gatb_gpu_sort_routed), all ranks played by one GPU: the items
+    # routed to destination r, sorted, must be exactly the partitions key % world == r of the one-shot count, every other key empty
+    import torch
+    from gatb_core_b200.multigpu import _as_tensor
+    fx = fixtures.Fixture(name, oracle)
+    seqs = [s.replace(b"N", b"A") for s in fx.seqs]
+    packed, offs, _ = pack_seqs(oracle, seqs)
+    W = 1 if fx.k < 32 else 2
+    n_keys = fx.nb_partitions * fx.nb_passes
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, nb_passes=fx.nb_passes, abundance_min=2)
+    want = gpu.count(packed, offs, len(seqs), params, repart=fx.repart)
+    dev = torch.device("cuda", 0)
+    d_reads = torch.from_numpy(packed).cuda()
+    d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+    total_kmers = sum(max(len(s) - fx.k + 1, 0) for s in seqs)
+    geom = gpu.plan(params, total_kmers, len(seqs), 1)
+    bins = torch.empty(geom.nb1 * geom.cap * geom.record_bytes, dtype=torch.uint8, device=dev)
+    cursors = torch.zeros(geom.nb1, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    st = gpu.partition_into(params, geom, d_reads.data_ptr(), d_offs.data_ptr(), len(seqs), bins.data_ptr(), cursors.data_ptr())
+    assert st[3] == 0
+    res1, d_keys, send, cap = gpu.count_bins_routed(params, geom, [bins.data_ptr()], [cursors.data_ptr()], geom.nb1, total_kmers, world, repart=fx.repart)
+    assert sum(send) == int(res1.n_items) == want["stats"]["kmers_nb_solid"]
+    lo = _as_tensor(res1.kmers_lo, cap * world, torch.int64, dev).clone()
+    hi = _as_tensor(res1.kmers_hi, cap * world, torch.int64, dev).clone() if W == 2 else None
+    cn = _as_tensor(res1.counts, cap * world, torch.int32, dev).clone()
+    ky = _as_tensor(d_keys, cap * world * 2, torch.uint8, dev).clone()
+    seen = 0
+    for r in range(world):
+        a, b = r * cap, r * cap + send[r]
+        r_lo, r_cn, r_ky = lo[a:b].clone(), cn[a:b].clone(), ky[2 * a:2 * b].clone()
+        r_hi = hi[a:b].clone() if W == 2 else None
+        torch.cuda.synchronize()
+        res = gpu.sort_routed(params, r_lo.data_ptr(), r_hi.data_ptr() if W == 2 else None, r_cn.data_ptr(), r_ky.data_ptr(), send[r], world, r)
+        got = gpu.result_to_host(res, params)
+        for key in range(n_keys):
+            glo, ghi, gcn = got["parts"][key]
+            if key % world != r:
+                assert len(glo) == 0, (r, key)
+                continue
+            wlo, whi, wcn = want["parts"][key]
+            assert len(glo) == len(wlo) and (glo == wlo).all() and (gcn == wcn).all(), (r, key)
+            if W == 2:
+                assert (ghi == whi).all(), (r, key)
+            seen += len(glo)
+    assert seen == want["stats"]["kmers_nb_solid"]
+
+
 # ---- BASELINE.json configs 3 and 4 at a down-sampled size, against the REFERENCE itself (oracle/_ref: SortingCountAlgorithm on all
 #      host cores with its own configuration and Repartitor table): same generator and seeds as SURVEY.md 8d, n / 1000 ----
 @pytest.mark.parametrize("name,k,L,n,seed", [("cfg3_k31", 31, 150, 1000000, 43), ("cfg4_k63", 63, 250, 500000, 44)])

@@ -30,7 +30,7 @@ def main():
         torch.cuda.synchronize()      # torch's zero fill vs the library's own stream
         gpu.synth_reads_dev(7, genome, rank * n, n, L, reads.data_ptr())
         gpu.synchronize()
-        res, stats = multigpu.count_distributed(gpu, params, reads.data_ptr(), n, n_global, n_global * (L - k + 1), rank, world, repart=repart)
+        res, stats = multigpu.count_distributed(gpu, params, reads.data_ptr(), n, n_global, n_global * (L - k + 1), rank, world, repart=repart, route=True)
         mine = gpu.result_to_host(res, params)
         bloom, bloom_bits = multigpu.bloom_distributed(gpu, "neighbor", k, res, stats["kmers_nb_solid"], world)
         bloom = bloom.cpu().numpy()
