@@ -67,11 +67,11 @@ def check_invariants(res, occurrences):
 
 def ncu_traffic(kernel, reads):
     """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` capture of this workload
-    (profiles/r01_traffic.json: {kernel: {reads: bytes}}); None when no capture of this size exists."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    (profiles/r02_traffic.json: {kernel: {reads: bytes}}); None when no capture of this size exists."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         t = json.load(open(p))
-        return float(t[kernel][str(reads)]), "ncu --set full capture, profiles/r01_traffic.json"
+        return float(t[kernel][str(reads)]), "ncu --set full capture, profiles/r02_traffic.json"
     except Exception:
         return None, None
 
