@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "gatb_tables.h"
+#include "repart_host.h"
 
 #include <math.h>
 #include <stdarg.h>
@@ -12,6 +13,8 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <queue>
+#include <algorithm>
 
 static std::string g_create_error;
 
@@ -1287,6 +1290,62 @@ int gatb_gpu_reads_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uin
 // =====================================================================================================================
 //  GATB-exact super-k-mers (rows A3-A6)
 // =====================================================================================================================
+// ---- Repartitor table (row f3): sampling pass on the device (k_repart.cu), distribution on the host (repart_host.h) ----
+int gatb_gpu_repartition (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint8_t* packed_reads, const uint64_t* read_offsets_nt,
+                          uint64_t n_reads, const uint32_t* n_mask, uint64_t nb_seqs_to_see, uint16_t* table_out, uint64_t* info3)
+{
+    if (!ctx) return 1;
+    cudaSetDevice (ctx->device);
+    if (!table_out) return fail (ctx, "table_out is NULL");
+    const int k = p->kmer_size, m = p->minimizer_size;
+    if (k < 2 || k > 31) return fail (ctx, "gatb_gpu_repartition: kmer_size %d not supported (Kmer<32> only)", k);
+    if (m < 2 || m > 12 || m >= k) return fail (ctx, "Bad values for kmer %d and minimizer %d", k, m);
+    if (p->nb_partitions < 1 || p->nb_partitions > 65535) return fail (ctx, "nb_partitions must be in [1,65535]");
+    if (p->minimizer_type != 0) return fail (ctx, "minimizer_type %d (frequency order) is not supported on the device path yet", p->minimizer_type);
+    if (!read_offsets_nt && p->read_len <= 0) return fail (ctx, "read_offsets_nt is NULL and read_len <= 0");
+    LaunchCtx L = lctx (ctx);
+    const uint64_t total_nt = read_offsets_nt ? read_offsets_nt[n_reads] : n_reads * (uint64_t)p->read_len;
+    const uint64_t bytes = (total_nt + 3) / 4;
+    if (ensure (ctx, S_READS, bytes + 64)) return 1;
+    CK (cudaMemsetAsync ((uint8_t*)ctx->slot[S_READS] + (bytes & ~15ULL), 0, (bytes & 15) + 48, ctx->stream));
+    CK (cudaMemcpyAsync (ctx->slot[S_READS], packed_reads, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t* d_off = 0; const uint32_t* d_mask = 0;
+    if (read_offsets_nt)
+    {
+        if (ensure (ctx, S_OFFSETS, (n_reads + 1) * 8)) return 1;
+        CK (cudaMemcpyAsync (ctx->slot[S_OFFSETS], read_offsets_nt, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_off = (const uint64_t*)ctx->slot[S_OFFSETS];
+    }
+    if (n_mask)
+    {
+        uint64_t mw = (total_nt + 31) / 32;
+        if (ensure (ctx, S_NMASK, mw * 4 + 16)) return 1;
+        CK (cudaMemsetAsync ((uint8_t*)ctx->slot[S_NMASK] + mw * 4, 0, 16, ctx->stream));
+        CK (cudaMemcpyAsync (ctx->slot[S_NMASK], n_mask, mw * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = (const uint32_t*)ctx->slot[S_NMASK];
+    }
+    const uint64_t nb_minims = 1ULL << (2 * m);
+    if (ensure (ctx, S_MISC, (n_reads + 1) * 4)) return 1;
+    if (ensure (ctx, S_MISC2, nb_minims * 8)) return 1;
+    // pass 1: super-k-mers per read; the reference's iteration is cancelled after the read with which their running number passes
+    // nb_seqs_to_see (SampleRepart::processSuperkmer, RepartitionAlgorithm.cpp:204-209; the flag is looked at between two reads)
+    CK (launch_repart_sample (L, (const uint64_t*)ctx->slot[S_READS], d_off, p->read_len, d_mask, n_reads, k, m, (uint32_t*)ctx->slot[S_MISC], 0));
+    std::vector<uint32_t> per_read (n_reads);
+    CK (cudaMemcpyAsync (per_read.data (), ctx->slot[S_MISC], n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    uint64_t n_sampled = n_reads, seen = 0;
+    for (uint64_t r = 0; r < n_reads; r++) { seen += per_read[r]; if (seen > nb_seqs_to_see) { n_sampled = r + 1; break; } }
+    // pass 2: kx-mers per minimizer over the sampled reads
+    CK (cudaMemsetAsync (ctx->slot[S_MISC2], 0, nb_minims * 8, ctx->stream));
+    CK (launch_repart_sample (L, (const uint64_t*)ctx->slot[S_READS], d_off, p->read_len, d_mask, n_sampled, k, m, 0, (unsigned long long*)ctx->slot[S_MISC2]));
+    std::vector<unsigned long long> kx (nb_minims);
+    CK (cudaMemcpyAsync (kx.data (), ctx->slot[S_MISC2], nb_minims * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    repartition_distribute (kx, p->nb_partitions, table_out);
+    if (info3) { unsigned long long tot = 0; for (uint64_t i = 0; i < nb_minims; i++) tot += kx[i]; info3[0] = n_sampled; info3[1] = seen; info3[2] = tot; }
+    return 0;
+}
+
 int gatb_gpu_superkmers (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t* repart_table,
                          const uint8_t* packed_reads, const uint64_t* read_offsets_nt, uint64_t n_reads,
                          const uint32_t* n_mask, uint8_t** streams, uint64_t* stream_sizes, uint64_t* stats_out)

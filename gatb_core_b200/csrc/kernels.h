@@ -196,3 +196,6 @@ cudaError_t launch_text_pack (const LaunchCtx&, const char* text, const uint64_t
 cudaError_t launch_text_stats (const LaunchCtx&, const uint64_t* offsets, uint64_t n, unsigned long long* out);
 cudaError_t launch_synth_reads_zipf (const LaunchCtx&, uint64_t seed, uint64_t n_species, const uint64_t* d_cdf, const uint64_t* d_goff,
                                      uint64_t first_read, uint64_t n_reads, int len, uint8_t* packed);
+// k_repart.cu
+cudaError_t launch_repart_sample (const LaunchCtx&, const uint64_t* words, const uint64_t* offsets, int read_len, const uint32_t* nmask,
+                                  uint64_t n_reads, int k, int m, uint32_t* sk_count, unsigned long long* kx_table);

@@ -229,6 +229,16 @@ int gatb_gpu_superkmers (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* 
                          const uint32_t* n_mask, uint8_t** streams, uint64_t* stream_sizes, uint64_t* stats_out);
 void gatb_gpu_free_host (void*);
 
+/* ---- Repartitor table: replaces RepartitorAlgorithm<span>::computeRepartition (kmer/impl/RepartitionAlgorithm.cpp:394-492;
+ *      minimizer_type 0, one bank, Kmer<32>).  The serial sampling pass over the first reads of the bank (SampleRepart :157-243: super-k-mers
+ *      in GATB's minimizer order, kx-mers charged to their minimizer, cancelled after nb_seqs_to_see super-k-mers -- the reference uses
+ *      max (5 % of the estimated number of reads, 10^6), :451) runs on the device, thread <-> read; the distribution (largest minimizer bin
+ *      into the emptiest partition, Repartitor::computeDistrib kmer/impl/PartiInfo.cpp:48-106) is host arithmetic on the 4^m counters.
+ *      HOST buffers in; table_out: u16[4^m], the table gatb_gpu_count takes; info3 (may be NULL): reads sampled, super-k-mers seen,
+ *      kx-mers charged. ---- */
+int gatb_gpu_repartition (gatb_gpu_ctx*, const gatb_gpu_params*, const uint8_t* packed_reads, const uint64_t* read_offsets_nt,
+                          uint64_t n_reads, const uint32_t* n_mask, uint64_t nb_seqs_to_see, uint16_t* table_out, uint64_t* info3);
+
 /* ---- Bloom filter of solid k-mers ---------------------------------------------------------------------------- */
 enum { GATB_BLOOM_BASIC = 0, GATB_BLOOM_CACHE = 1, GATB_BLOOM_NEIGHBOR = 2 };
 /* bloom_size = (u64)((float)nb_solid * (float)rvalues[k][1]); nb_hash = floorf(0.7 * bits) */
