@@ -180,7 +180,7 @@ static int check_params (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint
 {
     if (!p) return fail (ctx, "params is NULL");
     if (p->kmer_size < 2 || p->kmer_size > 63) return fail (ctx, "kmer_size %d not supported (2..63: Kmer<32> and Kmer<64>)", p->kmer_size);
-    if (p->minimizer_size < 1 || p->minimizer_size > 12 || p->minimizer_size >= p->kmer_size)
+    if (p->minimizer_size < 2 || p->minimizer_size > 12 || p->minimizer_size >= p->kmer_size)      // (m = 1 has no "AA" mask: (m-2)*2 bits)
         return fail (ctx, "Bad values for kmer %d and minimizer %d", p->kmer_size, p->minimizer_size);     // Model.hpp:1014
     if (p->nb_partitions < 1 || p->nb_passes < 1) return fail (ctx, "nb_partitions and nb_passes must be >= 1");
     if ((uint64_t)p->nb_partitions * p->nb_passes > 65535) return fail (ctx, "too many partition keys");
@@ -577,7 +577,7 @@ static int count_bins_impl (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const g
     // ---- compact layout of the fine-split copy: coarse_off = exclusive scan of the gathered record counts ----
     if (ensure (ctx, S_TOTCUR, (size_t)nb1_local * 4)) return 1;
     if (ensure (ctx, S_COARSEOFF, ((size_t)nb1_local + 1) * 8)) return 1;
-    if (ensure (ctx, S_SCAN, scan_scratch_elems (nb1_local > (n_keys << 24) ? nb1_local : (n_keys << 24)) * 8)) return 1;
+    if (ensure (ctx, S_SCAN, scan_scratch_elems (nb1_local) * 8)) return 1;          // (the sort stage sizes it again for its buckets)
     const uint64_t desc_cap = nbins + nbins / 8 + 1024;          // (adaptive bins: at most one per fine id, plus the bins of the two-pass fallback)
     if (ensure (ctx, S_BINDESC, desc_cap * 8)) return 1;
     CursorList CL; CL.n = n_src; for (int s = 0; s < n_src; s++) CL.cur[s] = d_src_cursors[s];

@@ -716,7 +716,8 @@ public:
         gatb_gpu_params p; memset (&p, 0, sizeof(p));
         p.kmer_size = (int32_t)_config._kmerSize; p.minimizer_size = (int32_t)_config._minim_size;
         p.nb_partitions = (int32_t)_config._nb_partitions; p.nb_passes = (int32_t)_config._nb_passes;
-        p.abundance_min = (int32_t)_config._abundance[0].getBegin (); p.abundance_max = (int32_t)std::min<int64_t> (_config._abundance[0].getEnd (), 0x7fffffff);
+        const tools::misc::CountRange range0 = _config._abundance.empty () ? tools::misc::CountRange (2, 0x7fffffff) : _config._abundance[0];
+        p.abundance_min = (int32_t)range0.getBegin (); p.abundance_max = (int32_t)std::min<int64_t> (range0.getEnd (), 0x7fffffff);
         p.histo_max = (int32_t)_config._histogramMax; p.minimizer_type = (int32_t)_config._minimizerType; p.emit_all = fast ? 0 : 1;
         const uint16_t* table = (_repartitor && !_repartitor->getTable ().empty ()) ? _repartitor->getTable ().data () : 0;
         gatb_gpu_result r;
