@@ -209,6 +209,8 @@ def run_reference(args):
     import oracle_lib
     orc = oracle_lib.Oracle()
     n = args.ref_reads
+    if n <= 0:          # auto: 10^7 reads per step (~9 s on 16 cores), fewer when many steps are asked for, so that the arm ends within minutes
+        n = int(min(10_000_000, max(1_000_000, 160_000_000 // max(args.steps + args.warmup, 1))))
     cores = os.cpu_count() or 1
     codes = orc.synth_reads(SEED, n * L // COVERAGE, 0, n, L)
     packed = orc.pack_2bit(codes)
@@ -436,7 +438,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (BASELINE configs[1]: 1e8)")
-    ap.add_argument("--ref-reads", type=int, default=1_000_000, help="reads per step of the reference arm")
+    ap.add_argument("--ref-reads", type=int, default=0, help="reads per step of the reference arm; 0 = 10^7 (a tenth of one GPU's workload, ~9 s per step on 16 cores), fewer when steps + warmup exceed 16")
     ap.add_argument("--cpu-sample-reads", type=int, default=10_000_000, help="reads of the cpu_baseline / e2e_api sample (one FASTA, both arms)")
     ap.add_argument("--nb-partitions", type=int, default=0, help="0 = the reference's own configuration for this workload and host")
     ap.add_argument("--repart-sample-reads", type=int, default=2_000_000, help="reads the reference's RepartitorAlgorithm samples from")
