@@ -84,3 +84,34 @@ def test_merge_sorted_runs():
     runs = [(full[owner == r], hi[owner == r], cn[owner == r]) for r in range(3)]
     lo2, hi2, cn2 = multigpu.merge_sorted_runs(runs)
     assert (lo2 == full).all() and (hi2 == hi).all() and (cn2 == cn).all()
+
+
+def test_pieces_and_bounds():
+    # a rank cuts its reads into pieces so that ranks x pieces stays within the sources a count accepts; pieces start on multiples of 32 reads
+    assert multigpu.pieces_per_rank(1, 10 ** 8) == 1
+    assert multigpu.pieces_per_rank(8, 100) == 1                        # tiny inputs are not cut
+    for world in (2, 4, 8):
+        npc = multigpu.pieces_per_rank(world, 10 ** 8)
+        assert npc >= 1 and world * npc <= multigpu.MAX_SOURCES
+        b = multigpu.piece_bounds(10 ** 8 + 17, npc)
+        assert b[0] == 0 and b[-1] == 10 ** 8 + 17 and len(b) == npc + 1
+        assert all(x % 32 == 0 for x in b[:-1]) and all(b[i] < b[i + 1] for i in range(npc))
+
+
+def test_owner_of_routed_keys():
+    # second exchange: key k lives on rank k % world as the (k // world)-th key of that rank; the offsets of all keys follow from the
+    # local ones (the arithmetic gatb_gpu_sort_routed does on the host)
+    for n_keys, world in ((5, 8), (176, 2), (2816, 8), (7, 3)):
+        for rank in range(world):
+            owned = [k for k in range(n_keys) if k % world == rank]
+            n_local = (n_keys - rank + world - 1) // world if n_keys > rank else 0
+            assert n_local == len(owned)
+            sizes = np.arange(1, n_local + 1)
+            loc = np.concatenate([[0], np.cumsum(sizes)]) if n_local else np.zeros(1, np.int64)
+            offs = []
+            for key in range(n_keys + 1):
+                j = (key - rank + world - 1) // world if key > rank else 0
+                offs.append(int(loc[min(j, n_local)]))
+            got = np.diff(offs)
+            for key in range(n_keys):
+                assert got[key] == (sizes[key // world] if key % world == rank else 0), (n_keys, world, rank, key)
