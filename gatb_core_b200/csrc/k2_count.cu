@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k2a_dedup_split (const K2aSrc S
         }
         auto src_of = [&] (uint32_t g) -> const uint4*
         {
+            if (S.n == 1) return S.bins[0] + k2a_record_index (S, 0, b, g, nb);          // one GPU: no search among the sources
             int s = 0;
             #pragma unroll
             for (int u = K2A_MAXSRC / 2; u > 0; u >>= 1) if (s + u < K2A_MAXSRC && g >= s_first[s + u]) s += u;
@@ -264,8 +265,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k2a_dedup_split (const K2aSrc S
                 {
                     const uint32_t w = recs[e & 0xFFFFu].w;
                     const uint32_t f = (w >> (DEV_FINE_SHIFT_W1 - 32)) & idmask;
-                    atomicAdd (&s_tmp[f], 1u);
-                    atomicAdd (&s_cur[f], (w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u);
+                    // one atomic for both counters: records of the id in the low 13 bits (a pass stages at most 8191), their k-mers above
+                    atomicAdd (&s_tmp[f], 1u | (((w >> (DEV_LEN_SHIFT_W1 - 32)) & 31u) << 13));
                 }
             }
             __syncthreads ();
@@ -275,7 +276,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k2a_dedup_split (const K2aSrc S
             for (uint32_t c = tid >> 5; c < nch; c += NT / 32)
             {
                 const uint32_t idx = f_lo + 32 * c + lane;
-                const uint32_t v = idx < f_hi ? s_tmp[idx] : 0u, kv = idx < f_hi ? s_cur[idx] : 0u;
+                const uint32_t both = idx < f_hi ? s_tmp[idx] : 0u;
+                const uint32_t v = both & 0x1FFFu, kv = both >> 13;
                 uint32_t incl = v, kincl = kv;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1)
