@@ -25,7 +25,7 @@ EXPORTS = ["gatb_gpu_create", "gatb_gpu_destroy", "gatb_gpu_last_error", "gatb_g
            "gatb_gpu_synchronize", "gatb_gpu_synth_reads_dev", "gatb_gpu_pack_ascii", "gatb_gpu_plan",
            "gatb_gpu_partition_into", "gatb_gpu_partition_range_into", "gatb_gpu_count_bins", "gatb_gpu_reads_begin",
            "gatb_gpu_reads_push_ascii", "gatb_gpu_reads_count", "gatb_gpu_reads_push_text", "gatb_gpu_reads_info", "gatb_gpu_synth_zipf_dev",
-           "gatb_gpu_count_bins_routed", "gatb_gpu_sort_routed", "gatb_gpu_repartition"]
+           "gatb_gpu_count_bins_routed", "gatb_gpu_sort_routed", "gatb_gpu_repartition", "gatb_gpu_count_multi"]
 
 
 class GatbGpuError(RuntimeError):
@@ -107,6 +107,7 @@ def load_library():
                                       C.c_uint32, VP, U64, C.POINTER(Result)]
     L.gatb_gpu_count_bins_routed.argtypes = [VP, C.POINTER(Params), C.POINTER(Geometry), I32, C.POINTER(VP), C.POINTER(VP),
                                              C.c_uint32, VP, U64, I32, VP, C.POINTER(VP), C.POINTER(Result)]
+    L.gatb_gpu_count_multi.argtypes = [C.POINTER(VP), I32, C.POINTER(Params), VP, VP, VP, U64, VP, C.POINTER(Result)]
     L.gatb_gpu_repartition.argtypes = [VP, C.POINTER(Params), VP, VP, U64, VP, U64, VP, VP]
     L.gatb_gpu_sort_routed.argtypes = [VP, C.POINTER(Params), VP, VP, VP, VP, U64, I32, I32, C.POINTER(Result)]
     return L
@@ -310,6 +311,16 @@ class GatbGpu:
         res = Result()
         self._check(self.L.gatb_gpu_sort_routed(self.ctx, C.byref(params), _ptr(d_lo), _ptr(d_hi), _ptr(d_counts), _ptr(d_keys), n_items, n_ranks, rank, C.byref(res)))
         return res
+
+    def count_multi(self, others, packed, offsets, n_reads, params, repart=None, n_mask=None):
+        """One process, several devices (this context first, then `others`: GatbGpu objects of other devices): gatb_gpu_count_multi.
+        Host arrays in, the same dict as count() out."""
+        ctxs = (C.c_void_p * (1 + len(others)))(self.ctx, *[o.ctx for o in others])
+        res = Result()
+        rp = None if repart is None else np.ascontiguousarray(repart, np.uint16)
+        self._check(self.L.gatb_gpu_count_multi(ctxs, 1 + len(others), C.byref(params), _ptr(rp), _ptr(packed),
+                                                _ptr(None if offsets is None else np.ascontiguousarray(offsets, np.uint64)), n_reads, _ptr(n_mask), C.byref(res)))
+        return self._unpack_host(res, params)
 
     def repartition(self, packed, offsets, n_reads, params, nb_seqs_to_see, n_mask=None):
         """The Repartitor table (u16[4^m]) of these reads: sampling pass on the device, distribution on the host.

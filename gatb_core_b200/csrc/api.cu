@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 #include <queue>
+#include <thread>
 #include <algorithm>
 
 static std::string g_create_error;
@@ -33,6 +34,7 @@ struct gatb_gpu_ctx
     const uint16_t* repart_host_cached; uint64_t repart_bytes_cached;
     // streaming input (gatb_gpu_reads_*): reads pushed so far live in S_READS / S_OFFSETS / S_NMASK
     uint64_t push_nt, push_seqs, push_invalid;
+    void* multi_buf; size_t multi_cap;          // merged host result of gatb_gpu_count_multi (first context)
 };
 
 static int fail (gatb_gpu_ctx* c, const char* fmt, ...)
@@ -81,7 +83,7 @@ gatb_gpu_ctx* gatb_gpu_create (int device)
     if ((e = cudaSetDevice (device)) != cudaSuccess) { fail (0, "cudaSetDevice(%d): %s", device, cudaGetErrorString (e)); return 0; }
     gatb_gpu_ctx* ctx = new gatb_gpu_ctx ();
     ctx->device = device; ctx->launches = 0; ctx->pinned = 0; ctx->pinned_cap = 0; ctx->repart_host_cached = 0; ctx->repart_bytes_cached = 0;
-    ctx->push_nt = ctx->push_seqs = ctx->push_invalid = 0;
+    ctx->push_nt = ctx->push_seqs = ctx->push_invalid = 0; ctx->multi_buf = 0; ctx->multi_cap = 0;
     memset (ctx->slot, 0, sizeof(ctx->slot)); memset (ctx->slot_cap, 0, sizeof(ctx->slot_cap));
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties (&prop, device)) != cudaSuccess) { fail (0, "cudaGetDeviceProperties: %s", cudaGetErrorString (e)); delete ctx; return 0; }
@@ -100,6 +102,7 @@ void gatb_gpu_destroy (gatb_gpu_ctx* ctx)
     cudaStreamSynchronize (ctx->stream);
     for (int s = 0; s < S_NSLOTS; s++) if (ctx->slot[s]) cudaFree (ctx->slot[s]);
     if (ctx->pinned) cudaFreeHost (ctx->pinned);
+    free (ctx->multi_buf);
     for (int i = 0; i < 8; i++) cudaEventDestroy (ctx->ev[i]);
     for (int i = 0; i < 16; i++) cudaEventDestroy (ctx->kev[i]);
     for (int i = 0; i < 40; i++) cudaEventDestroy (ctx->cev[i]);
@@ -1119,6 +1122,200 @@ int gatb_gpu_count (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uint16_t*
     float ms;
     cudaEventElapsedTime (&ms, ctx->ev[0], ctx->ev[7]); h.seconds[7] = ms * 1e-3;
     *out = h;
+    return 0;
+}
+
+// =====================================================================================================================
+//  several devices driven by ONE process (SURVEY.md 8b "gatb_gpu_create (n_gpus, dev_ids)"): the staged sequence -- plan, partition,
+//  exchange of the coarse-bin regions, count -- with one host thread per device and peer copies instead of a collective library, then
+//  the per-device ascending runs of every partition merged on the host: a C or C++ caller gets one result, as from gatb_gpu_count.
+// =====================================================================================================================
+struct MultiDev { gatb_gpu_ctx* ctx; uint64_t r0, r1; unsigned long long st[4]; int rc; gatb_gpu_result res; };
+
+static int multi_partition (MultiDev* D, const gatb_gpu_params* p, const gatb_gpu_geometry* g, const uint8_t* packed, uint64_t bytes,
+                            const uint64_t* offs, uint64_t n_reads, const uint32_t* n_mask, uint64_t total_nt)
+{
+    gatb_gpu_ctx* ctx = D->ctx;
+    cudaSetDevice (ctx->device);
+    if (ensure (ctx, S_READS, bytes + 64)) return 1;
+    uint8_t* d_reads = (uint8_t*)ctx->slot[S_READS];
+    const uint64_t nt_lo = offs ? offs[D->r0] : D->r0 * (uint64_t)p->read_len, nt_hi = offs ? offs[D->r1] : D->r1 * (uint64_t)p->read_len;
+    // the device keeps the stream at its absolute offsets but receives only the bytes of its own reads (16-byte units; the
+    // partition kernel looks up to 32 bytes past the last nucleotide)
+    const uint64_t b_lo = (nt_lo / 4) & ~15ULL;
+    uint64_t b_hi = (((nt_hi + 3) / 4) + 48 + 15) & ~15ULL; if (b_hi > bytes) b_hi = bytes;
+    CK (cudaMemsetAsync (d_reads + (bytes & ~15ULL), 0, (bytes & 15) + 48, ctx->stream));
+    if (b_hi > b_lo) CK (cudaMemcpyAsync (d_reads + b_lo, packed + b_lo, b_hi - b_lo, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t* d_off = 0; const uint32_t* d_mask = 0;
+    if (offs)
+    {
+        if (ensure (ctx, S_OFFSETS, (n_reads + 1) * 8)) return 1;
+        CK (cudaMemcpyAsync ((uint64_t*)ctx->slot[S_OFFSETS] + D->r0, offs + D->r0, (D->r1 - D->r0 + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_off = (const uint64_t*)ctx->slot[S_OFFSETS];
+    }
+    if (n_mask)
+    {
+        const uint64_t mw = (total_nt + 31) / 32;
+        if (ensure (ctx, S_NMASK, mw * 4 + 16)) return 1;
+        const uint64_t w_lo = nt_lo / 32; uint64_t w_hi = (nt_hi + 31) / 32 + 2; if (w_hi > mw) w_hi = mw;
+        CK (cudaMemsetAsync ((uint8_t*)ctx->slot[S_NMASK] + mw * 4, 0, 16, ctx->stream));
+        if (w_hi > w_lo) CK (cudaMemcpyAsync ((uint32_t*)ctx->slot[S_NMASK] + w_lo, n_mask + w_lo, (w_hi - w_lo) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = (const uint32_t*)ctx->slot[S_NMASK];
+    }
+    if (ensure (ctx, S_COARSE, (size_t)g->nb1 * g->cap * g->record_bytes)) return 1;
+    if (ensure (ctx, S_CURSORS, (size_t)g->nb1 * 4)) return 1;
+    uint64_t st4[4];
+    if (gatb_gpu_partition_range_into (ctx, p, g, d_reads, d_off, D->r0, D->r1 - D->r0, d_mask, ctx->slot[S_COARSE], (uint32_t*)ctx->slot[S_CURSORS], st4)) return 1;
+    for (int i = 0; i < 4; i++) D->st[i] = st4[i];
+    return 0;
+}
+
+int gatb_gpu_count_multi (gatb_gpu_ctx* const* ctxs, int n_dev, const gatb_gpu_params* p, const uint16_t* repart_table,
+                          const uint8_t* packed_reads, const uint64_t* read_offsets_nt, uint64_t n_reads, const uint32_t* n_mask,
+                          gatb_gpu_result* out)
+{
+    if (!ctxs || n_dev < 1 || !ctxs[0]) return 1;
+    gatb_gpu_ctx* ctx = ctxs[0];                                     // errors are reported on the first context
+    if (n_dev > GATB_GPU_MAX_RANKS) return fail (ctx, "at most %d devices", GATB_GPU_MAX_RANKS);
+    for (int d = 0; d < n_dev; d++) if (!ctxs[d]) return fail (ctx, "context %d is NULL", d);
+    if (!out) return fail (ctx, "out is NULL");
+    if (n_dev == 1) return gatb_gpu_count (ctx, p, repart_table, 0, packed_reads, read_offsets_nt, n_reads, n_mask, out);
+    cudaSetDevice (ctx->device);
+    if (check_params (ctx, p, repart_table)) return 1;
+    if (!read_offsets_nt && p->read_len <= 0) return fail (ctx, "read_offsets_nt is NULL and read_len <= 0");
+    const int k = p->kmer_size, W = (k < 32) ? 1 : 2;
+    const uint64_t n_keys = (uint64_t)p->nb_partitions * p->nb_passes;
+    const uint64_t total_nt = read_offsets_nt ? read_offsets_nt[n_reads] : n_reads * (uint64_t)p->read_len;
+    const uint64_t bytes = (total_nt + 3) / 4;
+    uint64_t total_kmers = 0;
+    if (read_offsets_nt) { for (uint64_t i = 0; i < n_reads; i++) { const uint64_t len = read_offsets_nt[i+1] - read_offsets_nt[i]; if (len >= (uint64_t)k) total_kmers += len - k + 1; } }
+    else if (p->read_len >= k) total_kmers = n_reads * (uint64_t)(p->read_len - k + 1);
+    gatb_gpu_geometry g;
+    if (plan_geometry (ctx, p, total_kmers, n_reads, n_dev, &g)) return 1;
+    std::vector<MultiDev> D (n_dev);
+    for (int d = 0; d < n_dev; d++) { D[d].ctx = ctxs[d]; D[d].r0 = (n_reads * (uint64_t)d / n_dev) & ~31ULL; D[d].rc = 0; memset (&D[d].res, 0, sizeof(D[d].res)); }
+    for (int d = 0; d < n_dev; d++) D[d].r1 = (d + 1 < n_dev) ? D[d + 1].r0 : n_reads;
+    for (int d = 0; d < n_dev; d++) for (int e = 0; e < n_dev; e++) if (e != d)
+    {   // direct peer copies where the devices allow them (cudaMemcpyPeer works either way)
+        cudaSetDevice (ctxs[d]->device);
+        int can = 0; cudaDeviceCanAccessPeer (&can, ctxs[d]->device, ctxs[e]->device);
+        if (can) { cudaError_t pe = cudaDeviceEnablePeerAccess (ctxs[e]->device, 0); if (pe != cudaSuccess) cudaGetLastError (); }
+    }
+    // ---- stage 1: every device partitions its slice of the reads into all regions (one host thread per device) ----
+    for (int attempt = 0; ; attempt++)
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < n_dev; d++) th.emplace_back ([&, d] () { D[d].rc = multi_partition (&D[d], p, &g, packed_reads, bytes, read_offsets_nt, n_reads, n_mask, total_nt); });
+        for (auto& t : th) t.join ();
+        for (int d = 0; d < n_dev; d++) if (D[d].rc) return fail (ctx, "device %d: %s", ctxs[d]->device, ctxs[d]->error.c_str ());
+        unsigned long long dropped = 0; for (int d = 0; d < n_dev; d++) dropped += D[d].st[3];
+        if (!dropped) break;
+        if (attempt >= 1) return fail (ctx, "a coarse bin overflowed twice");
+        // a bin overflowed somewhere: every device runs again with room for the largest demand seen
+        uint32_t need = g.cap;
+        for (int d = 0; d < n_dev; d++)
+        {
+            cudaSetDevice (ctxs[d]->device);
+            std::vector<uint32_t> cur (g.nb1);
+            if (cudaMemcpy (cur.data (), ctxs[d]->slot[S_CURSORS], (size_t)g.nb1 * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return fail (ctx, "cursor copy failed");
+            for (uint32_t b = 0; b < g.nb1; b++) if (cur[b] > need) need = cur[b];
+        }
+        g.cap = (need + COARSE_BLK - 1) / COARSE_BLK * COARSE_BLK;
+    }
+    // ---- stage 2: region d of every device goes to device d (peer copies; the whole region: its unused rounds are slack) ----
+    const size_t region_bytes = (size_t)g.bins_per_rank * g.cap * g.record_bytes, cur_bytes = (size_t)g.bins_per_rank * 4;
+    for (int d = 0; d < n_dev; d++)
+    {
+        cudaSetDevice (ctxs[d]->device);
+        if (ensure (ctxs[d], S_MISC, region_bytes * (n_dev - 1))) return fail (ctx, "device %d: %s", ctxs[d]->device, ctxs[d]->error.c_str ());
+        if (ensure (ctxs[d], S_MISC2, cur_bytes * (n_dev - 1))) return fail (ctx, "device %d: %s", ctxs[d]->device, ctxs[d]->error.c_str ());
+    }
+    for (int d = 0; d < n_dev; d++)
+    {
+        cudaSetDevice (ctxs[d]->device);
+        int slot = 0;
+        for (int s = 0; s < n_dev; s++) if (s != d)
+        {
+            CK (cudaMemcpyPeerAsync ((uint8_t*)ctxs[d]->slot[S_MISC] + region_bytes * slot, ctxs[d]->device,
+                                     (const uint8_t*)ctxs[s]->slot[S_COARSE] + region_bytes * d, ctxs[s]->device, region_bytes, ctxs[d]->stream));
+            CK (cudaMemcpyPeerAsync ((uint8_t*)ctxs[d]->slot[S_MISC2] + cur_bytes * slot, ctxs[d]->device,
+                                     (const uint8_t*)ctxs[s]->slot[S_CURSORS] + cur_bytes * d, ctxs[s]->device, cur_bytes, ctxs[d]->stream));
+            slot++;
+        }
+    }
+    for (int d = 0; d < n_dev; d++) { cudaSetDevice (ctxs[d]->device); CK (cudaStreamSynchronize (ctxs[d]->stream)); }
+    // ---- stage 3: every device counts the bins it owns from all sources; results into its pinned host buffer ----
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < n_dev; d++) th.emplace_back ([&, d] ()
+        {
+            gatb_gpu_ctx* c = ctxs[d];
+            cudaSetDevice (c->device);
+            const void* bins[GATB_GPU_MAX_RANKS]; const uint32_t* curs[GATB_GPU_MAX_RANKS];
+            int slot = 0;
+            for (int s = 0; s < n_dev; s++)
+            {
+                if (s == d) { bins[s] = (const uint8_t*)c->slot[S_COARSE] + region_bytes * d; curs[s] = (const uint32_t*)((const uint8_t*)c->slot[S_CURSORS] + cur_bytes * d); }
+                else        { bins[s] = (const uint8_t*)c->slot[S_MISC] + region_bytes * slot; curs[s] = (const uint32_t*)((const uint8_t*)c->slot[S_MISC2] + cur_bytes * slot); slot++; }
+            }
+            cudaEventRecord (c->ev[1], c->stream);
+            D[d].rc = count_bins_impl (c, p, &g, n_dev, bins, curs, g.bins_per_rank, repart_table, total_kmers, &D[d].res, true);
+        });
+        for (auto& t : th) t.join ();
+        for (int d = 0; d < n_dev; d++) if (D[d].rc) return fail (ctx, "device %d: %s", ctxs[d]->device, ctxs[d]->error.c_str ());
+    }
+    // ---- stage 4 (host): a k-mer lives on one device, so the runs of a partition are disjoint: merged into one ascending sequence ----
+    uint64_t n_items = 0; for (int d = 0; d < n_dev; d++) n_items += D[d].res.n_items;
+    const size_t hist_bytes = (size_t)(p->histo_max + 1) * 8, off_bytes = (n_keys + 1) * 8;
+    const size_t need = off_bytes + hist_bytes + (n_items + 1) * (8 * W + 4) + 64;
+    if (ctx->multi_cap < need) { free (ctx->multi_buf); ctx->multi_buf = malloc (need); ctx->multi_cap = ctx->multi_buf ? need : 0; }
+    if (!ctx->multi_buf) return fail (ctx, "host allocation of the merged result (%zu bytes) failed", need);
+    uint8_t* mb = (uint8_t*)ctx->multi_buf;
+    uint64_t* m_lo = (uint64_t*)mb; mb += (n_items + 1) * 8;
+    uint64_t* m_hi = 0; if (W == 2) { m_hi = (uint64_t*)mb; mb += (n_items + 1) * 8; }
+    uint64_t* m_off = (uint64_t*)mb; mb += off_bytes;
+    uint64_t* m_hist = (uint64_t*)mb; mb += hist_bytes;
+    int32_t* m_cnt = (int32_t*)mb;
+    uint64_t at = 0;
+    for (uint64_t key = 0; key < n_keys; key++)
+    {
+        m_off[key] = at;
+        uint64_t pos[GATB_GPU_MAX_RANKS], end[GATB_GPU_MAX_RANKS];
+        for (int d = 0; d < n_dev; d++) { pos[d] = D[d].res.part_offsets[key]; end[d] = D[d].res.part_offsets[key + 1]; }
+        for (;;)
+        {
+            int best = -1;
+            for (int d = 0; d < n_dev; d++)
+            {
+                if (pos[d] >= end[d]) continue;
+                if (best < 0) { best = d; continue; }
+                const uint64_t bl = D[best].res.kmers_lo[pos[best]], dl = D[d].res.kmers_lo[pos[d]];
+                if (W == 2)
+                {
+                    const uint64_t bh = D[best].res.kmers_hi[pos[best]], dh = D[d].res.kmers_hi[pos[d]];
+                    if (dh < bh || (dh == bh && dl < bl)) best = d;
+                }
+                else if (dl < bl) best = d;
+            }
+            if (best < 0) break;
+            m_lo[at] = D[best].res.kmers_lo[pos[best]]; if (W == 2) m_hi[at] = D[best].res.kmers_hi[pos[best]];
+            m_cnt[at] = D[best].res.counts[pos[best]]; pos[best]++; at++;
+        }
+    }
+    m_off[n_keys] = at;
+    memset (m_hist, 0, hist_bytes);
+    for (int d = 0; d < n_dev; d++) for (int i = 0; i <= p->histo_max; i++) m_hist[i] += D[d].res.histogram[i];
+    memset (out, 0, sizeof(*out));
+    out->n_keys = n_keys; out->n_items = n_items; out->part_offsets = m_off; out->kmers_lo = m_lo; out->kmers_hi = m_hi; out->counts = m_cnt; out->histogram = m_hist;
+    out->on_device = 0;
+    for (int d = 0; d < n_dev; d++)
+    {
+        out->stats[GATB_STAT_KMERS_VALID] += D[d].st[0]; out->stats[GATB_STAT_KMERS_INVALID] += D[d].st[1];
+        for (int i : { (int)GATB_STAT_DISTINCT, (int)GATB_STAT_SOLID, (int)GATB_STAT_RECORDS, (int)GATB_STAT_BINS, (int)GATB_STAT_OVERFLOW_BINS, (int)GATB_STAT_RECORD_BYTES, (int)GATB_STAT_UNIQUE_RECORDS, 11, 12 })
+            out->stats[i] += D[d].res.stats[i];
+        for (int i = 0; i < 8; i++) { if (D[d].res.seconds[i] > out->seconds[i]) out->seconds[i] = D[d].res.seconds[i]; if (i < 5 && D[d].res.kernel_seconds[i] > out->kernel_seconds[i]) out->kernel_seconds[i] = D[d].res.kernel_seconds[i]; }
+    }
+    out->stats[GATB_STAT_SEQUENCES] = n_reads; out->stats[GATB_STAT_NUCLEOTIDES] = total_nt;
     return 0;
 }
 

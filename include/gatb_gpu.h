@@ -204,6 +204,15 @@ int gatb_gpu_count_bins (gatb_gpu_ctx*, const gatb_gpu_params*, const gatb_gpu_g
                          const void* const* d_src_bins, const uint32_t* const* d_src_cursors,
                          uint32_t nb1_local, const uint16_t* repart_table, uint64_t kmers_bound, gatb_gpu_result* out);
 
+/* Several devices driven by ONE process (no collective library: one host thread per device, peer copies of the bin regions): the whole
+ * staged sequence above for the reads of one batch, split evenly over the contexts (one per device, from gatb_gpu_create), and the
+ * per-device ascending runs of every partition merged on the host -- the result is what gatb_gpu_count returns (HOST arrays, owned by
+ * ctxs[0], valid until its next call).  For C / C++ callers such as SortingCountAlgorithm<span>::execute (); the multi-process path
+ * (one process per GPU, NCCL) is gatb_core_b200/multigpu.py. */
+int gatb_gpu_count_multi (gatb_gpu_ctx* const* ctxs, int n_dev, const gatb_gpu_params*, const uint16_t* repart_table,
+                          const uint8_t* packed_reads, const uint64_t* read_offsets_nt, uint64_t n_reads, const uint32_t* n_mask,
+                          gatb_gpu_result* out);
+
 /* Second exchange of a multi-GPU run: the result of a partition must be ONE ascending sequence (what ICountProcessor::process sees in
  * the reference, kmer/impl/PartitionsCommand.cpp:1599-1805), but a k-mer's device bin -- hence the rank that counted it -- is unrelated
  * to its GATB partition.  gatb_gpu_count_bins_routed counts like gatb_gpu_count_bins and, instead of sorting, groups the emitted

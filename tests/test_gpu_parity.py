@@ -434,6 +434,31 @@ def test_staged_multi_gpu_path_on_one_rank(gpu, oracle):
     assert stats["kmers_nb_distinct"] == want["stats"]["kmers_nb_distinct"]
 
 
+@pytest.mark.parametrize("name", ["dsk_k31_parts", "dsk_k63_w16", "dsk_k21_cfg1"])
+def test_several_devices_in_one_process(gpu, oracle, name):
+    # gatb_gpu_count_multi: one host thread per device, peer copies of the bin regions, host merge == the single-device count
+    import torch
+    import gatb_core_b200
+    n_dev = min(torch.cuda.device_count(), 4)
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    fx = fixtures.Fixture(name, oracle)
+    packed, offs, mask = pack_seqs(oracle, fx.seqs)
+    W = 1 if fx.k < 32 else 2
+    params = gpu.make_params(fx.k, fx.m, nb_partitions=fx.nb_partitions, nb_passes=fx.nb_passes, abundance_min=fx.abundance_min)
+    want = gpu.count(packed, offs, len(fx.seqs), params, repart=fx.repart, n_mask=mask)
+    others = [gatb_core_b200.GatbGpu(d) for d in range(1, n_dev)]
+    try:
+        got = gpu.count_multi(others, packed, offs, len(fx.seqs), params, repart=fx.repart, n_mask=mask)
+    finally:
+        for o in others:
+            o.close()
+    check_parts(got, want["parts"], fx.nb_partitions * fx.nb_passes, W)
+    assert (got["histogram"] == want["histogram"]).all()
+    for key in ("kmers_nb_valid", "kmers_nb_invalid", "kmers_nb_distinct", "kmers_nb_solid"):
+        assert got["stats"][key] == want["stats"][key], key
+
+
 @pytest.mark.parametrize("name,world", [("dsk_k31_parts", 3), ("dsk_k63_w16", 2), ("dsk_k21_cfg1", 8)])
 def test_routed_result_on_one_gpu(gpu, oracle, name, world):
     # second exchange of a multi-GPU run (gatb_gpu_count_bins_routed + gatb_gpu_sort_routed), all ranks played by one GPU: the items
