@@ -1495,7 +1495,7 @@ int gatb_gpu_repartition (gatb_gpu_ctx* ctx, const gatb_gpu_params* p, const uin
     cudaSetDevice (ctx->device);
     if (!table_out) return fail (ctx, "table_out is NULL");
     const int k = p->kmer_size, m = p->minimizer_size;
-    if (k < 2 || k > 31) return fail (ctx, "gatb_gpu_repartition: kmer_size %d not supported (Kmer<32> only)", k);
+    if (k < 2 || k > 63) return fail (ctx, "gatb_gpu_repartition: kmer_size %d not supported (1 < k <= 63)", k);
     if (m < 2 || m > 12 || m >= k) return fail (ctx, "Bad values for kmer %d and minimizer %d", k, m);
     if (p->nb_partitions < 1 || p->nb_partitions > 65535) return fail (ctx, "nb_partitions must be in [1,65535]");
     if (p->minimizer_type != 0) return fail (ctx, "minimizer_type %d (frequency order) is not supported on the device path yet", p->minimizer_type);

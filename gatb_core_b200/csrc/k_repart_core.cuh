@@ -5,7 +5,8 @@
 //   SampleRepart<span>::processSuperkmer        kmer/impl/RepartitionAlgorithm.cpp:157-243   (kx-mer accounting, _kx = 4)
 //   Sequence2SuperKmer<span>::operator()        kmer/impl/Sequence2SuperKmer.hpp:81-159      (super-k-mer cuts)
 //   ModelCanonical / ModelMinimizer first/next  kmer/impl/Model.hpp:857-884, 1082-1139, 1254-1287
-// k <= 31 (Kmer<32>); m-mer key = min(m-mer, revcomp) with the "AA" rule applied arithmetically (common.cuh gatb_mmer_key).
+// k <= 63 (Kmer<32> and Kmer<64>: the k-mer is kept in 128 bits, the super-k-mer capacity follows the span like Sequence2SuperKmer.hpp:147);
+// m-mer key = min(m-mer, revcomp) with the "AA" rule applied arithmetically (common.cuh gatb_mmer_key).
 // __host__ __device__: tests/cpp/test_repart_core.cpp runs the same code on the CPU against the oracle's restatement.
 #pragma once
 #include <stdint.h>
@@ -26,10 +27,11 @@ KRP_HD uint32_t krp_mmer_key (uint32_t mm, int m, uint32_t mmask, uint32_t mask_
     a1 = ((a1 >> 1) & a1) & mask_ma1;                      // an "AA" anywhere but at the prefix: not allowed
     return a1 ? mmask : cm;
 }
-KRP_HD uint64_t krp_revcomp (uint64_t x, int k)
+typedef unsigned __int128 krp_u128;
+KRP_HD krp_u128 krp_revcomp (krp_u128 x, int k)
 {
-    uint64_t r = 0;
-    for (int i = 0; i < k; i++) { r = (r << 2) | ((x & 3u) ^ 2u); x >>= 2; }
+    krp_u128 r = 0;
+    for (int i = 0; i < k; i++) { r = (r << 2) | (krp_u128)(((uint32_t)x & 3u) ^ 2u); x >>= 2; }
     return r;
 }
 
@@ -41,17 +43,17 @@ KRP_HD uint32_t krp_scan_read (Nuc nuc, Bad bad, int len, int k, int m, Sink sin
     if (len < k) return 0;                                                               // Sequence2SuperKmer.hpp:144
     const uint32_t mmask = (uint32_t)((1ULL << (2 * m)) - 1), DEF = mmask;                // Model.hpp:1032
     const uint32_t mask_ma1 = (uint32_t)(0x5555555555555555ULL & ((1ULL << ((m - 2) * 2)) - 1));
-    const uint64_t kmask = k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
-    const int nbm = k - m + 1, maxs = 28, KX = 4;                                         // Sequence2SuperKmer.hpp:147 (Kmer<32>)
-    uint64_t fwd = 0; int badidx = -1;
+    const krp_u128 kmask = (((krp_u128)1) << (2 * k)) - 1;                                // k <= 63
+    const int nbm = k - m + 1, maxs = k < 32 ? 28 : 60, KX = 4;                           // (8 * sizeof (Type) - 8) / 2, Sequence2SuperKmer.hpp:147
+    krp_u128 fwd = 0; int badidx = -1;
     for (int i = 0; i < k; i++) { fwd = (fwd << 2) + nuc (i); if (bad (i)) badidx = i; }
-    uint64_t rev = krp_revcomp (fwd, k);
+    krp_u128 rev = krp_revcomp (fwd, k);
     bool valid = badidx < 0;
     uint32_t mini = DEF; int pos = -1;
     auto new_minimizer = [&] ()
     {   // Model.hpp:1254-1287: the m-mers of the k-mer from the last to the first, strictly smaller wins
         mini = DEF; pos = -1;
-        uint64_t v = fwd;
+        krp_u128 v = fwd;
         for (int idx = nbm - 1; idx >= 0; idx--)
         {
             const uint32_t c = krp_mmer_key ((uint32_t)v & mmask, m, mmask, mask_ma1);
@@ -90,7 +92,7 @@ KRP_HD uint32_t krp_scan_read (Nuc nuc, Bad bad, int len, int k, int m, Sink sin
         const uint32_t c = nuc (idx);
         if (bad (idx)) badidx = k - 1; else badidx--;                                      // Model.hpp:753-754
         fwd = ((fwd << 2) + c) & kmask;
-        rev = ((rev >> 2) + ((uint64_t)(c ^ 2u) << (2 * (k - 1)))) & kmask;
+        rev = ((rev >> 2) + ((krp_u128)(c ^ 2u) << (2 * (k - 1)))) & kmask;
         valid = badidx < 0;
         const uint32_t mmer = krp_mmer_key ((uint32_t)fwd & mmask, m, mmask, mask_ma1);
         pos--;

@@ -239,7 +239,7 @@ int gatb_gpu_superkmers (gatb_gpu_ctx*, const gatb_gpu_params*, const uint16_t* 
 void gatb_gpu_free_host (void*);
 
 /* ---- Repartitor table: replaces RepartitorAlgorithm<span>::computeRepartition (kmer/impl/RepartitionAlgorithm.cpp:394-492;
- *      minimizer_type 0, one bank, Kmer<32>).  The serial sampling pass over the first reads of the bank (SampleRepart :157-243: super-k-mers
+ *      minimizer_type 0, one bank, k <= 63).  The serial sampling pass over the first reads of the bank (SampleRepart :157-243: super-k-mers
  *      in GATB's minimizer order, kx-mers charged to their minimizer, cancelled after nb_seqs_to_see super-k-mers -- the reference uses
  *      max (5 % of the estimated number of reads, 10^6), :451) runs on the device, thread <-> read; the distribution (largest minimizer bin
  *      into the emptiest partition, Repartitor::computeDistrib kmer/impl/PartiInfo.cpp:48-106) is host arithmetic on the 4^m counters.

@@ -32,7 +32,8 @@ def write_fasta(path, seqs):
 
 # the reference samples max(5 % of the estimated reads, 10^6) super-k-mers (RepartitionAlgorithm.cpp:451): with 100000 reads of 150 nt
 # (~14 super-k-mers each) the iteration is cancelled inside the bank, with the smaller inputs it runs to the end
-CASES = [(31, 10, 13, 100000, 150, 0.0), (21, 8, 4, 3000, 100, 0.01), (31, 10, 64, 5000, 150, 0.0), (25, 6, 7, 2000, 120, 0.02)]
+CASES = [(31, 10, 13, 100000, 150, 0.0), (21, 8, 4, 3000, 100, 0.01), (31, 10, 64, 5000, 150, 0.0), (25, 6, 7, 2000, 120, 0.02),
+         (63, 10, 9, 3000, 250, 0.01), (32, 8, 5, 2000, 150, 0.0), (47, 9, 16, 2000, 200, 0.0)]
 
 
 def host_table(tmp_path, seqs, k, m, nparts, to_see):
